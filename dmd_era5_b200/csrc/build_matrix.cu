@@ -1,0 +1,162 @@
+// (a) Matrix build: native ERA5 layout (time, point) -> snapshot matrix rows (point, time),
+// fused with time-mean removal, optional unit-variance scaling, optional area weights, cast.
+//
+// Reference semantics restated (not copied):
+//   standardize_data            src/dmd_era5/slice_tools/slice_tools.py:171-177
+//   flatten_era5_variables      src/dmd_era5/slice_tools/slice_tools.py:323-336
+//   check_array finiteness      sklearn/utils/extmath.py:546
+//
+// HBM-bound.  Two kernels per (variable, level) block:
+//   row_stats_kernel  : one thread per grid point walks the T snapshots (a warp reads 32
+//                       consecutive points = one 128 B line per snapshot, fully coalesced);
+//                       float64 accumulation, NaN skipping.
+//   transpose_kernel  : 32x32 shared-memory tile transpose; reads coalesced along points,
+//                       writes coalesced along time, applies (x - mean) / std * w and the cast.
+// Algorithmic bytes per element: read 4 (stats) [+4 second stats pass when scaling] + read 4 +
+// write 4 (f32).  See DESIGN.md for the single-read fused variant.
+#include "common.cuh"
+
+namespace era5svd {
+
+// Centre in the wider of (source, matrix) types, then round to the matrix type.  With equal types
+// (the reference's behaviour) this is exactly `x - mean` in that type.
+template <typename Ts, typename Tx>
+__device__ __forceinline__ Tx centre(Ts raw, Tx mean) {
+  if (sizeof(Ts) > sizeof(Tx)) return (Tx)((double)raw - (double)mean);
+  return (Tx)raw - mean;
+}
+
+template <typename Ts, typename Tx>
+__global__ void __launch_bounds__(128)
+row_stats_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t P,
+                 Tx* __restrict__ mean_out, Tx* __restrict__ std_out, int do_scale) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const Ts* col = src + p;
+  // pass 1: NaN-skipping mean (xarray's mean(dim) default), float64 accumulation.
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t cnt = 0;
+  int64_t t = 0;
+  for (; t + 4 <= T; t += 4) {
+    double v0 = (double)col[(t + 0) * src_ld];
+    double v1 = (double)col[(t + 1) * src_ld];
+    double v2 = (double)col[(t + 2) * src_ld];
+    double v3 = (double)col[(t + 3) * src_ld];
+    if (v0 == v0) { s0 += v0; ++cnt; }
+    if (v1 == v1) { s1 += v1; ++cnt; }
+    if (v2 == v2) { s2 += v2; ++cnt; }
+    if (v3 == v3) { s3 += v3; ++cnt; }
+  }
+  for (; t < T; ++t) {
+    double v = (double)col[t * src_ld];
+    if (v == v) { s0 += v; ++cnt; }
+  }
+  double mean = cnt > 0 ? ((s0 + s1) + (s2 + s3)) / (double)cnt : __longlong_as_double(0x7ff8000000000000LL);
+  Tx mean_x = (Tx)mean;
+  mean_out[p] = mean_x;
+  if (!do_scale) return;
+  // pass 2: std (ddof = 0) of the CENTRED data, as the reference computes it: the centred values
+  // are formed in the matrix dtype (x - mean), their own (tiny) mean is removed again by nanstd.
+  double a = 0.0, q = 0.0;
+  for (t = 0; t < T; ++t) {
+    Ts raw = col[t * src_ld];
+    if (raw == raw) {
+      double xc = (double)centre<Ts, Tx>(raw, mean_x);
+      a += xc;
+      q += xc * xc;
+    }
+  }
+  double m2 = cnt > 0 ? a / (double)cnt : 0.0;
+  double var = cnt > 0 ? q / (double)cnt - m2 * m2 : __longlong_as_double(0x7ff8000000000000LL);
+  if (var < 0.0) var = 0.0;
+  std_out[p] = (Tx)sqrt(var);
+}
+
+template <typename Ts, typename Tx>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t P,
+                 Tx* __restrict__ X, int64_t ldx, const Tx* __restrict__ mean,
+                 const Tx* __restrict__ stdv, const Tx* __restrict__ weights,
+                 int check_finite, int* __restrict__ nonfinite_flag) {
+  __shared__ Ts tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int64_t t0 = (int64_t)blockIdx.y * 32;
+  int bad = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t t = t0 + ty + 8 * i, p = p0 + tx;
+    Ts v = Ts(0);
+    if (t < T && p < P) {
+      v = src[t * src_ld + p];
+      if (check_finite && !isfinite((double)v)) bad = 1;
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t p = p0 + ty + 8 * i, t = t0 + tx;
+    if (p < P && t < T) {
+      Ts raw = tile[tx][ty + 8 * i];
+      Tx v = mean ? centre<Ts, Tx>(raw, mean[p]) : (Tx)raw;
+      if (stdv) v = v / stdv[p];
+      if (weights) v = v * weights[p];
+      X[p * ldx + t] = v;
+    }
+  }
+  if (check_finite) {
+    int any = __syncthreads_or(bad);
+    if (any && tx == 0 && ty == 0) atomicExch(nonfinite_flag, 1);
+  }
+}
+
+template <typename Ts, typename Tx>
+int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void* X, int64_t ldx,
+                    void* mean_out, void* std_out, const void* weights, unsigned flags,
+                    int* nonfinite_flag, cudaStream_t st) {
+  const bool center = flags & ERA5SVD_BUILD_MEAN_CENTER;
+  const bool scale = flags & ERA5SVD_BUILD_SCALE;
+  const bool check = (flags & ERA5SVD_BUILD_CHECK_FINITE) && nonfinite_flag;
+  if (center) {
+    int threads = 128;
+    int64_t blocks = ceil_div(P, threads);
+    row_stats_kernel<Ts, Tx><<<(unsigned)blocks, threads, 0, st>>>(
+        (const Ts*)src, T, src_ld, P, (Tx*)mean_out, (Tx*)std_out, scale ? 1 : 0);
+    int rc = check_launch("row_stats_kernel");
+    if (rc) return rc;
+  }
+  dim3 block(32, 8);
+  dim3 grid((unsigned)ceil_div(P, 32), (unsigned)ceil_div(T, 32));
+  transpose_kernel<Ts, Tx><<<grid, block, 0, st>>>(
+      (const Ts*)src, T, src_ld, P, (Tx*)X, ldx, center ? (const Tx*)mean_out : nullptr,
+      (center && scale) ? (const Tx*)std_out : nullptr, (const Tx*)weights, check ? 1 : 0,
+      nonfinite_flag);
+  return check_launch("transpose_kernel");
+}
+
+}  // namespace era5svd
+
+extern "C" int era5svd_build_rows(const void* src, int dtype_src, int64_t T, int64_t src_ld,
+                                  int64_t P, void* X, int dtype_x, int64_t ldx, void* mean_out,
+                                  void* std_out, const void* weights, unsigned flags,
+                                  int* nonfinite_flag, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(src && X, "build_rows: null src/X");
+  ERA5SVD_REQUIRE(valid_dtype(dtype_src) && valid_dtype(dtype_x), "build_rows: bad dtype");
+  ERA5SVD_REQUIRE(T > 0 && P > 0 && src_ld >= P && ldx >= T, "build_rows: bad shape T=%lld P=%lld src_ld=%lld ldx=%lld",
+                  (long long)T, (long long)P, (long long)src_ld, (long long)ldx);
+  ERA5SVD_REQUIRE(ceil_div(T, 32) <= 65535, "build_rows: T too large for one launch");
+  if (flags & ERA5SVD_BUILD_SCALE)
+    ERA5SVD_REQUIRE(flags & ERA5SVD_BUILD_MEAN_CENTER, "build_rows: SCALE requires MEAN_CENTER (reference quirk Q4: scale alone is ignored by the caller)");
+  if (flags & ERA5SVD_BUILD_MEAN_CENTER) ERA5SVD_REQUIRE(mean_out, "build_rows: mean_out required with MEAN_CENTER");
+  if (flags & ERA5SVD_BUILD_SCALE) ERA5SVD_REQUIRE(std_out, "build_rows: std_out required with SCALE");
+  cudaStream_t st = as_stream(stream);
+  if (dtype_src == ERA5SVD_F32 && dtype_x == ERA5SVD_F32)
+    return build_rows_impl<float, float>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st);
+  if (dtype_src == ERA5SVD_F64 && dtype_x == ERA5SVD_F64)
+    return build_rows_impl<double, double>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st);
+  if (dtype_src == ERA5SVD_F32 && dtype_x == ERA5SVD_F64)
+    return build_rows_impl<float, double>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st);
+  return build_rows_impl<double, float>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st);
+}

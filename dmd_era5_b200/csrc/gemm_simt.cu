@@ -1,0 +1,322 @@
+// (b) Tall GEMM passes, native-precision path (FP64 DFMA / FP32 FFMA on the CUDA cores).
+//
+//   sketch :  Y[m x l]  = X[m x n] * Om[n x l]              (`A @ Q`,   sklearn/utils/extmath.py:378,383)
+//   project:  Z[n x l] += X[m x n]^T * Y[m x l]  (float64)  (`A.T @ Q`, extmath.py:379; `Q.T @ M`, :606)
+//
+// This is the accuracy-first path (FP64 parity mode, and the checker for the tcgen05 path in
+// gemm_tc.cu); it is a register-tiled 128 x (16*TN) x 16 SIMT GEMM, 256 threads, 8 x TN outputs per
+// thread, register prefetch of the next k-tile.  Both passes share one inner product core because
+// both stage their operands k-major in shared memory:
+//   sketch : As[k][row]  <- X[row][k]   (transposed on the way in)   Bs[k][col] <- Om[k][col]
+//   project: As[k][time] <- X[k=row][time] (straight copy)           Bs[k][col] <- Y[k=row][col]
+// project splits the row (k) range over blockIdx.z; partial tiles go to the workspace in the
+// accumulate type and reduce_partials_kernel sums them in float64 in a fixed order.
+#include "common.cuh"
+
+namespace era5svd {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int NTHREADS = 256;
+constexpr int PAD = 4;
+
+template <typename T, int TN>
+struct Tile {
+  static constexpr int BN = 16 * TN;
+  T As[BK][BM + PAD];
+  T Bs[BK][BN];
+};
+
+template <typename T, int TN>
+__device__ __forceinline__ void mma_tile(const Tile<T, TN>& s, T (&acc)[8][TN], int ty, int tx) {
+#pragma unroll
+  for (int kk = 0; kk < BK; ++kk) {
+    T a[8], b[TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = s.As[kk][ty * 8 + i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b[j] = s.Bs[kk][tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sketch
+// ---------------------------------------------------------------------------------------------
+template <typename T, int TN>
+__global__ void __launch_bounds__(NTHREADS)
+sketch_kernel(const T* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const T* __restrict__ Om,
+              int64_t l, int64_t ldo, T* __restrict__ Y, int64_t ldy) {
+  __shared__ Tile<T, TN> s;
+  constexpr int BN = 16 * TN;
+  const int t = threadIdx.x;
+  const int ty = t / 16, tx = t % 16;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int64_t col0 = (int64_t)blockIdx.y * BN;
+
+  // A loader: thread -> (row = t % 128, 8 consecutive k starting at (t / 128) * 8)
+  const int a_row = t % BM, a_k0 = (t / BM) * 8;
+  const int64_t g_row = row0 + a_row;
+  const T* a_ptr = X + (g_row < m ? g_row : 0) * ldx;
+  // B loader: thread -> (k = t / 16, cols tx + 16 * jj)
+  const int b_k = t / 16;
+
+  T a_reg[8], b_reg[TN];
+  T acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+  auto load = [&](int64_t k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t k = k0 + a_k0 + i;
+      a_reg[i] = (g_row < m && k < n) ? a_ptr[k] : T(0);
+    }
+    int64_t kb = k0 + b_k;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int64_t c = col0 + tx + 16 * j;
+      b_reg[j] = (kb < n && c < l) ? Om[kb * ldo + c] : T(0);
+    }
+  };
+
+  load(0);
+  for (int64_t k0 = 0; k0 < n; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.As[a_k0 + i][a_row] = a_reg[i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) s.Bs[b_k][tx + 16 * j] = b_reg[j];
+    __syncthreads();
+    if (k0 + BK < n) load(k0 + BK);
+    mma_tile<T, TN>(s, acc, ty, tx);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t r = row0 + ty * 8 + i;
+    if (r < m) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int64_t c = col0 + tx + 16 * j;
+        if (c < l) Y[r * ldy + c] = acc[i][j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// project
+// ---------------------------------------------------------------------------------------------
+template <typename T, int TN>
+__global__ void __launch_bounds__(NTHREADS)
+project_kernel(const T* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const T* __restrict__ Y,
+               int64_t l, int64_t ldy, T* __restrict__ part, int64_t rows_per_split) {
+  __shared__ Tile<T, TN> s;
+  constexpr int BN = 16 * TN;
+  const int t = threadIdx.x;
+  const int ty = t / 16, tx = t % 16;
+  const int64_t t0 = (int64_t)blockIdx.x * BM;     // time tile
+  const int64_t col0 = (int64_t)blockIdx.y * BN;   // sketch-column tile
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t r_end = min(m, r_begin + rows_per_split);
+
+  // A loader: thread -> (k = t / 16, 8 consecutive time values starting at (t % 16) * 8)
+  const int a_k = t / 16, a_i0 = (t % 16) * 8;
+  const int b_k = t / 16;
+
+  T a_reg[8], b_reg[TN];
+  T acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+  auto load = [&](int64_t r0) {
+    int64_t r = r0 + a_k;
+    const T* xr = X + (r < r_end ? r : r_begin) * ldx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t tt = t0 + a_i0 + i;
+      a_reg[i] = (r < r_end && tt < n) ? xr[tt] : T(0);
+    }
+    const T* yr = Y + (r < r_end ? r : r_begin) * ldy;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int64_t c = col0 + tx + 16 * j;
+      b_reg[j] = (r < r_end && c < l) ? yr[c] : T(0);
+    }
+  };
+
+  if (r_begin < r_end) {
+    load(r_begin);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += BK) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s.As[a_k][a_i0 + i] = a_reg[i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) s.Bs[b_k][tx + 16 * j] = b_reg[j];
+      __syncthreads();
+      if (r0 + BK < r_end) load(r0 + BK);
+      mma_tile<T, TN>(s, acc, ty, tx);
+      __syncthreads();
+    }
+  }
+  // partial tile -> workspace [split][n][l]
+  T* out = part + (int64_t)blockIdx.z * n * l;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t tt = t0 + ty * 8 + i;
+    if (tt < n) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int64_t c = col0 + tx + 16 * j;
+        if (c < l) out[tt * l + c] = acc[i][j];
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, int64_t l,
+                       double* __restrict__ Z, int64_t ldz, int accumulate) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = n * l;
+  if (idx >= total) return;
+  double s = 0.0;
+  for (int64_t k = 0; k < splits; ++k) s += (double)part[k * total + idx];
+  int64_t r = idx / l, c = idx % l;
+  double* z = Z + r * ldz + c;
+  *z = accumulate ? (*z + s) : s;
+}
+
+struct ProjectPlan {
+  int64_t splits;
+  int64_t rows_per_split;
+  size_t bytes;
+};
+
+// Rows per split: at most 4096 (bounds the length of any float32 running sum), but never so
+// many splits that the partial-tile workspace exceeds 256 MiB.
+static ProjectPlan project_plan(int dtype, int64_t m, int64_t n, int64_t l) {
+  const int64_t cap = (int64_t)256 << 20;
+  const int64_t tile_bytes = n * l * (int64_t)dtype_size(dtype);
+  int64_t max_splits = cap / (tile_bytes > 0 ? tile_bytes : 1);
+  if (max_splits < 1) max_splits = 1;
+  int64_t splits = ceil_div(m, 4096);
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  int64_t rps = ceil_div(ceil_div(m, splits), BK) * BK;
+  splits = ceil_div(m, rps);
+  ProjectPlan p;
+  p.splits = splits;
+  p.rows_per_split = rps;
+  p.bytes = (size_t)(splits * tile_bytes);
+  return p;
+}
+
+// Column tile width: 112 (TN = 7) or 128 (TN = 8), whichever pads l = k + 10 less.
+static bool use_tn7(int64_t l) { return ceil_div(l, 112) * 112 <= ceil_div(l, 128) * 128; }
+
+template <typename T>
+int sketch_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void* Om, int64_t l,
+                  int64_t ldo, void* Y, int64_t ldy, cudaStream_t st) {
+  if (use_tn7(l)) {
+    dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, 112));
+    sketch_kernel<T, 7><<<grid, NTHREADS, 0, st>>>((const T*)X, m, n, ldx, (const T*)Om, l, ldo, (T*)Y, ldy);
+  } else {
+    dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, 128));
+    sketch_kernel<T, 8><<<grid, NTHREADS, 0, st>>>((const T*)X, m, n, ldx, (const T*)Om, l, ldo, (T*)Y, ldy);
+  }
+  return check_launch("sketch_kernel");
+}
+
+template <typename T>
+int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void* Y, int64_t l,
+                   int64_t ldy, double* Z, int64_t ldz, int accumulate, void* ws,
+                   const ProjectPlan& plan, cudaStream_t st) {
+  if (use_tn7(l)) {
+    dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 112), (unsigned)plan.splits);
+    project_kernel<T, 7><<<grid, NTHREADS, 0, st>>>((const T*)X, m, n, ldx, (const T*)Y, l, ldy, (T*)ws, plan.rows_per_split);
+  } else {
+    dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 128), (unsigned)plan.splits);
+    project_kernel<T, 8><<<grid, NTHREADS, 0, st>>>((const T*)X, m, n, ldx, (const T*)Y, l, ldy, (T*)ws, plan.rows_per_split);
+  }
+  int rc = check_launch("project_kernel");
+  if (rc) return rc;
+  int64_t total = n * l;
+  reduce_partials_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const T*)ws, plan.splits, n, l, Z, ldz, accumulate);
+  return check_launch("reduce_partials_kernel");
+}
+
+// tcgen05 path (gemm_tc.cu)
+int sketch_tf32x3(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Om, int64_t l,
+                  int64_t ldo, float* Y, int64_t ldy, cudaStream_t st);
+int project_tf32x3(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,
+                   int64_t ldy, double* Z, int64_t ldz, int accumulate, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+size_t project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l);
+
+}  // namespace era5svd
+
+extern "C" {
+
+int era5svd_sketch(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx, const void* Om,
+                   int64_t l, int64_t ldo, void* Y, int64_t ldy, int precision, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(X && Om && Y, "sketch: null pointer");
+  ERA5SVD_REQUIRE(valid_dtype(dtype), "sketch: bad dtype %d", dtype);
+  ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldo >= l && ldy >= l,
+                  "sketch: bad shape m=%lld n=%lld l=%lld ldx=%lld ldo=%lld ldy=%lld", (long long)m,
+                  (long long)n, (long long)l, (long long)ldx, (long long)ldo, (long long)ldy);
+  ERA5SVD_REQUIRE(ceil_div(l, 112) <= 65535, "sketch: l too large");
+  cudaStream_t st = as_stream(stream);
+  if (precision == ERA5SVD_PREC_TF32X3) {
+    ERA5SVD_REQUIRE(dtype == ERA5SVD_F32, "sketch: TF32X3 needs float32 storage");
+    return sketch_tf32x3((const float*)X, m, n, ldx, (const float*)Om, l, ldo, (float*)Y, ldy, st);
+  }
+  ERA5SVD_REQUIRE(precision == ERA5SVD_PREC_NATIVE, "sketch: bad precision %d", precision);
+  if (dtype == ERA5SVD_F32) return sketch_native<float>(X, m, n, ldx, Om, l, ldo, Y, ldy, st);
+  return sketch_native<double>(X, m, n, ldx, Om, l, ldo, Y, ldy, st);
+}
+
+size_t era5svd_project_workspace_bytes(int dtype, int64_t m, int64_t n, int64_t l, int precision) {
+  using namespace era5svd;
+  if (!valid_dtype(dtype) || m <= 0 || n <= 0 || l <= 0) return 0;
+  if (precision == ERA5SVD_PREC_TF32X3) return project_tf32x3_workspace_bytes(m, n, l);
+  return project_plan(dtype, m, n, l).bytes;
+}
+
+int era5svd_project(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx, const void* Y,
+                    int64_t l, int64_t ldy, double* Z, int64_t ldz, int accumulate, int precision,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(X && Y && Z, "project: null pointer");
+  ERA5SVD_REQUIRE(valid_dtype(dtype), "project: bad dtype %d", dtype);
+  ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldy >= l && ldz >= l,
+                  "project: bad shape m=%lld n=%lld l=%lld ldx=%lld ldy=%lld ldz=%lld", (long long)m,
+                  (long long)n, (long long)l, (long long)ldx, (long long)ldy, (long long)ldz);
+  cudaStream_t st = as_stream(stream);
+  if (precision == ERA5SVD_PREC_TF32X3) {
+    ERA5SVD_REQUIRE(dtype == ERA5SVD_F32, "project: TF32X3 needs float32 storage");
+    return project_tf32x3((const float*)X, m, n, ldx, (const float*)Y, l, ldy, Z, ldz, accumulate,
+                          workspace, workspace_bytes, st);
+  }
+  ERA5SVD_REQUIRE(precision == ERA5SVD_PREC_NATIVE, "project: bad precision %d", precision);
+  ERA5SVD_REQUIRE(ceil_div(l, 112) <= 65535, "project: l too large");
+  ProjectPlan plan = project_plan(dtype, m, n, l);
+  if (!workspace || workspace_bytes < plan.bytes) {
+    set_error("project: workspace too small (%zu < %zu)", workspace_bytes, plan.bytes);
+    return ERA5SVD_ERR_WORKSPACE;
+  }
+  if (dtype == ERA5SVD_F32)
+    return project_native<float>(X, m, n, ldx, Y, l, ldy, Z, ldz, accumulate, workspace, plan, st);
+  return project_native<double>(X, m, n, ldx, Y, l, ldy, Z, ldz, accumulate, workspace, plan, st);
+}
+
+}  // extern "C"

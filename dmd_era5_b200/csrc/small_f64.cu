@@ -1,0 +1,408 @@
+// (c)/(d) Small float64 factor kernels: everything that is time-sized (n) or sketch-sized (l).
+// These replace the LAPACK calls behind sklearn's normalisers and small SVD
+// (scipy.linalg.lu / qr / svd, sklearn/utils/extmath.py:371-383, :615) and the eigensolve of the
+// Gram-route standard SVD (np.linalg.svd, src/dmd_era5/era5_svd/era5_svd.py:251).
+// They are latency-bound, replicated on every GPU, and run as one CTA (the solvers) or a handful of
+// CTAs (the small GEMM).
+#include "common.cuh"
+
+namespace era5svd {
+
+// ---------------------------------------------------------------------------------------------
+// C = alpha * op(A) * op(B) + beta * C     (32 x 32 tile, 16 x 16 threads, 2 x 2 per thread)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_f64_kernel(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                double beta, double* __restrict__ C, int64_t ldc) {
+  constexpr int TS = 32, KS = 32;
+  __shared__ double As[KS][TS + 1];
+  __shared__ double Bs[KS][TS + 1];
+  const int t = threadIdx.x;
+  const int ty = t / 16, tx = t % 16;
+  const int64_t i0 = (int64_t)blockIdx.y * TS, j0 = (int64_t)blockIdx.x * TS;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  for (int64_t k0 = 0; k0 < K; k0 += KS) {
+    // 32 x 32 elements each, 4 per thread
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int idx = t + 256 * e;
+      {
+        // A element (i, k): choose the mapping that is contiguous in memory
+        int ii, kk;
+        if (transA) { ii = idx % TS; kk = idx / TS; } else { kk = idx % KS; ii = idx / KS; }
+        int64_t gi = i0 + ii, gk = k0 + kk;
+        double v = 0.0;
+        if (gi < M && gk < K) v = transA ? A[gk * lda + gi] : A[gi * lda + gk];
+        As[kk][ii] = v;
+      }
+      {
+        int jj, kk;
+        if (transB) { kk = idx % KS; jj = idx / KS; } else { jj = idx % TS; kk = idx / TS; }
+        int64_t gj = j0 + jj, gk = k0 + kk;
+        double v = 0.0;
+        if (gj < N && gk < K) v = transB ? B[gj * ldb + gk] : B[gk * ldb + gj];
+        Bs[kk][jj] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      double a0 = As[kk][ty], a1 = As[kk][ty + 16];
+      double b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
+      acc[0][0] = fma(a0, b0, acc[0][0]);
+      acc[0][1] = fma(a0, b1, acc[0][1]);
+      acc[1][0] = fma(a1, b0, acc[1][0]);
+      acc[1][1] = fma(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      int64_t gi = i0 + ty + 16 * a, gj = j0 + tx + 16 * b;
+      if (gi < M && gj < N) {
+        double* c = C + gi * ldc + gj;
+        double v = alpha * acc[a][b];
+        if (beta != 0.0) v += beta * (*c);
+        *c = v;
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Symmetric eigensolver: parallel cyclic two-sided Jacobi, one CTA of 1024 threads.
+// Round-robin ordering: n_pad - 1 steps per sweep, n_pad / 2 disjoint (p, q) pairs per step.
+// Working copies Aw, Vw live in shared memory when 2 n^2 doubles fit, else in the global
+// workspace (L1/L2 resident; one CTA, so block barriers order the accesses).
+// ---------------------------------------------------------------------------------------------
+constexpr int JAC_THREADS = 1024;
+
+__device__ __forceinline__ void jacobi_pair(int step, int i, int n_pad, int& p, int& q) {
+  const int r = n_pad - 1;
+  if (i == 0) {
+    p = r;
+    q = step;
+  } else {
+    p = (step + i) % r;
+    q = (step + r - i) % r;
+  }
+  if (p > q) { int tmp = p; p = q; q = tmp; }
+}
+
+__global__ void __launch_bounds__(JAC_THREADS, 1)
+syevj_kernel(double* __restrict__ A, int n, int64_t lda, double* __restrict__ W,
+             double* __restrict__ V, int64_t ldv, int max_sweeps, double* __restrict__ ws,
+             int use_smem) {
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  const int n_pad = n + (n & 1);
+  const int npairs = n_pad / 2;
+  // layout: [cs: 2 * npairs doubles][pq: 2 * npairs ints (as one double each pair)][Aw][Vw]
+  double* cs = smem;                                   // c, s per pair
+  int* pq = reinterpret_cast<int*>(smem + 2 * npairs);  // p, q per pair
+  double* Aw;
+  double* Vw;
+  int ldw = n;
+  if (use_smem) {
+    Aw = smem + 3 * npairs + 1;
+    Vw = Aw + (size_t)n * n;
+  } else {
+    Aw = ws;
+    Vw = ws + (size_t)n * n;
+  }
+  for (int idx = t; idx < n * n; idx += JAC_THREADS) {
+    int r = idx / n, c = idx % n;
+    Aw[idx] = 0.5 * (A[(int64_t)r * lda + c] + A[(int64_t)c * lda + r]);  // enforce symmetry
+    Vw[idx] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  // relative off-diagonal threshold |a_pq| <= tol * sqrt(|a_pp a_qq|), tol = eps * sqrt(n) (as LAPACK's xGESVJ)
+  const double tol = 2.220446049250313e-16 * sqrt((double)n);
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    int rotated_in_sweep = 0;
+    for (int step = 0; step < n_pad - 1; ++step) {
+      int did = 0;
+      if (t < npairs) {
+        int p, q;
+        jacobi_pair(step, t, n_pad, p, q);
+        double c = 1.0, s = 0.0;
+        if (q < n) {  // q == n only for the padding index of odd n
+          double app = Aw[p * ldw + p], aqq = Aw[q * ldw + q];
+          double apq = Aw[p * ldw + q];
+          double thresh = tol * sqrt(fabs(app) * fabs(aqq));
+          if (fabs(apq) > thresh && fabs(apq) > 1e-300) {
+            double tau = (aqq - app) / (2.0 * apq);
+            double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + tt * tt);
+            s = tt * c;
+            did = 1;
+          }
+        } else {
+          q = -1;
+        }
+        cs[2 * t] = c;
+        cs[2 * t + 1] = s;
+        pq[2 * t] = p;
+        pq[2 * t + 1] = q;
+      }
+      rotated_in_sweep |= __syncthreads_or(did);
+      // right multiplication on A and V:  columns p, q
+      for (int idx = t; idx < 2 * n * npairs; idx += JAC_THREADS) {
+        int which = idx / (n * npairs);
+        int rem = idx - which * n * npairs;
+        int r = rem / npairs, i = rem - r * npairs;
+        int p = pq[2 * i], q = pq[2 * i + 1];
+        double c = cs[2 * i], s = cs[2 * i + 1];
+        if (q >= 0 && s != 0.0) {
+          double* M = which ? Vw : Aw;
+          double x = M[r * ldw + p], y = M[r * ldw + q];
+          M[r * ldw + p] = c * x - s * y;
+          M[r * ldw + q] = s * x + c * y;
+        }
+      }
+      __syncthreads();
+      // left multiplication on A: rows p, q
+      for (int idx = t; idx < n * npairs; idx += JAC_THREADS) {
+        int i = idx / n, col = idx - i * n;
+        int p = pq[2 * i], q = pq[2 * i + 1];
+        double c = cs[2 * i], s = cs[2 * i + 1];
+        if (q >= 0 && s != 0.0) {
+          double x = Aw[p * ldw + col], y = Aw[q * ldw + col];
+          Aw[p * ldw + col] = c * x - s * y;
+          Aw[q * ldw + col] = s * x + c * y;
+        }
+      }
+      __syncthreads();
+    }
+    if (!rotated_in_sweep) break;
+  }
+  // eigenvalues = diag(Aw); rank them in descending order (stable on ties) and scatter.
+  for (int j = t; j < n; j += JAC_THREADS) {
+    double wj = Aw[j * ldw + j];
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+      double wi = Aw[i * ldw + i];
+      rank += (wi > wj) || (wi == wj && i < j);
+    }
+    W[rank] = wj;
+    pq[j] = rank;  // reuse: npairs*2 >= n ints available
+  }
+  __syncthreads();
+  for (int idx = t; idx < n * n; idx += JAC_THREADS) {
+    int r = idx / n, c = idx % n;
+    V[(int64_t)r * ldv + pq[c]] = Vw[idx];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky G = R^T R (upper R) + explicit inverse, one CTA.  Works in the caller's R buffer.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __restrict__ R,
+                int64_t ldr, double* __restrict__ Rinv, int64_t ldri, double rel_tol) {
+  const int t = threadIdx.x, nt = blockDim.x;
+  __shared__ double s_piv;
+  // copy the upper triangle (symmetrised), zero the strictly lower part
+  for (int idx = t; idx < l * l; idx += nt) {
+    int r = idx / l, c = idx % l;
+    R[(int64_t)r * ldr + c] = (c >= r) ? 0.5 * (G[(int64_t)r * ldg + c] + G[(int64_t)c * ldg + r]) : 0.0;
+    Rinv[(int64_t)r * ldri + c] = 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < l; ++j) {
+    if (t == 0) {
+      double d = R[(int64_t)j * ldr + j];
+      double g = G[(int64_t)j * ldg + j];
+      // dependent (or non-positive) pivot -> huge: the direction is dropped, never NaN
+      s_piv = (d > rel_tol * g && d > 0.0) ? sqrt(d) : 1e150;
+    }
+    __syncthreads();
+    const double piv = s_piv;
+    for (int c = j + t; c < l; c += nt) {
+      double v = R[(int64_t)j * ldr + c];
+      R[(int64_t)j * ldr + c] = (c == j) ? piv : v / piv;
+    }
+    __syncthreads();
+    // trailing update: R[i][c] -= R[j][i] * R[j][c],  j < i <= c
+    const int rem = l - j - 1;
+    for (int idx = t; idx < rem * rem; idx += nt) {
+      int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
+      if (c >= i) R[(int64_t)i * ldr + c] -= R[(int64_t)j * ldr + i] * R[(int64_t)j * ldr + c];
+    }
+    __syncthreads();
+  }
+  // inverse by back substitution, one warp per column c:  R * x = e_c
+  const int warp = t / 32, lane = t % 32, nwarps = nt / 32;
+  for (int c = warp; c < l; c += nwarps) {
+    for (int i = c; i >= 0; --i) {
+      double sum = 0.0;
+      for (int k = i + 1 + lane; k <= c; k += 32) sum += R[(int64_t)i * ldr + k] * Rinv[(int64_t)k * ldri + c];
+      sum = warp_sum(sum);
+      if (lane == 0) Rinv[(int64_t)i * ldri + c] = ((i == c ? 1.0 : 0.0) - sum) / R[(int64_t)i * ldr + i];
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+col_normalize_kernel(double* __restrict__ P, int64_t n, int64_t l, int64_t ldp,
+                     double* __restrict__ norms_out) {
+  const int64_t j = blockIdx.x;
+  __shared__ double red[4];
+  __shared__ double s_norm;
+  double s = 0.0;
+  for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+    double v = P[r * ldp + j];
+    s = fma(v, v, s);
+  }
+  s = warp_sum(s);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double nrm = sqrt(red[0] + red[1] + red[2] + red[3]);
+    s_norm = nrm;
+    if (norms_out) norms_out[j] = nrm;
+  }
+  __syncthreads();
+  const double nrm = s_norm;
+  if (nrm > 0.0)
+    for (int64_t r = threadIdx.x; r < n; r += blockDim.x) P[r * ldp + j] /= nrm;
+}
+
+template <typename Ts, typename Td>
+__global__ void __launch_bounds__(256)
+convert_kernel(const Ts* __restrict__ src, int64_t lds, Td* __restrict__ dst, int64_t ldd,
+               int64_t rows, int64_t cols) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int64_t r = idx / cols, c = idx % cols;
+  dst[r * ldd + c] = (Td)src[r * lds + c];
+}
+
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(double* __restrict__ V, int64_t k, int64_t n, int64_t ldv,
+                  const double* __restrict__ scale) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= k * n) return;
+  int64_t r = idx / n, c = idx % n;
+  V[r * ldv + c] *= scale[r];
+}
+
+// s = sqrt(max(w, 0)), inv_s = 1 / s (0 where s == 0)
+__global__ void __launch_bounds__(128)
+sigma_from_eig_kernel(const double* __restrict__ w, int64_t l, double* __restrict__ s,
+                      double* __restrict__ inv_s) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  double v = w[i];
+  double sv = v > 0.0 ? sqrt(v) : 0.0;
+  s[i] = sv;
+  if (inv_s) inv_s[i] = sv > 0.0 ? 1.0 / sv : 0.0;
+}
+
+}  // namespace era5svd
+
+extern "C" {
+
+int era5svd_sigma_from_eig_f64(const double* w, int64_t l, double* s, double* inv_s, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(w && s && l > 0, "sigma_from_eig: bad argument");
+  sigma_from_eig_kernel<<<(unsigned)ceil_div(l, 128), 128, 0, as_stream(stream)>>>(w, l, s, inv_s);
+  return check_launch("sigma_from_eig_kernel");
+}
+
+int era5svd_gemm_f64(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                     const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
+                     double* C, int64_t ldc, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(A && B && C, "gemm_f64: null pointer");
+  ERA5SVD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f64: bad shape");
+  ERA5SVD_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm_f64: bad leading dimension");
+  ERA5SVD_REQUIRE(ceil_div(M, 32) <= 65535, "gemm_f64: M too large");
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 32));
+  gemm_f64_kernel<<<grid, 256, 0, as_stream(stream)>>>(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  return check_launch("gemm_f64_kernel");
+}
+
+static size_t syevj_smem_bytes(int64_t n) {
+  int64_t npairs = (n + (n & 1)) / 2;
+  return (size_t)(3 * npairs + 1 + 2 * n * n) * sizeof(double);
+}
+
+size_t era5svd_syevj_workspace_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  return (size_t)(2 * n * n) * sizeof(double);
+}
+
+int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
+                      int max_sweeps, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(A && W && V, "syevj: null pointer");
+  ERA5SVD_REQUIRE(n > 0 && n <= 16384 && lda >= n && ldv >= n, "syevj: bad shape n=%lld", (long long)n);
+  if (max_sweeps <= 0) max_sweeps = 30;
+  const size_t full = syevj_smem_bytes(n);
+  const size_t limit = 227 * 1024;
+  int use_smem = full <= limit;
+  size_t smem = use_smem ? full : (size_t)(3 * ((n + 1) / 2) + 2) * sizeof(double);
+  if (!use_smem) {
+    size_t need = era5svd_syevj_workspace_bytes(n);
+    if (!workspace || workspace_bytes < need) {
+      set_error("syevj: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return ERA5SVD_ERR_WORKSPACE;
+    }
+  }
+  ERA5SVD_CUDA(cudaFuncSetAttribute(syevj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+  syevj_kernel<<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, (double*)workspace, use_smem);
+  return check_launch("syevj_kernel");
+}
+
+int era5svd_chol_inv_f64(const double* G, int64_t l, int64_t ldg, double* R, int64_t ldr,
+                         double* Rinv, int64_t ldri, double rel_tol, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(G && R && Rinv, "chol_inv: null pointer");
+  ERA5SVD_REQUIRE(l > 0 && l <= 8192 && ldg >= l && ldr >= l && ldri >= l, "chol_inv: bad shape l=%lld", (long long)l);
+  chol_inv_kernel<<<1, 1024, 0, as_stream(stream)>>>(G, (int)l, ldg, R, ldr, Rinv, ldri, rel_tol);
+  return check_launch("chol_inv_kernel");
+}
+
+int era5svd_col_normalize_f64(double* P, int64_t n, int64_t l, int64_t ldp, double* norms_out,
+                              void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(P, "col_normalize: null pointer");
+  ERA5SVD_REQUIRE(n > 0 && l > 0 && ldp >= l, "col_normalize: bad shape");
+  col_normalize_kernel<<<(unsigned)l, 128, 0, as_stream(stream)>>>(P, n, l, ldp, norms_out);
+  return check_launch("col_normalize_kernel");
+}
+
+int era5svd_convert(const void* src, int dtype_src, int64_t lds, void* dst, int dtype_dst,
+                    int64_t ldd, int64_t rows, int64_t cols, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(src && dst, "convert: null pointer");
+  ERA5SVD_REQUIRE(valid_dtype(dtype_src) && valid_dtype(dtype_dst), "convert: bad dtype");
+  ERA5SVD_REQUIRE(rows > 0 && cols > 0 && lds >= cols && ldd >= cols, "convert: bad shape");
+  cudaStream_t st = as_stream(stream);
+  unsigned blocks = (unsigned)ceil_div(rows * cols, 256);
+  if (dtype_src == ERA5SVD_F64 && dtype_dst == ERA5SVD_F32)
+    convert_kernel<double, float><<<blocks, 256, 0, st>>>((const double*)src, lds, (float*)dst, ldd, rows, cols);
+  else if (dtype_src == ERA5SVD_F32 && dtype_dst == ERA5SVD_F64)
+    convert_kernel<float, double><<<blocks, 256, 0, st>>>((const float*)src, lds, (double*)dst, ldd, rows, cols);
+  else if (dtype_src == ERA5SVD_F32)
+    convert_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols);
+  else
+    convert_kernel<double, double><<<blocks, 256, 0, st>>>((const double*)src, lds, (double*)dst, ldd, rows, cols);
+  return check_launch("convert_kernel");
+}
+
+int era5svd_scale_rows_f64(double* V, int64_t k, int64_t n, int64_t ldv, const double* scale,
+                           void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(V && scale, "scale_rows: null pointer");
+  ERA5SVD_REQUIRE(k > 0 && n > 0 && ldv >= n, "scale_rows: bad shape");
+  scale_rows_kernel<<<(unsigned)ceil_div(k * n, 256), 256, 0, as_stream(stream)>>>(V, k, n, ldv, scale);
+  return check_launch("scale_rows_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+"""Thin typed layer between torch tensor handles and the C ABI (``include/era5svd.h``).
+
+torch is used only for device memory, streams and (in ``dist.py``) the process group: every
+method below hands raw device pointers + leading dimensions to ``libera5svd.so`` on torch's
+current CUDA stream.  Tensors must be CUDA, 2-D row-major views (``stride(1) == 1``); a
+delay-embedded block is simply the view ``X[:, j : j + n]`` (same leading dimension).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+from ._cabi import F32, F64, PREC_NATIVE, PREC_TF32X3, check
+
+_DT = {torch.float32: F32, torch.float64: F64}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}; float32 / float64 only") from None
+
+
+def _mat(t: torch.Tensor, name: str) -> tuple[int, int]:
+    """pointer, leading dimension of a row-major CUDA matrix view."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (dmd_era5_b200 has no CPU path)")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D, got shape {tuple(t.shape)}")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError(f"{name} must be row-major (stride(1) == 1)")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    return t.data_ptr(), ld
+
+
+def _vec(t: torch.Tensor | None, name: str) -> int | None:
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous CUDA tensor")
+    return t.data_ptr()
+
+
+class CudaOps:
+    """Kernel launcher bound to one device.  All calls are asynchronous on the current stream."""
+
+    name = "cuda"
+
+    def __init__(self, device: torch.device | str | int):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("CudaOps needs a CUDA device")
+        self.lib = _cabi.lib()
+        self._ws: dict[str, torch.Tensor] = {}
+
+    # -- memory ------------------------------------------------------------------------------
+    def empty(self, shape, dtype) -> torch.Tensor:
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype) -> torch.Tensor:
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def to_device(self, host: torch.Tensor, non_blocking: bool = True) -> torch.Tensor:
+        return host.to(self.device, non_blocking=non_blocking)
+
+    def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # -- (a) matrix build --------------------------------------------------------------------
+    def build_rows(self, src: torch.Tensor, X: torch.Tensor, mean: torch.Tensor | None,
+                   std: torch.Tensor | None, weights: torch.Tensor | None, flags: int,
+                   nonfinite_flag: torch.Tensor | None = None) -> None:
+        """src: (T, P) native time-major view; X: (P, T) destination rows."""
+        sp, sld = _mat(src, "src")
+        xp, xld = _mat(X, "X")
+        T, P = src.shape
+        if tuple(X.shape) != (P, T):
+            raise ValueError(f"X must be ({P}, {T}), got {tuple(X.shape)}")
+        check(self.lib.era5svd_build_rows(sp, _dt(src), T, sld, P, xp, _dt(X), xld, _vec(mean, "mean"),
+                                          _vec(std, "std"), _vec(weights, "weights"), flags,
+                                          _vec(nonfinite_flag, "flag"), self._stream()), "era5svd_build_rows")
+
+    # -- (b) tall passes ---------------------------------------------------------------------
+    def sketch(self, X: torch.Tensor, Om: torch.Tensor, Y: torch.Tensor | None = None,
+               precision: int = PREC_NATIVE) -> torch.Tensor:
+        m, n = X.shape
+        if Om.shape[0] != n or Om.dtype != X.dtype:
+            raise ValueError("sketch: Om must be (n, l) with X's dtype")
+        l = Om.shape[1]
+        if Y is None:
+            Y = self.empty((m, l), X.dtype)
+        xp, xld = _mat(X, "X"); op, old = _mat(Om, "Om"); yp, yld = _mat(Y, "Y")
+        check(self.lib.era5svd_sketch(xp, _dt(X), m, n, xld, op, l, old, yp, yld, precision, self._stream()),
+              "era5svd_sketch")
+        return Y
+
+    def project(self, X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor | None = None,
+                accumulate: bool = False, precision: int = PREC_NATIVE) -> torch.Tensor:
+        m, n = X.shape
+        if Y.shape[0] != m or Y.dtype != X.dtype:
+            raise ValueError("project: Y must be (m, l) with X's dtype")
+        l = Y.shape[1]
+        if Z is None:
+            Z = self.empty((n, l), torch.float64)
+            accumulate = False
+        xp, xld = _mat(X, "X"); yp, yld = _mat(Y, "Y"); zp, zld = _mat(Z, "Z")
+        nbytes = int(self.lib.era5svd_project_workspace_bytes(_dt(X), m, n, l, precision))
+        ws = self._workspace("project", nbytes)
+        check(self.lib.era5svd_project(xp, _dt(X), m, n, xld, yp, l, yld, zp, zld, int(accumulate), precision,
+                                       ws.data_ptr(), ws.numel(), self._stream()), "era5svd_project")
+        return Z
+
+    # -- (c)/(d) small float64 factors -------------------------------------------------------
+    def gemm(self, A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool = False,
+             alpha: float = 1.0, beta: float = 0.0, C: torch.Tensor | None = None) -> torch.Tensor:
+        M = A.shape[1] if transA else A.shape[0]
+        K = A.shape[0] if transA else A.shape[1]
+        N = B.shape[0] if transB else B.shape[1]
+        Kb = B.shape[1] if transB else B.shape[0]
+        if K != Kb or A.dtype != torch.float64 or B.dtype != torch.float64:
+            raise ValueError("gemm: shape / dtype mismatch (float64 only)")
+        if C is None:
+            C = self.empty((M, N), torch.float64)
+            beta = 0.0
+        ap, ald = _mat(A, "A"); bp, bld = _mat(B, "B"); cp, cld = _mat(C, "C")
+        check(self.lib.era5svd_gemm_f64(int(transA), int(transB), M, N, K, alpha, ap, ald, bp, bld, beta, cp, cld,
+                                        self._stream()), "era5svd_gemm_f64")
+        return C
+
+    def syevj(self, A: torch.Tensor, max_sweeps: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+        """Eigen-decomposition of symmetric A (destroyed).  Returns (W descending, V columns)."""
+        n = A.shape[0]
+        ap, ald = _mat(A, "A")
+        W = self.empty((n,), torch.float64)
+        V = self.empty((n, n), torch.float64)
+        nbytes = int(self.lib.era5svd_syevj_workspace_bytes(n))
+        ws = self._workspace("syevj", nbytes)
+        check(self.lib.era5svd_syevj_f64(ap, n, ald, W.data_ptr(), V.data_ptr(), n, max_sweeps, ws.data_ptr(),
+                                         ws.numel(), self._stream()), "era5svd_syevj_f64")
+        return W, V
+
+    def chol_inv(self, G: torch.Tensor, rel_tol: float) -> tuple[torch.Tensor, torch.Tensor]:
+        l = G.shape[0]
+        gp, gld = _mat(G, "G")
+        R = self.empty((l, l), torch.float64)
+        Rinv = self.empty((l, l), torch.float64)
+        check(self.lib.era5svd_chol_inv_f64(gp, l, gld, R.data_ptr(), l, Rinv.data_ptr(), l, rel_tol, self._stream()),
+              "era5svd_chol_inv_f64")
+        return R, Rinv
+
+    def col_normalize(self, P: torch.Tensor) -> torch.Tensor:
+        n, l = P.shape
+        pp, pld = _mat(P, "P")
+        norms = self.empty((l,), torch.float64)
+        check(self.lib.era5svd_col_normalize_f64(pp, n, l, pld, norms.data_ptr(), self._stream()),
+              "era5svd_col_normalize_f64")
+        return norms
+
+    def sigma_from_eig(self, W: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        l = W.shape[0]
+        s = self.empty((l,), torch.float64)
+        inv = self.empty((l,), torch.float64)
+        check(self.lib.era5svd_sigma_from_eig_f64(W.data_ptr(), l, s.data_ptr(), inv.data_ptr(), self._stream()),
+              "era5svd_sigma_from_eig_f64")
+        return s, inv
+
+    def convert(self, src: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        if src.dtype == dtype:
+            return src
+        rows, cols = src.shape
+        dst = self.empty((rows, cols), dtype)
+        sp, sld = _mat(src, "src")
+        check(self.lib.era5svd_convert(sp, _dt(src), sld, dst.data_ptr(), _DT[dtype], cols, rows, cols, self._stream()),
+              "era5svd_convert")
+        return dst
+
+    # -- svd_flip ----------------------------------------------------------------------------
+    def col_absmax(self, U: torch.Tensor, row_offset: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        m, k = U.shape
+        up, uld = _mat(U, "U")
+        a = self.empty((k,), torch.float64)
+        row = self.empty((k,), torch.int64)
+        sgn = self.empty((k,), torch.float64)
+        nbytes = int(self.lib.era5svd_col_absmax_workspace_bytes(m, k))
+        ws = self._workspace("absmax", nbytes)
+        check(self.lib.era5svd_col_absmax(up, _dt(U), m, k, uld, row_offset, a.data_ptr(), row.data_ptr(),
+                                          sgn.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
+              "era5svd_col_absmax")
+        return a, row, sgn
+
+    def maxloc_combine(self, a: torch.Tensor, row: torch.Tensor, sgn: torch.Tensor) -> torch.Tensor:
+        """a, row, sgn: (R, k) stacked candidate sets -> sign (k,)."""
+        R, k = a.shape
+        a, row, sgn = a.contiguous(), row.contiguous(), sgn.contiguous()
+        out = self.empty((k,), torch.float64)
+        check(self.lib.era5svd_maxloc_combine(a.data_ptr(), row.data_ptr(), sgn.data_ptr(), R, k,
+                                              out.data_ptr(), self._stream()), "era5svd_maxloc_combine")
+        return out
+
+    def scale_cols(self, U: torch.Tensor, scale: torch.Tensor) -> None:
+        m, k = U.shape
+        up, uld = _mat(U, "U")
+        check(self.lib.era5svd_scale_cols(up, _dt(U), m, k, uld, scale.data_ptr(), self._stream()),
+              "era5svd_scale_cols")
+
+    def scale_rows(self, V: torch.Tensor, scale: torch.Tensor) -> None:
+        k, n = V.shape
+        vp, vld = _mat(V, "V")
+        check(self.lib.era5svd_scale_rows_f64(vp, k, n, vld, scale.data_ptr(), self._stream()),
+              "era5svd_scale_rows_f64")

@@ -1,0 +1,93 @@
+"""Drop-in for the numerical core of ``dmd_era5.era5_svd`` (reference:
+src/dmd_era5/era5_svd/era5_svd.py).
+
+``svd_on_era5(da, parsed_config)`` keeps the reference's signature, return contract
+(U (m, k), s (k,), V (k, n) as NumPy arrays in the dtype of X), log messages and error text
+(era5_svd.py:230-263), but factorises on the GPU through the C ABI.  There is no CPU fallback.
+
+Opt-in extension keys read from ``parsed_config`` (all default to the reference's behaviour;
+the reference's parser ignores unknown keys):
+    random_seed : int | None   - None draws Omega from NumPy's global RandomState exactly like the
+                                 unseeded reference call (quirk Q6)
+    precision   : "native" (FP64 for float64 X, FP32 FMA for float32 X) | "tf32x3"
+    device      : torch device (default "cuda:0")
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from .device_ops import CudaOps
+from .pipeline import padded_ld, svd_device
+
+logger = logging.getLogger("ERA5-SVD")
+
+
+def log_and_print(lg: logging.Logger, msg: str, level: str = "info") -> None:
+    """src/dmd_era5/logger.py:42-46: log and print."""
+    getattr(lg, level)(msg)
+    print(msg)
+
+
+_OPS: dict[str, CudaOps] = {}
+
+
+def get_ops(device="cuda:0") -> CudaOps:
+    key = str(device)
+    if key not in _OPS:
+        if not torch.cuda.is_available():
+            raise RuntimeError("dmd_era5_b200 needs a CUDA device: there is no CPU fallback for the SVD stage")
+        _OPS[key] = CudaOps(device)
+    return _OPS[key]
+
+
+def _values(da) -> np.ndarray:
+    """``da.values`` for an xarray.DataArray / our DataArray shim, or the array itself."""
+    X = da.values if hasattr(da, "values") else da
+    X = np.asarray(X)
+    if X.ndim != 2:
+        raise ValueError("Input array must be 2D.")
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)
+    return X
+
+
+def host_to_device_matrix(ops: CudaOps, X: np.ndarray) -> torch.Tensor:
+    """Copy a host (m, n) matrix into a padded device buffer (rows 32-byte aligned); returns the
+    (m, n) view.  Pinned staging + async copy on the current stream."""
+    m, n = X.shape
+    t = torch.from_numpy(np.ascontiguousarray(X))
+    ld = padded_ld(n, t.dtype)
+    buf = ops.empty((m, ld), t.dtype)
+    view = buf[:, :n]
+    view.copy_(t.pin_memory() if m * n >= 1 << 16 else t, non_blocking=True)
+    return view
+
+
+def svd_on_era5(da, parsed_config: dict) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Perform SVD on the pre-processed ERA5 slice (era5_svd.py:230-263).
+
+    Returns U (n_samples, n_components), s (n_components,), V (n_components, n_features).
+    """
+    X = _values(da)
+    svd_type = parsed_config["svd_type"]
+    n_components = parsed_config["n_components"]
+    if svd_type not in ("standard", "randomized"):
+        msg = f"SVD type {svd_type} is not supported."
+        raise ValueError(msg)
+    ops = get_ops(parsed_config.get("device", "cuda:0"))
+    label = "standard" if svd_type == "standard" else "randomized"
+    log_and_print(logger, f"Performing {label} SVD...")
+    with torch.cuda.device(ops.device):
+        Xd = host_to_device_matrix(ops, X)
+        U, s, V = svd_device(ops, Xd, svd_type=svd_type, n_components=n_components,
+                             seed=parsed_config.get("random_seed"),
+                             precision=parsed_config.get("precision", "native"))
+        out_dtype = Xd.dtype
+        U_h = U.to(out_dtype).cpu().numpy()
+        s_h = s.to(out_dtype).cpu().numpy()
+        V_h = V.to(out_dtype).cpu().numpy()
+    log_and_print(logger, f"{label.capitalize()} SVD complete.")
+    return U_h, s_h, V_h

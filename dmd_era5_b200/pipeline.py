@@ -1,0 +1,86 @@
+"""Device pipeline of the SVD stage: native ERA5 arrays -> snapshot matrix -> U, s, V.
+
+Host-side mirror of the compute part of ``era5_svd.main``
+(src/dmd_era5/era5_svd/era5_svd.py:384-415): variable / level stacking, time-mean removal,
+optional scaling, flattening, (virtual) delay embedding and the SVD, all on the GPU.
+Row layout of the snapshot matrix (slice_tools.py:323-336): r = v * S + (l * A + a) * O + o.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from ._cabi import BUILD_CHECK_FINITE, BUILD_MEAN_CENTER, BUILD_SCALE, PREC_NATIVE
+from .device_ops import CudaOps
+from .dist import LocalComm, shard_rows
+from .rsvd import PRECISIONS, draw_omega, n_iter_auto, randomized_svd_device
+from .standard import standard_svd_device
+
+
+def padded_ld(T: int, dtype: torch.dtype) -> int:
+    """Leading dimension of X: rows start on 32-byte boundaries (TMA needs 16)."""
+    q = 8 if dtype == torch.float32 else 4
+    return -(-T // q) * q
+
+
+@dataclass
+class BuiltMatrix:
+    X: torch.Tensor                 # (m0_local, T) view into a padded buffer, tall dtype
+    mean: torch.Tensor | None       # (m0_local,) or None
+    std: torch.Tensor | None
+    row_offset: int                 # global index of the first local base row
+    m0_global: int
+    nonfinite: torch.Tensor | None = None
+    buffers: list = field(default_factory=list)
+
+
+def build_matrix_device(ops: CudaOps, var_blocks: list[torch.Tensor], *, mean_center: bool, scale: bool,
+                        dtype: torch.dtype | None = None, weights: torch.Tensor | None = None,
+                        check_finite: bool = False, comm=None) -> BuiltMatrix:
+    """Stack (variable, level) blocks into this rank's rows of the snapshot matrix.
+
+    var_blocks : DEVICE tensors (T, P_i) in the native time-major layout, in row order: one per
+                 variable (its selected levels flattened to S = L*A*O points) on a single rank, or
+                 the pieces of those blocks that fall into this rank's row range (``shard_rows``
+                 over the concatenated row index) when the matrix is row-sharded.
+    Reference quirk Q4 (era5_svd.py:389-395): ``scale`` without ``mean_center`` does nothing.
+    """
+    T = var_blocks[0].shape[0]
+    dtype = dtype or var_blocks[0].dtype
+    m0 = sum(int(b.shape[1]) for b in var_blocks)
+    ld = padded_ld(T, dtype)
+    buf = ops.empty((m0, ld), dtype)
+    X = buf[:, :T]
+    do_center = bool(mean_center)
+    do_scale = bool(mean_center and scale)
+    mean = ops.empty((m0,), dtype) if do_center else None
+    std = ops.empty((m0,), dtype) if do_scale else None
+    flag = ops.zeros((1,), torch.int32) if check_finite else None
+    flags = (BUILD_MEAN_CENTER if do_center else 0) | (BUILD_SCALE if do_scale else 0) | (BUILD_CHECK_FINITE if check_finite else 0)
+    r = 0
+    for b in var_blocks:
+        P = int(b.shape[1])
+        ops.build_rows(b, X[r : r + P], mean[r : r + P] if do_center else None, std[r : r + P] if do_scale else None,
+                       weights[r : r + P] if weights is not None else None, flags, flag)
+        r += P
+    return BuiltMatrix(X=X, mean=mean, std=std, row_offset=0, m0_global=m0, nonfinite=flag, buffers=[buf])
+
+
+def svd_device(ops: CudaOps, X: torch.Tensor, *, svd_type: str, n_components: int, delay: int = 1,
+               seed: int | None = None, precision: str = "native", comm=None, row_offset: int = 0,
+               m0_global: int | None = None, n_iter: int | None = None, stats: dict | None = None):
+    """SVD of the (virtual) delay-embedded matrix whose base rows are X (device, tall dtype).
+    Dispatch and error text follow svd_on_era5 (era5_svd.py:247-262)."""
+    n = X.shape[1] - delay + 1
+    if svd_type == "standard":
+        return standard_svd_device(ops, X, n_components, delay=delay, comm=comm)
+    if svd_type == "randomized":
+        omega0 = draw_omega(n, n_components, seed, X.dtype)
+        return randomized_svd_device(ops, X, n_components, omega0, n_iter=n_iter, delay=delay,
+                                     precision=PRECISIONS[precision], comm=comm, row_offset=row_offset,
+                                     m0_global=m0_global, stats=stats)
+    msg = f"SVD type {svd_type} is not supported."
+    raise ValueError(msg)

@@ -1,0 +1,160 @@
+"""Randomized SVD driver on the device - the B200 schedule of sklearn's ``_randomized_svd``.
+
+Reference control flow being replaced (scikit-learn 1.9.0, called from
+src/dmd_era5/era5_svd/era5_svd.py:258 with all defaults):
+    _randomized_range_finder  sklearn/utils/extmath.py:313-385
+        Q = normal(n x l)                                   :323   (host RandomState, l = k + 10)
+        n_iter x { Q = lu(A @ Q); Q = lu(A.T @ Q) }         :377-379
+        Q = qr(A @ Q)                                       :383
+    _randomized_svd           extmath.py:560-633
+        B = Q.T @ M; Uhat, s, Vt = svd(B); U = Q @ Uhat     :606-619
+        svd_flip (u-based); truncate to k                   :623, :633
+
+In exact arithmetic U, s, Vt depend only on span((A^T A)^q Omega_0); the LU / QR normalisers are
+there for floating-point stability only.  The device schedule therefore keeps the
+same Omega_0, q and flip rule but never factorises a TALL matrix inside the power iterations:
+
+    Omega = orth(Omega_0)                                   (n x l, float64, CholeskyQR2)
+    q x { Y = X Omega            [tall pass, not normalised]
+          Z = X^T Y              [tall pass -> n x l float64, all-reduce over row shards]
+          T = Omega^T Z = Y^T Y  -> eig(T) = W L W^T        (l x l Jacobi)
+          Omega = orth(Z W)      }                          (Rayleigh-Ritz rotation + CholeskyQR2)
+    Y = X Omega; Z' = X^T Y; G = Y^T Y                      (last tall passes)
+    R = chol(G); B = R^-T Z'^T (= Q^T X with Q = Y R^-1)    (l x n)
+    eig(B B^T) -> Uhat, s;  Vt = S^-1 Uhat^T B;  U = Y (R^-1 Uhat)
+    svd_flip via a MAXLOC reduction over row shards; truncate to k.
+
+The Rayleigh-Ritz rotation makes the columns of Y = X Omega nearly orthogonal with norms ~ sigma_j,
+so (i) storing Y in float32 keeps every direction at full relative precision and (ii) the Gram
+matrices handed to Cholesky are well conditioned after diagonal scaling.
+All small factors are float64 and replicated on every rank.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._cabi import PREC_NATIVE, PREC_TF32X3
+from .dist import LocalComm
+
+PRECISIONS = {"native": PREC_NATIVE, "fp64": PREC_NATIVE, "fp32": PREC_NATIVE, "tf32x3": PREC_TF32X3}
+
+
+def n_iter_auto(m: int, n: int, k: int) -> int:
+    """extmath.py:586-589: 7 power iterations if k < 0.1 * min(M.shape) else 4."""
+    return 7 if k < 0.1 * min(m, n) else 4
+
+
+def draw_omega(n_features: int, k: int, seed: int | None, dtype: torch.dtype, n_oversamples: int = 10) -> np.ndarray:
+    """The reference's test matrix, drawn on the host exactly as extmath.py:323-334 does:
+    ``random_state.normal(size=(n, k + 10))`` from NumPy's RandomState (the global one when the
+    reference's call is unseeded, era5_svd.py:258), cast to float32 when X is float32.
+    Returned as float64 (the cast is value-preserving)."""
+    rs = np.random.mtrand._rand if seed is None else np.random.RandomState(seed)
+    om = rs.normal(size=(n_features, k + n_oversamples))
+    if dtype == torch.float32:
+        om = om.astype(np.float32)
+    return np.ascontiguousarray(om, dtype=np.float64)
+
+
+class _Blocks:
+    """The (virtual) delay-embedded operator: block j is the view X[:, j : j + n]
+    (src/dmd_era5/slice_tools/slice_tools.py:207-211, never materialised)."""
+
+    def __init__(self, X: torch.Tensor, d: int):
+        self.X = X
+        self.d = d
+        self.m0 = X.shape[0]
+        self.n = X.shape[1] - d + 1
+        if self.n < 1:
+            raise ValueError("delay embedding larger than the number of snapshots")
+
+    def view(self, j: int) -> torch.Tensor:
+        return self.X[:, j : j + self.n]
+
+
+def _orth(ops, P: torch.Tensor, rel_tol: float) -> torch.Tensor:
+    """Orthonormal basis of span(P) for a small (n x l) float64 matrix: column scaling followed by
+    CholeskyQR2 (Gram -> Cholesky -> triangular inverse -> GEMM, twice)."""
+    ops.col_normalize(P)
+    for _ in range(2):
+        G = ops.gemm(P, P, transA=True)
+        _, Rinv = ops.chol_inv(G, rel_tol)
+        P = ops.gemm(P, Rinv)
+    return P
+
+
+def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_iter: int | None = None,
+                          delay: int = 1, precision: int = PREC_NATIVE, comm=None, row_offset: int = 0,
+                          m0_global: int | None = None, m_global: int | None = None, stats: dict | None = None):
+    """Randomized SVD of the (row-sharded, optionally delay-embedded) snapshot matrix.
+
+    X          : this rank's rows of the BASE matrix, (m0_local, T) tall-dtype device tensor
+    omega0     : (n, l) test matrix (host ndarray or tensor), n = T - delay + 1
+    row_offset : global index of this rank's first base row; m0_global: total base rows
+    Returns (U_local (m0_local * delay, k) tall dtype, s (k,) float64, Vt (k, n) float64).
+    Rows of U_local are ordered block-major: block j holds rows [j * m0_local, (j + 1) * m0_local),
+    i.e. global rows j * m0_global + row_offset + r.
+    """
+    comm = comm or LocalComm()
+    blocks = _Blocks(X, delay)
+    m0, n, d = blocks.m0, blocks.n, delay
+    m0_global = m0 if m0_global is None else m0_global
+    m_global = m0_global * d if m_global is None else m_global
+    k = int(n_components)
+    om = torch.as_tensor(np.asarray(omega0) if not torch.is_tensor(omega0) else omega0, dtype=torch.float64)
+    if om.shape[0] != n:
+        raise ValueError(f"omega0 must have {n} rows, got {tuple(om.shape)}")
+    l = min(om.shape[1], n)  # a sketch wider than the row space adds nothing (exact SVD either way)
+    om = om[:, :l].contiguous()
+    if n_iter is None:
+        n_iter = n_iter_auto(m_global, n, k)
+    tall = X.dtype
+    rel_tol = 1e-13 if tall == torch.float64 else 1e-6
+    Omega = _orth(ops, ops.to_device(om, non_blocking=False).clone(), 1e-13)
+
+    Y = ops.empty((m0 * d, l), tall)
+
+    def tall_pass(Omega64: torch.Tensor) -> torch.Tensor:
+        """Y = X_d Omega (kept in the preallocated Y), returns Z = X_d^T Y (all-reduced)."""
+        Om_t = ops.convert(Omega64, tall)
+        Z = None
+        for j in range(d):
+            Yj = Y[j * m0 : (j + 1) * m0]
+            ops.sketch(blocks.view(j), Om_t, Yj, precision)
+            Z = ops.project(blocks.view(j), Yj, Z, accumulate=j > 0, precision=precision)
+        comm.allreduce_sum_(Z)
+        if stats is not None:
+            stats["tall_passes"] = stats.get("tall_passes", 0) + 2
+        return Z
+
+    for _ in range(n_iter):
+        Z = tall_pass(Omega)
+        T = ops.gemm(Omega, Z, transA=True)            # = Y^T Y, l x l
+        _, W = ops.syevj(T)                            # Ritz rotation, columns by descending Ritz value
+        Omega = _orth(ops, ops.gemm(Z, W), 1e-13)
+
+    Zp = tall_pass(Omega)                              # n x l
+    G = ops.project(Y, Y, precision=PREC_NATIVE)       # l x l, from the stored (rounded) Y
+    comm.allreduce_sum_(G)
+    _, Rinv = ops.chol_inv(G, rel_tol)
+    B = ops.gemm(Rinv, Zp, transA=True, transB=True)   # l x n  = R^-T Z'^T = Q^T X
+    BBt = ops.gemm(B, B, transB=True)                  # l x l
+    lam, Uh = ops.syevj(BBt)
+    s, inv_s = ops.sigma_from_eig(lam)
+    Vt = ops.gemm(Uh, B, transA=True)                  # l x n
+    ops.scale_rows(Vt, inv_s)
+    kk = min(k, l)
+    M = ops.gemm(Rinv, Uh[:, :kk])                     # l x k
+    U = ops.sketch(Y, ops.convert(M, tall), None, PREC_NATIVE)   # (m0 * d) x k
+
+    # svd_flip (extmath.py:964-972): first row of max |U[:, j]| over ALL rows decides the sign
+    cands = [ops.col_absmax(U[j * m0 : (j + 1) * m0], j * m0_global + row_offset) for j in range(d)]
+    a = torch.stack([c[0] for c in cands]); r = torch.stack([c[1] for c in cands]); sg = torch.stack([c[2] for c in cands])
+    if comm.world > 1:
+        a = comm.allgather(a).reshape(-1, kk); r = comm.allgather(r).reshape(-1, kk); sg = comm.allgather(sg).reshape(-1, kk)
+    sign = ops.maxloc_combine(a, r, sg)
+    ops.scale_cols(U, sign)
+    Vk = Vt[:kk]
+    ops.scale_rows(Vk, sign)
+    return U, s[:kk], Vk

@@ -1,0 +1,162 @@
+/*
+ * era5svd.h - C ABI of the B200-native DMD-ERA5 SVD stage (libera5svd.so, sm_100a).
+ *
+ * The reference (ClimeTrend/DMD-ERA5) is pure Python and has NO FFI of its own
+ * (SURVEY.md section 8b); its seam for this path is
+ *     svd_on_era5(da, parsed_config) -> (U, s, V)      src/dmd_era5/era5_svd/era5_svd.py:230-263
+ * plus the matrix-build calls of era5_svd.main          era5_svd.py:384-414
+ * which bottom out in NumPy / SciPy / scikit-learn BLAS+LAPACK calls.  Each entry point
+ * below replaces one of those library call sites (cited per function); INTEGRATION.md
+ * shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative era5svd_status otherwise;
+ *     era5svd_last_error() returns a thread-local message for the last failure.
+ *   - the caller owns ALL memory (device pointers, e.g. torch tensors' data_ptr());
+ *     the library allocates nothing persistent; ops that need scratch take a workspace
+ *     pointer + size and have a *_workspace_bytes() query.
+ *   - all ops are asynchronous on the cudaStream_t passed as `void* stream`
+ *     (0 = legacy default stream); no hidden synchronisation, re-entrant across streams.
+ *   - all matrices are ROW-MAJOR with an explicit leading dimension in ELEMENTS.
+ *   - dtype: ERA5SVD_F32 / ERA5SVD_F64 for the tall (space-sized) operands; every small
+ *     (time- or sketch-sized) factor is float64.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     ERA5SVD_ERR_CUDA.
+ */
+#ifndef ERA5SVD_H
+#define ERA5SVD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERA5SVD_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  ERA5SVD_OK = 0,
+  ERA5SVD_ERR_ARG = -1,       /* invalid argument (shape, dtype, alignment, null) */
+  ERA5SVD_ERR_CUDA = -2,      /* CUDA runtime / launch error, or no device       */
+  ERA5SVD_ERR_WORKSPACE = -3, /* workspace too small                             */
+  ERA5SVD_ERR_UNSUPPORTED = -4
+} era5svd_status;
+
+typedef enum { ERA5SVD_F32 = 0, ERA5SVD_F64 = 1 } era5svd_dtype;
+
+/* arithmetic used by the tall GEMM passes */
+typedef enum {
+  ERA5SVD_PREC_NATIVE = 0, /* FMA in the storage dtype (FP64 DFMA for f64, FP32 FFMA for f32) */
+  ERA5SVD_PREC_TF32X3 = 1  /* f32 storage, tcgen05 kind::tf32 with 3-term hi/lo split, fp32 accumulate in TMEM */
+} era5svd_precision;
+
+/* build flags */
+#define ERA5SVD_BUILD_MEAN_CENTER 1u
+#define ERA5SVD_BUILD_SCALE 2u
+#define ERA5SVD_BUILD_CHECK_FINITE 4u
+
+int era5svd_version(void);
+const char* era5svd_last_error(void);
+/* number of CUDA kernels launched by this library in the calling process (bench's gpu_launches) */
+unsigned long long era5svd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (a) matrix build.  Replaces standardize_data (slice_tools.py:171-177: xarray mean / subtract /
+ * std(ddof=0) / divide), flatten_era5_variables' transpose+concat copy (slice_tools.py:323-336)
+ * and the sklearn check_array finiteness pass (sklearn/utils/extmath.py:546).
+ *
+ * src : one (variable, level) block in the NATIVE ERA5 layout, time-major:
+ *       element (t, p) at src[t * src_ld + p], t < T, p < P  (P = lat*lon points, or a shard of them)
+ * X   : destination rows [P] x columns [T], row r = p, X[p * ldx + t]   (space x time, time fastest)
+ *       value = (src - mean_p) / std_p * weight_p   following the flags; dtype_x may differ from
+ *       dtype_src (explicit cast, opt-in extension; default equal = reference behaviour)
+ * mean_out / std_out : length-P arrays in dtype_x, nullable; std is of the CENTRED data, ddof = 0,
+ *       NaN-skipping like xarray; no epsilon guard (std == 0 -> inf/nan exactly like the reference)
+ * weights : nullable length-P array (dtype_x), e.g. sqrt(cos(lat)) - opt-in extension
+ * nonfinite_flag : nullable device int, set to 1 if any non-finite input was seen (CHECK_FINITE)
+ */
+int era5svd_build_rows(const void* src, int dtype_src, int64_t T, int64_t src_ld, int64_t P,
+                       void* X, int dtype_x, int64_t ldx, void* mean_out, void* std_out,
+                       const void* weights, unsigned flags, int* nonfinite_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) tall GEMM passes of the randomized range finder.
+ *
+ * era5svd_sketch:  Y[m x l] = X[m x n] * Om[n x l]           replaces `A @ Q`   extmath.py:378, 383
+ *                  (also U = Q * Uhat, extmath.py:619, with X := Y, Om := small factor)
+ * era5svd_project: Z[n x l] (float64) (+)= X[m x n]^T * Y[m x l]   replaces `A.T @ Q` extmath.py:379
+ *                  and `Q.T @ M` extmath.py:606 (transposed), and the Gram matrices Y^T Y / X^T X
+ *                  (pass Y := X).  Partial sums over row ranges go to the workspace in the accumulate
+ *                  type and are reduced in float64 in a fixed order (deterministic).
+ * X, Om, Y share `dtype`.  A delay-embedded block j is addressed by passing X + j with the same ldx
+ * (slice_tools.py:207-211 is never materialised).
+ */
+int era5svd_sketch(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx, const void* Om,
+                   int64_t l, int64_t ldo, void* Y, int64_t ldy, int precision, void* stream);
+
+size_t era5svd_project_workspace_bytes(int dtype, int64_t m, int64_t n, int64_t l, int precision);
+int era5svd_project(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx, const void* Y,
+                    int64_t l, int64_t ldy, double* Z, int64_t ldz, int accumulate, int precision,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (c)/(d) small float64 factor kernels (replicated on every GPU; per-CTA solvers).
+ */
+/* C[M x N] = alpha * op(A) * op(B) + beta * C, row-major; transX != 0 means the operand is stored
+ * transposed (op(A) = A^T with A stored [K x M]). */
+int era5svd_gemm_f64(int transA, int transB, int64_t M, int64_t N, int64_t K, double alpha,
+                     const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
+                     double* C, int64_t ldc, void* stream);
+
+/* Symmetric eigen-decomposition by parallel cyclic Jacobi (one CTA).  A[n x n] is destroyed;
+ * W[n] = eigenvalues in DESCENDING order, V[n x n] = eigenvectors in columns (same order).
+ * Replaces the small dense solves of scipy.linalg.svd(B, gesdd) (extmath.py:615) and the
+ * eigensolve behind the Gram-route standard SVD (np.linalg.svd, era5_svd.py:251).
+ * max_sweeps <= 0 selects the default (30); iteration stops early at convergence. */
+size_t era5svd_syevj_workspace_bytes(int64_t n);
+int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
+                      int max_sweeps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Cholesky G = R^T R (R upper triangular) of a symmetric positive (semi-)definite l x l matrix and
+ * the explicit inverse Rinv = R^{-1} (upper triangular), one CTA.  Replaces scipy qr / lu
+ * normalisers (extmath.py:371-383) in CholeskyQR form.  A pivot that falls below
+ * rel_tol * G[j][j] (column j numerically dependent on the previous ones) is replaced by a huge
+ * value so that row/column j of Rinv vanish: rank-deficient directions give zero columns, not NaN. */
+int era5svd_chol_inv_f64(const double* G, int64_t l, int64_t ldg, double* R, int64_t ldr,
+                         double* Rinv, int64_t ldri, double rel_tol, void* stream);
+
+/* P[:, j] /= ||P[:, j]||_2 for an n x l float64 matrix; norms_out (nullable) receives the norms. */
+int era5svd_col_normalize_f64(double* P, int64_t n, int64_t l, int64_t ldp, double* norms_out,
+                              void* stream);
+
+/* s[i] = sqrt(max(w[i], 0)), inv_s[i] = 1 / s[i] (0 where s[i] == 0; nullable): singular values from
+ * the eigenvalues of B B^T. */
+int era5svd_sigma_from_eig_f64(const double* w, int64_t l, double* s, double* inv_s, void* stream);
+
+/* dst[r x c] (dtype_dst) = src[r x c] (dtype_src), row-major with leading dimensions. */
+int era5svd_convert(const void* src, int dtype_src, int64_t lds, void* dst, int dtype_dst,
+                    int64_t ldd, int64_t rows, int64_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * svd_flip (extmath.py:964-972, u-based): per column of U the FIRST row holding max |U[:, j]|.
+ * col_absmax writes, per column j < k: absmax[j], row[j] = row_offset + local row (lowest on ties),
+ * sign[j] = sign of that entry (+1 / -1 / 0).  combine reduces R stacked candidate sets
+ * ([R x k] each, e.g. all-gathered over ranks) with the same tie rule.  scale_cols applies
+ * U[:, j] *= sign[j]; scale_rows applies V[j, :] *= sign[j] (float64).
+ */
+size_t era5svd_col_absmax_workspace_bytes(int64_t m, int64_t k);
+int era5svd_col_absmax(const void* U, int dtype, int64_t m, int64_t k, int64_t ldu,
+                       int64_t row_offset, double* absmax, int64_t* row, double* sign,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int era5svd_maxloc_combine(const double* absmax, const int64_t* row, const double* sign, int64_t R,
+                           int64_t k, double* sign_out, void* stream);
+int era5svd_scale_cols(void* U, int dtype, int64_t m, int64_t k, int64_t ldu, const double* scale,
+                       void* stream);
+int era5svd_scale_rows_f64(double* V, int64_t k, int64_t n, int64_t ldv, const double* scale,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERA5SVD_H */

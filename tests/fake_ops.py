@@ -1,0 +1,124 @@
+"""CPU stand-in for ``dmd_era5_b200.device_ops.CudaOps`` - TEST INFRASTRUCTURE ONLY.
+
+It lets the host-side drivers (rsvd.py, standard.py, dist.py) run on CPU tensors so that their
+control flow, the delay-block bookkeeping and the gloo collectives can be tested without a GPU.
+The product never imports this module; CudaOps refuses CPU tensors.
+Semantics mirror include/era5svd.h; tall ops round to the tall dtype like the kernels do.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class FakeOps:
+    name = "fake-cpu"
+
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.calls: dict[str, int] = {}
+
+    def _count(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    def empty(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype)
+
+    def to_device(self, host, non_blocking=True):
+        return host.clone()
+
+    def sketch(self, X, Om, Y=None, precision=0):
+        self._count("sketch")
+        out = (X.double() @ Om.double()).to(X.dtype)
+        if Y is None:
+            return out
+        Y.copy_(out)
+        return Y
+
+    def project(self, X, Y, Z=None, accumulate=False, precision=0):
+        self._count("project")
+        out = X.double().t() @ Y.double()
+        if Z is None:
+            return out
+        if accumulate:
+            Z += out
+        else:
+            Z.copy_(out)
+        return Z
+
+    def gemm(self, A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None):
+        self._count("gemm")
+        a = A.t() if transA else A
+        b = B.t() if transB else B
+        out = alpha * (a @ b)
+        if C is None:
+            return out.contiguous()
+        C.copy_(out + beta * C)
+        return C
+
+    def syevj(self, A, max_sweeps=0):
+        self._count("syevj")
+        w, v = np.linalg.eigh(0.5 * (A.numpy() + A.numpy().T))
+        return torch.from_numpy(w[::-1].copy()), torch.from_numpy(np.ascontiguousarray(v[:, ::-1]))
+
+    def chol_inv(self, G, rel_tol):
+        self._count("chol_inv")
+        g = 0.5 * (G.numpy() + G.numpy().T)
+        R = np.linalg.cholesky(g).T
+        Rinv = np.linalg.inv(R)
+        return torch.from_numpy(R.copy()), torch.from_numpy(np.ascontiguousarray(Rinv))
+
+    def col_normalize(self, P):
+        self._count("col_normalize")
+        nrm = torch.linalg.norm(P, dim=0)
+        P /= nrm
+        return nrm
+
+    def sigma_from_eig(self, W):
+        s = torch.sqrt(torch.clamp(W, min=0))
+        inv = torch.where(s > 0, 1.0 / s, torch.zeros_like(s))
+        return s, inv
+
+    def convert(self, src, dtype):
+        return src.to(dtype)
+
+    def col_absmax(self, U, row_offset):
+        self._count("col_absmax")
+        a = U.double().abs()
+        idx = torch.from_numpy(np.argmax(a.numpy(), axis=0))  # numpy argmax: FIRST maximum
+        k = U.shape[1]
+        vals = U.double()[idx, torch.arange(k)]
+        return a[idx, torch.arange(k)], idx + row_offset, torch.sign(vals)
+
+    def maxloc_combine(self, a, row, sgn):
+        a, row, sgn = a.numpy(), row.numpy(), sgn.numpy()
+        R, k = a.shape
+        out = np.zeros(k)
+        for c in range(k):
+            best = max(range(R), key=lambda i: (a[i, c], -row[i, c]))
+            out[c] = sgn[best, c]
+        return torch.from_numpy(out)
+
+    def scale_cols(self, U, scale):
+        U *= scale.to(U.dtype)
+
+    def scale_rows(self, V, scale):
+        V *= scale[:, None]
+
+    def build_rows(self, src, X, mean, std, weights, flags, nonfinite_flag=None):
+        from oracle.slice_tools_np import standardize_np
+        a = src.numpy()
+        if flags & 1:
+            out, mu, sd = standardize_np(a, scale=bool(flags & 2), axis=0)
+            mean.copy_(torch.from_numpy(np.ascontiguousarray(mu)))
+            if flags & 2:
+                std.copy_(torch.from_numpy(np.ascontiguousarray(sd)))
+        else:
+            out = a
+        out = torch.from_numpy(np.ascontiguousarray(out.T)).to(X.dtype)
+        if weights is not None:
+            out = out * weights[:, None]
+        X.copy_(out)

@@ -1,0 +1,108 @@
+"""CPU: host-side drivers (randomized / standard schedule, delay blocks, row sharding, MAXLOC flip)
+exercised with the test-only FakeOps stand-in, single process and 2-rank gloo."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from fake_ops import FakeOps
+from dmd_era5_b200.dist import LocalComm, shard_rows
+from dmd_era5_b200.rsvd import draw_omega, n_iter_auto, randomized_svd_device
+from dmd_era5_b200.standard import standard_svd_device
+from oracle.compare import sigma_rel_err, signs_agree, vector_angles
+from oracle.slice_tools_np import delay_embed_np
+from oracle.svd_ref import omega_ref, randomized_svd_ref, standard_svd_ref
+from oracle.synthetic_np import lowrank_field_np
+
+
+def test_draw_omega_matches_reference_rng():
+    for dt, nd in ((torch.float64, np.float64), (torch.float32, np.float32)):
+        assert np.array_equal(draw_omega(50, 7, 3, dt), omega_ref(50, 7, 3, nd).astype(np.float64))
+    np.random.seed(5)
+    a = draw_omega(9, 2, None, torch.float64)          # unseeded: global RandomState, like the reference
+    np.random.seed(5)
+    assert np.array_equal(a, np.random.normal(size=(9, 12)))
+    assert n_iter_auto(1038240, 744, 100) == 4 and n_iter_auto(40491360, 1460, 100) == 7
+
+
+@pytest.mark.parametrize("d", [1, 2])
+def test_randomized_driver_matches_oracle(d):
+    X = lowrank_field_np(3000, 160, r=60, rho=0.88, seed=3)
+    k = 12
+    Xd = delay_embed_np(X, d)
+    U0, s0, V0 = randomized_svd_ref(Xd, k, 7)
+    U, s, Vt = randomized_svd_device(FakeOps(), torch.from_numpy(X), k, draw_omega(Xd.shape[1], k, 7, torch.float64), delay=d)
+    assert sigma_rel_err(s, s0) < 1e-9
+    assert vector_angles(U.numpy(), U0).max() < 1e-6 and vector_angles(Vt.numpy().T, V0.T).max() < 1e-6
+    assert signs_agree(U.numpy(), U0)
+
+
+def test_standard_driver_matches_oracle():
+    X = lowrank_field_np(2000, 64, r=64, rho=0.9, seed=5)
+    U0, s0, V0 = standard_svd_ref(delay_embed_np(X, 2), 10)
+    U, s, Vt = standard_svd_device(FakeOps(), torch.from_numpy(X), 10, delay=2)
+    assert sigma_rel_err(s, s0) < 1e-9 and vector_angles(U.numpy(), U0).max() < 1e-6
+
+
+def test_sketch_wider_than_time_axis():
+    X = lowrank_field_np(500, 12, r=12, rho=0.7, seed=1)
+    U0, s0, V0 = randomized_svd_ref(X, 8, 2)           # l = 18 > n = 12
+    U, s, Vt = randomized_svd_device(FakeOps(), torch.from_numpy(X), 8, draw_omega(12, 8, 2, torch.float64))
+    assert sigma_rel_err(s, s0) < 1e-9 and vector_angles(U.numpy(), U0).max() < 1e-6
+
+
+def test_shard_rows():
+    assert shard_rows(1000, 1, 0) == (0, 1000)
+    parts = [shard_rows(1038240, 8, r) for r in range(8)]
+    assert parts[0][0] == 0 and parts[-1][1] == 1038240
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(7))
+    assert all(p[0] % 128 == 0 for p in parts)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dmd_era5_b200.dist import TorchDistComm
+
+        comm = TorchDistComm()
+        X = lowrank_field_np(1030, 90, r=40, rho=0.85, seed=9)
+        k, d = 9, 2
+        r0, r1 = shard_rows(X.shape[0], world, rank, align=128)
+        n = X.shape[1] - d + 1
+        U, s, Vt = randomized_svd_device(FakeOps(), torch.from_numpy(X[r0:r1].copy()), k,
+                                         draw_omega(n, k, 4, torch.float64), delay=d, comm=comm,
+                                         row_offset=r0, m0_global=X.shape[0])
+        q.put((rank, r0, r1, U.numpy(), s.numpy(), Vt.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_row_sharding():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X = lowrank_field_np(1030, 90, r=40, rho=0.85, seed=9)
+    k, d, m0 = 9, 2, 1030
+    U0, s0, V0 = randomized_svd_ref(delay_embed_np(X, d), k, 4)
+    U = np.zeros((m0 * d, k))
+    for rank, r0, r1, Ul, s, Vt in res:
+        ml = r1 - r0
+        for j in range(d):                               # local block-major -> global rows
+            U[j * m0 + r0 : j * m0 + r1] = Ul[j * ml : (j + 1) * ml]
+        assert sigma_rel_err(s, s0) < 1e-9 and vector_angles(Vt.T, V0.T).max() < 1e-6
+    assert np.array_equal(res[0][4], res[1][4])          # replicated small factors agree bitwise
+    assert vector_angles(U, U0).max() < 1e-6 and signs_agree(U, U0)

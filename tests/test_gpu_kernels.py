@@ -1,0 +1,205 @@
+"""GPU: every C-ABI kernel against a float64 NumPy statement of the same operation."""
+import numpy as np
+import pytest
+import torch
+
+from dmd_era5_b200._cabi import BUILD_CHECK_FINITE, BUILD_MEAN_CENTER, BUILD_SCALE, PREC_NATIVE
+from oracle.slice_tools_np import standardize_np
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 2e-6)])
+@pytest.mark.parametrize("flags", [0, BUILD_MEAN_CENTER, BUILD_MEAN_CENTER | BUILD_SCALE])
+def test_build_rows(ops, dtype, tol, flags):
+    rng = np.random.RandomState(0)
+    T, P, ld_src = 37, 301, 320
+    src = (rng.rand(T, ld_src) * 30 + 250).astype(dtype)
+    d_src = dev(src)[:, :P]
+    ldx = 40
+    buf = torch.zeros((P, ldx), dtype=d_src.dtype, device="cuda")
+    X = buf[:, :T]
+    mean = torch.zeros(P, dtype=d_src.dtype, device="cuda")
+    std = torch.zeros(P, dtype=d_src.dtype, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.build_rows(d_src, X, mean if flags & 1 else None, std if flags & 2 else None, None,
+                   flags | BUILD_CHECK_FINITE, flag)
+    a = src[:, :P]
+    if flags & 1:
+        ref, mu, sd = standardize_np(a, scale=bool(flags & 2))
+        assert np.allclose(mean.cpu().numpy(), mu, rtol=tol, atol=0)
+        if flags & 2:
+            assert np.allclose(std.cpu().numpy(), sd, rtol=10 * tol, atol=0)
+    else:
+        ref = a
+    scale = 1.0 if flags & 2 else 300.0
+    assert np.max(np.abs(X.cpu().numpy() - ref.T)) <= 20 * tol * scale
+    assert int(flag.item()) == 0
+    assert float(buf[:, T:].abs().max()) == 0.0       # padding untouched
+
+
+def test_build_rows_nan_and_flag(ops):
+    src = np.random.RandomState(1).rand(16, 64)
+    src[3, 5] = np.nan
+    src[7, 9] = np.inf
+    X = torch.zeros((64, 16), dtype=torch.float64, device="cuda")
+    mean = torch.zeros(64, dtype=torch.float64, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.build_rows(dev(src), X, mean, None, None, BUILD_MEAN_CENTER | BUILD_CHECK_FINITE, flag)
+    assert int(flag.item()) == 1
+    assert np.isclose(mean[5].item(), np.nanmean(src[:, 5]))   # NaN skipped like xarray's mean
+
+
+def test_build_rows_weights_and_cast(ops):
+    rng = np.random.RandomState(2)
+    src = rng.rand(20, 50)
+    w = rng.rand(50).astype(np.float32)
+    X = torch.zeros((50, 24), dtype=torch.float32, device="cuda")[:, :20]
+    mean = torch.zeros(50, dtype=torch.float32, device="cuda")
+    ops.build_rows(dev(src), X, mean, None, dev(w), BUILD_MEAN_CENTER, None)
+    ref = ((src - src.mean(0)).T * w[:, None])
+    assert np.allclose(X.cpu().numpy(), ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 1e-5)])
+@pytest.mark.parametrize("m,n,l", [(1000, 96, 22), (257, 33, 110), (130, 200, 130), (5, 3, 2)])
+def test_sketch_and_project_native(ops, dtype, tol, m, n, l):
+    rng = np.random.RandomState(m + n + l)
+    ldx = n + 3
+    Xh = rng.standard_normal((m, ldx)).astype(dtype)
+    Om = rng.standard_normal((n, l)).astype(dtype)
+    X = dev(Xh)[:, :n]
+    Y = ops.sketch(X, dev(Om), None, PREC_NATIVE)
+    Yref = Xh[:, :n].astype(np.float64) @ Om.astype(np.float64)
+    assert np.max(np.abs(Y.cpu().numpy() - Yref)) <= tol * np.sqrt(n) * 10
+    Z = ops.project(X, Y, None, False, PREC_NATIVE)
+    Zref = Xh[:, :n].astype(np.float64).T @ Y.cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(Z.cpu().numpy() - Zref)) <= tol * np.abs(Zref).max() * 20
+    Z2 = ops.project(X, Y, Z.clone(), True, PREC_NATIVE)
+    assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
+
+
+def test_project_many_splits_deterministic(ops):
+    rng = np.random.RandomState(5)
+    X = dev(rng.standard_normal((20000, 70)))
+    Y = dev(rng.standard_normal((20000, 30)))
+    Z1 = ops.project(X, Y).cpu().numpy()
+    Z2 = ops.project(X, Y).cpu().numpy()
+    assert np.array_equal(Z1, Z2)
+    ref = X.cpu().numpy().T @ Y.cpu().numpy()
+    assert np.max(np.abs(Z1 - ref)) < 1e-10
+
+
+def test_delay_block_views(ops):
+    rng = np.random.RandomState(6)
+    Xh = rng.standard_normal((300, 41))
+    X = dev(Xh)
+    Om = rng.standard_normal((38, 9))
+    for j in range(4):
+        Y = ops.sketch(X[:, j : j + 38], dev(Om))
+        assert np.allclose(Y.cpu().numpy(), Xh[:, j : j + 38] @ Om, atol=1e-12)
+
+
+@pytest.mark.parametrize("tA,tB", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_f64(ops, tA, tB):
+    rng = np.random.RandomState(7)
+    M, N, K = 110, 75, 744
+    A = rng.standard_normal((K, M) if tA else (M, K))
+    B = rng.standard_normal((N, K) if tB else (K, N))
+    C = ops.gemm(dev(A), dev(B), transA=tA, transB=tB)
+    ref = (A.T if tA else A) @ (B.T if tB else B)
+    assert np.max(np.abs(C.cpu().numpy() - ref)) < 1e-11
+    C0 = rng.standard_normal((M, N))
+    C2 = ops.gemm(dev(A), dev(B), transA=tA, transB=tB, alpha=0.5, beta=2.0, C=dev(C0))
+    assert np.max(np.abs(C2.cpu().numpy() - (0.5 * ref + 2.0 * C0))) < 1e-11
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 24, 110, 111, 150])
+def test_syevj(ops, n):
+    rng = np.random.RandomState(n)
+    Q = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    w = np.sort(10.0 ** rng.uniform(-6, 2, size=n))[::-1]
+    A = (Q * w) @ Q.T
+    W, V = ops.syevj(dev(A))
+    W, V = W.cpu().numpy(), V.cpu().numpy()
+    assert np.all(np.diff(W) <= 0)
+    assert np.max(np.abs(W - w) / w) < 1e-9 * max(1.0, w[0] / w[-1] * 1e-6) or np.max(np.abs(W - w)) < 1e-13 * w[0] * n
+    assert np.max(np.abs(V.T @ V - np.eye(n))) < 1e-13 * n
+    assert np.max(np.abs(A @ V - V * W)) < 1e-12 * w[0] * n
+
+
+def test_syevj_psd_relative_accuracy(ops):
+    # graded PSD matrix: Jacobi keeps small eigenvalues to high relative accuracy
+    rng = np.random.RandomState(3)
+    n = 60
+    B = rng.standard_normal((200, n)) * (0.8 ** np.arange(n))
+    A = B.T @ B
+    W, _ = ops.syevj(dev(A))
+    ref = np.linalg.svd(B, compute_uv=False) ** 2
+    assert np.max(np.abs(W.cpu().numpy() - ref) / ref) < 1e-9
+
+
+@pytest.mark.parametrize("l", [1, 5, 110, 200])
+def test_chol_inv(ops, l):
+    rng = np.random.RandomState(l)
+    B = rng.standard_normal((3 * l + 5, l))
+    G = B.T @ B
+    R, Rinv = ops.chol_inv(dev(G), 1e-13)
+    R, Rinv = R.cpu().numpy(), Rinv.cpu().numpy()
+    assert np.allclose(np.tril(R, -1), 0) and np.allclose(np.tril(Rinv, -1), 0)
+    assert np.max(np.abs(R.T @ R - G)) < 1e-11 * np.abs(G).max()
+    assert np.max(np.abs(R @ Rinv - np.eye(l))) < 1e-9
+
+
+def test_chol_inv_rank_deficient(ops):
+    rng = np.random.RandomState(0)
+    B = rng.standard_normal((50, 6))
+    B[:, 4] = B[:, 1] + B[:, 2]          # dependent column
+    R, Rinv = ops.chol_inv(dev(B.T @ B), 1e-10)
+    Q = B @ Rinv.cpu().numpy()
+    assert np.all(np.isfinite(Q))
+    assert np.linalg.norm(Q[:, 4]) < 1e-100                      # dropped direction
+    keep = [0, 1, 2, 3, 5]
+    assert np.max(np.abs(Q[:, keep].T @ Q[:, keep] - np.eye(5))) < 1e-8
+
+
+def test_small_helpers(ops):
+    rng = np.random.RandomState(1)
+    P = rng.standard_normal((744, 110))
+    Pd = dev(P)
+    nrm = ops.col_normalize(Pd)
+    assert np.allclose(nrm.cpu().numpy(), np.linalg.norm(P, axis=0))
+    assert np.allclose(np.linalg.norm(Pd.cpu().numpy(), axis=0), 1.0)
+    s, inv = ops.sigma_from_eig(dev(np.array([4.0, 1.0, 0.0, -1e-20])))
+    assert np.allclose(s.cpu().numpy(), [2, 1, 0, 0]) and np.allclose(inv.cpu().numpy(), [0.5, 1, 0, 0])
+    c = ops.convert(dev(P), torch.float32)
+    assert c.dtype == torch.float32 and np.array_equal(c.cpu().numpy(), P.astype(np.float32))
+    V = dev(P[:5].copy())
+    ops.scale_rows(V, dev(np.array([1., -1., 2., 0., 1.])))
+    assert np.allclose(V.cpu().numpy(), P[:5] * np.array([1., -1., 2., 0., 1.])[:, None])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_col_absmax_first_max_and_flip(ops, dtype):
+    rng = np.random.RandomState(4)
+    m, k = 70001, 37
+    U = rng.standard_normal((m, k)).astype(dtype)
+    U[123, 0] = -9.0; U[60000, 0] = 9.0; U[124, 0] = -9.0      # tie in |.| -> first row wins
+    U[69999, 1] = 50.0
+    a, row, sg = ops.col_absmax(dev(U), 1000)
+    ref_idx = np.argmax(np.abs(U), axis=0)
+    assert np.array_equal(row.cpu().numpy(), ref_idx + 1000)
+    assert np.array_equal(sg.cpu().numpy(), np.sign(U[ref_idx, np.arange(k)]))
+    assert np.allclose(a.cpu().numpy(), np.abs(U).max(axis=0))
+    # combine: two candidate sets, second has the same |max| at a lower row for column 0
+    a2, r2, s2 = a.clone(), row.clone(), sg.clone()
+    r2[0] = 5; s2[0] = 1.0
+    sign = ops.maxloc_combine(torch.stack([a, a2]), torch.stack([row, r2]), torch.stack([sg, s2]))
+    assert sign[0].item() == 1.0 and np.array_equal(sign.cpu().numpy()[1:], sg.cpu().numpy()[1:])
+    Ud = dev(U)
+    ops.scale_cols(Ud, sg)
+    assert np.array_equal(Ud.cpu().numpy(), U * sg.cpu().numpy().astype(dtype))
