@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the DMD-ERA5 SVD stage: snapshot-matrix GB/s factorised (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c2|c3] [--precision native|tf32x3] [--rows R]
+
+One "step" = one pass of the hot path over one synthetic ERA5-shaped input: matrix build
+(stack + time-mean removal + transpose into the space x time snapshot matrix) followed by the
+randomized SVD (k = 100, l = 110, n_iter by sklearn's 'auto' rule) through U, s, V on the device.
+
+Workloads (per rank; rows shard over ranks with no data-path collective other than the small
+n x l / l x l all-reduces, so N > 1 is WEAK scaling: every rank holds one such shard):
+  c2 : 721 x 1440 points x 744 hourly snapshots, float32  -> 1 038 240 x 744  (BASELINE configs[1])
+  c3 : 1/8 of 3 vars x 13 levels x 721 x 1440 x 1460 6-hourly, float32 -> 5 061 420 x 1460 per rank
+       (8 ranks = BASELINE configs[2] exactly)
+
+value  : whole-job GB/s with the native arrays already resident in HBM (CUDA events, max over ranks)
+e2e    : same metric through the host-facing call: pinned host arrays -> H2D -> build -> SVD -> D2H
+         of U, s, V inside the timed region
+roofline / cpu_baseline : see DESIGN.md "Measurement"
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (points per rank, snapshots, description)
+    "c2": (721 * 1440, 744, "0.25deg single level 721x1440 x 744 hourly, f32, randomized k=100 (n_iter=4)"),
+    "c3": (3 * 13 * 721 * 1440 // 8, 1460, "1/8 of 0.25deg t/u/v x 13 levels x 1460 6-hourly per rank, f32, randomized k=100 (n_iter=7)"),
+}
+K_COMPONENTS = 100
+METRIC = "snapshot_matrix_GBps_factorised"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(rows: int, T: int, k: int, seed: int, threads: int):
+    """The reference's own numerics on the host cores for a bounded row sample of the workload:
+    NumPy restatement of the build (oracle) + sklearn.utils.extmath.randomized_svd, exactly the
+    call of src/dmd_era5/era5_svd/era5_svd.py:258.  Returns (seconds, bytes of the matrix)."""
+    from oracle.slice_tools_np import build_matrix_np
+    from oracle.svd_ref import randomized_svd_ref
+
+    rng = np.random.RandomState(seed)
+    r = 160
+    Bt = rng.standard_normal((T, r)).astype(np.float32)
+    Bt -= Bt.mean(axis=0)
+    Bt = np.linalg.qr(Bt)[0] * (100.0 * 0.93 ** np.arange(r)).astype(np.float32)
+    A = (rng.standard_normal((r, rows)) / np.sqrt(rows)).astype(np.float32)
+    field = (Bt @ A + 250.0).astype(np.float32)            # (T, rows) native layout
+    field = field.reshape(T, 1, 1, rows)
+    t0 = time.perf_counter()
+    X, _, _ = build_matrix_np([field], True, False, 1)
+    U, s, V = randomized_svd_ref(X, k, 1)
+    dt = time.perf_counter() - t0
+    return dt, X.nbytes, float(s[0])
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S, T, desc = WORKLOADS[args.workload]
+    threads = len(os.sched_getaffinity(0))
+    rows = args.cpu_rows or min(S, 262144)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, nbytes, _ = cpu_reference_run(rows, T, K_COMPONENTS, seed=i, threads=threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = nbytes / 1e9 / (ms / 1e3)
+    sample = f"{rows} of {S} rows x {T} snapshots f32 per step (bounded CPU sample of {args.workload})"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "k": K_COMPONENTS},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("ERA5SVD_PRECISION", "native"), choices=["native", "tf32x3"])
+    ap.add_argument("--rows", type=int, default=0, help="override points per rank (debug only; invalidates the number)")
+    ap.add_argument("--cpu-rows", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from dmd_era5_b200 import _cabi
+    from dmd_era5_b200.device_ops import CudaOps, KernelTimer
+    from dmd_era5_b200.dist import LocalComm, TorchDistComm
+    from dmd_era5_b200.pipeline import build_matrix_device, svd_device
+    from dmd_era5_b200.rsvd import n_iter_auto
+    from dmd_era5_b200.synthetic import synthetic_field
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+        comm = TorchDistComm()
+    else:
+        comm = LocalComm()
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    S, T, desc = WORKLOADS[args.workload]
+    if args.rows:
+        S = args.rows
+    k = K_COMPONENTS
+    ops = CudaOps(device)
+    field = synthetic_field(T, S, device=device, seed=1000 + rank)          # native (T, S) f32, outside the timed region
+    m_global = S * world
+    row_offset = rank * S
+    q = n_iter_auto(m_global, T, k)
+    x_bytes = float(S) * T * 4
+
+    def step(src_dev, timer=None):
+        ops.timer = timer
+        built = build_matrix_device(ops, [src_dev], mean_center=True, scale=False)
+        U, s, V = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=1, precision=args.precision,
+                             comm=comm, row_offset=row_offset, m0_global=m_global)
+        ops.timer = None
+        return U, s, V
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        comm.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---------------- device-resident timing ("value") ----------------
+    for _ in range(args.warmup):
+        step(field)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    timer = KernelTimer()
+    launches0 = _cabi.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        U, s, V = step(field, timer)
+    e1.record()
+    sync_all()
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = x_bytes * world / 1e9 / (ms / 1e3)
+    ksum = timer.summary()
+    s_first = float(s[0].item())
+
+    # ---------------- end-to-end through the host-facing path ----------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((T, S), dtype=torch.float32, pin_memory=True)
+        host.copy_(field)
+        dev_in = torch.empty_like(field)
+        hU = torch.empty((S, k), dtype=torch.float32, pin_memory=True)
+        hs = torch.empty((k,), dtype=torch.float64, pin_memory=True)
+        hV = torch.empty((k, T), dtype=torch.float64, pin_memory=True)
+
+        def e2e_step():
+            dev_in.copy_(host, non_blocking=True)
+            U, s, V = step(dev_in)
+            hU.copy_(U, non_blocking=True); hs.copy_(s, non_blocking=True); hV.copy_(V, non_blocking=True)
+
+        e2e_step()
+        sync_all()
+        n_e2e = max(2, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        sync_all()
+        ms_e2e = (time.perf_counter() - t0) * 1e3 / n_e2e
+        t = torch.tensor([ms_e2e], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+        e2e = {"value": x_bytes * world / 1e9 / (ms_e2e / 1e3), "unit": "GB/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(x_bytes), "d2h_bytes_per_step": int(hU.numel() * 4 + hs.numel() * 8 + hV.numel() * 8)}
+        del host, dev_in
+
+    # ---------------- roofline of the dominant kernel ----------------
+    pk = peaks()
+    dom = max((n for n in ksum if n in ("sketch", "project")), key=lambda n: ksum[n]["ms"], default=None)
+    roofline = None
+    if dom:
+        d = ksum[dom]
+        avg_ms = d["ms"] / d["calls"]
+        if args.precision == "tf32x3":
+            peak = pk["bf16_tflops"] / 2.0       # dense TF32 = 1/2 dense BF16 on the same pipe
+            ach = 3.0 * d["flops"] / d["calls"] / (avg_ms / 1e3) / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None,
+                        "note": f"3xTF32 tensor flops (3 * 2mnl) vs 1/2 of bf16 peak, {pk['source']}"}
+        else:
+            ach = d["bytes"] / d["calls"] / (avg_ms / 1e3) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / pk["hbm_gbs"], "traffic": None,
+                        "note": f"FP32-FMA (CUDA-core) pass, algorithmic bytes m*n*4 + m*l*4 per launch; {pk['source']}"}
+        roofline["avg_launch_ms"] = avg_ms
+    kernels = {n: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps} for n, v in ksum.items()}
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        rows = args.cpu_rows or min(S, 262144)
+        dt, nbytes, _ = cpu_reference_run(rows, T, k, seed=0, threads=threads)
+        cpu = {"value": nbytes / 1e9 / dt, "unit": "GB/s", "cores": threads, "kind": "reference",
+               "sample": f"sklearn randomized_svd + NumPy build on {rows} of {S} rows x {T} f32 ({dt:.2f} s, single run)"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "native" else "tf32x3", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "rows_per_rank": S, "snapshots": T, "k": k, "l": k + 10,
+                       "n_iter": q, "mean_center": True, "precision": args.precision,
+                       "l2": "inputs larger than L2 (matrix shard >= 3 GB vs 126 MB)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kernels, "sigma_1": s_first,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

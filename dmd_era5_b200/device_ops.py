@@ -42,6 +42,31 @@ def _vec(t: torch.Tensor | None, name: str) -> int | None:
     return t.data_ptr()
 
 
+class KernelTimer:
+    """CUDA-event timing of individual C-ABI calls on the launching stream (used by bench.py for the
+    roofline numbers).  Events are only recorded; durations are read after a synchronize."""
+
+    def __init__(self):
+        self.records: list[tuple[str, torch.cuda.Event, torch.cuda.Event, dict]] = []
+
+    def start(self, name: str, **meta):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.records.append((name, e0, e1, meta))
+        return e1
+
+    def summary(self) -> dict:
+        out: dict[str, dict] = {}
+        for name, e0, e1, meta in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0})
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += meta.get("bytes", 0.0)
+            d["flops"] += meta.get("flops", 0.0)
+        return out
+
+
 class CudaOps:
     """Kernel launcher bound to one device.  All calls are asynchronous on the current stream."""
 
@@ -53,6 +78,7 @@ class CudaOps:
             raise RuntimeError("CudaOps needs a CUDA device")
         self.lib = _cabi.lib()
         self._ws: dict[str, torch.Tensor] = {}
+        self.timer: KernelTimer | None = None   # bench.py attaches one to time kernels with CUDA events
 
     # -- memory ------------------------------------------------------------------------------
     def empty(self, shape, dtype) -> torch.Tensor:
@@ -84,9 +110,12 @@ class CudaOps:
         T, P = src.shape
         if tuple(X.shape) != (P, T):
             raise ValueError(f"X must be ({P}, {T}), got {tuple(X.shape)}")
+        end = self.timer.start("build_rows", bytes=float(T * P) * (src.element_size() + X.element_size())) if self.timer else None
         check(self.lib.era5svd_build_rows(sp, _dt(src), T, sld, P, xp, _dt(X), xld, _vec(mean, "mean"),
                                           _vec(std, "std"), _vec(weights, "weights"), flags,
                                           _vec(nonfinite_flag, "flag"), self._stream()), "era5svd_build_rows")
+        if end is not None:
+            end.record()
 
     # -- (b) tall passes ---------------------------------------------------------------------
     def sketch(self, X: torch.Tensor, Om: torch.Tensor, Y: torch.Tensor | None = None,
@@ -98,8 +127,13 @@ class CudaOps:
         if Y is None:
             Y = self.empty((m, l), X.dtype)
         xp, xld = _mat(X, "X"); op, old = _mat(Om, "Om"); yp, yld = _mat(Y, "Y")
+        es = X.element_size()
+        end = self.timer.start("sketch" if n > 2 * l else "apply_basis", bytes=float(es) * (m * n + m * l + n * l),
+                               flops=2.0 * m * n * l) if self.timer else None
         check(self.lib.era5svd_sketch(xp, _dt(X), m, n, xld, op, l, old, yp, yld, precision, self._stream()),
               "era5svd_sketch")
+        if end is not None:
+            end.record()
         return Y
 
     def project(self, X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor | None = None,
@@ -114,8 +148,13 @@ class CudaOps:
         xp, xld = _mat(X, "X"); yp, yld = _mat(Y, "Y"); zp, zld = _mat(Z, "Z")
         nbytes = int(self.lib.era5svd_project_workspace_bytes(_dt(X), m, n, l, precision))
         ws = self._workspace("project", nbytes)
+        es = X.element_size()
+        end = self.timer.start("project" if n > 2 * l else "gram", bytes=float(es) * (m * n + m * l) + 8.0 * n * l,
+                               flops=2.0 * m * n * l) if self.timer else None
         check(self.lib.era5svd_project(xp, _dt(X), m, n, xld, yp, l, yld, zp, zld, int(accumulate), precision,
                                        ws.data_ptr(), ws.numel(), self._stream()), "era5svd_project")
+        if end is not None:
+            end.record()
         return Z
 
     # -- (c)/(d) small float64 factors -------------------------------------------------------
