@@ -19,7 +19,7 @@ __device__ __forceinline__ bool better(double a, int64_t row, double b, int64_t 
 
 constexpr int AM_COLS = 32;   // columns per block-row of threads
 constexpr int AM_ROWS = 8;    // thread rows
-constexpr int AM_MAXBLOCKS = 1184;  // 8 x 148
+constexpr int AM_MAXBLOCKS = 592;   // 4 x 148
 
 // grid.x = row chunks, grid.y = column groups of 32
 template <typename T>
@@ -65,28 +65,43 @@ col_absmax_kernel(const T* __restrict__ U, int64_t m, int64_t k, int64_t ldu, in
   }
 }
 
-// Reduce R candidate sets [R x k] with the first-maximum rule.
+// Reduce R candidate sets [R x k] with the first-maximum rule: one warp per column, lanes stride
+// over the candidate sets, shuffle tree at the end.
 __global__ void __launch_bounds__(128)
 maxloc_reduce_kernel(const double* __restrict__ a, const int64_t* __restrict__ row,
                      const double* __restrict__ sgn, int64_t R, int64_t k,
                      double* __restrict__ a_out, int64_t* __restrict__ row_out,
                      double* __restrict__ sgn_out) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x % 32;
+  const int64_t c = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   if (c >= k) return;
   double best = -1.0, bsgn = 0.0;
-  int64_t brow = INT64_MAX;
-  for (int64_t i = 0; i < R; ++i) {
+  long long brow = INT64_MAX;
+  for (int64_t i = lane; i < R; i += 32) {
     double ai = a[i * k + c];
-    int64_t ri = row[i * k + c];
+    long long ri = row[i * k + c];
     if (better(ai, ri, best, brow)) {
       best = ai;
       brow = ri;
       bsgn = sgn[i * k + c];
     }
   }
-  if (a_out) a_out[c] = best;
-  if (row_out) row_out[c] = brow;
-  sgn_out[c] = bsgn;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double oa = __shfl_xor_sync(0xffffffffu, best, o);
+    long long orow = __shfl_xor_sync(0xffffffffu, brow, o);
+    double os = __shfl_xor_sync(0xffffffffu, bsgn, o);
+    if (better(oa, orow, best, brow)) {
+      best = oa;
+      brow = orow;
+      bsgn = os;
+    }
+  }
+  if (lane == 0) {
+    if (a_out) a_out[c] = best;
+    if (row_out) row_out[c] = brow;
+    sgn_out[c] = bsgn;
+  }
 }
 
 template <typename T>
@@ -145,7 +160,7 @@ int era5svd_col_absmax(const void* U, int dtype, int64_t m, int64_t k, int64_t l
     col_absmax_kernel<double><<<grid, AM_COLS * AM_ROWS, 0, st>>>((const double*)U, m, k, ldu, row_offset, rpb, ws_a, ws_row, ws_sgn);
   int rc = check_launch("col_absmax_kernel");
   if (rc) return rc;
-  maxloc_reduce_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, st>>>(ws_a, ws_row, ws_sgn, nb, k, absmax, row, sign);
+  maxloc_reduce_kernel<<<(unsigned)ceil_div(k, 4), 128, 0, st>>>(ws_a, ws_row, ws_sgn, nb, k, absmax, row, sign);
   return check_launch("maxloc_reduce_kernel");
 }
 
@@ -154,7 +169,7 @@ int era5svd_maxloc_combine(const double* absmax, const int64_t* row, const doubl
   using namespace era5svd;
   ERA5SVD_REQUIRE(absmax && row && sign && sign_out, "maxloc_combine: null pointer");
   ERA5SVD_REQUIRE(R > 0 && k > 0, "maxloc_combine: bad shape");
-  maxloc_reduce_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, as_stream(stream)>>>(absmax, row, sign, R, k, nullptr, nullptr, sign_out);
+  maxloc_reduce_kernel<<<(unsigned)ceil_div(k, 4), 128, 0, as_stream(stream)>>>(absmax, row, sign, R, k, nullptr, nullptr, sign_out);
   return check_launch("maxloc_reduce_kernel");
 }
 

@@ -74,10 +74,15 @@ gemm_f64_kernel(int transA, int transB, int64_t M, int64_t N, int64_t K, double 
 // ---------------------------------------------------------------------------------------------
 // Symmetric eigensolver: parallel cyclic two-sided Jacobi, one CTA of 1024 threads.
 // Round-robin ordering: n_pad - 1 steps per sweep, n_pad / 2 disjoint (p, q) pairs per step.
-// Working copies Aw, Vw live in shared memory when 2 n^2 doubles fit, else in the global
-// workspace (L1/L2 resident; one CTA, so block barriers order the accesses).
+// A group of 16 lanes owns one pair per step: it computes the rotation from the 2 x 2 block,
+// applies it to columns p, q of A and V (phase 1), and after a block barrier to rows p, q of A
+// (phase 2).  Working copies live in shared memory with an ODD leading dimension (conflict-free
+// column walks for doubles) when they fit, else in the global workspace (one CTA: block barriers
+// order the accesses; L1/L2 resident).  FP64-pipe bound: ~4 DFMA per updated element pair.
 // ---------------------------------------------------------------------------------------------
 constexpr int JAC_THREADS = 1024;
+constexpr int JAC_GROUP = 16;
+constexpr int JAC_GROUPS = JAC_THREADS / JAC_GROUP;
 
 __device__ __forceinline__ void jacobi_pair(int step, int i, int n_pad, int& p, int& q) {
   const int r = n_pad - 1;
@@ -85,165 +90,162 @@ __device__ __forceinline__ void jacobi_pair(int step, int i, int n_pad, int& p, 
     p = r;
     q = step;
   } else {
-    p = (step + i) % r;
-    q = (step + r - i) % r;
+    p = step + i;
+    if (p >= r) p -= r;
+    q = step + r - i;
+    if (q >= r) q -= r;
   }
   if (p > q) { int tmp = p; p = q; q = tmp; }
 }
 
 __global__ void __launch_bounds__(JAC_THREADS, 1)
-syevj_kernel(double* __restrict__ A, int n, int64_t lda, double* __restrict__ W,
+syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restrict__ W,
              double* __restrict__ V, int64_t ldv, int max_sweeps, double* __restrict__ ws,
              int use_smem) {
   extern __shared__ double smem[];
   const int t = threadIdx.x;
+  const int g = t / JAC_GROUP, gl = t % JAC_GROUP;
+  const unsigned gmask = 0xFFFFu << (16 * (g & 1));   // the 16 lanes of this group within its warp
   const int n_pad = n + (n & 1);
   const int npairs = n_pad / 2;
-  // layout: [cs: 2 * npairs doubles][pq: 2 * npairs ints (as one double each pair)][Aw][Vw]
-  double* cs = smem;                                   // c, s per pair
-  int* pq = reinterpret_cast<int*>(smem + 2 * npairs);  // p, q per pair
-  double* Aw;
-  double* Vw;
-  int ldw = n;
-  if (use_smem) {
-    Aw = smem + 3 * npairs + 1;
-    Vw = Aw + (size_t)n * n;
-  } else {
-    Aw = ws;
-    Vw = ws + (size_t)n * n;
-  }
-  for (int idx = t; idx < n * n; idx += JAC_THREADS) {
-    int r = idx / n, c = idx % n;
-    Aw[idx] = 0.5 * (A[(int64_t)r * lda + c] + A[(int64_t)c * lda + r]);  // enforce symmetry
-    Vw[idx] = (r == c) ? 1.0 : 0.0;
-  }
+  const int ldw = n | 1;
+  // layout: [cs: 2 * npairs doubles][rank: n ints][Aw][Vw]
+  double* cs = smem;
+  int* rank = reinterpret_cast<int*>(smem + 2 * npairs);
+  double* Aw = use_smem ? smem + 2 * npairs + (n + 1) / 2 : ws;
+  double* Vw = Aw + (size_t)n * ldw;
+  for (int r = t / 32; r < n; r += JAC_THREADS / 32)
+    for (int c = t % 32; c < n; c += 32) {
+      Aw[r * ldw + c] = 0.5 * (A[(int64_t)r * lda + c] + A[(int64_t)c * lda + r]);  // enforce symmetry
+      Vw[r * ldw + c] = (r == c) ? 1.0 : 0.0;
+    }
   __syncthreads();
 
-  // relative off-diagonal threshold |a_pq| <= tol * sqrt(|a_pp a_qq|), tol = eps * sqrt(n) (as LAPACK's xGESVJ)
+  // relative off-diagonal threshold |a_pq| <= tol * sqrt(|a_pp a_qq|), tol = eps * sqrt(n) (cf. xGESVJ)
   const double tol = 2.220446049250313e-16 * sqrt((double)n);
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    int rotated_in_sweep = 0;
+    int did = 0;
     for (int step = 0; step < n_pad - 1; ++step) {
-      int did = 0;
-      if (t < npairs) {
+      // phase 1: rotation parameters + right multiplication (columns p, q of A and V)
+      for (int i = g; i < npairs; i += JAC_GROUPS) {
         int p, q;
-        jacobi_pair(step, t, n_pad, p, q);
+        jacobi_pair(step, i, n_pad, p, q);
         double c = 1.0, s = 0.0;
         if (q < n) {  // q == n only for the padding index of odd n
-          double app = Aw[p * ldw + p], aqq = Aw[q * ldw + q];
-          double apq = Aw[p * ldw + q];
-          double thresh = tol * sqrt(fabs(app) * fabs(aqq));
-          if (fabs(apq) > thresh && fabs(apq) > 1e-300) {
-            double tau = (aqq - app) / (2.0 * apq);
-            double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + tt * tt);
+          const double app = Aw[p * ldw + p], aqq = Aw[q * ldw + q], apq = Aw[p * ldw + q];
+          __syncwarp(gmask);  // every lane of the group has read the 2 x 2 block before any lane overwrites it
+          if (fabs(apq) > tol * sqrt(fabs(app) * fabs(aqq)) && fabs(apq) > 1e-300) {
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = rsqrt(1.0 + tt * tt);
             s = tt * c;
             did = 1;
+            for (int r = gl; r < n; r += JAC_GROUP) {
+              double x = Aw[r * ldw + p], y = Aw[r * ldw + q];
+              Aw[r * ldw + p] = c * x - s * y;
+              Aw[r * ldw + q] = s * x + c * y;
+              x = Vw[r * ldw + p]; y = Vw[r * ldw + q];
+              Vw[r * ldw + p] = c * x - s * y;
+              Vw[r * ldw + q] = s * x + c * y;
+            }
           }
-        } else {
-          q = -1;
         }
-        cs[2 * t] = c;
-        cs[2 * t + 1] = s;
-        pq[2 * t] = p;
-        pq[2 * t + 1] = q;
-      }
-      rotated_in_sweep |= __syncthreads_or(did);
-      // right multiplication on A and V:  columns p, q
-      for (int idx = t; idx < 2 * n * npairs; idx += JAC_THREADS) {
-        int which = idx / (n * npairs);
-        int rem = idx - which * n * npairs;
-        int r = rem / npairs, i = rem - r * npairs;
-        int p = pq[2 * i], q = pq[2 * i + 1];
-        double c = cs[2 * i], s = cs[2 * i + 1];
-        if (q >= 0 && s != 0.0) {
-          double* M = which ? Vw : Aw;
-          double x = M[r * ldw + p], y = M[r * ldw + q];
-          M[r * ldw + p] = c * x - s * y;
-          M[r * ldw + q] = s * x + c * y;
-        }
+        if (gl == 0) { cs[2 * i] = c; cs[2 * i + 1] = s; }
       }
       __syncthreads();
-      // left multiplication on A: rows p, q
-      for (int idx = t; idx < n * npairs; idx += JAC_THREADS) {
-        int i = idx / n, col = idx - i * n;
-        int p = pq[2 * i], q = pq[2 * i + 1];
-        double c = cs[2 * i], s = cs[2 * i + 1];
-        if (q >= 0 && s != 0.0) {
-          double x = Aw[p * ldw + col], y = Aw[q * ldw + col];
-          Aw[p * ldw + col] = c * x - s * y;
-          Aw[q * ldw + col] = s * x + c * y;
+      // phase 2: left multiplication (rows p, q of A)
+      for (int i = g; i < npairs; i += JAC_GROUPS) {
+        const double c = cs[2 * i], s = cs[2 * i + 1];
+        if (s != 0.0) {
+          int p, q;
+          jacobi_pair(step, i, n_pad, p, q);
+          for (int col = gl; col < n; col += JAC_GROUP) {
+            const double x = Aw[p * ldw + col], y = Aw[q * ldw + col];
+            Aw[p * ldw + col] = c * x - s * y;
+            Aw[q * ldw + col] = s * x + c * y;
+          }
         }
       }
       __syncthreads();
     }
-    if (!rotated_in_sweep) break;
+    if (!__syncthreads_or(did)) break;
   }
   // eigenvalues = diag(Aw); rank them in descending order (stable on ties) and scatter.
   for (int j = t; j < n; j += JAC_THREADS) {
-    double wj = Aw[j * ldw + j];
-    int rank = 0;
+    const double wj = Aw[j * ldw + j];
+    int rk = 0;
     for (int i = 0; i < n; ++i) {
-      double wi = Aw[i * ldw + i];
-      rank += (wi > wj) || (wi == wj && i < j);
+      const double wi = Aw[i * ldw + i];
+      rk += (wi > wj) || (wi == wj && i < j);
     }
-    W[rank] = wj;
-    pq[j] = rank;  // reuse: npairs*2 >= n ints available
+    W[rk] = wj;
+    rank[j] = rk;
   }
   __syncthreads();
-  for (int idx = t; idx < n * n; idx += JAC_THREADS) {
-    int r = idx / n, c = idx % n;
-    V[(int64_t)r * ldv + pq[c]] = Vw[idx];
-  }
+  for (int r = t / 32; r < n; r += JAC_THREADS / 32)
+    for (int c = t % 32; c < n; c += 32) V[(int64_t)r * ldv + rank[c]] = Vw[r * ldw + c];
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cholesky G = R^T R (upper R) + explicit inverse, one CTA.  Works in the caller's R buffer.
+// Cholesky G = R^T R (upper R) + explicit inverse, one CTA (32 x 32 threads).  Working copies in
+// shared memory when they fit (l <= 118), else in the caller's R / Rinv buffers.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __restrict__ R,
-                int64_t ldr, double* __restrict__ Rinv, int64_t ldri, double rel_tol) {
-  const int t = threadIdx.x, nt = blockDim.x;
+                int64_t ldr, double* __restrict__ Rinv, int64_t ldri, double rel_tol, int use_smem) {
+  extern __shared__ double smem[];
+  const int t = threadIdx.x, tx = t % 32, ty = t / 32;
   __shared__ double s_piv;
+  const int ldw = use_smem ? (l | 1) : 0;
+  double* Rw = use_smem ? smem : R;
+  double* Iw = use_smem ? smem + (size_t)l * ldw : Rinv;
+  const int64_t ld_r = use_smem ? ldw : ldr, ld_i = use_smem ? ldw : ldri;
   // copy the upper triangle (symmetrised), zero the strictly lower part
-  for (int idx = t; idx < l * l; idx += nt) {
-    int r = idx / l, c = idx % l;
-    R[(int64_t)r * ldr + c] = (c >= r) ? 0.5 * (G[(int64_t)r * ldg + c] + G[(int64_t)c * ldg + r]) : 0.0;
-    Rinv[(int64_t)r * ldri + c] = 0.0;
-  }
+  for (int r = ty; r < l; r += 32)
+    for (int c = tx; c < l; c += 32) {
+      Rw[r * ld_r + c] = (c >= r) ? 0.5 * (G[(int64_t)r * ldg + c] + G[(int64_t)c * ldg + r]) : 0.0;
+      Iw[r * ld_i + c] = 0.0;
+    }
   __syncthreads();
   for (int j = 0; j < l; ++j) {
     if (t == 0) {
-      double d = R[(int64_t)j * ldr + j];
-      double g = G[(int64_t)j * ldg + j];
+      const double d = Rw[j * ld_r + j];
+      const double g = G[(int64_t)j * ldg + j];
       // dependent (or non-positive) pivot -> huge: the direction is dropped, never NaN
       s_piv = (d > rel_tol * g && d > 0.0) ? sqrt(d) : 1e150;
     }
     __syncthreads();
     const double piv = s_piv;
-    for (int c = j + t; c < l; c += nt) {
-      double v = R[(int64_t)j * ldr + c];
-      R[(int64_t)j * ldr + c] = (c == j) ? piv : v / piv;
+    for (int c = j + t; c < l; c += 1024) {
+      const double v = Rw[j * ld_r + c];
+      Rw[j * ld_r + c] = (c == j) ? piv : v / piv;
     }
     __syncthreads();
     // trailing update: R[i][c] -= R[j][i] * R[j][c],  j < i <= c
-    const int rem = l - j - 1;
-    for (int idx = t; idx < rem * rem; idx += nt) {
-      int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
-      if (c >= i) R[(int64_t)i * ldr + c] -= R[(int64_t)j * ldr + i] * R[(int64_t)j * ldr + c];
+    for (int i = j + 1 + ty; i < l; i += 32) {
+      const double rji = Rw[j * ld_r + i];
+      for (int c = j + 1 + tx; c < l; c += 32)
+        if (c >= i) Rw[i * ld_r + c] -= rji * Rw[j * ld_r + c];
     }
     __syncthreads();
   }
   // inverse by back substitution, one warp per column c:  R * x = e_c
-  const int warp = t / 32, lane = t % 32, nwarps = nt / 32;
-  for (int c = warp; c < l; c += nwarps) {
+  for (int c = ty; c < l; c += 32) {
     for (int i = c; i >= 0; --i) {
       double sum = 0.0;
-      for (int k = i + 1 + lane; k <= c; k += 32) sum += R[(int64_t)i * ldr + k] * Rinv[(int64_t)k * ldri + c];
+      for (int k = i + 1 + tx; k <= c; k += 32) sum += Rw[i * ld_r + k] * Iw[k * ld_i + c];
       sum = warp_sum(sum);
-      if (lane == 0) Rinv[(int64_t)i * ldri + c] = ((i == c ? 1.0 : 0.0) - sum) / R[(int64_t)i * ldr + i];
+      if (tx == 0) Iw[i * ld_i + c] = ((i == c ? 1.0 : 0.0) - sum) / Rw[i * ld_r + i];
       __syncwarp();
     }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int r = ty; r < l; r += 32)
+      for (int c = tx; c < l; c += 32) {
+        R[(int64_t)r * ldr + c] = Rw[r * ldw + c];
+        Rinv[(int64_t)r * ldri + c] = Iw[r * ldw + c];
+      }
   }
 }
 
@@ -327,14 +329,17 @@ int era5svd_gemm_f64(int transA, int transB, int64_t M, int64_t N, int64_t K, do
   return check_launch("gemm_f64_kernel");
 }
 
-static size_t syevj_smem_bytes(int64_t n) {
+static size_t syevj_small_smem_doubles(int64_t n) {
   int64_t npairs = (n + (n & 1)) / 2;
-  return (size_t)(3 * npairs + 1 + 2 * n * n) * sizeof(double);
+  return (size_t)(2 * npairs + (n + 1) / 2);
+}
+static size_t syevj_smem_bytes(int64_t n) {
+  return (syevj_small_smem_doubles(n) + (size_t)(2 * n * (n | 1))) * sizeof(double);
 }
 
 size_t era5svd_syevj_workspace_bytes(int64_t n) {
   if (n <= 0) return 0;
-  return (size_t)(2 * n * n) * sizeof(double);
+  return (size_t)(2 * n * (n | 1)) * sizeof(double);
 }
 
 int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
@@ -346,7 +351,7 @@ int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, i
   const size_t full = syevj_smem_bytes(n);
   const size_t limit = 227 * 1024;
   int use_smem = full <= limit;
-  size_t smem = use_smem ? full : (size_t)(3 * ((n + 1) / 2) + 2) * sizeof(double);
+  size_t smem = use_smem ? full : syevj_small_smem_doubles(n) * sizeof(double);
   if (!use_smem) {
     size_t need = era5svd_syevj_workspace_bytes(n);
     if (!workspace || workspace_bytes < need) {
@@ -364,7 +369,10 @@ int era5svd_chol_inv_f64(const double* G, int64_t l, int64_t ldg, double* R, int
   using namespace era5svd;
   ERA5SVD_REQUIRE(G && R && Rinv, "chol_inv: null pointer");
   ERA5SVD_REQUIRE(l > 0 && l <= 8192 && ldg >= l && ldr >= l && ldri >= l, "chol_inv: bad shape l=%lld", (long long)l);
-  chol_inv_kernel<<<1, 1024, 0, as_stream(stream)>>>(G, (int)l, ldg, R, ldr, Rinv, ldri, rel_tol);
+  const size_t smem = (size_t)(2 * l * (l | 1)) * sizeof(double);
+  const int use_smem = smem <= 220 * 1024;
+  ERA5SVD_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  chol_inv_kernel<<<1, 1024, use_smem ? smem : 0, as_stream(stream)>>>(G, (int)l, ldg, R, ldr, Rinv, ldri, rel_tol, use_smem);
   return check_launch("chol_inv_kernel");
 }
 

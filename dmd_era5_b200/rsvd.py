@@ -128,11 +128,16 @@ def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_
             stats["tall_passes"] = stats.get("tall_passes", 0) + 2
         return Z
 
-    for _ in range(n_iter):
+    for it in range(n_iter):
         Z = tall_pass(Omega)
-        T = ops.gemm(Omega, Z, transA=True)            # = Y^T Y, l x l
-        _, W = ops.syevj(T)                            # Ritz rotation, columns by descending Ritz value
-        Omega = _orth(ops, ops.gemm(Z, W), 1e-13)
+        if it == 0 or it == n_iter - 1:
+            # Rayleigh-Ritz rotation: T = Omega^T Z = Y^T Y (l x l), columns of Z W nearly orthogonal.
+            # Needed after the random start (cond(Z) ~ kappa^2 otherwise) and before the final pass
+            # (well-conditioned Gram of Y); in between Z = X^T X (near-Ritz vectors) stays benign.
+            T = ops.gemm(Omega, Z, transA=True)
+            _, W = ops.syevj(T)
+            Z = ops.gemm(Z, W)
+        Omega = _orth(ops, Z, 1e-13)
 
     Zp = tall_pass(Omega)                              # n x l
     G = ops.project(Y, Y, precision=PREC_NATIVE)       # l x l, from the stored (rounded) Y
