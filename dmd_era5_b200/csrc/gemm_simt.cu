@@ -254,13 +254,11 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
   return check_launch("reduce_partials_kernel");
 }
 
-// tcgen05 path (gemm_tc.cu)
-int sketch_tf32x3(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Om, int64_t l,
-                  int64_t ldo, float* Y, int64_t ldy, cudaStream_t st);
-int project_tf32x3(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,
-                   int64_t ldy, double* Z, int64_t ldz, int accumulate, void* ws, size_t ws_bytes,
-                   cudaStream_t st);
-size_t project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l);
+// shared with the tcgen05 path (gemm_tc.cu): float32 partial tiles -> float64 sum
+void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
+                                int64_t ldz, int accumulate, cudaStream_t st) {
+  reduce_partials_kernel<float><<<(unsigned)ceil_div(n * l, 256), 256, 0, st>>>(part, splits, n, l, Z, ldz, accumulate);
+}
 
 }  // namespace era5svd
 
@@ -277,8 +275,8 @@ int era5svd_sketch(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx, 
   ERA5SVD_REQUIRE(ceil_div(l, 112) <= 65535, "sketch: l too large");
   cudaStream_t st = as_stream(stream);
   if (precision == ERA5SVD_PREC_TF32X3) {
-    ERA5SVD_REQUIRE(dtype == ERA5SVD_F32, "sketch: TF32X3 needs float32 storage");
-    return sketch_tf32x3((const float*)X, m, n, ldx, (const float*)Om, l, ldo, (float*)Y, ldy, st);
+    set_error("sketch: the tensor-core path takes pre-split operands: use era5svd_sketch_tf32x3");
+    return ERA5SVD_ERR_UNSUPPORTED;
   }
   ERA5SVD_REQUIRE(precision == ERA5SVD_PREC_NATIVE, "sketch: bad precision %d", precision);
   if (dtype == ERA5SVD_F32) return sketch_native<float>(X, m, n, ldx, Om, l, ldo, Y, ldy, st);
@@ -288,7 +286,7 @@ int era5svd_sketch(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx, 
 size_t era5svd_project_workspace_bytes(int dtype, int64_t m, int64_t n, int64_t l, int precision) {
   using namespace era5svd;
   if (!valid_dtype(dtype) || m <= 0 || n <= 0 || l <= 0) return 0;
-  if (precision == ERA5SVD_PREC_TF32X3) return project_tf32x3_workspace_bytes(m, n, l);
+  if (precision == ERA5SVD_PREC_TF32X3) return era5svd_project_tf32x3_workspace_bytes(m, n, l);
   return project_plan(dtype, m, n, l).bytes;
 }
 
@@ -303,9 +301,8 @@ int era5svd_project(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx,
                   (long long)n, (long long)l, (long long)ldx, (long long)ldy, (long long)ldz);
   cudaStream_t st = as_stream(stream);
   if (precision == ERA5SVD_PREC_TF32X3) {
-    ERA5SVD_REQUIRE(dtype == ERA5SVD_F32, "project: TF32X3 needs float32 storage");
-    return project_tf32x3((const float*)X, m, n, ldx, (const float*)Y, l, ldy, Z, ldz, accumulate,
-                          workspace, workspace_bytes, st);
+    set_error("project: the tensor-core path takes pre-split operands: use era5svd_project_tf32x3");
+    return ERA5SVD_ERR_UNSUPPORTED;
   }
   ERA5SVD_REQUIRE(precision == ERA5SVD_PREC_NATIVE, "project: bad precision %d", precision);
   ERA5SVD_REQUIRE(ceil_div(l, 112) <= 65535, "project: l too large");

@@ -1,21 +1,593 @@
-// tcgen05 / TMA path for the tall GEMM passes (3xTF32 split).  Placeholder until the kernels land:
-// the entry points exist so that the ABI is stable, and fail loudly.
+// (b) Tall GEMM passes on the 5th-generation tensor cores: tcgen05.mma kind::tf32 fed by TMA, fp32
+// accumulators in TMEM, 3-term TF32 split for fp32-level accuracy ("3xTF32"):
+//
+//     x = x_hi + x_lo,  x_hi = tf32(x),  x_lo = x - x_hi         (both exactly representable operands)
+//     a * b  ~=  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo                (drops a_lo*b_lo ~ 2^-22 |a b|)
+//
+// The tall operands are stored pre-split in HBM (X_hi / X_lo written once by era5svd_split_tf32,
+// Y_hi / Y_lo written by the sketch epilogue), so both kernels are pure TMA -> UMMA pipelines with
+// no register-path transform.
+//
+//   sketch :  Y[m x l]   = X[m x n] * Om[n x l]     A = X tile   (K-major, K = time)
+//                                                   B = Om^T     (K-major)        D: 128 rows x Npad
+//   project:  Z^T[l x n] = Y^T[l x m] * X[m x n]    A = Y tile   (MN-major, K = space rows)
+//                                                   B = X tile   (MN-major)       D: 128 (l) x time chunk
+//
+// The same 128 B-swizzled shared-memory image of an X tile ([rows][32 time values]) serves as a
+// K-major operand for sketch and as an MN-major operand for project, so X is never transposed.
+// Replaces `A @ Q` / `A.T @ Q` / `Q.T @ M` (sklearn/utils/extmath.py:378-383, :606) for float32 data.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace era5svd {
 
-int sketch_tf32x3(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, float*,
-                  int64_t, cudaStream_t) {
-  set_error("sketch: TF32X3 path not built into this library");
-  return ERA5SVD_ERR_UNSUPPORTED;
+// from gemm_simt.cu
+void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
+                                int64_t ldz, int accumulate, cudaStream_t st);
+
+namespace tc {
+
+constexpr int BM = 128;          // sketch: rows per tile (UMMA M)
+constexpr int BK = 32;           // tf32 elements per 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32: 32 bytes of K per instruction
+constexpr int SWIZZLE_ATOM = 1024;   // 8 rows x 128 B
+
+// ---------------------------------------------------------------------------------------------
+// host: TMA descriptors
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
 }
 
-int project_tf32x3(const float*, int64_t, int64_t, int64_t, const float*, int64_t, int64_t, double*,
-                   int64_t, int, void*, size_t, cudaStream_t) {
-  set_error("project: TF32X3 path not built into this library");
-  return ERA5SVD_ERR_UNSUPPORTED;
+// 2-D float32 tensor [outer rows][inner elements], row pitch ld elements, box = box_inner x box_outer,
+// 128 B swizzle, out-of-bounds elements read as zero.  `base` may be any 4-byte aligned address: the
+// map is anchored at the enclosing 16-byte boundary and *col_shift returns the element offset to add
+// to every inner coordinate (this is how delay-embedded column windows X[:, j:] are addressed).
+static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
+                     uint32_t box_inner, uint32_t box_outer, int* col_shift) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return ERA5SVD_ERR_CUDA;
+  }
+  uintptr_t addr = reinterpret_cast<uintptr_t>(base);
+  int shift = (int)((addr & 15u) / 4u);
+  addr &= ~(uintptr_t)15u;
+  if ((ld * 4) % 16 != 0) {
+    set_error("tf32x3: row pitch (%lld floats) must be a multiple of 4", (long long)ld);
+    return ERA5SVD_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)(inner + shift), (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, reinterpret_cast<void*>(addr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%ux%u", (int)r, (long long)inner,
+              (long long)outer, (long long)ld, box_inner, box_outer);
+    return ERA5SVD_ERR_CUDA;
+  }
+  *col_shift = shift;
+  return ERA5SVD_OK;
 }
 
-size_t project_tf32x3_workspace_bytes(int64_t, int64_t, int64_t) { return 0; }
+// ---------------------------------------------------------------------------------------------
+// split kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int64_t ldx,
+                  float* __restrict__ hi, float* __restrict__ lo, int64_t ldo) {
+  const int64_t total = rows * cols;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    int64_t r = idx / cols, c = idx - r * cols;
+    float x = X[r * ldx + c];
+    float h = tf32_hi(x);
+    hi[r * ldo + c] = h;
+    lo[r * ldo + c] = x - h;
+  }
+}
+
+// Om (float64, n x l) -> Om^T hi / lo (float32, [npad][ldt]); rows >= l and the tail of each row are
+// zero.  The float64 source lets lo carry bits beyond fp32: lo = fp32(om - hi).
+__global__ void __launch_bounds__(256)
+split_omega_t_kernel(const double* __restrict__ Om, int64_t n, int64_t l, int64_t ldo,
+                     float* __restrict__ hi, float* __restrict__ lo, int64_t npad, int64_t ldt) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npad * ldt) return;
+  int64_t j = idx / ldt, t = idx - j * ldt;   // j = sketch column, t = time
+  float h = 0.f, w = 0.f;
+  if (j < l && t < n) {
+    double v = Om[t * ldo + j];
+    h = tf32_hi((float)v);
+    w = (float)(v - (double)h);
+  }
+  hi[idx] = h;
+  lo[idx] = w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sketch kernel (persistent, warp specialised)
+// ---------------------------------------------------------------------------------------------
+struct SketchParams {
+  int64_t m;
+  int64_t num_tiles;
+  int num_k;          // ceil(n / 32)
+  int npad;           // UMMA N (multiple of 16, <= 256)
+  int stages;
+  int xshift, oshift; // inner-coordinate shifts of the X / Om^T maps
+  float* Y;           // nullable
+  float* Yhi;         // nullable
+  float* Ylo;         // nullable
+  int64_t ldy;
+};
+
+constexpr int SK_THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+__global__ void __launch_bounds__(SK_THREADS, 1)
+sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                 const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo,
+                 const SketchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t a_bytes = BM * BK * 4;                 // 16 KB
+  const uint32_t b_bytes = (uint32_t)p.npad * BK * 4;   // npad x 128 B
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  // barriers + tmem pointer live after the stages
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  const uint32_t acc_cols = p.npad <= 128 ? 128u : 256u;    // columns per accumulator buffer
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_xhi); tma_prefetch_desc(&tm_xlo);
+    tma_prefetch_desc(&tm_ohi); tma_prefetch_desc(&tm_olo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * acc_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int32_t row0 = (int32_t)(tile * BM);
+        for (int kc = 0; kc < p.num_k; ++kc) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+          tma_load_2d(st, &tm_xhi, p.xshift + kc * BK, row0, full_bar(s));
+          tma_load_2d(st + a_bytes, &tm_xlo, p.xshift + kc * BK, row0, full_bar(s));
+          tma_load_2d(st + 2 * a_bytes, &tm_ohi, p.oshift + kc * BK, 0, full_bar(s));
+          tma_load_2d(st + 2 * a_bytes + b_bytes, &tm_olo, p.oshift + kc * BK, 0, full_bar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    const uint32_t idesc = make_idesc_tf32(BM, p.npad, 0, 0);
+    int s = 0; uint32_t ph = 0;
+    int buf = 0; uint32_t aph = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(buf), aph ^ 1u);      // epilogue has drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)buf * acc_cols;
+      for (int kc = 0; kc < p.num_k; ++kc) {
+        mbar_wait(full_bar(s), ph);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint32_t koff = kk * UMMA_K * 4;   // 32 bytes per k-step inside the swizzle row
+            const uint64_t a_hi = make_smem_desc(st + koff, 16, SWIZZLE_ATOM);
+            const uint64_t a_lo = make_smem_desc(st + a_bytes + koff, 16, SWIZZLE_ATOM);
+            const uint64_t b_hi = make_smem_desc(st + 2 * a_bytes + koff, 16, SWIZZLE_ATOM);
+            const uint64_t b_lo = make_smem_desc(st + 2 * a_bytes + b_bytes + koff, 16, SWIZZLE_ATOM);
+            umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | kk) != 0);   // small terms first
+            umma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1);
+            umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1);
+          }
+          umma_commit(empty_bar(s));               // smem stage free once these MMAs retire
+          if (kc == p.num_k - 1) umma_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      if (++buf == 2) { buf = 0; aph ^= 1u; }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global (Y, Y_hi, Y_lo) =====
+    const int q = warp % 4;                        // TMEM lane quadrant this warp may access
+    int buf = 0; uint32_t aph = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tfull_bar(buf), aph);
+      tcgen05_fence_after();
+      const int64_t row = tile * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.npad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_wait_ld();
+        if (row < p.m) {
+          const int64_t off = row * p.ldy + c0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float4 y = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                   __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            if (p.Y) *reinterpret_cast<float4*>(p.Y + off + 4 * g) = y;
+            if (p.Yhi) {
+              float4 h = make_float4(tf32_hi(y.x), tf32_hi(y.y), tf32_hi(y.z), tf32_hi(y.w));
+              float4 w = make_float4(y.x - h.x, y.y - h.y, y.z - h.z, y.w - h.w);
+              *reinterpret_cast<float4*>(p.Yhi + off + 4 * g) = h;
+              *reinterpret_cast<float4*>(p.Ylo + off + 4 * g) = w;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (++buf == 2) { buf = 0; aph ^= 1u; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * acc_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// project kernel: one CTA = (time chunk, row split); accumulates Z^T chunk over its rows in TMEM
+// ---------------------------------------------------------------------------------------------
+struct ProjectParams {
+  int64_t m, n;
+  int l;
+  int ks;             // rows per stage (16)
+  int ncc;            // 32-wide time chunks per CTA
+  int nmma;           // UMMA pieces per k-step (N = ncc*32 / nmma each)
+  int stages;
+  int xshift, yshift;
+  int64_t rows_per_split;
+  float* part;        // [splits][n][l]
+};
+
+constexpr int PJ_THREADS = 192;
+
+__global__ void __launch_bounds__(PJ_THREADS, 1)
+project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                  const __grid_constant__ CUtensorMap tm_yhi, const __grid_constant__ CUtensorMap tm_ylo,
+                  const ProjectParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t box_bytes = (uint32_t)p.ks * BK * 4;       // one [ks rows x 32] box (2 KB for ks = 16)
+  const uint32_t y_bytes = 4 * box_bytes;                   // 128 sketch columns
+  const uint32_t x_bytes = (uint32_t)p.ncc * box_bytes;
+  const uint32_t stage_bytes = 2 * y_bytes + 2 * x_bytes;
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * p.stages);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
+  const uint32_t nc = (uint32_t)p.ncc * BK;                 // time columns of this CTA
+  const uint32_t tmem_cols = nc <= 32 ? 32u : nc <= 64 ? 64u : nc <= 128 ? 128u : nc <= 256 ? 256u : 512u;
+
+  const int64_t t0 = (int64_t)blockIdx.x * nc;              // first time column
+  const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
+  const int64_t r_end = min(p.m, r_begin + p.rows_per_split);
+  const int num_k = (int)((r_end - r_begin + p.ks - 1) / p.ks);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_xhi); tma_prefetch_desc(&tm_xlo);
+    tma_prefetch_desc(&tm_yhi); tma_prefetch_desc(&tm_ylo);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kc = 0; kc < num_k; ++kc) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+        const int32_t row0 = (int32_t)(r_begin + (int64_t)kc * p.ks);
+        mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+        for (int c = 0; c < 4; ++c) {
+          tma_load_2d(st + c * box_bytes, &tm_yhi, p.yshift + c * BK, row0, full_bar(s));
+          tma_load_2d(st + y_bytes + c * box_bytes, &tm_ylo, p.yshift + c * BK, row0, full_bar(s));
+        }
+        for (int c = 0; c < p.ncc; ++c) {
+          const int32_t tc0 = (int32_t)(t0 + (int64_t)c * BK) + p.xshift;
+          tma_load_2d(st + 2 * y_bytes + c * box_bytes, &tm_xhi, tc0, row0, full_bar(s));
+          tma_load_2d(st + 2 * y_bytes + x_bytes + c * box_bytes, &tm_xlo, tc0, row0, full_bar(s));
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t npiece = nc / (uint32_t)p.nmma;                 // UMMA N
+    const uint32_t idesc = make_idesc_tf32(128, (int)npiece, 1, 1);
+    int s = 0; uint32_t ph = 0;
+    for (int kc = 0; kc < num_k; ++kc) {
+      mbar_wait(full_bar(s), ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+        for (int ks = 0; ks < p.ks / UMMA_K; ++ks) {
+          const uint32_t koff = (uint32_t)ks * SWIZZLE_ATOM;       // next 8-row K group
+          const uint64_t a_hi = make_smem_desc(st + koff, box_bytes, SWIZZLE_ATOM);
+          const uint64_t a_lo = make_smem_desc(st + y_bytes + koff, box_bytes, SWIZZLE_ATOM);
+          for (int pc = 0; pc < p.nmma; ++pc) {
+            const uint32_t xoff = (uint32_t)pc * (npiece / BK) * box_bytes + koff;
+            const uint64_t b_hi = make_smem_desc(st + 2 * y_bytes + xoff, box_bytes, SWIZZLE_ATOM);
+            const uint64_t b_lo = make_smem_desc(st + 2 * y_bytes + x_bytes + xoff, box_bytes, SWIZZLE_ATOM);
+            const uint32_t d_tmem = tmem_base + (uint32_t)pc * npiece;
+            umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
+            umma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1);
+            umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1);
+          }
+        }
+        umma_commit(empty_bar(s));
+        if (kc == num_k - 1) umma_commit(tfull_bar);
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // epilogue: lane i of the accumulator = sketch column i; columns = time offsets
+    const int q = warp % 4;
+    const int i = q * 32 + lane;
+    float* out = p.part + (int64_t)blockIdx.y * p.n * p.l;
+    if (num_k > 0) {
+      mbar_wait(tfull_bar, 0);
+      tcgen05_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (uint32_t c0 = 0; c0 < nc; c0 += 16) {
+      uint32_t v[16];
+      if (num_k > 0) {
+        tmem_ld16(taddr + c0, v);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (i < p.l) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int64_t t = t0 + c0 + j;
+          if (t < p.n) out[t * p.l + i] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host entry points
+// ---------------------------------------------------------------------------------------------
+static int round_up(int64_t a, int64_t b) { return (int)(ceil_div(a, b) * b); }
+
+struct PjPlan {
+  int nchunks, ncc, nmma;
+  int64_t splits, rows_per_split;
+  size_t bytes;
+};
+
+static PjPlan pj_plan(int64_t m, int64_t n, int64_t l) {
+  PjPlan pl;
+  pl.nchunks = (int)ceil_div(n, 512);
+  pl.ncc = (int)ceil_div(ceil_div(n, pl.nchunks), 32);          // 32-wide chunks per CTA (<= 16)
+  // UMMA N = ncc * 32 / nmma must be <= 256 and a multiple of 32 (whole boxes per piece)
+  pl.nmma = 1;
+  while (pl.ncc * 32 / pl.nmma > 256 || pl.ncc % pl.nmma != 0) {
+    ++pl.nmma;
+    if (pl.nmma > pl.ncc) { pl.ncc += 1; pl.nmma = 1; }
+  }
+  // rows per split <= 4096 (bounds the fp32 running sums), CTA count a multiple of the SM count
+  const int sms = sm_count();
+  int64_t splits = ceil_div(m, 4096);
+  int64_t ctas = splits * pl.nchunks;
+  ctas = ceil_div(ctas, sms) * sms;
+  splits = ceil_div(ctas, pl.nchunks);
+  const int64_t cap = ((int64_t)512 << 20) / (n * l * 4 > 0 ? n * l * 4 : 1);
+  if (splits > cap) splits = cap > 0 ? cap : 1;
+  if (splits > 65535) splits = 65535;
+  int64_t rps = ceil_div(ceil_div(m, splits), 16) * 16;
+  splits = ceil_div(m, rps);
+  pl.splits = splits;
+  pl.rows_per_split = rps;
+  pl.bytes = (size_t)(splits * n * l * 4);
+  return pl;
+}
 
 }  // namespace era5svd
+
+extern "C" {
+
+int era5svd_split_tf32(const float* X, int64_t rows, int64_t cols, int64_t ldx, float* hi, float* lo,
+                       int64_t ld_out, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(X && hi && lo, "split_tf32: null pointer");
+  ERA5SVD_REQUIRE(rows > 0 && cols > 0 && ldx >= cols && ld_out >= cols, "split_tf32: bad shape");
+  int64_t blocks = ceil_div(rows * cols, 256 * 8);
+  int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  tc::split_tf32_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(X, rows, cols, ldx, hi, lo, ld_out);
+  return check_launch("split_tf32_kernel");
+}
+
+size_t era5svd_sketch_tf32x3_workspace_bytes(int64_t n, int64_t l) {
+  using namespace era5svd;
+  if (n <= 0 || l <= 0) return 0;
+  return (size_t)2 * round_up(l, 16) * round_up(n, 4) * sizeof(float);
+}
+
+int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                          const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
+                          int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(Xhi && Xlo && Om, "sketch_tf32x3: null pointer");
+  ERA5SVD_REQUIRE(Y || Yhi, "sketch_tf32x3: no output requested");
+  ERA5SVD_REQUIRE((Yhi == nullptr) == (Ylo == nullptr), "sketch_tf32x3: Yhi and Ylo go together");
+  ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldo >= l, "sketch_tf32x3: bad shape");
+  const int npad = round_up(l, 16);
+  if (npad > 256) {
+    set_error("sketch_tf32x3: l = %lld > 256 is not supported by the tensor-core path", (long long)l);
+    return ERA5SVD_ERR_UNSUPPORTED;
+  }
+  ERA5SVD_REQUIRE(ldy >= npad && ldy % 4 == 0, "sketch_tf32x3: ldy must be >= round_up(l, 16) = %d and a multiple of 4", npad);
+  ERA5SVD_REQUIRE(m < ((int64_t)1 << 31), "sketch_tf32x3: m too large for TMA coordinates");
+  for (const float* ptr : {Y, Yhi, Ylo})
+    ERA5SVD_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "sketch_tf32x3: outputs must be 16-byte aligned");
+  const size_t need = era5svd_sketch_tf32x3_workspace_bytes(n, l);
+  if (!workspace || workspace_bytes < need) {
+    set_error("sketch_tf32x3: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return ERA5SVD_ERR_WORKSPACE;
+  }
+  ERA5SVD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "sketch_tf32x3: workspace must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int64_t ldt = round_up(n, 4);
+  float* ohi = (float*)workspace;
+  float* olo = ohi + (int64_t)npad * ldt;
+  tc::split_omega_t_kernel<<<(unsigned)ceil_div((int64_t)npad * ldt, 256), 256, 0, st>>>(Om, n, l, ldo, ohi, olo, npad, ldt);
+  int rc = check_launch("split_omega_t_kernel");
+  if (rc) return rc;
+
+  CUtensorMap tm_xhi, tm_xlo, tm_ohi, tm_olo;
+  int xs = 0, xs2 = 0, os = 0, os2 = 0;
+  if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, tc::BM, &xs))) return rc;
+  if ((rc = tc::make_tmap(&tm_xlo, Xlo, n, m, ldx, tc::BK, tc::BM, &xs2))) return rc;
+  if ((rc = tc::make_tmap(&tm_ohi, ohi, n, npad, ldt, tc::BK, (uint32_t)npad, &os))) return rc;
+  if ((rc = tc::make_tmap(&tm_olo, olo, n, npad, ldt, tc::BK, (uint32_t)npad, &os2))) return rc;
+  ERA5SVD_REQUIRE(xs == xs2, "sketch_tf32x3: Xhi and Xlo must have the same 16-byte phase");
+
+  tc::SketchParams p;
+  p.m = m;
+  p.num_tiles = ceil_div(m, tc::BM);
+  p.num_k = (int)ceil_div(n, tc::BK);
+  p.npad = npad;
+  p.xshift = xs;
+  p.oshift = os;
+  p.Y = Y; p.Yhi = Yhi; p.Ylo = Ylo;
+  p.ldy = ldy;
+  const size_t stage_bytes = 2 * (size_t)tc::BM * tc::BK * 4 + 2 * (size_t)npad * tc::BK * 4;
+  const size_t budget = 227 * 1024 - 1024 - 256;
+  p.stages = (int)(budget / stage_bytes);
+  if (p.stages > 6) p.stages = 6;
+  ERA5SVD_REQUIRE(p.stages >= 2, "sketch_tf32x3: not enough shared memory for two stages");
+  const size_t smem = p.stages * stage_bytes + 1024 + 256;
+  ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  tc::sketch_tc_kernel<<<(unsigned)grid, tc::SK_THREADS, smem, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, p);
+  return check_launch("sketch_tc_kernel");
+}
+
+size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l) {
+  using namespace era5svd;
+  if (m <= 0 || n <= 0 || l <= 0) return 0;
+  return pj_plan(m, n, l).bytes;
+}
+
+int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                           const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,
+                           int64_t ldz, int accumulate, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(Xhi && Xlo && Yhi && Ylo && Z, "project_tf32x3: null pointer");
+  ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldy >= l && ldz >= l, "project_tf32x3: bad shape");
+  if (l > 128) {
+    set_error("project_tf32x3: l = %lld > 128 is not supported by the tensor-core path", (long long)l);
+    return ERA5SVD_ERR_UNSUPPORTED;
+  }
+  ERA5SVD_REQUIRE(m < ((int64_t)1 << 31), "project_tf32x3: m too large for TMA coordinates");
+  const PjPlan pl = pj_plan(m, n, l);
+  if (!workspace || workspace_bytes < pl.bytes) {
+    set_error("project_tf32x3: workspace too small (%zu < %zu)", workspace_bytes, pl.bytes);
+    return ERA5SVD_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  constexpr int KS = 16;
+  CUtensorMap tm_xhi, tm_xlo, tm_yhi, tm_ylo;
+  int xs = 0, xs2 = 0, ys = 0, ys2 = 0, rc;
+  if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, KS, &xs))) return rc;
+  if ((rc = tc::make_tmap(&tm_xlo, Xlo, n, m, ldx, tc::BK, KS, &xs2))) return rc;
+  if ((rc = tc::make_tmap(&tm_yhi, Yhi, l, m, ldy, tc::BK, KS, &ys))) return rc;
+  if ((rc = tc::make_tmap(&tm_ylo, Ylo, l, m, ldy, tc::BK, KS, &ys2))) return rc;
+  ERA5SVD_REQUIRE(xs == xs2 && ys == ys2, "project_tf32x3: hi / lo operands must have the same 16-byte phase");
+
+  tc::ProjectParams p;
+  p.m = m; p.n = n; p.l = (int)l;
+  p.ks = KS;
+  p.ncc = pl.ncc;
+  p.nmma = pl.nmma;
+  p.xshift = xs; p.yshift = ys;
+  p.rows_per_split = pl.rows_per_split;
+  p.part = (float*)workspace;
+  const size_t box = (size_t)KS * tc::BK * 4;
+  const size_t stage_bytes = 2 * 4 * box + 2 * (size_t)pl.ncc * box;
+  const size_t budget = 227 * 1024 - 1024 - 256;
+  p.stages = (int)(budget / stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  ERA5SVD_REQUIRE(p.stages >= 2, "project_tf32x3: not enough shared memory for two stages");
+  const size_t smem = p.stages * stage_bytes + 1024 + 256;
+  ERA5SVD_CUDA(cudaFuncSetAttribute(tc::project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)pl.nchunks, (unsigned)pl.splits);
+  tc::project_tc_kernel<<<grid, tc::PJ_THREADS, smem, st>>>(tm_xhi, tm_xlo, tm_yhi, tm_ylo, p);
+  if ((rc = check_launch("project_tc_kernel"))) return rc;
+  launch_reduce_partials_f32(p.part, pl.splits, n, l, Z, ldz, accumulate, st);
+  return check_launch("reduce_partials_kernel");
+}
+
+}  // extern "C"

@@ -157,6 +157,72 @@ class CudaOps:
             end.record()
         return Z
 
+    # -- (b') tensor-core passes (tcgen05, 3xTF32) ---------------------------------------------
+    def split_tf32(self, X: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """hi / lo float32 images of X (same shape; row pitch padded to a multiple of 4 floats)."""
+        if X.dtype != torch.float32:
+            raise TypeError("split_tf32: float32 only")
+        m, n = X.shape
+        ld = -(-n // 4) * 4
+        hi = self.empty((m, ld), torch.float32)[:, :n]
+        lo = self.empty((m, ld), torch.float32)[:, :n]
+        xp, xld = _mat(X, "X")
+        end = self.timer.start("split_tf32", bytes=12.0 * m * n) if self.timer else None
+        check(self.lib.era5svd_split_tf32(xp, m, n, xld, hi.data_ptr(), lo.data_ptr(), ld, self._stream()),
+              "era5svd_split_tf32")
+        if end is not None:
+            end.record()
+        return hi, lo
+
+    @staticmethod
+    def tf32_ldy(l: int) -> int:
+        """Row pitch the tensor-core sketch needs for its outputs: round_up(l, 16)."""
+        return -(-l // 16) * 16
+
+    def sketch_tf32x3(self, Xhi: torch.Tensor, Xlo: torch.Tensor, Om: torch.Tensor, Y: torch.Tensor | None,
+                      Yhi: torch.Tensor | None, Ylo: torch.Tensor | None) -> None:
+        """Y (and/or the split pair Yhi, Ylo) = X @ Om; Om is the float64 (n, l) small factor.
+        Outputs are (m, l) views of buffers whose row pitch is tf32_ldy(l)."""
+        m, n = Xhi.shape
+        l = Om.shape[1]
+        if Om.dtype != torch.float64 or Om.shape[0] != n:
+            raise ValueError("sketch_tf32x3: Om must be float64 (n, l)")
+        hp, hld = _mat(Xhi, "Xhi"); lp, lld = _mat(Xlo, "Xlo"); op, old = _mat(Om, "Om")
+        outs = [t for t in (Y, Yhi, Ylo) if t is not None]
+        lds = {_mat(t, "Y")[1] for t in outs}
+        if hld != lld or len(lds) != 1:
+            raise ValueError("sketch_tf32x3: hi/lo operands and outputs must share their row pitch")
+        ldy = lds.pop()
+        nbytes = int(self.lib.era5svd_sketch_tf32x3_workspace_bytes(n, l))
+        ws = self._workspace("sketch_tc", nbytes)
+        end = self.timer.start("sketch_tc", bytes=4.0 * (m * n + m * l + n * l), flops=2.0 * m * n * l) if self.timer else None
+        check(self.lib.era5svd_sketch_tf32x3(hp, lp, m, n, hld, op, l, old, Y.data_ptr() if Y is not None else None,
+                                             Yhi.data_ptr() if Yhi is not None else None,
+                                             Ylo.data_ptr() if Ylo is not None else None, ldy, ws.data_ptr(), ws.numel(),
+                                             self._stream()), "era5svd_sketch_tf32x3")
+        if end is not None:
+            end.record()
+
+    def project_tf32x3(self, Xhi: torch.Tensor, Xlo: torch.Tensor, Yhi: torch.Tensor, Ylo: torch.Tensor,
+                       Z: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
+        m, n = Xhi.shape
+        l = Yhi.shape[1]
+        if Z is None:
+            Z = self.empty((n, l), torch.float64)
+            accumulate = False
+        hp, hld = _mat(Xhi, "Xhi"); lp, lld = _mat(Xlo, "Xlo")
+        yhp, yhld = _mat(Yhi, "Yhi"); ylp, ylld = _mat(Ylo, "Ylo"); zp, zld = _mat(Z, "Z")
+        if hld != lld or yhld != ylld:
+            raise ValueError("project_tf32x3: hi/lo operands must share their row pitch")
+        nbytes = int(self.lib.era5svd_project_tf32x3_workspace_bytes(m, n, l))
+        ws = self._workspace("project", nbytes)
+        end = self.timer.start("project_tc", bytes=4.0 * (m * n + m * l) + 8.0 * n * l, flops=2.0 * m * n * l) if self.timer else None
+        check(self.lib.era5svd_project_tf32x3(hp, lp, m, n, hld, yhp, ylp, l, yhld, zp, zld, int(accumulate),
+                                              ws.data_ptr(), ws.numel(), self._stream()), "era5svd_project_tf32x3")
+        if end is not None:
+            end.record()
+        return Z
+
     # -- (c)/(d) small float64 factors -------------------------------------------------------
     def gemm(self, A: torch.Tensor, B: torch.Tensor, transA: bool = False, transB: bool = False,
              alpha: float = 1.0, beta: float = 0.0, C: torch.Tensor | None = None) -> torch.Tensor:

@@ -113,16 +113,36 @@ def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_
     rel_tol = 1e-13 if tall == torch.float64 else 1e-6
     Omega = _orth(ops, ops.to_device(om, non_blocking=False).clone(), 1e-13)
 
-    Y = ops.empty((m0 * d, l), tall)
+    use_tc = precision == PREC_TF32X3
+    if use_tc:
+        # tensor-core path: operands pre-split into tf32 hi / lo images (see csrc/gemm_tc.cu)
+        if tall != torch.float32:
+            raise TypeError("precision 'tf32x3' needs a float32 snapshot matrix")
+        if l > 128:
+            raise ValueError(f"precision 'tf32x3' supports sketch widths up to 128, got l = {l}")
+        Xhi, Xlo = ops.split_tf32(X)
+        ldy = ops.tf32_ldy(l)
+        Y = ops.empty((m0 * d, ldy), tall)[:, :l]
+        Yhi = ops.empty((m0 * d, ldy), tall)[:, :l]
+        Ylo = ops.empty((m0 * d, ldy), tall)[:, :l]
+    else:
+        Y = ops.empty((m0 * d, l), tall)
 
-    def tall_pass(Omega64: torch.Tensor) -> torch.Tensor:
-        """Y = X_d Omega (kept in the preallocated Y), returns Z = X_d^T Y (all-reduced)."""
-        Om_t = ops.convert(Omega64, tall)
+    def tall_pass(Omega64: torch.Tensor, keep_y: bool = False) -> torch.Tensor:
+        """Y = X_d Omega (kept in the preallocated buffers), returns Z = X_d^T Y (all-reduced)."""
         Z = None
-        for j in range(d):
-            Yj = Y[j * m0 : (j + 1) * m0]
-            ops.sketch(blocks.view(j), Om_t, Yj, precision)
-            Z = ops.project(blocks.view(j), Yj, Z, accumulate=j > 0, precision=precision)
+        if use_tc:
+            for j in range(d):
+                rows = slice(j * m0, (j + 1) * m0)
+                xh, xl = Xhi[:, j : j + n], Xlo[:, j : j + n]
+                ops.sketch_tf32x3(xh, xl, Omega64, Y[rows] if keep_y else None, Yhi[rows], Ylo[rows])
+                Z = ops.project_tf32x3(xh, xl, Yhi[rows], Ylo[rows], Z, accumulate=j > 0)
+        else:
+            Om_t = ops.convert(Omega64, tall)
+            for j in range(d):
+                Yj = Y[j * m0 : (j + 1) * m0]
+                ops.sketch(blocks.view(j), Om_t, Yj, PREC_NATIVE)
+                Z = ops.project(blocks.view(j), Yj, Z, accumulate=j > 0, precision=PREC_NATIVE)
         comm.allreduce_sum_(Z)
         if stats is not None:
             stats["tall_passes"] = stats.get("tall_passes", 0) + 2
@@ -139,7 +159,7 @@ def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_
             Z = ops.gemm(Z, W)
         Omega = _orth(ops, Z, 1e-13)
 
-    Zp = tall_pass(Omega)                              # n x l
+    Zp = tall_pass(Omega, keep_y=True)                 # n x l
     G = ops.project(Y, Y, precision=PREC_NATIVE)       # l x l, from the stored (rounded) Y
     comm.allreduce_sum_(G)
     _, Rinv = ops.chol_inv(G, rel_tol)

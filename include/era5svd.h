@@ -101,6 +101,32 @@ int era5svd_project(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (b') the same passes on the tensor cores: tcgen05.mma kind::tf32 fed by TMA, fp32 accumulators in
+ * TMEM, 3-term split x = hi + lo (hi = tf32(x), lo = x - hi, both stored as float32) so that
+ * a*b ~ a_hi*b_hi + a_lo*b_hi + a_hi*b_lo keeps fp32-level accuracy.  float32 storage only.
+ *
+ * era5svd_split_tf32      : hi / lo images of a tall float32 matrix (done once per matrix).
+ * era5svd_sketch_tf32x3   : Y = X * Om with X given as (Xhi, Xlo); Om is the float64 small factor
+ *                           (n x l, split on the fly into the workspace).  Writes any of Y (plain
+ *                           float32) and the pair (Yhi, Ylo) for a following project; all share ldy,
+ *                           which must be >= round_up(l, 16) and a multiple of 4 (pad columns get 0).
+ * era5svd_project_tf32x3  : Z (float64, n x l) (+)= X^T Y from (Xhi, Xlo), (Yhi, Ylo); l <= 128.
+ * Pointers may carry a column offset (delay-embedded window X + j): only 4-byte alignment of the
+ * tall operands is required, row pitches must be multiples of 4 floats.
+ */
+int era5svd_split_tf32(const float* X, int64_t rows, int64_t cols, int64_t ldx, float* hi, float* lo,
+                       int64_t ld_out, void* stream);
+size_t era5svd_sketch_tf32x3_workspace_bytes(int64_t n, int64_t l);
+int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                          const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
+                          int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l);
+int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                           const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,
+                           int64_t ldz, int accumulate, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (c)/(d) small float64 factor kernels (replicated on every GPU; per-CTA solvers).
  */
 /* C[M x N] = alpha * op(A) * op(B) + beta * C, row-major; transX != 0 means the operand is stored

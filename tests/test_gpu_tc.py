@@ -1,0 +1,93 @@
+"""GPU: the tcgen05 / TMA kernels (3xTF32 split) against float64 statements of the same products,
+and the end-to-end randomized SVD in precision='tf32x3' against the oracle (1e-4 on sigma)."""
+import numpy as np
+import pytest
+import torch
+
+from dmd_era5_b200.era5_svd import svd_on_era5
+from oracle.compare import recon_rel_err, sigma_rel_err, signs_agree, vector_angles
+from oracle.svd_ref import randomized_svd_ref
+from oracle.synthetic_np import lowrank_field_np
+
+pytestmark = pytest.mark.gpu
+
+# 3xTF32: ~2^-21 per product, fp32 accumulation; bound used below: 4e-6 * ||x_row|| * ||y_col||
+TC_REL = 4e-6
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_split_tf32_exact(ops):
+    x = np.random.RandomState(0).standard_normal((257, 99)).astype(np.float32) * 1e3
+    hi, lo = ops.split_tf32(dev(x))
+    hi, lo = hi.cpu().numpy(), lo.cpu().numpy()
+    assert np.array_equal(hi + lo, x)                              # exact decomposition
+    assert np.all((hi.view(np.uint32) & 0x1FFF) == 0)              # hi is a tf32 value
+    assert np.all(np.abs(lo) <= np.abs(x) * 2.0 ** -11 * 1.0001)
+
+
+@pytest.mark.parametrize("m,n,l,off", [(128, 32, 16, 0), (1000, 744, 110, 0), (300, 100, 130, 0),
+                                       (5000, 1460, 110, 0), (2000, 742, 110, 2), (77, 25, 20, 1)])
+def test_sketch_tf32x3(ops, m, n, l, off):
+    rng = np.random.RandomState(m + n)
+    Xfull = rng.standard_normal((m, n + off)).astype(np.float32)
+    Om = rng.standard_normal((n, l))
+    hi, lo = ops.split_tf32(dev(Xfull))
+    ldy = ops.tf32_ldy(l)
+    Y = torch.zeros((m, ldy), device="cuda")[:, :l]
+    Yh = torch.zeros((m, ldy), device="cuda")[:, :l]
+    Yl = torch.zeros((m, ldy), device="cuda")[:, :l]
+    ops.sketch_tf32x3(hi[:, off:off + n], lo[:, off:off + n], dev(Om), Y, Yh, Yl)
+    ref = Xfull[:, off:].astype(np.float64) @ Om
+    bound = TC_REL * np.linalg.norm(Xfull[:, off:], axis=1)[:, None] * np.linalg.norm(Om, axis=0)[None, :]
+    assert np.all(np.abs(Y.cpu().numpy() - ref) <= bound + 1e-30)
+    assert np.array_equal((Yh + Yl).cpu().numpy(), Y.cpu().numpy())
+
+
+@pytest.mark.parametrize("m,n,l", [(16, 32, 16), (1000, 744, 110), (50000, 1460, 110), (4097, 25, 20), (333, 600, 128)])
+def test_project_tf32x3(ops, m, n, l):
+    rng = np.random.RandomState(m + l)
+    Xh = rng.standard_normal((m, n)).astype(np.float32)
+    Yh = rng.standard_normal((m, l)).astype(np.float32)
+    ldy = ops.tf32_ldy(l)
+    Yb = torch.zeros((m, ldy), device="cuda")
+    Yb[:, :l] = dev(Yh)
+    xhi, xlo = ops.split_tf32(dev(Xh))
+    yhi, ylo = ops.split_tf32(Yb)
+    Z = ops.project_tf32x3(xhi, xlo, yhi[:, :l], ylo[:, :l])
+    ref = Xh.astype(np.float64).T @ Yh.astype(np.float64)
+    bound = TC_REL * np.linalg.norm(Xh, axis=0)[:, None] * np.linalg.norm(Yh, axis=0)[None, :]
+    assert np.all(np.abs(Z.cpu().numpy() - ref) <= bound)
+    Z2 = ops.project_tf32x3(xhi, xlo, yhi[:, :l], ylo[:, :l], Z.clone(), accumulate=True)
+    assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("d", [1, 2])
+def test_randomized_tf32x3_vs_oracle(d):
+    """float32 storage, tensor-core passes: sigma within 1e-4 of the float64 oracle on the same data."""
+    from oracle.slice_tools_np import delay_embed_np
+    from dmd_era5_b200.era5_svd import get_ops, host_to_device_matrix
+    from dmd_era5_b200.pipeline import svd_device
+
+    X = lowrank_field_np(20000, 744, r=160, rho=0.93, seed=0, dtype=np.float32)
+    Xd = delay_embed_np(X.astype(np.float64), d)
+    U0, s0, V0 = randomized_svd_ref(Xd, 100, 1)
+    ops = get_ops()
+    U, s, V = svd_device(ops, host_to_device_matrix(ops, X), svd_type="randomized", n_components=100, delay=d,
+                         seed=1, precision="tf32x3")
+    U, s, V = U.cpu().numpy(), s.cpu().numpy(), V.cpu().numpy()
+    assert sigma_rel_err(s, s0) < 1e-4
+    ang = vector_angles(U, U0)
+    assert ang[:50].max() < 1e-3 and ang.max() < 2e-2
+    assert signs_agree(U, U0)
+    ref = recon_rel_err(Xd, U0, s0, V0)
+    assert abs(recon_rel_err(Xd, U, s, V) - ref) <= 0.01 * ref
+
+
+def test_svd_on_era5_tf32x3_api():
+    X = lowrank_field_np(8192, 200, r=60, rho=0.85, seed=5, dtype=np.float32)
+    U0, s0, V0 = randomized_svd_ref(X.astype(np.float64), 20, 4)
+    U, s, V = svd_on_era5(X, {"svd_type": "randomized", "n_components": 20, "random_seed": 4, "precision": "tf32x3"})
+    assert U.dtype == np.float32 and sigma_rel_err(s, s0) < 1e-4 and signs_agree(U, U0)
