@@ -102,16 +102,20 @@ split_tf32_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int64
   }
 }
 
-// Om (float64, n x l) -> Om^T hi / lo (float32, [npad][ldt]); rows >= l and the tail of each row are
-// zero.  The float64 source lets lo carry bits beyond fp32: lo = fp32(om - hi).
+// Om (float64, n x l) -> Om^T hi / lo (float32, [npad][ldt]), shifted right by `shift` columns:
+// out[j][t] = Om[t - shift][j] for shift <= t < shift + n, zero elsewhere (rows >= l are zero too).
+// The shift is how a column window X[:, c : c + n] whose start is not 16-byte aligned is addressed:
+// TMA boxes must start on 16-byte boundaries under the 128 B swizzle, so the box starts at the
+// aligned column below c and the zero rows of Om cancel the extra columns.
+// The float64 source lets lo carry bits beyond fp32: lo = fp32(om - hi).
 __global__ void __launch_bounds__(256)
 split_omega_t_kernel(const double* __restrict__ Om, int64_t n, int64_t l, int64_t ldo,
-                     float* __restrict__ hi, float* __restrict__ lo, int64_t npad, int64_t ldt) {
+                     float* __restrict__ hi, float* __restrict__ lo, int64_t npad, int64_t ldt, int shift) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= npad * ldt) return;
-  int64_t j = idx / ldt, t = idx - j * ldt;   // j = sketch column, t = time
+  int64_t j = idx / ldt, t = idx - j * ldt - shift;   // j = sketch column, t = time
   float h = 0.f, w = 0.f;
-  if (j < l && t < n) {
+  if (j < l && t >= 0 && t < n) {
     double v = Om[t * ldo + j];
     h = tf32_hi((float)v);
     w = (float)(v - (double)h);
@@ -129,7 +133,6 @@ struct SketchParams {
   int num_k;          // ceil(n / 32)
   int npad;           // UMMA N (multiple of 16, <= 256)
   int stages;
-  int xshift, oshift; // inner-coordinate shifts of the X / Om^T maps
   float* Y;           // nullable
   float* Yhi;         // nullable
   float* Ylo;         // nullable
@@ -189,10 +192,10 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-          tma_load_2d(st, &tm_xhi, p.xshift + kc * BK, row0, full_bar(s));
-          tma_load_2d(st + a_bytes, &tm_xlo, p.xshift + kc * BK, row0, full_bar(s));
-          tma_load_2d(st + 2 * a_bytes, &tm_ohi, p.oshift + kc * BK, 0, full_bar(s));
-          tma_load_2d(st + 2 * a_bytes + b_bytes, &tm_olo, p.oshift + kc * BK, 0, full_bar(s));
+          tma_load_2d(st, &tm_xhi, kc * BK, row0, full_bar(s));
+          tma_load_2d(st + a_bytes, &tm_xlo, kc * BK, row0, full_bar(s));
+          tma_load_2d(st + 2 * a_bytes, &tm_ohi, kc * BK, 0, full_bar(s));
+          tma_load_2d(st + 2 * a_bytes + b_bytes, &tm_olo, kc * BK, 0, full_bar(s));
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -280,7 +283,7 @@ struct ProjectParams {
   int ncc;            // 32-wide time chunks per CTA
   int nmma;           // UMMA pieces per k-step (N = ncc*32 / nmma each)
   int stages;
-  int xshift, yshift;
+  int xshift;         // the window starts xshift (0..3) columns right of the 16-byte aligned map origin
   int64_t rows_per_split;
   float* part;        // [splits][n][l]
 };
@@ -339,11 +342,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         const int32_t row0 = (int32_t)(r_begin + (int64_t)kc * p.ks);
         mbar_arrive_expect_tx(full_bar(s), stage_bytes);
         for (int c = 0; c < 4; ++c) {
-          tma_load_2d(st + c * box_bytes, &tm_yhi, p.yshift + c * BK, row0, full_bar(s));
-          tma_load_2d(st + y_bytes + c * box_bytes, &tm_ylo, p.yshift + c * BK, row0, full_bar(s));
+          tma_load_2d(st + c * box_bytes, &tm_yhi, c * BK, row0, full_bar(s));
+          tma_load_2d(st + y_bytes + c * box_bytes, &tm_ylo, c * BK, row0, full_bar(s));
         }
         for (int c = 0; c < p.ncc; ++c) {
-          const int32_t tc0 = (int32_t)(t0 + (int64_t)c * BK) + p.xshift;
+          const int32_t tc0 = (int32_t)(t0 + (int64_t)c * BK);
           tma_load_2d(st + 2 * y_bytes + c * box_bytes, &tm_xhi, tc0, row0, full_bar(s));
           tma_load_2d(st + 2 * y_bytes + x_bytes + c * box_bytes, &tm_xlo, tc0, row0, full_bar(s));
         }
@@ -401,8 +404,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       if (i < p.l) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int64_t t = t0 + c0 + j;
-          if (t < p.n) out[t * p.l + i] = __uint_as_float(v[j]);
+          const int64_t t = t0 + c0 + j - p.xshift;     // window-relative time index
+          if (t >= 0 && t < p.n) out[t * p.l + i] = __uint_as_float(v[j]);
         }
       }
     }
@@ -471,7 +474,7 @@ int era5svd_split_tf32(const float* X, int64_t rows, int64_t cols, int64_t ldx, 
 size_t era5svd_sketch_tf32x3_workspace_bytes(int64_t n, int64_t l) {
   using namespace era5svd;
   if (n <= 0 || l <= 0) return 0;
-  return (size_t)2 * round_up(l, 16) * round_up(n, 4) * sizeof(float);
+  return (size_t)2 * round_up(l, 16) * round_up(n + 3, 4) * sizeof(float);
 }
 
 int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
@@ -498,28 +501,26 @@ int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t
   }
   ERA5SVD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "sketch_tf32x3: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
-  const int64_t ldt = round_up(n, 4);
-  float* ohi = (float*)workspace;
-  float* olo = ohi + (int64_t)npad * ldt;
-  tc::split_omega_t_kernel<<<(unsigned)ceil_div((int64_t)npad * ldt, 256), 256, 0, st>>>(Om, n, l, ldo, ohi, olo, npad, ldt);
-  int rc = check_launch("split_omega_t_kernel");
-  if (rc) return rc;
-
   CUtensorMap tm_xhi, tm_xlo, tm_ohi, tm_olo;
-  int xs = 0, xs2 = 0, os = 0, os2 = 0;
+  int xs = 0, xs2 = 0, os = 0, os2 = 0, rc;
   if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, tc::BM, &xs))) return rc;
   if ((rc = tc::make_tmap(&tm_xlo, Xlo, n, m, ldx, tc::BK, tc::BM, &xs2))) return rc;
-  if ((rc = tc::make_tmap(&tm_ohi, ohi, n, npad, ldt, tc::BK, (uint32_t)npad, &os))) return rc;
-  if ((rc = tc::make_tmap(&tm_olo, olo, n, npad, ldt, tc::BK, (uint32_t)npad, &os2))) return rc;
   ERA5SVD_REQUIRE(xs == xs2, "sketch_tf32x3: Xhi and Xlo must have the same 16-byte phase");
+  const int64_t kspan = n + xs;                  // K extent seen from the aligned map origin
+  const int64_t ldt = round_up(kspan, 4);
+  float* ohi = (float*)workspace;
+  float* olo = ohi + (int64_t)npad * ldt;
+  tc::split_omega_t_kernel<<<(unsigned)ceil_div((int64_t)npad * ldt, 256), 256, 0, st>>>(Om, n, l, ldo, ohi, olo, npad, ldt, xs);
+  if ((rc = check_launch("split_omega_t_kernel"))) return rc;
+  if ((rc = tc::make_tmap(&tm_ohi, ohi, kspan, npad, ldt, tc::BK, (uint32_t)npad, &os))) return rc;
+  if ((rc = tc::make_tmap(&tm_olo, olo, kspan, npad, ldt, tc::BK, (uint32_t)npad, &os2))) return rc;
+  ERA5SVD_REQUIRE(os == 0 && os2 == 0, "sketch_tf32x3: workspace must be 16-byte aligned");
 
   tc::SketchParams p;
   p.m = m;
   p.num_tiles = ceil_div(m, tc::BM);
-  p.num_k = (int)ceil_div(n, tc::BK);
+  p.num_k = (int)ceil_div(kspan, tc::BK);
   p.npad = npad;
-  p.xshift = xs;
-  p.oshift = os;
   p.Y = Y; p.Yhi = Yhi; p.Ylo = Ylo;
   p.ldy = ldy;
   const size_t stage_bytes = 2 * (size_t)tc::BM * tc::BK * 4 + 2 * (size_t)npad * tc::BK * 4;
@@ -537,7 +538,7 @@ int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l) {
   using namespace era5svd;
   if (m <= 0 || n <= 0 || l <= 0) return 0;
-  return pj_plan(m, n, l).bytes;
+  return pj_plan(m, n + 3, l).bytes;
 }
 
 int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
@@ -552,7 +553,8 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
     return ERA5SVD_ERR_UNSUPPORTED;
   }
   ERA5SVD_REQUIRE(m < ((int64_t)1 << 31), "project_tf32x3: m too large for TMA coordinates");
-  const PjPlan pl = pj_plan(m, n, l);
+  // plan for the widest window (xshift <= 3) so that the workspace query needs no pointer
+  const PjPlan pl = pj_plan(m, n + 3, l);
   if (!workspace || workspace_bytes < pl.bytes) {
     set_error("project_tf32x3: workspace too small (%zu < %zu)", workspace_bytes, pl.bytes);
     return ERA5SVD_ERR_WORKSPACE;
@@ -565,14 +567,15 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
   if ((rc = tc::make_tmap(&tm_xlo, Xlo, n, m, ldx, tc::BK, KS, &xs2))) return rc;
   if ((rc = tc::make_tmap(&tm_yhi, Yhi, l, m, ldy, tc::BK, KS, &ys))) return rc;
   if ((rc = tc::make_tmap(&tm_ylo, Ylo, l, m, ldy, tc::BK, KS, &ys2))) return rc;
-  ERA5SVD_REQUIRE(xs == xs2 && ys == ys2, "project_tf32x3: hi / lo operands must have the same 16-byte phase");
+  ERA5SVD_REQUIRE(xs == xs2, "project_tf32x3: Xhi and Xlo must have the same 16-byte phase");
+  ERA5SVD_REQUIRE(ys == 0 && ys2 == 0, "project_tf32x3: Yhi / Ylo must be 16-byte aligned");
 
   tc::ProjectParams p;
   p.m = m; p.n = n; p.l = (int)l;
   p.ks = KS;
   p.ncc = pl.ncc;
   p.nmma = pl.nmma;
-  p.xshift = xs; p.yshift = ys;
+  p.xshift = xs;
   p.rows_per_split = pl.rows_per_split;
   p.part = (float*)workspace;
   const size_t box = (size_t)KS * tc::BK * 4;
