@@ -13,8 +13,9 @@
 //   project:  Z^T[l x n] = Y^T[l x m] * X[m x n]    A = Y tile   (MN-major, K = space rows)
 //                                                   B = X tile   (MN-major)       D: 128 (l) x time chunk
 //
-// The same 128 B-swizzled shared-memory image of an X tile ([rows][32 time values]) serves as a
-// K-major operand for sketch and as an MN-major operand for project, so X is never transposed.
+// Both kernels read X tiles as [rows][32 time values] boxes, so X is never transposed in HBM: sketch
+// consumes them K-major (16 B swizzle granules), project MN-major (32-bit MN-major operands use the
+// 32 B-granule 128 B swizzle, TMA mode SWIZZLE_128B_ATOM_32B).
 // Replaces `A @ Q` / `A.T @ Q` / `Q.T @ M` (sklearn/utils/extmath.py:378-383, :606) for float32 data.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -56,7 +57,8 @@ static EncodeTiledFn encode_fn() {
 // map is anchored at the enclosing 16-byte boundary and *col_shift returns the element offset to add
 // to every inner coordinate (this is how delay-embedded column windows X[:, j:] are addressed).
 static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
-                     uint32_t box_inner, uint32_t box_outer, int* col_shift) {
+                     uint32_t box_inner, uint32_t box_outer, int* col_shift,
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -74,7 +76,7 @@ static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, reinterpret_cast<void*>(addr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%ux%u", (int)r, (long long)inner,
@@ -363,13 +365,13 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       if (lane == 0) {
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
         for (int ks = 0; ks < p.ks / UMMA_K; ++ks) {
-          const uint32_t koff = (uint32_t)ks * SWIZZLE_ATOM;       // next 8-row K group
-          const uint64_t a_hi = make_smem_desc(st + koff, box_bytes, SWIZZLE_ATOM);
-          const uint64_t a_lo = make_smem_desc(st + y_bytes + koff, box_bytes, SWIZZLE_ATOM);
+          const uint32_t koff = (uint32_t)ks * UMMA_K * 128;       // next 8 K rows (two 4-row swizzle atoms)
+          const uint64_t a_hi = make_smem_desc(st + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
+          const uint64_t a_lo = make_smem_desc(st + y_bytes + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
           for (int pc = 0; pc < p.nmma; ++pc) {
             const uint32_t xoff = (uint32_t)pc * (npiece / BK) * box_bytes + koff;
-            const uint64_t b_hi = make_smem_desc(st + 2 * y_bytes + xoff, box_bytes, SWIZZLE_ATOM);
-            const uint64_t b_lo = make_smem_desc(st + 2 * y_bytes + x_bytes + xoff, box_bytes, SWIZZLE_ATOM);
+            const uint64_t b_hi = make_smem_desc(st + 2 * y_bytes + xoff, box_bytes, 512, LAYOUT_SW128_BASE32B);
+            const uint64_t b_lo = make_smem_desc(st + 2 * y_bytes + x_bytes + xoff, box_bytes, 512, LAYOUT_SW128_BASE32B);
             const uint32_t d_tmem = tmem_base + (uint32_t)pc * npiece;
             umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
             umma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1);
@@ -563,10 +565,10 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
   constexpr int KS = 16;
   CUtensorMap tm_xhi, tm_xlo, tm_yhi, tm_ylo;
   int xs = 0, xs2 = 0, ys = 0, ys2 = 0, rc;
-  if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, KS, &xs))) return rc;
-  if ((rc = tc::make_tmap(&tm_xlo, Xlo, n, m, ldx, tc::BK, KS, &xs2))) return rc;
-  if ((rc = tc::make_tmap(&tm_yhi, Yhi, l, m, ldy, tc::BK, KS, &ys))) return rc;
-  if ((rc = tc::make_tmap(&tm_ylo, Ylo, l, m, ldy, tc::BK, KS, &ys2))) return rc;
+  if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, KS, &xs, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = tc::make_tmap(&tm_xlo, Xlo, n, m, ldx, tc::BK, KS, &xs2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = tc::make_tmap(&tm_yhi, Yhi, l, m, ldy, tc::BK, KS, &ys, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = tc::make_tmap(&tm_ylo, Ylo, l, m, ldy, tc::BK, KS, &ys2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   ERA5SVD_REQUIRE(xs == xs2, "project_tf32x3: Xhi and Xlo must have the same 16-byte phase");
   ERA5SVD_REQUIRE(ys == 0 && ys2 == 0, "project_tf32x3: Yhi / Ylo must be 16-byte aligned");
 

@@ -78,19 +78,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA -----------------------------------------------------------------------------------
-// Shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (Blackwell).
+// Shared-memory matrix descriptor, descriptor version 1 (Blackwell).
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
-//   bits [32,46) stride-dim byte offset >> 4   bits [46,48) version = 1   bits [61,64) layout = 2 (128B swizzle)
-// K-major tile  (rows = M/N index, 128 B = 32 tf32 of K per row): SBO = 1024 (8-row group stride), LBO unused (1).
-// MN-major tile (rows = K index, 128 B = 32 tf32 of M/N per row): LBO = stride between 32-element M/N groups,
-//                                                               SBO = 1024 (8-row K group stride).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   bits [32,46) stride-dim byte offset >> 4   bits [46,48) version = 1   bits [61,64) swizzle layout
+// K-major tile  (rows = M/N index, 128 B = 32 tf32 of K per row), LAYOUT_SW128 (16 B granules, 8-row atom,
+//   TMA CU_TENSOR_MAP_SWIZZLE_128B):            SBO = 1024 (8-row group stride), LBO unused (1).
+// MN-major tile (rows = K index, 128 B = 32 tf32 of M/N per row): 32-bit MN-major operands only exist in
+//   LAYOUT_SW128_BASE32B (32 B granules, 4-row atom, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+//   LBO = stride between 32-element M/N groups, SBO = 512 (4-row K group stride).
+constexpr uint32_t LAYOUT_SW128 = 2;
+constexpr uint32_t LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = LAYOUT_SW128) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate:
