@@ -123,6 +123,7 @@ syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restric
 
   // relative off-diagonal threshold |a_pq| <= tol * sqrt(|a_pp a_qq|), tol = eps * sqrt(n) (cf. xGESVJ)
   const double tol = 2.220446049250313e-16 * sqrt((double)n);
+  const double tol2 = tol * tol;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     int did = 0;
     for (int step = 0; step < n_pad - 1; ++step) {
@@ -134,11 +135,22 @@ syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restric
         if (q < n) {  // q == n only for the padding index of odd n
           const double app = Aw[p * ldw + p], aqq = Aw[q * ldw + q], apq = Aw[p * ldw + q];
           __syncwarp(gmask);  // every lane of the group has read the 2 x 2 block before any lane overwrites it
-          if (fabs(apq) > tol * sqrt(fabs(app) * fabs(aqq)) && fabs(apq) > 1e-300) {
-            const double tau = (aqq - app) / (2.0 * apq);
-            const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = rsqrt(1.0 + tt * tt);
-            s = tt * c;
+          if (apq * apq > tol2 * fabs(app * aqq) && fabs(apq) > 1e-300) {
+            // tan(theta) only steers convergence: any t gives an exactly orthogonal rotation as long as
+            // c = 1 / sqrt(1 + t^2), s = t c are formed in float64.  So t comes from fast float32 ops
+            // (relative error ~1e-7: the rotated a_pq drops by 1e-7 instead of to zero).
+            const float dq = (float)(aqq - app), ap2 = 2.0f * (float)apq;
+            double t64;
+            if (fabsf(ap2) > 1e-30f && fabsf(dq) < 1e30f) {
+              const float tau = __fdividef(dq, ap2);
+              const float tf = __fdividef(copysignf(1.0f, tau), fabsf(tau) + sqrtf(fmaf(tau, tau, 1.0f)));
+              t64 = (double)tf;
+            } else {
+              const double tau = (aqq - app) / (2.0 * apq);
+              t64 = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            }
+            c = rsqrt(fma(t64, t64, 1.0));
+            s = t64 * c;
             did = 1;
             for (int r = gl; r < n; r += JAC_GROUP) {
               double x = Aw[r * ldw + p], y = Aw[r * ldw + q];
@@ -195,10 +207,12 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
                 int64_t ldr, double* __restrict__ Rinv, int64_t ldri, double rel_tol, int use_smem) {
   extern __shared__ double smem[];
   const int t = threadIdx.x, tx = t % 32, ty = t / 32;
-  __shared__ double s_piv;
+  // smem: [gdiag: l][scale: l][Rw][Iw]  (Rw, Iw only when use_smem)
+  double* gdiag = smem;
+  double* scale = smem + l;
   const int ldw = use_smem ? (l | 1) : 0;
-  double* Rw = use_smem ? smem : R;
-  double* Iw = use_smem ? smem + (size_t)l * ldw : Rinv;
+  double* Rw = use_smem ? smem + 2 * l : R;
+  double* Iw = use_smem ? Rw + (size_t)l * ldw : Rinv;
   const int64_t ld_r = use_smem ? ldw : ldr, ld_i = use_smem ? ldw : ldri;
   // copy the upper triangle (symmetrised), zero the strictly lower part
   for (int r = ty; r < l; r += 32)
@@ -206,29 +220,34 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
       Rw[r * ld_r + c] = (c >= r) ? 0.5 * (G[(int64_t)r * ldg + c] + G[(int64_t)c * ldg + r]) : 0.0;
       Iw[r * ld_i + c] = 0.0;
     }
-  __syncthreads();
+  for (int j = t; j < l; j += 1024) gdiag[j] = G[(int64_t)j * ldg + j];
+  // Right-looking Cholesky with the row scaling deferred: one barrier per step.  At step j the
+  // (unscaled) pivot row is final; trailing rows get  R[i][c] -= R[j][i] R[j][c] / d_j.
   for (int j = 0; j < l; ++j) {
-    if (t == 0) {
-      const double d = Rw[j * ld_r + j];
-      const double g = G[(int64_t)j * ldg + j];
-      // dependent (or non-positive) pivot -> huge: the direction is dropped, never NaN
-      s_piv = (d > rel_tol * g && d > 0.0) ? sqrt(d) : 1e150;
-    }
     __syncthreads();
-    const double piv = s_piv;
-    for (int c = j + t; c < l; c += 1024) {
-      const double v = Rw[j * ld_r + c];
-      Rw[j * ld_r + c] = (c == j) ? piv : v / piv;
-    }
-    __syncthreads();
-    // trailing update: R[i][c] -= R[j][i] * R[j][c],  j < i <= c
+    const double d = Rw[j * ld_r + j];
+    // dependent (or non-positive) pivot: the direction is dropped (no update, zero row), never NaN
+    const double inv_d = (d > rel_tol * gdiag[j] && d > 0.0) ? 1.0 / d : 0.0;
     for (int i = j + 1 + ty; i < l; i += 32) {
-      const double rji = Rw[j * ld_r + i];
+      const double f = Rw[j * ld_r + i] * inv_d;
       for (int c = j + 1 + tx; c < l; c += 32)
-        if (c >= i) Rw[i * ld_r + c] -= rji * Rw[j * ld_r + c];
+        if (c >= i) Rw[i * ld_r + c] -= f * Rw[j * ld_r + c];
     }
-    __syncthreads();
   }
+  __syncthreads();
+  for (int j = t; j < l; j += 1024) {
+    const double d = Rw[j * ld_r + j];
+    scale[j] = (d > rel_tol * gdiag[j] && d > 0.0) ? rsqrt(d) : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < l; r += 32) {
+    const double sc = scale[r];
+    for (int c = r + tx; c < l; c += 32) {
+      const double v = Rw[r * ld_r + c];
+      Rw[r * ld_r + c] = (c == r) ? (sc > 0.0 ? v * sc : 1e150) : v * sc;
+    }
+  }
+  __syncthreads();
   // inverse by back substitution, one warp per column c:  R * x = e_c
   for (int c = ty; c < l; c += 32) {
     for (int i = c; i >= 0; --i) {
@@ -369,10 +388,12 @@ int era5svd_chol_inv_f64(const double* G, int64_t l, int64_t ldg, double* R, int
   using namespace era5svd;
   ERA5SVD_REQUIRE(G && R && Rinv, "chol_inv: null pointer");
   ERA5SVD_REQUIRE(l > 0 && l <= 8192 && ldg >= l && ldr >= l && ldri >= l, "chol_inv: bad shape l=%lld", (long long)l);
-  const size_t smem = (size_t)(2 * l * (l | 1)) * sizeof(double);
-  const int use_smem = smem <= 220 * 1024;
+  const size_t small = (size_t)(2 * l) * sizeof(double);
+  const size_t full = small + (size_t)(2 * l * (l | 1)) * sizeof(double);
+  const int use_smem = full <= 220 * 1024;
+  const size_t smem = use_smem ? full : small;
   ERA5SVD_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  chol_inv_kernel<<<1, 1024, use_smem ? smem : 0, as_stream(stream)>>>(G, (int)l, ldg, R, ldr, Rinv, ldri, rel_tol, use_smem);
+  chol_inv_kernel<<<1, 1024, smem, as_stream(stream)>>>(G, (int)l, ldg, R, ldr, Rinv, ldri, rel_tol, use_smem);
   return check_launch("chol_inv_kernel");
 }
 

@@ -188,6 +188,8 @@ class CudaOps:
         if Om.dtype != torch.float64 or Om.shape[0] != n:
             raise ValueError("sketch_tf32x3: Om must be float64 (n, l)")
         hp, hld = _mat(Xhi, "Xhi"); lp, lld = _mat(Xlo, "Xlo"); op, old = _mat(Om, "Om")
+        if (Yhi is None) != (Ylo is None):
+            raise ValueError("sketch_tf32x3: Yhi and Ylo go together")
         outs = [t for t in (Y, Yhi, Ylo) if t is not None]
         lds = {_mat(t, "Y")[1] for t in outs}
         if hld != lld or len(lds) != 1:
@@ -195,7 +197,8 @@ class CudaOps:
         ldy = lds.pop()
         nbytes = int(self.lib.era5svd_sketch_tf32x3_workspace_bytes(n, l))
         ws = self._workspace("sketch_tc", nbytes)
-        end = self.timer.start("sketch_tc", bytes=4.0 * (m * n + m * l + n * l), flops=2.0 * m * n * l) if self.timer else None
+        end = self.timer.start("sketch_tc" if n > 2 * l else "apply_basis_tc", bytes=4.0 * (m * n + m * l + n * l),
+                               flops=2.0 * m * n * l) if self.timer else None
         check(self.lib.era5svd_sketch_tf32x3(hp, lp, m, n, hld, op, l, old, Y.data_ptr() if Y is not None else None,
                                              Yhi.data_ptr() if Yhi is not None else None,
                                              Ylo.data_ptr() if Ylo is not None else None, ldy, ws.data_ptr(), ws.numel(),
@@ -216,7 +219,8 @@ class CudaOps:
             raise ValueError("project_tf32x3: hi/lo operands must share their row pitch")
         nbytes = int(self.lib.era5svd_project_tf32x3_workspace_bytes(m, n, l))
         ws = self._workspace("project", nbytes)
-        end = self.timer.start("project_tc", bytes=4.0 * (m * n + m * l) + 8.0 * n * l, flops=2.0 * m * n * l) if self.timer else None
+        end = self.timer.start("project_tc" if n > 2 * l else "gram_tc", bytes=4.0 * (m * n + m * l) + 8.0 * n * l,
+                               flops=2.0 * m * n * l) if self.timer else None
         check(self.lib.era5svd_project_tf32x3(hp, lp, m, n, hld, yhp, ylp, l, yhld, zp, zld, int(accumulate),
                                               ws.data_ptr(), ws.numel(), self._stream()), "era5svd_project_tf32x3")
         if end is not None:

@@ -17,8 +17,8 @@ same Omega_0, q and flip rule but never factorises a TALL matrix inside the powe
     Omega = orth(Omega_0)                                   (n x l, float64, CholeskyQR2)
     q x { Y = X Omega            [tall pass, not normalised]
           Z = X^T Y              [tall pass -> n x l float64, all-reduce over row shards]
-          T = Omega^T Z = Y^T Y  -> eig(T) = W L W^T        (l x l Jacobi)
-          Omega = orth(Z W)      }                          (Rayleigh-Ritz rotation + CholeskyQR2)
+          last iteration only: T = Omega^T Z = Y^T Y = W L W^T (l x l Jacobi), Z <- Z W   (Rayleigh-Ritz)
+          Omega = orth(Z)        }  (CholeskyQR2; shifted CholeskyQR3 after the random start)
     Y = X Omega; Z' = X^T Y; G = Y^T Y                      (last tall passes)
     R = chol(G); B = R^-T Z'^T (= Q^T X with Q = Y R^-1)    (l x n)
     eig(B B^T) -> Uhat, s;  Vt = S^-1 Uhat^T B;  U = Y (R^-1 Uhat)
@@ -73,10 +73,20 @@ class _Blocks:
         return self.X[:, j : j + self.n]
 
 
-def _orth(ops, P: torch.Tensor, rel_tol: float) -> torch.Tensor:
+def _orth(ops, P: torch.Tensor, rel_tol: float, shifted: bool = False) -> torch.Tensor:
     """Orthonormal basis of span(P) for a small (n x l) float64 matrix: column scaling followed by
-    CholeskyQR2 (Gram -> Cholesky -> triangular inverse -> GEMM, twice)."""
+    CholeskyQR2 (Gram -> Cholesky -> triangular inverse -> GEMM, twice).  ``shifted`` prepends one
+    shifted CholeskyQR pass (Fukaya et al., shifted CholeskyQR3): with the shift
+    s = 11 (n l + l (l + 1)) u ||P||^2 the first Cholesky cannot break down, so the procedure is
+    stable for cond(P) up to ~1/u; used after the random start where cond(Z) ~ kappa(X)^2."""
     ops.col_normalize(P)
+    n, l = P.shape
+    if shifted:
+        shift = 11.0 * (n * l + l * (l + 1)) * 1.1e-16 * l      # ||P||_2^2 <= ||P||_F^2 = l
+        G = shift * torch.eye(l, dtype=torch.float64, device=P.device)
+        G = ops.gemm(P, P, transA=True, beta=1.0, C=G)
+        _, Rinv = ops.chol_inv(G, rel_tol)
+        P = ops.gemm(P, Rinv)
     for _ in range(2):
         G = ops.gemm(P, P, transA=True)
         _, Rinv = ops.chol_inv(G, rel_tol)
@@ -150,17 +160,19 @@ def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_
 
     for it in range(n_iter):
         Z = tall_pass(Omega)
-        if it == 0 or it == n_iter - 1:
-            # Rayleigh-Ritz rotation: T = Omega^T Z = Y^T Y (l x l), columns of Z W nearly orthogonal.
-            # Needed after the random start (cond(Z) ~ kappa^2 otherwise) and before the final pass
-            # (well-conditioned Gram of Y); in between Z = X^T X (near-Ritz vectors) stays benign.
+        if it == n_iter - 1:
+            # Rayleigh-Ritz rotation before the final pass: T = Omega^T Z = Y^T Y (l x l) = W L W^T, so
+            # the columns of X (Z W) come out nearly orthogonal and graded (~ sigma_j u_j) and the Gram
+            # matrix of the stored float32 Y is well conditioned after diagonal scaling.
             T = ops.gemm(Omega, Z, transA=True)
             _, W = ops.syevj(T)
             Z = ops.gemm(Z, W)
-        Omega = _orth(ops, Z, 1e-13)
+        # cond(Z) ~ kappa(X)^2 after the random start (shifted CholeskyQR3), <~ kappa(X) afterwards
+        Omega = _orth(ops, Z, 1e-13, shifted=(it == 0 and n_iter > 1))
 
-    Zp = tall_pass(Omega, keep_y=True)                 # n x l
-    G = ops.project(Y, Y, precision=PREC_NATIVE)       # l x l, from the stored (rounded) Y
+    Zp = tall_pass(Omega, keep_y=not use_tc)           # n x l
+    # l x l Gram matrix of the STORED (rounded) Y, so that Q = Y R^-1 is orthonormal for the Y we keep
+    G = ops.project_tf32x3(Yhi, Ylo, Yhi, Ylo) if use_tc else ops.project(Y, Y, precision=PREC_NATIVE)
     comm.allreduce_sum_(G)
     _, Rinv = ops.chol_inv(G, rel_tol)
     B = ops.gemm(Rinv, Zp, transA=True, transB=True)   # l x n  = R^-T Z'^T = Q^T X
@@ -171,7 +183,11 @@ def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_
     ops.scale_rows(Vt, inv_s)
     kk = min(k, l)
     M = ops.gemm(Rinv, Uh[:, :kk])                     # l x k
-    U = ops.sketch(Y, ops.convert(M, tall), None, PREC_NATIVE)   # (m0 * d) x k
+    if use_tc:
+        U = ops.empty((m0 * d, ops.tf32_ldy(kk)), tall)[:, :kk]
+        ops.sketch_tf32x3(Yhi, Ylo, M, U, None, None)            # (m0 * d) x k, Y = Yhi + Ylo exactly
+    else:
+        U = ops.sketch(Y, ops.convert(M, tall), None, PREC_NATIVE)
 
     # svd_flip (extmath.py:964-972): first row of max |U[:, j]| over ALL rows decides the sign
     cands = [ops.col_absmax(U[j * m0 : (j + 1) * m0], j * m0_global + row_offset) for j in range(d)]
