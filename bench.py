@@ -160,7 +160,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("ERA5SVD_PRECISION", "native"), choices=["native", "tf32x3"])
+    ap.add_argument("--precision", default=os.environ.get("ERA5SVD_PRECISION", "tf32x3"), choices=["native", "tf32x3"],
+                    help="tf32x3 (default, headline): tcgen05 3xTF32 passes; native: FP32 FMA passes on the CUDA cores")
     ap.add_argument("--rows", type=int, default=0, help="override points per rank (debug only; invalidates the number)")
     ap.add_argument("--cpu-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -207,9 +208,11 @@ def main():
 
     def step(src_dev, timer=None):
         ops.timer = timer
-        built = build_matrix_device(ops, [src_dev], mean_center=True, scale=False)
+        tc = args.precision == "tf32x3"
+        built = build_matrix_device(ops, [src_dev], mean_center=True, scale=False, split=tc, keep_x=not tc)
         U, s, V = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=1, precision=args.precision,
-                             comm=comm, row_offset=row_offset, m0_global=m_global)
+                             comm=comm, row_offset=row_offset, m0_global=m_global,
+                             split=(built.Xhi, built.Xlo) if tc else None)
         ops.timer = None
         return U, s, V
 

@@ -24,6 +24,7 @@ PROTOTYPES = {
     "era5svd_last_error": (C.c_char_p, []),
     "era5svd_launch_count": (C.c_ulonglong, []),
     "era5svd_build_rows": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _vp, _vp, C.c_uint, _vp, _vp]),
+    "era5svd_build_rows_split": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_uint, _vp, _vp]),
     "era5svd_sketch": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int, _vp]),
     "era5svd_project_workspace_bytes": (_sz, [_int, _i64, _i64, _i64, _int]),
     "era5svd_project": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int, _int, _vp, _sz, _vp]),

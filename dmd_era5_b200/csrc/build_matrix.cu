@@ -15,6 +15,7 @@
 // Algorithmic bytes per element: read 4 (stats) [+4 second stats pass when scaling] + read 4 +
 // write 4 (f32).  See DESIGN.md for the single-read fused variant.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace era5svd {
 
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(256)
 transpose_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t P,
                  Tx* __restrict__ X, int64_t ldx, const Tx* __restrict__ mean,
                  const Tx* __restrict__ stdv, const Tx* __restrict__ weights,
-                 int check_finite, int* __restrict__ nonfinite_flag) {
+                 int check_finite, int* __restrict__ nonfinite_flag,
+                 float* __restrict__ Xhi, float* __restrict__ Xlo) {
   __shared__ Ts tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
   const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -102,7 +104,12 @@ transpose_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t 
       Tx v = mean ? centre<Ts, Tx>(raw, mean[p]) : (Tx)raw;
       if (stdv) v = v / stdv[p];
       if (weights) v = v * weights[p];
-      X[p * ldx + t] = v;
+      if (X) X[p * ldx + t] = v;
+      if (Xhi) {   // tf32 hi / lo images for the tensor-core passes (float32 matrices only)
+        const float h = tc::tf32_hi((float)v);
+        Xhi[p * ldx + t] = h;
+        Xlo[p * ldx + t] = (float)v - h;
+      }
     }
   }
   if (check_finite) {
@@ -114,7 +121,7 @@ transpose_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t 
 template <typename Ts, typename Tx>
 int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void* X, int64_t ldx,
                     void* mean_out, void* std_out, const void* weights, unsigned flags,
-                    int* nonfinite_flag, cudaStream_t st) {
+                    int* nonfinite_flag, cudaStream_t st, float* Xhi = nullptr, float* Xlo = nullptr) {
   const bool center = flags & ERA5SVD_BUILD_MEAN_CENTER;
   const bool scale = flags & ERA5SVD_BUILD_SCALE;
   const bool check = (flags & ERA5SVD_BUILD_CHECK_FINITE) && nonfinite_flag;
@@ -131,7 +138,7 @@ int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void*
   transpose_kernel<Ts, Tx><<<grid, block, 0, st>>>(
       (const Ts*)src, T, src_ld, P, (Tx*)X, ldx, center ? (const Tx*)mean_out : nullptr,
       (center && scale) ? (const Tx*)std_out : nullptr, (const Tx*)weights, check ? 1 : 0,
-      nonfinite_flag);
+      nonfinite_flag, Xhi, Xlo);
   return check_launch("transpose_kernel");
 }
 
@@ -159,4 +166,24 @@ extern "C" int era5svd_build_rows(const void* src, int dtype_src, int64_t T, int
   if (dtype_src == ERA5SVD_F32 && dtype_x == ERA5SVD_F64)
     return build_rows_impl<float, double>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st);
   return build_rows_impl<double, float>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st);
+}
+
+extern "C" int era5svd_build_rows_split(const void* src, int dtype_src, int64_t T, int64_t src_ld,
+                                        int64_t P, float* X, float* Xhi, float* Xlo, int64_t ldx,
+                                        float* mean_out, float* std_out, const float* weights,
+                                        unsigned flags, int* nonfinite_flag, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(src && Xhi && Xlo, "build_rows_split: null src/Xhi/Xlo");
+  ERA5SVD_REQUIRE(valid_dtype(dtype_src), "build_rows_split: bad dtype");
+  ERA5SVD_REQUIRE(T > 0 && P > 0 && src_ld >= P && ldx >= T, "build_rows_split: bad shape T=%lld P=%lld src_ld=%lld ldx=%lld",
+                  (long long)T, (long long)P, (long long)src_ld, (long long)ldx);
+  ERA5SVD_REQUIRE(ceil_div(T, 32) <= 65535, "build_rows_split: T too large for one launch");
+  if (flags & ERA5SVD_BUILD_SCALE)
+    ERA5SVD_REQUIRE(flags & ERA5SVD_BUILD_MEAN_CENTER, "build_rows_split: SCALE requires MEAN_CENTER");
+  if (flags & ERA5SVD_BUILD_MEAN_CENTER) ERA5SVD_REQUIRE(mean_out, "build_rows_split: mean_out required with MEAN_CENTER");
+  if (flags & ERA5SVD_BUILD_SCALE) ERA5SVD_REQUIRE(std_out, "build_rows_split: std_out required with SCALE");
+  cudaStream_t st = as_stream(stream);
+  if (dtype_src == ERA5SVD_F32)
+    return build_rows_impl<float, float>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st, Xhi, Xlo);
+  return build_rows_impl<double, float>(src, T, src_ld, P, X, ldx, mean_out, std_out, weights, flags, nonfinite_flag, st, Xhi, Xlo);
 }

@@ -213,7 +213,8 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
   const int ldw = use_smem ? (l | 1) : 0;
   double* Rw = use_smem ? smem + 2 * l : R;
   double* Iw = use_smem ? Rw + (size_t)l * ldw : Rinv;
-  const int64_t ld_r = use_smem ? ldw : ldr, ld_i = use_smem ? ldw : ldri;
+  // 32-bit index arithmetic: l <= 8192, so l * ld fits comfortably
+  const int ld_r = use_smem ? ldw : (int)ldr, ld_i = use_smem ? ldw : (int)ldri;
   // copy the upper triangle (symmetrised), zero the strictly lower part
   for (int r = ty; r < l; r += 32)
     for (int c = tx; c < l; c += 32) {
@@ -228,10 +229,13 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
     const double d = Rw[j * ld_r + j];
     // dependent (or non-positive) pivot: the direction is dropped (no update, zero row), never NaN
     const double inv_d = (d > rel_tol * gdiag[j] && d > 0.0) ? 1.0 / d : 0.0;
+    const double* prow = Rw + j * ld_r;
     for (int i = j + 1 + ty; i < l; i += 32) {
-      const double f = Rw[j * ld_r + i] * inv_d;
+      const double f = prow[i] * inv_d;
+      double* row = Rw + i * ld_r;
+      // columns c >= i only, lanes strided: first column handled by lane ((i - j - 1) % 32)
       for (int c = j + 1 + tx; c < l; c += 32)
-        if (c >= i) Rw[i * ld_r + c] -= f * Rw[j * ld_r + c];
+        if (c >= i) row[c] = fma(-f, prow[c], row[c]);
     }
   }
   __syncthreads();

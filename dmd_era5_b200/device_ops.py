@@ -117,6 +117,28 @@ class CudaOps:
         if end is not None:
             end.record()
 
+    def build_rows_split(self, src: torch.Tensor, X: torch.Tensor | None, Xhi: torch.Tensor, Xlo: torch.Tensor,
+                         mean: torch.Tensor | None, std: torch.Tensor | None, weights: torch.Tensor | None,
+                         flags: int, nonfinite_flag: torch.Tensor | None = None) -> None:
+        """Like build_rows for a float32 matrix, writing the tf32 hi / lo images in the same pass
+        (X itself optional).  All outputs share one row pitch."""
+        sp, sld = _mat(src, "src")
+        T, P = src.shape
+        hp, hld = _mat(Xhi, "Xhi"); lp, lld = _mat(Xlo, "Xlo")
+        xp = None
+        if X is not None:
+            xp, xld = _mat(X, "X")
+            if xld != hld:
+                raise ValueError("build_rows_split: X, Xhi, Xlo must share their row pitch")
+        if hld != lld or tuple(Xhi.shape) != (P, T) or Xhi.dtype != torch.float32:
+            raise ValueError("build_rows_split: Xhi / Xlo must be float32 (P, T) with one row pitch")
+        end = self.timer.start("build_rows", bytes=float(T * P) * (src.element_size() + 4)) if self.timer else None
+        check(self.lib.era5svd_build_rows_split(sp, _dt(src), T, sld, P, xp, hp, lp, hld, _vec(mean, "mean"),
+                                                _vec(std, "std"), _vec(weights, "weights"), flags,
+                                                _vec(nonfinite_flag, "flag"), self._stream()), "era5svd_build_rows_split")
+        if end is not None:
+            end.record()
+
     # -- (b) tall passes ---------------------------------------------------------------------
     def sketch(self, X: torch.Tensor, Om: torch.Tensor, Y: torch.Tensor | None = None,
                precision: int = PREC_NATIVE) -> torch.Tensor:

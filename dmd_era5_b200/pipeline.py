@@ -28,32 +28,40 @@ def padded_ld(T: int, dtype: torch.dtype) -> int:
 
 @dataclass
 class BuiltMatrix:
-    X: torch.Tensor                 # (m0_local, T) view into a padded buffer, tall dtype
-    mean: torch.Tensor | None       # (m0_local,) or None
-    std: torch.Tensor | None
-    row_offset: int                 # global index of the first local base row
-    m0_global: int
+    X: torch.Tensor | None          # (m0_local, T) view into a padded buffer, tall dtype (None if only split)
+    Xhi: torch.Tensor | None = None # tf32 hi / lo images (precision "tf32x3"): Xhi + Xlo == X exactly
+    Xlo: torch.Tensor | None = None
+    mean: torch.Tensor | None = None    # (m0_local,) or None
+    std: torch.Tensor | None = None
+    row_offset: int = 0             # global index of the first local base row
+    m0_global: int = 0
     nonfinite: torch.Tensor | None = None
     buffers: list = field(default_factory=list)
 
 
 def build_matrix_device(ops: CudaOps, var_blocks: list[torch.Tensor], *, mean_center: bool, scale: bool,
                         dtype: torch.dtype | None = None, weights: torch.Tensor | None = None,
-                        check_finite: bool = False, comm=None) -> BuiltMatrix:
+                        check_finite: bool = False, comm=None, split: bool = False,
+                        keep_x: bool = True) -> BuiltMatrix:
     """Stack (variable, level) blocks into this rank's rows of the snapshot matrix.
 
     var_blocks : DEVICE tensors (T, P_i) in the native time-major layout, in row order: one per
                  variable (its selected levels flattened to S = L*A*O points) on a single rank, or
                  the pieces of those blocks that fall into this rank's row range (``shard_rows``
                  over the concatenated row index) when the matrix is row-sharded.
+    split      : also write the tf32 hi / lo images for precision "tf32x3" (same pass, float32 only);
+                 keep_x=False then skips X itself (Xhi + Xlo == X exactly, so nothing is lost).
     Reference quirk Q4 (era5_svd.py:389-395): ``scale`` without ``mean_center`` does nothing.
     """
     T = var_blocks[0].shape[0]
     dtype = dtype or var_blocks[0].dtype
     m0 = sum(int(b.shape[1]) for b in var_blocks)
     ld = padded_ld(T, dtype)
-    buf = ops.empty((m0, ld), dtype)
-    X = buf[:, :T]
+    if split and dtype != torch.float32:
+        raise TypeError("split=True needs a float32 snapshot matrix")
+    X = ops.empty((m0, ld), dtype)[:, :T] if (keep_x or not split) else None
+    Xhi = ops.empty((m0, ld), dtype)[:, :T] if split else None
+    Xlo = ops.empty((m0, ld), dtype)[:, :T] if split else None
     do_center = bool(mean_center)
     do_scale = bool(mean_center and scale)
     mean = ops.empty((m0,), dtype) if do_center else None
@@ -63,24 +71,35 @@ def build_matrix_device(ops: CudaOps, var_blocks: list[torch.Tensor], *, mean_ce
     r = 0
     for b in var_blocks:
         P = int(b.shape[1])
-        ops.build_rows(b, X[r : r + P], mean[r : r + P] if do_center else None, std[r : r + P] if do_scale else None,
-                       weights[r : r + P] if weights is not None else None, flags, flag)
+        mu = mean[r : r + P] if do_center else None
+        sd = std[r : r + P] if do_scale else None
+        w = weights[r : r + P] if weights is not None else None
+        if split:
+            ops.build_rows_split(b, X[r : r + P] if X is not None else None, Xhi[r : r + P], Xlo[r : r + P], mu, sd, w,
+                                 flags, flag)
+        else:
+            ops.build_rows(b, X[r : r + P], mu, sd, w, flags, flag)
         r += P
-    return BuiltMatrix(X=X, mean=mean, std=std, row_offset=0, m0_global=m0, nonfinite=flag, buffers=[buf])
+    return BuiltMatrix(X=X, Xhi=Xhi, Xlo=Xlo, mean=mean, std=std, row_offset=0, m0_global=m0, nonfinite=flag)
 
 
-def svd_device(ops: CudaOps, X: torch.Tensor, *, svd_type: str, n_components: int, delay: int = 1,
+def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_components: int, delay: int = 1,
                seed: int | None = None, precision: str = "native", comm=None, row_offset: int = 0,
-               m0_global: int | None = None, n_iter: int | None = None, stats: dict | None = None):
+               m0_global: int | None = None, n_iter: int | None = None, stats: dict | None = None,
+               split: tuple[torch.Tensor, torch.Tensor] | None = None):
     """SVD of the (virtual) delay-embedded matrix whose base rows are X (device, tall dtype).
+    ``split`` = (Xhi, Xlo) passes pre-split tf32 images (precision "tf32x3"); X may then be None.
     Dispatch and error text follow svd_on_era5 (era5_svd.py:247-262)."""
-    n = X.shape[1] - delay + 1
+    ref = X if X is not None else split[0]
+    n = ref.shape[1] - delay + 1
     if svd_type == "standard":
+        if X is None:
+            X = split[0] + split[1]
         return standard_svd_device(ops, X, n_components, delay=delay, comm=comm)
     if svd_type == "randomized":
-        omega0 = draw_omega(n, n_components, seed, X.dtype)
+        omega0 = draw_omega(n, n_components, seed, ref.dtype)
         return randomized_svd_device(ops, X, n_components, omega0, n_iter=n_iter, delay=delay,
                                      precision=PRECISIONS[precision], comm=comm, row_offset=row_offset,
-                                     m0_global=m0_global, stats=stats)
+                                     m0_global=m0_global, stats=stats, split=split)
     msg = f"SVD type {svd_type} is not supported."
     raise ValueError(msg)

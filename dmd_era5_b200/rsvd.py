@@ -73,11 +73,13 @@ class _Blocks:
         return self.X[:, j : j + self.n]
 
 
-def _orth(ops, P: torch.Tensor, rel_tol: float, shifted: bool = False) -> torch.Tensor:
-    """Orthonormal basis of span(P) for a small (n x l) float64 matrix: column scaling followed by
-    CholeskyQR2 (Gram -> Cholesky -> triangular inverse -> GEMM, twice).  ``shifted`` prepends one
-    shifted CholeskyQR pass (Fukaya et al., shifted CholeskyQR3): with the shift
-    s = 11 (n l + l (l + 1)) u ||P||^2 the first Cholesky cannot break down, so the procedure is
+def _orth(ops, P: torch.Tensor, rel_tol: float, shifted: bool = False, passes: int = 1) -> torch.Tensor:
+    """Well-conditioned basis of span(P) for a small (n x l) float64 matrix: column scaling followed by
+    ``passes`` CholeskyQR sweeps (Gram -> Cholesky -> triangular inverse -> GEMM).  The power
+    iteration only needs a WELL-CONDITIONED basis, not an orthonormal one (T = Omega^T Z = Y^T Y and the
+    final Q = Y R^-1 hold for any basis), so one sweep (orthonormal to ~cond(P)^2 u) is enough.
+    ``shifted`` prepends one shifted CholeskyQR pass (Fukaya et al., shifted CholeskyQR3): with the
+    shift s = 11 (n l + l (l + 1)) u ||P||^2 the first Cholesky cannot break down, so the procedure is
     stable for cond(P) up to ~1/u; used after the random start where cond(Z) ~ kappa(X)^2."""
     ops.col_normalize(P)
     n, l = P.shape
@@ -87,27 +89,32 @@ def _orth(ops, P: torch.Tensor, rel_tol: float, shifted: bool = False) -> torch.
         G = ops.gemm(P, P, transA=True, beta=1.0, C=G)
         _, Rinv = ops.chol_inv(G, rel_tol)
         P = ops.gemm(P, Rinv)
-    for _ in range(2):
+    for _ in range(passes):
         G = ops.gemm(P, P, transA=True)
         _, Rinv = ops.chol_inv(G, rel_tol)
         P = ops.gemm(P, Rinv)
     return P
 
 
-def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_iter: int | None = None,
+def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0, *, n_iter: int | None = None,
                           delay: int = 1, precision: int = PREC_NATIVE, comm=None, row_offset: int = 0,
-                          m0_global: int | None = None, m_global: int | None = None, stats: dict | None = None):
+                          m0_global: int | None = None, m_global: int | None = None, stats: dict | None = None,
+                          split: tuple[torch.Tensor, torch.Tensor] | None = None):
     """Randomized SVD of the (row-sharded, optionally delay-embedded) snapshot matrix.
 
     X          : this rank's rows of the BASE matrix, (m0_local, T) tall-dtype device tensor
     omega0     : (n, l) test matrix (host ndarray or tensor), n = T - delay + 1
     row_offset : global index of this rank's first base row; m0_global: total base rows
+    split      : (Xhi, Xlo) pre-split tf32 images of X for precision tf32x3 (X may then be None)
     Returns (U_local (m0_local * delay, k) tall dtype, s (k,) float64, Vt (k, n) float64).
     Rows of U_local are ordered block-major: block j holds rows [j * m0_local, (j + 1) * m0_local),
     i.e. global rows j * m0_global + row_offset + r.
     """
     comm = comm or LocalComm()
-    blocks = _Blocks(X, delay)
+    if X is None:
+        if split is None or precision != PREC_TF32X3:
+            raise ValueError("X may only be omitted when pre-split images are given with precision tf32x3")
+    blocks = _Blocks(X if X is not None else split[0], delay)
     m0, n, d = blocks.m0, blocks.n, delay
     m0_global = m0 if m0_global is None else m0_global
     m_global = m0_global * d if m_global is None else m_global
@@ -119,7 +126,7 @@ def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_
     om = om[:, :l].contiguous()
     if n_iter is None:
         n_iter = n_iter_auto(m_global, n, k)
-    tall = X.dtype
+    tall = blocks.X.dtype
     rel_tol = 1e-13 if tall == torch.float64 else 1e-6
     Omega = _orth(ops, ops.to_device(om, non_blocking=False).clone(), 1e-13)
 
@@ -130,7 +137,7 @@ def randomized_svd_device(ops, X: torch.Tensor, n_components: int, omega0, *, n_
             raise TypeError("precision 'tf32x3' needs a float32 snapshot matrix")
         if l > 128:
             raise ValueError(f"precision 'tf32x3' supports sketch widths up to 128, got l = {l}")
-        Xhi, Xlo = ops.split_tf32(X)
+        Xhi, Xlo = split if split is not None else ops.split_tf32(X)
         ldy = ops.tf32_ldy(l)
         Y = ops.empty((m0 * d, ldy), tall)[:, :l]
         Yhi = ops.empty((m0 * d, ldy), tall)[:, :l]

@@ -80,6 +80,13 @@ int era5svd_build_rows(const void* src, int dtype_src, int64_t T, int64_t src_ld
                        void* X, int dtype_x, int64_t ldx, void* mean_out, void* std_out,
                        const void* weights, unsigned flags, int* nonfinite_flag, void* stream);
 
+/* Same build, float32 matrix, writing the tf32 hi / lo images the tensor-core passes consume
+ * (Xhi + Xlo == X exactly) in the same pass; X itself is optional (nullable). */
+int era5svd_build_rows_split(const void* src, int dtype_src, int64_t T, int64_t src_ld, int64_t P,
+                             float* X, float* Xhi, float* Xlo, int64_t ldx, float* mean_out,
+                             float* std_out, const float* weights, unsigned flags,
+                             int* nonfinite_flag, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (b) tall GEMM passes of the randomized range finder.
  *

@@ -86,6 +86,27 @@ def test_randomized_tf32x3_vs_oracle(d):
     assert abs(recon_rel_err(Xd, U, s, V) - ref) <= 0.01 * ref
 
 
+def test_fused_build_split_pipeline(ops):
+    """Native layout -> (centre, transpose, tf32 split) in one pass -> SVD without materialising X."""
+    from dmd_era5_b200.pipeline import build_matrix_device, svd_device
+    from dmd_era5_b200.synthetic import synthetic_field
+
+    field = synthetic_field(200, 30000, device="cuda", seed=3, rank=60, rho=0.85)
+    ref = build_matrix_device(ops, [field], mean_center=True, scale=True)
+    both = build_matrix_device(ops, [field], mean_center=True, scale=True, split=True, keep_x=True)
+    only = build_matrix_device(ops, [field], mean_center=True, scale=True, split=True, keep_x=False)
+    assert only.X is None
+    assert torch.equal(both.X, ref.X) and torch.equal(both.Xhi + both.Xlo, ref.X)
+    assert torch.equal(only.Xhi, both.Xhi) and torch.equal(only.Xlo, both.Xlo)
+    assert torch.equal(only.mean, ref.mean) and torch.equal(only.std, ref.std)
+    U1, s1, V1 = svd_device(ops, ref.X, svd_type="randomized", n_components=20, seed=2, precision="tf32x3")
+    U2, s2, V2 = svd_device(ops, None, svd_type="randomized", n_components=20, seed=2, precision="tf32x3",
+                            split=(only.Xhi, only.Xlo))
+    assert torch.equal(s1, s2) and torch.equal(U1, U2)            # same kernels, same bits
+    U0, s0, V0 = randomized_svd_ref(ref.X.double().cpu().numpy(), 20, 2)
+    assert sigma_rel_err(s2.cpu().numpy(), s0) < 1e-4
+
+
 def test_svd_on_era5_tf32x3_api():
     X = lowrank_field_np(8192, 200, r=60, rho=0.85, seed=5, dtype=np.float32)
     U0, s0, V0 = randomized_svd_ref(X.astype(np.float64), 20, 4)
