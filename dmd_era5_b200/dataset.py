@@ -1,0 +1,218 @@
+"""Minimal labelled-array containers + NetCDF I/O for the SVD stage's inputs and outputs.
+
+The reference packages everything in xarray objects (src/dmd_era5/era5_svd/era5_svd.py:266-333) and
+writes ``to_netcdf(..., format="NETCDF4")`` (:434).  xarray / netCDF4 / h5py are not installable in
+this image, so the stage carries its own small containers with the same vocabulary
+(dims, coords, attrs, data_vars) and converts to real xarray objects when xarray is importable
+(``Dataset.to_xarray()``, ``write_netcdf`` then uses xarray's NETCDF4 writer = the reference's file
+layout).  Without xarray, files are written / read as NetCDF-3 64-bit-offset through
+``scipy.io.netcdf_file`` with the same variable / dimension / attribute schema; NetCDF-3 cannot hold
+int64, string arrays or list-of-string attributes, so: int64 -> int32, str coords -> char arrays,
+list[str] attrs -> one comma-joined string (split again on read), datetime64 -> CF "seconds since".
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class DataArray:
+    def __init__(self, values, dims, coords: dict | None = None, attrs: dict | None = None, name: str | None = None):
+        self.values = values if hasattr(values, "shape") else np.asarray(values)
+        self.dims = tuple(dims)
+        if len(self.dims) != self.values.ndim:
+            raise ValueError(f"dims {self.dims} do not match a {self.values.ndim}-D array")
+        # coords: name -> (dims tuple, 1-D ndarray)
+        self.coords: dict[str, tuple[tuple[str, ...], np.ndarray]] = {}
+        for k, v in (coords or {}).items():
+            self.coords[k] = (tuple(v[0]) if isinstance(v[0], (tuple, list)) else (v[0],), np.asarray(v[1])) \
+                if isinstance(v, tuple) else ((k,), np.asarray(v))
+        self.attrs = dict(attrs or {})
+        self.name = name
+
+    @property
+    def shape(self):
+        return tuple(self.values.shape)
+
+    @property
+    def sizes(self):
+        return dict(zip(self.dims, self.shape))
+
+    def coord(self, name: str) -> np.ndarray:
+        return self.coords[name][1]
+
+
+class Dataset:
+    def __init__(self, data_vars: dict | None = None, coords: dict | None = None, attrs: dict | None = None):
+        self.data_vars: dict[str, DataArray] = dict(data_vars or {})
+        self.coords: dict[str, tuple[tuple[str, ...], np.ndarray]] = {}
+        for k, v in (coords or {}).items():
+            self.coords[k] = (tuple(v[0]) if isinstance(v[0], (tuple, list)) else (v[0],), np.asarray(v[1])) \
+                if isinstance(v, tuple) else ((k,), np.asarray(v))
+        for da in self.data_vars.values():
+            for k, v in da.coords.items():
+                self.coords.setdefault(k, v)
+        self.attrs = dict(attrs or {})
+
+    def __getitem__(self, key):
+        if isinstance(key, (list, tuple)):
+            return Dataset({k: self.data_vars[k] for k in key}, self.coords, self.attrs)
+        return self.data_vars[key]
+
+    def __contains__(self, key):
+        return key in self.data_vars
+
+    @property
+    def sizes(self):
+        out = {}
+        for da in self.data_vars.values():
+            out.update(da.sizes)
+        for k, (dims, v) in self.coords.items():
+            if dims == (k,):
+                out.setdefault(k, v.shape[0])
+        return out
+
+    def coord(self, name: str) -> np.ndarray:
+        return self.coords[name][1]
+
+    def to_xarray(self):
+        import xarray as xr  # only when available
+
+        dv = {k: xr.DataArray(np.asarray(v.values), dims=v.dims, attrs=v.attrs) for k, v in self.data_vars.items()}
+        return xr.Dataset(dv, coords={k: (d, v) for k, (d, v) in self.coords.items()}, attrs=self.attrs)
+
+
+# ------------------------------------------------------------------------------------------------
+# NetCDF I/O
+# ------------------------------------------------------------------------------------------------
+_EPOCH = np.datetime64("1970-01-01T00:00:00", "s")
+
+
+def _have_xarray() -> bool:
+    try:
+        import xarray  # noqa: F401
+        import netCDF4  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def _encode_attr(v):
+    if isinstance(v, bool):
+        return int(v)
+    if isinstance(v, (list, tuple)):
+        if all(isinstance(x, str) for x in v):
+            return ",".join(v)
+        return np.asarray(v, dtype=np.int32 if all(isinstance(x, (int, np.integer)) for x in v) else np.float64)
+    if isinstance(v, (np.integer,)):
+        return int(v)
+    return v
+
+
+def _netcdf3(path: str, mode: str, **kw):
+    """scipy's netcdf_file mirrors every global attribute onto the instance, so an attribute named
+    "variables" (the reference's schema has one) would shadow ``netcdf_file.variables``; keep such
+    names in the attribute table only."""
+    from scipy.io import netcdf_file
+
+    class _File(netcdf_file):
+        def __setattr__(self, attr, value):
+            if attr in ("variables", "dimensions") and not isinstance(value, dict) and "_attributes" in self.__dict__:
+                self._attributes[attr] = value
+                return
+            super().__setattr__(attr, value)
+
+    return _File(path, mode, **kw)
+
+
+def write_netcdf(ds: Dataset, path: str) -> str:
+    """Write ``ds``; returns the format used ("NETCDF4" through xarray, else "NETCDF3_64BIT")."""
+    import os
+
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    if _have_xarray():
+        ds.to_xarray().to_netcdf(path, format="NETCDF4")     # the reference's call, era5_svd.py:434
+        return "NETCDF4"
+    with _netcdf3(path, "w", version=2) as f:
+        sizes = ds.sizes
+        strlen_dims = {}
+        for name, size in sizes.items():
+            f.createDimension(name, int(size))
+
+        def put(name, dims, arr, attrs=None):
+            arr = np.asarray(arr)
+            extra = {}
+            if np.issubdtype(arr.dtype, np.datetime64):
+                arr = (arr.astype("datetime64[s]") - _EPOCH).astype(np.float64)
+                extra = {"units": "seconds since 1970-01-01 00:00:00", "calendar": "proleptic_gregorian"}
+            if arr.dtype.kind in ("U", "O", "S"):
+                strs = np.asarray([str(x) for x in arr.ravel()], dtype="S")
+                n = strs.dtype.itemsize
+                dname = f"string{n}"
+                if dname not in strlen_dims:
+                    f.createDimension(dname, n)
+                    strlen_dims[dname] = n
+                var = f.createVariable(name, "c", tuple(dims) + (dname,))
+                var[:] = strs.view("S1").reshape(arr.shape + (n,))
+            else:
+                if arr.dtype == np.int64:
+                    arr = arr.astype(np.int32)
+                if arr.dtype == np.bool_:
+                    arr = arr.astype(np.int8)
+                var = f.createVariable(name, arr.dtype, tuple(dims))
+                var[:] = arr
+            for k, v in {**(attrs or {}), **extra}.items():
+                var._attributes[k] = _encode_attr(v)
+
+        for name, (dims, arr) in ds.coords.items():
+            put(name, dims, arr)
+        for name, da in ds.data_vars.items():
+            put(name, da.dims, da.values, da.attrs)
+        # straight into the attribute table: an attribute called "variables" (the reference's schema has
+        # one) must not shadow netcdf_file.variables
+        for k, v in ds.attrs.items():
+            f._attributes[k] = _encode_attr(v)
+        f._attributes["coordinates_hint"] = " ".join(ds.coords)   # which variables are coordinates (for read_netcdf)
+    return "NETCDF3_64BIT"
+
+
+def _decode_attr(k, v):
+    if isinstance(v, bytes):
+        v = v.decode()
+    if isinstance(v, np.ndarray) and v.ndim == 0:
+        v = v.item()
+    return v
+
+
+def read_netcdf(path: str) -> Dataset:
+    """Read a file written by ``write_netcdf`` (or any NetCDF the available backend can open)."""
+    if _have_xarray():
+        import xarray as xr
+
+        x = xr.open_dataset(path)
+        dv = {k: DataArray(v.values, v.dims, attrs=dict(v.attrs)) for k, v in x.data_vars.items()}
+        co = {k: (tuple(v.dims), v.values) for k, v in x.coords.items()}
+        return Dataset(dv, co, dict(x.attrs))
+    with _netcdf3(path, "r", mmap=False) as f:
+        attrs = {k: _decode_attr(k, v) for k, v in f._attributes.items()}
+        coord_names = set(str(attrs.pop("coordinates_hint", "")).split())
+        dv, co = {}, {}
+        for name, var in f.variables.items():
+            arr = np.array(var[:])
+            if arr.dtype.byteorder == ">":                      # NetCDF-3 is big-endian on disk
+                arr = arr.astype(arr.dtype.newbyteorder("="))
+            dims = tuple(var.dimensions)
+            vattrs = {k: _decode_attr(k, v) for k, v in var._attributes.items()}
+            if arr.dtype.kind == "S" and dims and dims[-1].startswith("string"):
+                arr = np.array([b"".join(row).decode().rstrip("\x00") for row in arr.reshape(-1, arr.shape[-1])],
+                               dtype=object).reshape(arr.shape[:-1])
+                arr = arr.astype(str)
+                dims = dims[:-1]
+            units = str(vattrs.get("units", ""))
+            if units.startswith("seconds since 1970-01-01"):
+                arr = (_EPOCH + arr.astype(np.int64).astype("timedelta64[s]")).astype("datetime64[ns]")
+                vattrs = {k: v for k, v in vattrs.items() if k not in ("units", "calendar")}
+            if name in coord_names or dims == (name,):
+                co[name] = (dims, arr)
+            else:
+                dv[name] = DataArray(arr, dims, attrs=vattrs)
+    return Dataset(dv, co, attrs)

@@ -91,3 +91,17 @@ def svd_on_era5(da, parsed_config: dict) -> tuple[np.ndarray, np.ndarray, np.nda
         V_h = V.to(out_dtype).cpu().numpy()
     log_and_print(logger, f"{label.capitalize()} SVD complete.")
     return U_h, s_h, V_h
+
+
+# Orchestration / packaging names of the reference's era5_svd module live in stage.py (which imports
+# from this module), so they are re-exported lazily to keep the reference's import surface:
+#   from dmd_era5_b200.era5_svd import main, combine_svd_results, add_config_attributes, ...
+_STAGE_NAMES = ("main", "combine_svd_results", "add_config_attributes", "retrieve_era5_slice", "retrieve_svd_results")
+
+
+def __getattr__(name):
+    if name in _STAGE_NAMES:
+        from . import stage
+
+        return getattr(stage, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -1,0 +1,254 @@
+"""Orchestration and packaging of the SVD stage - the reference's ``era5_svd.main`` and helpers
+(src/dmd_era5/era5_svd/era5_svd.py:42-227, 266-453) with the compute phase replaced by the fused
+device pipeline.  Same signatures, return tuple, phase-wrapped error messages, attribute schema and
+output layout (README.md:97-119): data_vars U (space, components), s (components), V (components,
+time), optional X, X_mean, X_std; coords space, components, time, original_variable, delay, level,
+latitude, longitude.
+
+DVC plumbing (dvc_tools.py) is out of scope for this build: ``use_dvc=True`` logs a warning and
+behaves like the reference when its DVC retrieval fails (falls through to compute / no add).
+"""
+from __future__ import annotations
+
+import os
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from .config_parser import config_parser
+from .dataset import DataArray, Dataset, read_netcdf, write_netcdf
+from .era5_svd import get_ops, log_and_print, logger
+from .pipeline import build_matrix_device, svd_device
+from .slice_tools import resample_era5_dataset, slice_era5_dataset, space_coord_to_level_lat_lon, space_coords
+
+
+def add_config_attributes(ds: Dataset, parsed_config: dict) -> Dataset:
+    """era5_svd.py:42-66."""
+    a = ds.attrs
+    a["source_path"] = parsed_config["source_path"]
+    a["n_components"] = parsed_config["n_components"]
+    a["variables"] = parsed_config["variables"]
+    a["levels"] = parsed_config["levels"]
+    a["mean_center"] = int(parsed_config["mean_center"])
+    a["scale"] = int(parsed_config["scale"])
+    a["delay_embedding"] = parsed_config["delay_embedding"]
+    a["svd_type"] = parsed_config["svd_type"]
+    a["era5_slice_path"] = parsed_config["era5_slice_path"]
+    a["date_processed"] = datetime.now().isoformat()
+    a["save_data_matrix"] = int(parsed_config["save_data_matrix"])
+    return ds
+
+
+def _as_str_list(obj) -> list[str]:
+    if isinstance(obj, (list, tuple, np.ndarray)):
+        return [str(x) for x in obj]
+    return [s for s in str(obj).split(",")]
+
+
+def _as_int_list(obj) -> list[int]:
+    """era5_svd.py:90-99: levels stored as a (possibly length-1) integer array."""
+    if isinstance(obj, (int, np.integer)):
+        return [int(obj)]
+    arr = np.asarray(obj)
+    if not np.issubdtype(arr.dtype, np.integer):
+        raise ValueError("Levels must be integers.")
+    return [int(x) for x in arr.ravel().tolist()]
+
+
+def _dvc_unavailable(what: str):
+    log_and_print(logger, f"Could not retrieve {what} from DVC: DVC plumbing is not part of this build", "warning")
+
+
+def retrieve_era5_slice(parsed_config: dict, use_dvc: bool = False):
+    """era5_svd.py:69-154: slice in the working directory whose attrs cover the request
+    (superset match on variables / levels, equal source_path)."""
+    path = parsed_config["era5_slice_path"]
+    if os.path.exists(path):
+        log_and_print(logger, "ERA5 slice found in working directory.")
+        ds = read_netcdf(path)
+        a = ds.attrs
+        ok = (sorted(parsed_config["variables"]) == sorted(set(_as_str_list(a["variables"])) & set(parsed_config["variables"]))
+              and sorted(parsed_config["levels"]) == sorted(set(_as_int_list(a["levels"])) & set(parsed_config["levels"]))
+              and parsed_config["source_path"] == a["source_path"])
+        if ok:
+            log_and_print(logger, "ERA5 slice matches configuration.")
+            return ds, False
+        log_and_print(logger, "ERA5 slice does not match configuration.")
+        if use_dvc:
+            _dvc_unavailable("ERA5 slice")
+        else:
+            log_and_print(logger, "ERA5 slice in working directory does not match configuration.", "warning")
+        return None, False
+    log_and_print(logger, "ERA5 slice not found in working directory.", "warning")
+    if use_dvc:
+        _dvc_unavailable("ERA5 slice")
+    return None, False
+
+
+def retrieve_svd_results(parsed_config: dict, use_dvc: bool = False):
+    """era5_svd.py:157-227: result-level memoisation; matches on the same seven attributes as the
+    reference (svd_type and save_data_matrix are NOT compared - quirk Q5)."""
+    path = parsed_config["save_path"]
+    if os.path.exists(path):
+        log_and_print(logger, "SVD results found in working directory.")
+        ds = read_netcdf(path)
+        a = ds.attrs
+        ok = (parsed_config["source_path"] == a["source_path"] and parsed_config["n_components"] == a["n_components"]
+              and parsed_config["variables"] == _as_str_list(a["variables"])
+              and parsed_config["levels"] == _as_int_list(a["levels"])
+              and parsed_config["mean_center"] == a["mean_center"] and parsed_config["scale"] == a["scale"]
+              and parsed_config["delay_embedding"] == a["delay_embedding"])
+        if ok:
+            log_and_print(logger, "SVD results match configuration.")
+            return ds, False
+        log_and_print(logger, "SVD results do not match configuration.")
+        if use_dvc:
+            _dvc_unavailable("SVD results")
+        else:
+            log_and_print(logger, "SVD results in working directory do not match configuration.", "warning")
+        return None, False
+    log_and_print(logger, "SVD results not found in working directory.", "warning")
+    if use_dvc:
+        _dvc_unavailable("SVD results")
+    return None, False
+
+
+def combine_svd_results(U, s, V, coords: dict, **kwargs) -> Dataset:
+    """era5_svd.py:266-333.  ``coords`` = coords of the (delay-embedded) matrix: space, time,
+    original_variable, delay (+ level / latitude / longitude carried along)."""
+    k = U.shape[1]
+    space_co = {name: coords[name] for name in ("space", "original_variable", "delay", "level", "latitude", "longitude")
+                if name in coords}
+    dv = {
+        "U": DataArray(U, ("space", "components"), {**space_co, "components": np.arange(k)}),
+        "s": DataArray(s, ("components",), {"components": np.arange(s.shape[0])}),
+        "V": DataArray(V, ("components", "time"), {"components": np.arange(V.shape[0]), "time": coords["time"]}),
+    }
+    for name, dims in (("X", ("space", "time")), ("X_mean", ("space",)), ("X_std", ("space",))):
+        val = kwargs.get(name)
+        if val is not None:
+            dv[name] = val if isinstance(val, DataArray) else DataArray(val, dims)
+    all_coords = dict(coords)
+    all_coords["components"] = (("components",), np.arange(k))
+    return Dataset(dv, all_coords)
+
+
+def _to_blocks(ds: Dataset, variables: list[str], ops) -> tuple[list[torch.Tensor], int]:
+    """Host (T, L, A, O) arrays of the selected variables -> device (T, S) native-layout blocks."""
+    blocks = []
+    for v in variables:
+        da = ds[v]
+        a = np.transpose(np.asarray(da.values), [da.dims.index(dm) for dm in ("time", "level", "latitude", "longitude")])
+        T = a.shape[0]
+        t = torch.from_numpy(np.ascontiguousarray(a.reshape(T, -1)))
+        blocks.append(t.pin_memory().to(ops.device, non_blocking=True) if t.numel() >= 1 << 16 else t.to(ops.device))
+    return blocks, blocks[0].shape[1]
+
+
+def main(config: dict | None = None, write_to_netcdf: bool = False, use_dvc: bool = False):
+    """era5_svd.py:336-453.  Returns (svd_results, added_to_dvc, retrieved_from_dvc)."""
+    if config is None:
+        from .config_parser import config_reader
+
+        config = config_reader("era5-svd")        # the reference reads config.ini at import (quirk Q8)
+    added_to_dvc = False
+    parsed_config = config_parser(config, "era5-svd")
+    try:
+        svd_results, retrieved_from_dvc = retrieve_svd_results(parsed_config, use_dvc)
+    except Exception as e:
+        msg = f"Error retrieving SVD results: {e}"
+        log_and_print(logger, msg, "error")
+        raise Exception(msg) from e
+
+    if svd_results is None:
+        try:
+            ds, _ = retrieve_era5_slice(parsed_config, use_dvc)
+            if ds is None:
+                msg = ("Could not retrieve ERA5 slice from working directory or DVC." if use_dvc else
+                       "\n                    Could not retrieve ERA5 slice from working directory.\n"
+                       "                    Consider using DVC to retrieve the ERA5 slice, if available.\n                    ")
+                log_and_print(logger, msg, "error")
+                raise FileNotFoundError(msg)
+        except Exception as e:
+            msg = f"Error retrieving ERA5 slice: {e}"
+            log_and_print(logger, msg, "error")
+            raise Exception(msg) from e
+        try:
+            svd_results = _compute(ds, parsed_config)
+        except Exception as e:
+            msg = f"Error in the SVD on ERA5 process: {e}"
+            log_and_print(logger, msg, "error")
+            raise Exception(msg) from e
+
+        if write_to_netcdf:
+            try:
+                log_and_print(logger, "Writing SVD results to NetCDF...")
+                write_netcdf(svd_results, parsed_config["save_path"])
+                log_and_print(logger, f"SVD results written to {parsed_config['save_path']}")
+            except Exception as e:
+                msg = f"Error writing SVD results to NetCDF: {e}"
+                log_and_print(logger, msg, "error")
+                raise Exception(msg) from e
+            if use_dvc:
+                log_and_print(logger, "DVC plumbing is not part of this build: results were not added to DVC.", "warning")
+    return svd_results, added_to_dvc, retrieved_from_dvc
+
+
+def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
+    """The compute phase of main (era5_svd.py:384-425) on the device."""
+    variables, d = parsed_config["variables"], parsed_config["delay_embedding"]
+    ds = ds[variables]                                                   # config order (:384)
+    ds = slice_era5_dataset(ds, levels=parsed_config["levels"])          # (:385) no start/end: quirk Q7
+    ds = resample_era5_dataset(ds, parsed_config["delta_time"])          # (:388)
+    mean_center = bool(parsed_config["mean_center"])
+    scale = bool(parsed_config["scale"]) and mean_center                 # quirk Q4 (:389-395)
+    ops = get_ops(parsed_config.get("device", "cuda:0"))
+    precision = parsed_config.get("precision", "native")
+    with torch.cuda.device(ops.device):
+        blocks, S = _to_blocks(ds, variables, ops)
+        tc = precision == "tf32x3" and blocks[0].dtype == torch.float32 and parsed_config["svd_type"] == "randomized"
+        weights = None
+        if parsed_config.get("area_weighting"):                          # opt-in extension (absent in the reference)
+            lat = np.deg2rad(np.asarray(ds.coord("latitude"), dtype=np.float64))
+            w = np.sqrt(np.clip(np.cos(lat), 0.0, None))
+            L, O = len(ds.coord("level")), len(ds.coord("longitude"))
+            w_rows = np.tile(np.tile(np.repeat(w, O), L), len(variables))
+            weights = torch.from_numpy(w_rows.astype(np.float32 if blocks[0].dtype == torch.float32 else np.float64)).to(ops.device)
+        built = build_matrix_device(ops, blocks, mean_center=mean_center, scale=scale, weights=weights,
+                                    check_finite=True, split=tc, keep_x=True)
+        label = "standard" if parsed_config["svd_type"] == "standard" else "randomized"
+        log_and_print(logger, f"Performing {label} SVD...")
+        U, s, V = svd_device(ops, built.X, svd_type=parsed_config["svd_type"], n_components=parsed_config["n_components"],
+                             delay=d, seed=parsed_config.get("random_seed"), precision=precision if tc else "native",
+                             split=(built.Xhi, built.Xlo) if tc else None)
+        log_and_print(logger, f"{label.capitalize()} SVD complete.")
+        if int(built.nonfinite.item()):
+            raise ValueError("Input contains NaN or infinity.")          # sklearn check_array (extmath.py:546)
+        dt = built.X.dtype
+        U_h, s_h, V_h = U.to(dt).cpu().numpy(), s.to(dt).cpu().numpy(), V.to(dt).cpu().numpy()
+        X_h = built.X.cpu().numpy() if parsed_config["save_data_matrix"] else None
+        mean_h = built.mean.cpu().numpy() if built.mean is not None else None
+        std_h = built.std.cpu().numpy() if built.std is not None else None
+
+    m0 = len(variables) * S
+    times = ds.coord("time")
+    lev, lat, lon = space_coords(ds.coord("level"), ds.coord("latitude"), ds.coord("longitude"), len(variables), d)
+    coords = {
+        "space": (("space",), np.arange(m0 * d)),
+        "time": (("time",), times[d - 1:]),
+        "original_variable": (("space",), np.tile(np.repeat(variables, S), d)),
+        "delay": (("space",), np.repeat(np.flip(np.arange(d)), m0)),
+        "level": (("space",), lev), "latitude": (("space",), lat), "longitude": (("space",), lon),
+    }
+    extra = {}
+    if X_h is not None:
+        n = X_h.shape[1] - d + 1
+        extra["X"] = np.concatenate([X_h[:, j : j + n] for j in range(d)], axis=0)
+    if mean_h is not None and d > 1:                                     # quirk Q3 (:400-414): dropped when d == 1
+        extra["X_mean"] = np.concatenate([mean_h] * d)
+        if std_h is not None:
+            extra["X_std"] = np.concatenate([std_h] * d)
+    out = combine_svd_results(U_h, s_h, V_h, coords, **extra)
+    out = add_config_attributes(out, parsed_config)
+    return space_coord_to_level_lat_lon(out)

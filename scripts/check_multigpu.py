@@ -1,0 +1,69 @@
+"""Row-sharded randomized SVD over NCCL vs the single-process oracle.
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/check_multigpu.py
+
+Every rank builds the same host matrix, keeps its row shard (delay-embedded, d = 2), runs the device
+driver with the NCCL communicator, and rank 0 compares the gathered U / s / V with sklearn's
+randomized_svd (float64) on the full matrix."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from dmd_era5_b200.device_ops import CudaOps
+from dmd_era5_b200.dist import TorchDistComm, shard_rows
+from dmd_era5_b200.pipeline import svd_device
+from oracle.compare import sigma_rel_err, signs_agree, vector_angles
+from oracle.slice_tools_np import delay_embed_np
+from oracle.svd_ref import randomized_svd_ref
+from oracle.synthetic_np import lowrank_field_np
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = TorchDistComm()
+    ops = CudaOps(f"cuda:{local}")
+    m0, T, k, d = 8192 * world + 77, 300, 24, 2
+    X = lowrank_field_np(m0, T, r=80, rho=0.9, seed=11, dtype=np.float32)
+    r0, r1 = shard_rows(m0, world, rank)
+    out = {}
+    for precision, tol in (("native", 1e-4), ("tf32x3", 1e-4)):
+        Xd = torch.from_numpy(X[r0:r1].copy()).cuda()
+        U, s, V = svd_device(ops, Xd, svd_type="randomized", n_components=k, delay=d, seed=5, precision=precision,
+                             comm=comm, row_offset=r0, m0_global=m0)
+        # gather the (unequal) shards of U on rank 0: pad to the largest shard
+        ml = torch.tensor([r1 - r0], device="cuda")
+        sizes = [torch.zeros_like(ml) for _ in range(world)]
+        dist.all_gather(sizes, ml)
+        mx = int(max(x.item() for x in sizes))
+        pad = torch.zeros((d, mx, k), device="cuda", dtype=U.dtype)
+        pad[:, : r1 - r0] = U.reshape(d, r1 - r0, k)
+        parts = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        if rank == 0:
+            Ufull = np.zeros((m0 * d, k))
+            for rk, (p, sz) in enumerate(zip(parts, sizes)):
+                a0, a1 = shard_rows(m0, world, rk)
+                for j in range(d):
+                    Ufull[j * m0 + a0 : j * m0 + a1] = p[j, : int(sz.item())].double().cpu().numpy()
+            U0, s0, V0 = randomized_svd_ref(delay_embed_np(X.astype(np.float64), d), k, 5)
+            out[precision] = {"sigma_rel_err": sigma_rel_err(s.cpu().numpy(), s0),
+                              "angle_U_max": float(vector_angles(Ufull, U0).max()),
+                              "angle_V_max": float(vector_angles(V.cpu().numpy().T, V0.T).max()),
+                              "signs_agree": signs_agree(Ufull, U0)}
+            out[precision]["pass"] = bool(out[precision]["sigma_rel_err"] < tol and out[precision]["signs_agree"]
+                                          and out[precision]["angle_U_max"] < 2e-2)
+    if rank == 0:
+        out["world"] = world
+        print(json.dumps(out))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+"""GPU: the drop-in `main()` path end to end (slice file -> device build -> SVD -> Dataset -> NetCDF ->
+cache hit), against the oracle's restatement of the reference flow (era5_svd.py:384-425), with the
+presence rules of tests/test_05_dvc_era5_svd.py:326-373 (X iff save_data_matrix, X_mean iff
+mean_center and d > 1, X_std iff scale)."""
+import os
+
+import numpy as np
+import pytest
+
+from dmd_era5_b200.dataset import DataArray, Dataset, read_netcdf, write_netcdf
+from oracle.compare import recon_rel_err, sigma_rel_err, vector_angles
+from oracle.slice_tools_np import build_matrix_np, standardize_np
+from oracle.svd_ref import randomized_svd_ref, standard_svd_ref
+from oracle.synthetic_np import mock_era5_np
+
+pytestmark = pytest.mark.gpu
+
+VARS = ["temperature", "u_component_of_wind"]
+LEVELS = [1000, 850, 500]
+
+
+def make_slice(root, config):
+    """What era5_download writes (era5_download.py:36-42, 114): per-variable (time, level, lat, lon)."""
+    from dmd_era5_b200.config_parser import config_parser
+
+    parsed = config_parser(config, "era5-svd")
+    m = mock_era5_np(25, VARS, LEVELS, seed=4)
+    dv = {k: DataArray(v, ("time", "level", "latitude", "longitude")) for k, v in m["vars"].items()}
+    ds = Dataset(dv, {"time": m["time"], "level": m["level"], "latitude": m["latitude"], "longitude": m["longitude"]},
+                 {"source_path": config["source_path"], "variables": VARS, "levels": LEVELS})
+    write_netcdf(ds, parsed["era5_slice_path"])
+    return m, parsed
+
+
+def base_config(**kw):
+    cfg = {"source_path": "gs://mock", "variables": "u_component_of_wind,temperature", "levels": "850,1000",
+           "svd_type": "randomized", "delay_embedding": 2, "mean_center": True, "scale": False,
+           "start_datetime": "2019-01-01T00", "end_datetime": "2019-01-02T00", "delta_time": "1h",
+           "n_components": 6, "save_data_matrix": True, "random_seed": 3}
+    cfg.update(kw)
+    return cfg
+
+
+def oracle_matrix(m, cfg):
+    # variables and levels in CONFIG order (era5_svd.py:384-385)
+    vs = [v.strip() for v in cfg["variables"].split(",")]
+    lv = [LEVELS.index(int(x)) for x in cfg["levels"].split(",")]
+    arrs = [m["vars"][v][:, lv] for v in vs]
+    return build_matrix_np(arrs, cfg["mean_center"], cfg["scale"], cfg["delay_embedding"])
+
+
+@pytest.mark.parametrize("svd_type,d,mc,sc", [("randomized", 2, True, False), ("standard", 1, True, True),
+                                               ("randomized", 3, False, False)])
+def test_main_end_to_end(tmp_path, monkeypatch, svd_type, d, mc, sc):
+    from dmd_era5_b200.era5_svd import main
+
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    cfg = base_config(svd_type=svd_type, delay_embedding=d, mean_center=mc, scale=sc)
+    m, parsed = make_slice(tmp_path, cfg)
+    res, added, retrieved = main(cfg, write_to_netcdf=True)
+    assert added is False and retrieved is False
+    X, Xm, Xs = oracle_matrix(m, cfg)
+    k = 6
+    U0, s0, V0 = (randomized_svd_ref(X, k, 3) if svd_type == "randomized" else standard_svd_ref(X, k))
+    assert res["U"].dims == ("space", "components") and res["V"].dims == ("components", "time")
+    assert res["U"].shape == (X.shape[0], k) and res["V"].shape == (k, X.shape[1]) and res["s"].shape == (k,)
+    assert sigma_rel_err(res["s"].values, s0) < 1e-6
+    ref = recon_rel_err(X, U0, s0, V0)
+    assert abs(recon_rel_err(X, res["U"].values, res["s"].values, res["V"].values) - ref) <= 0.01 * ref
+    assert np.max(np.abs(res["X"].values - X)) < 1e-10                      # save_data_matrix
+    assert ("X_mean" in res) == (mc and d > 1) and ("X_std" in res) == (sc and mc and d > 1)      # quirk Q3
+    if "X_mean" in res:
+        assert np.allclose(res["X_mean"].values, Xm)
+    S = 2 * 36 * 72
+    assert sorted(res.coords) == sorted(["space", "time", "components", "original_variable", "delay", "level",
+                                         "latitude", "longitude"])
+    assert np.array_equal(res.coord("space"), np.arange(2 * S * d))
+    assert res.coord("original_variable")[0] == "u_component_of_wind" and res.coord("original_variable")[S] == "temperature"
+    assert res.coord("level")[0] == 850 and res.coord("level")[36 * 72] == 1000
+    assert np.array_equal(res.coord("delay"), np.repeat(np.flip(np.arange(d)), 2 * S))
+    assert np.array_equal(res.coord("time"), m["time"][d - 1:])
+    a = res.attrs
+    assert a["variables"] == ["u_component_of_wind", "temperature"] and a["levels"] == [850, 1000]
+    assert a["mean_center"] == int(mc) and a["scale"] == int(sc) and a["delay_embedding"] == d
+    assert a["svd_type"] == svd_type and a["n_components"] == k and a["save_data_matrix"] == 1
+    # written file + result cache (era5_svd.py:157-227): second call returns the stored result
+    assert os.path.exists(parsed["save_path"])
+    res2, _, _ = main(cfg, write_to_netcdf=False)
+    assert np.allclose(res2["s"].values, res["s"].values) and sorted(res2.data_vars) == sorted(res.data_vars)
+    back = read_netcdf(parsed["save_path"])
+    assert np.array_equal(back["U"].values, res["U"].values)
+
+
+def test_main_phase_errors(tmp_path, monkeypatch):
+    from dmd_era5_b200.era5_svd import main
+
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    with pytest.raises(Exception, match="Error retrieving ERA5 slice"):
+        main(base_config())
+    cfg = base_config(levels="850,300")                  # level missing from the slice file attrs -> no match
+    make_slice(tmp_path, base_config())
+    with pytest.raises(Exception, match="Error retrieving ERA5 slice"):
+        main(cfg)
+
+
+def test_standardize_data_gpu():
+    from dmd_era5_b200 import slice_tools as st
+
+    m = mock_era5_np(25, VARS, [1000, 850], seed=1)
+    ds = Dataset({k: DataArray(v, ("time", "level", "latitude", "longitude")) for k, v in m["vars"].items()},
+                 {"time": m["time"], "level": m["level"], "latitude": m["latitude"], "longitude": m["longitude"]})
+    out, mean, std = st.standardize_data(ds)              # reference tests/test_02_slice_tools.py:108-152
+    for v in VARS:
+        ref, mu, sd = standardize_np(m["vars"][v], scale=True)
+        assert np.allclose(out[v].values.mean(axis=0), 0, atol=1e-6) and np.allclose(out[v].values.std(axis=0), 1, atol=1e-6)
+        assert np.allclose(out[v].values, ref, atol=1e-10) and np.allclose(mean[v].values, mu) and np.allclose(std[v].values, sd)
+    out2, mean2, std2 = st.standardize_data(ds, scale=False)
+    assert std2 is None and np.allclose(out2["temperature"].values.std(axis=0), m["vars"]["temperature"].std(axis=0))
+    out3, _, _ = st.standardize_data(ds, dim="level")     # test_02:180-212
+    assert np.allclose(out3["u_component_of_wind"].values.mean(axis=1), 0, atol=1e-6)
+    assert np.allclose(out3["u_component_of_wind"].values.std(axis=1), 1, atol=1e-6)

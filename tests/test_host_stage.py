@@ -1,0 +1,149 @@
+"""CPU: host-side drop-in contract - config parsing, containers + NetCDF round trip, index-level
+slice_tools semantics.  Cases follow the reference's tests (cited per test)."""
+import os
+from datetime import datetime, timedelta
+
+import numpy as np
+import pytest
+
+from dmd_era5_b200.config_parser import config_parser, config_reader
+from dmd_era5_b200.dataset import DataArray, Dataset, read_netcdf, write_netcdf
+from dmd_era5_b200 import slice_tools as st
+from oracle.synthetic_np import mock_era5_np
+
+
+@pytest.fixture
+def base_config():
+    # reference tests/test_03_era5_svd.py:22-38
+    return {"source_path": "gs://gcp-public-data-arco-era5/ar/1959-2022-full_37-1h-0p25deg-chunk-1.zarr-v2",
+            "variables": "temperature", "levels": "1000", "svd_type": "randomized", "delay_embedding": 2,
+            "mean_center": False, "scale": False, "start_datetime": "2019-01-01T06", "end_datetime": "2020-01-01T12",
+            "delta_time": "1h", "n_components": 10, "save_data_matrix": True}
+
+
+def mock_dataset(n_times=25, variables=("temperature", "u_component_of_wind"), levels=(1000, 850), seed=0):
+    m = mock_era5_np(n_times, list(variables), list(levels), seed=seed)
+    dv = {k: DataArray(v, ("time", "level", "latitude", "longitude")) for k, v in m["vars"].items()}
+    return Dataset(dv, {"time": m["time"], "level": m["level"], "latitude": m["latitude"], "longitude": m["longitude"]},
+                   {"source_path": "mock", "variables": list(variables), "levels": list(levels)})
+
+
+def test_config_parser_basic(base_config, monkeypatch, tmp_path):
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    p = config_parser(base_config, section="era5-svd")          # reference test_03_era5_svd.py:71-101
+    assert p["start_datetime"] == datetime(2019, 1, 1, 6) and p["end_datetime"] == datetime(2020, 1, 1, 12)
+    assert p["delta_time"] == timedelta(hours=1)
+    assert p["save_name"] == "2019-01-01T06_2020-01-01T12_1h.nc"
+    assert p["save_path"] == os.path.join(str(tmp_path), "data", "era5_svd", p["save_name"])
+    assert p["era5_slice_path"] == os.path.join(str(tmp_path), "data", "era5_download", p["save_name"])
+    assert p["era5_svd_path"] == p["save_path"]
+    assert p["variables"] == ["temperature"] and p["levels"] == [1000]
+
+
+@pytest.mark.parametrize("field", ["source_path", "variables", "levels", "svd_type", "delay_embedding", "mean_center",
+                                   "scale", "start_datetime", "end_datetime", "delta_time", "n_components",
+                                   "save_data_matrix"])
+def test_config_parser_missing_field(base_config, field):
+    del base_config[field]                                       # test_03_era5_svd.py:104-126
+    with pytest.raises(ValueError, match=f"Missing required field in config: {field}"):
+        config_parser(base_config, section="era5-svd")
+
+
+def test_config_parser_invalid_values(base_config):
+    for key, bad, msg in [("svd_type", "invalid", "Invalid SVD type in config"),
+                          ("delay_embedding", 0, "Invalid delay embedding in config"),
+                          ("delay_embedding", 1.2, "Invalid delay embedding in config"),
+                          ("n_components", "invalid", "Invalid number of components in config"),
+                          ("mean_center", 1, "Invalid mean centering in config"),
+                          ("variables", "2m_temperature", "Single level variables not currently supported"),
+                          ("levels", "999", "Unsupported level in config"),
+                          ("delta_time", "5x", "Error parsing delta_time from config")]:
+        cfg = dict(base_config); cfg[key] = bad
+        with pytest.raises(ValueError, match=msg):
+            config_parser(cfg, section="era5-svd")
+    with pytest.raises(ValueError, match="not currently supported"):
+        config_parser(base_config, section="nope")
+    assert config_parser({**base_config, "levels": "all"}, "era5-svd")["levels"].__len__() == 13
+    assert config_parser({**base_config, "precision": "tf32x3"}, "era5-svd")["precision"] == "tf32x3"
+
+
+def test_config_reader_literals(tmp_path):
+    ini = tmp_path / "config.ini"
+    ini.write_text('[era5-svd]\nsource_path = "gs://x"\nn_components = 10\nmean_center = True\nlevels = "1000,850"\n')
+    cfg = config_reader("era5-svd", str(ini))
+    assert cfg == {"source_path": "gs://x", "n_components": 10, "mean_center": True, "levels": "1000,850"}
+
+
+def test_slice_and_resample():
+    ds = mock_dataset()
+    out = st.slice_era5_dataset(ds, levels=[850, 1000])          # level order follows the request (test_02:62-65)
+    assert list(out.coord("level")) == [850, 1000]
+    assert np.array_equal(out["temperature"].values[:, 0], ds["temperature"].values[:, 1])
+    with pytest.raises(ValueError, match="Requested level is not available"):
+        st.slice_era5_dataset(ds, levels=[500])
+    with pytest.raises(ValueError, match="Start datetime must be before end datetime."):
+        st.slice_era5_dataset(ds, start_datetime="2019-01-01T05", end_datetime="2019-01-01T05")
+    with pytest.raises(ValueError, match="outside dataset"):
+        st.slice_era5_dataset(ds, start_datetime="2018-01-01T00")
+    r = st.resample_era5_dataset(ds, timedelta(hours=6))         # 25 hourly -> 5 six-hourly (test_02:85-101)
+    assert r.sizes["time"] == 5
+    assert np.all(np.diff(r.coord("time")) == np.timedelta64(6, "h"))
+    assert np.array_equal(r["temperature"].values, ds["temperature"].values[[0, 6, 12, 18, 24]])
+    same = st.resample_era5_dataset(ds, timedelta(hours=1))
+    assert np.array_equal(same["temperature"].values, ds["temperature"].values)
+
+
+def test_flatten_and_delay_embedding():
+    ds = mock_dataset()
+    da = st.flatten_era5_variables(ds)                            # test_02:291-333
+    sizes = ds.sizes
+    S = sizes["level"] * sizes["latitude"] * sizes["longitude"]
+    assert da.shape == (2 * S, sizes["time"]) and da.dims == ("space", "time")
+    assert da.attrs["original_variables"] == ["temperature", "u_component_of_wind"]
+    r = S + (1 * 36 + 3) * 72 + 5
+    assert da.coord("original_variable")[r] == "u_component_of_wind" and da.coord("level")[r] == 850
+    assert np.array_equal(da.values[r], ds["u_component_of_wind"].values[:, 1, 3, 5])
+    emb = st.apply_delay_embedding(da, 3)                         # test_02:366-490
+    n = sizes["time"] - 2
+    assert emb.shape == (2 * S * 3, n) and emb.attrs["delay_embedding"] == 3
+    for j in range(3):
+        block = emb.values[j * 2 * S:(j + 1) * 2 * S]
+        assert np.array_equal(block, da.values[:, j:j + n])
+        assert np.all(emb.coord("delay")[j * 2 * S:(j + 1) * 2 * S] == 2 - j)
+    assert np.array_equal(emb.coord("time"), da.coord("time")[2:])
+    with pytest.raises(ValueError, match="Input array must be 2D."):
+        st._apply_delay_embedding_np(np.zeros(3), 1)
+    with pytest.raises(ValueError, match="Delay must be an integer greater than 0."):
+        st._apply_delay_embedding_np(np.zeros((3, 3)), 0)
+    mean_field = Dataset({"temperature": DataArray(ds["temperature"].values.mean(0), ("level", "latitude", "longitude"))},
+                         {k: ds.coords[k] for k in ("level", "latitude", "longitude")})
+    assert st.flatten_era5_variables(mean_field).shape == (S,)   # no time axis -> 1-D (slice_tools.py:330-332)
+
+
+def test_netcdf_round_trip(tmp_path):
+    k, m, n = 3, 8, 5
+    rng = np.random.RandomState(0)
+    times = np.datetime64("2019-01-01T00", "ns") + np.arange(n) * np.timedelta64(6, "h")
+    coords = {"space": np.arange(m), "time": times, "components": np.arange(k),
+              "original_variable": (("space",), np.repeat(["temperature", "u_component_of_wind"], 4)),
+              "delay": (("space",), np.zeros(m, dtype=np.int64)), "level": (("space",), np.full(m, 1000)),
+              "latitude": (("space",), rng.rand(m)), "longitude": (("space",), rng.rand(m))}
+    ds = Dataset({"U": DataArray(rng.rand(m, k).astype(np.float32), ("space", "components")),
+                  "s": DataArray(rng.rand(k), ("components",)),
+                  "V": DataArray(rng.rand(k, n), ("components", "time"))}, coords,
+                 {"source_path": "gs://x", "n_components": k, "variables": ["temperature", "u_component_of_wind"],
+                  "levels": [1000, 850], "mean_center": 1, "svd_type": "randomized"})
+    path = str(tmp_path / "out.nc")
+    fmt = write_netcdf(ds, path)
+    back = read_netcdf(path)
+    assert fmt in ("NETCDF4", "NETCDF3_64BIT")
+    assert sorted(back.data_vars) == ["U", "V", "s"]
+    assert back["U"].dims == ("space", "components") and back["V"].dims == ("components", "time")
+    assert np.array_equal(back["U"].values, ds["U"].values) and back["U"].values.dtype == np.float32
+    assert np.array_equal(back.coord("time"), times)
+    assert list(back.coord("original_variable")) == list(ds.coord("original_variable"))
+    assert sorted(back.coords) == sorted(coords)
+    assert back.attrs["n_components"] == k and back.attrs["source_path"] == "gs://x"
+    from dmd_era5_b200.stage import _as_int_list, _as_str_list
+    assert _as_str_list(back.attrs["variables"]) == ["temperature", "u_component_of_wind"]
+    assert _as_int_list(back.attrs["levels"]) == [1000, 850]
