@@ -22,6 +22,11 @@
 
 namespace era5svd {
 
+// from gemm_tc2.cu: on-chip split variants (X given as one plain float32 matrix)
+int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
+                      int64_t ldo, float* Y, float* Yhi, float* Ylo, int64_t ldy, void* workspace,
+                      cudaStream_t st);
+
 // from gemm_simt.cu
 void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
                                 int64_t ldz, int accumulate, cudaStream_t st);
@@ -56,9 +61,14 @@ static EncodeTiledFn encode_fn() {
 // 128 B swizzle, out-of-bounds elements read as zero.  `base` may be any 4-byte aligned address: the
 // map is anchored at the enclosing 16-byte boundary and *col_shift returns the element offset to add
 // to every inner coordinate (this is how delay-embedded column windows X[:, j:] are addressed).
-static int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
-                     uint32_t box_inner, uint32_t box_outer, int* col_shift,
-                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
+              uint32_t box_inner, uint32_t box_outer, int* col_shift, CUtensorMapSwizzle swizzle);
+int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
+              uint32_t box_inner, uint32_t box_outer, int* col_shift) {
+  return make_tmap(map, base, inner, outer, ld, box_inner, box_outer, col_shift, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
+              uint32_t box_inner, uint32_t box_outer, int* col_shift, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -483,7 +493,7 @@ int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t
                           const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
                           int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace era5svd;
-  ERA5SVD_REQUIRE(Xhi && Xlo && Om, "sketch_tf32x3: null pointer");
+  ERA5SVD_REQUIRE(Xhi && Om, "sketch_tf32x3: null pointer");
   ERA5SVD_REQUIRE(Y || Yhi, "sketch_tf32x3: no output requested");
   ERA5SVD_REQUIRE((Yhi == nullptr) == (Ylo == nullptr), "sketch_tf32x3: Yhi and Ylo go together");
   ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldo >= l, "sketch_tf32x3: bad shape");
@@ -503,6 +513,8 @@ int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t
   }
   ERA5SVD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "sketch_tf32x3: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
+  if (!Xlo)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu), X read from HBM once
+    return sketch_tf32x3_raw(Xhi, m, n, ldx, Om, l, ldo, Y, Yhi, Ylo, ldy, workspace, st);
   CUtensorMap tm_xhi, tm_xlo, tm_ohi, tm_olo;
   int xs = 0, xs2 = 0, os = 0, os2 = 0, rc;
   if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, tc::BM, &xs))) return rc;

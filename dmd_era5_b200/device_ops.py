@@ -209,7 +209,9 @@ class CudaOps:
         l = Om.shape[1]
         if Om.dtype != torch.float64 or Om.shape[0] != n:
             raise ValueError("sketch_tf32x3: Om must be float64 (n, l)")
-        hp, hld = _mat(Xhi, "Xhi"); lp, lld = _mat(Xlo, "Xlo"); op, old = _mat(Om, "Om")
+        # Xlo is None: Xhi is the plain float32 matrix and the tf32 split happens on chip (gemm_tc2.cu)
+        hp, hld = _mat(Xhi, "Xhi"); op, old = _mat(Om, "Om")
+        lp, lld = _mat(Xlo, "Xlo") if Xlo is not None else (None, hld)
         if (Yhi is None) != (Ylo is None):
             raise ValueError("sketch_tf32x3: Yhi and Ylo go together")
         outs = [t for t in (Y, Yhi, Ylo) if t is not None]

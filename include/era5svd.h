@@ -113,7 +113,9 @@ int era5svd_project(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx,
  * a*b ~ a_hi*b_hi + a_lo*b_hi + a_hi*b_lo keeps fp32-level accuracy.  float32 storage only.
  *
  * era5svd_split_tf32      : hi / lo images of a tall float32 matrix (done once per matrix).
- * era5svd_sketch_tf32x3   : Y = X * Om with X given as (Xhi, Xlo); Om is the float64 small factor
+ * era5svd_sketch_tf32x3   : Y = X * Om with X given as (Xhi, Xlo) - or with Xlo == NULL and Xhi the plain
+ *                           float32 matrix, split on chip (X then crosses HBM once; l <= 128);
+ *                           Om is the float64 small factor
  *                           (n x l, split on the fly into the workspace).  Writes any of Y (plain
  *                           float32) and the pair (Yhi, Ylo) for a following project; all share ldy,
  *                           which must be >= round_up(l, 16) and a multiple of 4 (pad columns get 0).

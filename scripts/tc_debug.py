@@ -23,7 +23,7 @@ def report(name, got, ref, scale):
     return True
 
 
-def run_sketch(m, n, l, seed=0, off=0):
+def run_sketch(m, n, l, seed=0, off=0, raw=False):
     rng = np.random.RandomState(seed)
     Xfull = rng.standard_normal((m, n + off)).astype(np.float32)
     X = dev(Xfull)[:, off:]
@@ -32,10 +32,13 @@ def run_sketch(m, n, l, seed=0, off=0):
     hi, lo = hi[:, off:off + n], lo[:, off:off + n]
     ldy = ops.tf32_ldy(l)
     Y = torch.zeros((m, ldy), device="cuda")[:, :l]; Yh = torch.zeros((m, ldy), device="cuda")[:, :l]; Yl = torch.zeros((m, ldy), device="cuda")[:, :l]
-    ops.sketch_tf32x3(hi, lo, dev(Om), Y, Yh, Yl)
+    if raw:
+        ops.sketch_tf32x3(X, None, dev(Om), Y, Yh, Yl)
+    else:
+        ops.sketch_tf32x3(hi, lo, dev(Om), Y, Yh, Yl)
     torch.cuda.synchronize()
     ref = Xfull[:, off:].astype(np.float64) @ Om
-    ok = report(f"sketch m={m} n={n} l={l} off={off}", Y.cpu().numpy().astype(np.float64), ref, np.sqrt(n))
+    ok = report(f"sketch{'-raw' if raw else ''} m={m} n={n} l={l} off={off}", Y.cpu().numpy().astype(np.float64), ref, np.sqrt(n))
     ok &= report("   Yhi+Ylo", (Yh.double() + Yl.double()).cpu().numpy(), Y.cpu().numpy().astype(np.float64), 1.0)
     return ok
 
@@ -72,4 +75,22 @@ if __name__ == "__main__":
         ok &= run_project(1000, 744, 110)
         ok &= run_project(50000, 1460, 110)
         ok &= run_project(4097, 25, 20)
+    if which in ("all", "raw"):
+        ok &= run_sketch(128, 32, 16, raw=True)
+        ok &= run_sketch(128, 64, 110, raw=True)
+        ok &= run_sketch(1000, 744, 110, raw=True)
+        ok &= run_sketch(40000, 744, 110, raw=True)
+        ok &= run_sketch(2000, 742, 110, off=2, raw=True)
+        import time
+        X = torch.randn((1038240, 744), device="cuda"); Om = torch.randn((744, 110), device="cuda", dtype=torch.float64)
+        ldy = ops.tf32_ldy(110)
+        Yh = torch.zeros((1038240, ldy), device="cuda")[:, :110]; Yl = torch.zeros((1038240, ldy), device="cuda")[:, :110]
+        hi, lo = ops.split_tf32(X)
+        for name, a, b in (("v1 (hi/lo in HBM)", hi, lo), ("v2 (on-chip split)", X, None)):
+            for _ in range(2): ops.sketch_tf32x3(a, b, Om, None, Yh, Yl)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5): ops.sketch_tf32x3(a, b, Om, None, Yh, Yl)
+            e1.record(); torch.cuda.synchronize()
+            print(f"sketch {name}: {e0.elapsed_time(e1) / 5:.3f} ms per pass (c2 shape)")
     print("ALL OK" if ok else "FAILURES")
