@@ -40,8 +40,10 @@ struct Sketch2Params {
   int64_t ldy;
 };
 
-// warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: transform (smem -> hi/lo -> TMEM), warps 6-9: epilogue
-constexpr int SK2_THREADS = 320;
+// warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: transform (smem -> hi/lo -> TMEM; two groups of four
+// warps taking alternate k-chunks), warps 10-13: epilogue
+constexpr int SK2_THREADS = 448;
+constexpr int SK2_EPI_WARP0 = 10;
 constexpr int A_RING = 4;          // TMEM A buffers: 64 columns each (32 hi + 32 lo)
 constexpr uint32_t A_COLS = 64;
 
@@ -145,14 +147,21 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       if (++buf == 2) { buf = 0; tph ^= 1u; }
     }
-  } else if (warp < 6) {
+  } else if (warp < SK2_EPI_WARP0) {
     // ===== transform: raw X tile (smem, 128 B swizzle) -> hi / lo -> TMEM (lane = row) =====
     const int q = warp % 4;
+    const int grp = (warp - 2) / 4;                    // this group handles chunks with (count & 1) == grp
     const int r = q * 32 + lane;                       // row of the tile == TMEM lane
     int s = 0; uint32_t ph = 0;
     int ab = 0; uint32_t aph = 0;
+    uint32_t cnt = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int kc = 0; kc < p.num_k; ++kc) {
+      for (int kc = 0; kc < p.num_k; ++kc, ++cnt) {
+        if ((cnt & 1u) != (uint32_t)grp) {
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+          if (++ab == A_RING) { ab = 0; aph ^= 1u; }
+          continue;
+        }
         mbar_wait(full_bar(s), ph);
         mbar_wait(aempty_bar(ab), aph ^ 1u);           // MMAs that read this TMEM buffer have retired
         tcgen05_fence_after();
@@ -168,7 +177,9 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                          : "r"(row_addr + (uint32_t)((chunk ^ (r & 7)) << 4)));
-            const float h0 = tf32_hi(v.x), h1 = tf32_hi(v.y), h2 = tf32_hi(v.z), h3 = tf32_hi(v.w);
+            // truncation split (1 LOP + 1 FADD per element): hi = x with the low 13 mantissa bits cleared,
+            // lo = x - hi exact, |lo| < 2^-10 |x|
+            const float h0 = tf32_trunc(v.x), h1 = tf32_trunc(v.y), h2 = tf32_trunc(v.z), h3 = tf32_trunc(v.w);
             hi[4 * c + 0] = __float_as_uint(h0); lo[4 * c + 0] = __float_as_uint(v.x - h0);
             hi[4 * c + 1] = __float_as_uint(h1); lo[4 * c + 1] = __float_as_uint(v.y - h1);
             hi[4 * c + 2] = __float_as_uint(h2); lo[4 * c + 2] = __float_as_uint(v.z - h2);

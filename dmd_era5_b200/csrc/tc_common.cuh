@@ -160,5 +160,8 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(u);
 }
 
+// cheaper split for the on-chip transform: hi = x truncated to tf32, lo = x - hi exact, |lo| < 2^-10 |x|
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 }  // namespace tc
 }  // namespace era5svd
