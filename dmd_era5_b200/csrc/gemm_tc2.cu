@@ -1,21 +1,21 @@
 // (b) Tall GEMM passes, tcgen05 generation 2: X is read from HBM ONCE as plain float32 and split on
-// chip.  The raw tile lands in shared memory by TMA; four "transform" warps read it, form
-// hi = tf32(x), lo = x - hi in registers and store both into TENSOR MEMORY with tcgen05.st; the MMAs
-// then take A from TMEM (tcgen05.mma "TS" form) and only the small operand (Om^T resp. Y, pre-split,
+// chip.  The raw tile lands in shared memory by TMA; "transform" warps read it, form
+// hi = trunc_tf32(x), lo = x - hi in registers and store both into TENSOR MEMORY with tcgen05.st; the
+// MMAs then take A from TMEM (tcgen05.mma "TS" form) and only the small operand (Om^T, pre-split,
 // L2 resident) from shared memory.  Compared with gemm_tc.cu (hi / lo images of X in HBM) this halves
-// the HBM traffic of every pass and removes the A-operand reads from the shared-memory port, which
-// is what bounds the SS form (ncu: profiles/r01_ncu_full_tc_v1.md).
+// the HBM traffic of the pass and removes the A-operand reads from the shared-memory port, which is
+// what bounds the SS form (ncu: profiles/r01_ncu_full_tc_v1.md).
 //
-//   sketch :  Y = X Om        A = X tile   (TMEM: lane = row,  columns = time)     B = Om^T (K-major smem)
-//   project:  Z = X^T Y       A = X^T tile (TMEM: lane = time, columns = rows)     B = Y    (N-major smem)
+//   sketch :  Y = X Om        A = X tile (TMEM: lane = row, columns = time)     B = Om^T (K-major smem)
+//
+// Three decoupled rings, so that the HBM prefetch distance does not depend on MMA completion:
+//   raw-A ring (smem, 16 KB/slot) : TMA  -> transform warps          freed as soon as it has been read
+//   B ring     (smem, 28 KB/slot) : TMA  -> MMA                      freed by tcgen05.commit
+//   A ring     (TMEM, 64 cols)    : transform -> MMA                 freed by tcgen05.commit
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace era5svd {
-
-void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
-                                int64_t ldz, int accumulate, cudaStream_t st);
-
 namespace tc {
 
 int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
@@ -33,19 +33,31 @@ struct Sketch2Params {
   int64_t num_tiles;
   int num_k;
   int npad;
-  int stages;      // smem ring (raw A tile + B hi/lo)
+  int ra;          // raw-A ring depth
+  int rb;          // B ring depth
   float* Y;
   float* Yhi;
   float* Ylo;
   int64_t ldy;
 };
 
-// warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: transform (smem -> hi/lo -> TMEM; two groups of four
-// warps taking alternate k-chunks), warps 10-13: epilogue
-constexpr int SK2_THREADS = 448;
+// warp 0: TMA producer for raw A, warp 1: MMA issuer + TMEM alloc, warps 2-9: transform (two groups of four
+// warps taking alternate k-chunks), warps 10-13: epilogue, warp 14: TMA producer for B
+constexpr int SK2_THREADS = 480;
 constexpr int SK2_EPI_WARP0 = 10;
-constexpr int A_RING = 4;          // TMEM A buffers: 64 columns each (32 hi + 32 lo)
-constexpr uint32_t A_COLS = 64;
+constexpr int SK2_BPROD_WARP = 14;
+constexpr int AT_RING = 4;         // TMEM A buffers: 64 columns each (32 hi + 32 lo)
+constexpr uint32_t AT_COLS = 64;
+
+struct Ring {
+  int i = 0;
+  uint32_t ph = 0;
+  int depth;
+  __device__ explicit Ring(int d) : depth(d) {}
+  __device__ void next() {
+    if (++i == depth) { i = 0; ph ^= 1u; }
+  }
+};
 
 __global__ void __launch_bounds__(SK2_THREADS, 1)
 sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_ohi,
@@ -53,39 +65,46 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const uint32_t a_bytes = BM2 * BK2 * 4;
-  const uint32_t b_bytes = (uint32_t)p.npad * BK2 * 4;
-  const uint32_t stage_bytes = a_bytes + 2 * b_bytes;
-  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  auto aready_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + b); };
-  auto aempty_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + A_RING + b); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 2 * A_RING + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 2 * A_RING + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 2 * A_RING + 4);
+  const uint32_t a_bytes = BM2 * BK2 * 4;                   // raw A slot
+  const uint32_t b_half = (uint32_t)p.npad * BK2 * 4;       // Om^T hi (or lo) tile
+  const uint32_t b_bytes = 2 * b_half;                      // B slot
+  const uint32_t b_base = smem_base + (uint32_t)p.ra * a_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)p.rb * b_bytes;
+  int nb = 0;
+  const uint32_t araw_full = bar_base + 8u * nb;  nb += p.ra;
+  const uint32_t araw_empty = bar_base + 8u * nb; nb += p.ra;
+  const uint32_t b_full = bar_base + 8u * nb;     nb += p.rb;
+  const uint32_t b_empty = bar_base + 8u * nb;    nb += p.rb;
+  const uint32_t at_ready = bar_base + 8u * nb;   nb += AT_RING;
+  const uint32_t at_empty = bar_base + 8u * nb;   nb += AT_RING;
+  const uint32_t tfull = bar_base + 8u * nb;      nb += 2;
+  const uint32_t tempty = bar_base + 8u * nb;     nb += 2;
+  const uint32_t tmem_slot = bar_base + 8u * nb;
   // TMEM map (512 columns): [0,128) acc 0, [128,256) acc 1, [256,512) A ring
   const uint32_t acc_cols = 128;
-  const uint32_t a_col0 = 256;
+  const uint32_t at_col0 = 256;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int i = 0; i < p.ra; ++i) {
+      mbar_init(araw_full + 8u * i, 1);
+      mbar_init(araw_empty + 8u * i, 4);   // the four transform warps that read the slot
     }
-    for (int b = 0; b < A_RING; ++b) {
-      mbar_init(aready_bar(b), 4);    // one arrive per transform warp
-      mbar_init(aempty_bar(b), 1);
+    for (int i = 0; i < p.rb; ++i) {
+      mbar_init(b_full + 8u * i, 1);
+      mbar_init(b_empty + 8u * i, 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+    for (int i = 0; i < AT_RING; ++i) {
+      mbar_init(at_ready + 8u * i, 4);
+      mbar_init(at_empty + 8u * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull + 8u * i, 1);
+      mbar_init(tempty + 8u * i, 4);
     }
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_ohi); tma_prefetch_desc(&tm_olo);
-  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_x);
+  if (warp == SK2_BPROD_WARP && lane == 0) { tma_prefetch_desc(&tm_ohi); tma_prefetch_desc(&tm_olo); }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tcgen05_fence_before();
   __syncthreads();
@@ -94,117 +113,127 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: raw X tiles (HBM stream) =====
     if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
+      Ring ra(p.ra);
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int32_t row0 = (int32_t)(tile * BM2);
         for (int kc = 0; kc < p.num_k; ++kc) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-          tma_load_2d(st, &tm_x, kc * BK2, row0, full_bar(s));
-          tma_load_2d(st + a_bytes, &tm_ohi, kc * BK2, 0, full_bar(s));
-          tma_load_2d(st + a_bytes + b_bytes, &tm_olo, kc * BK2, 0, full_bar(s));
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
+          mbar_wait(araw_empty + 8u * ra.i, ra.ph ^ 1u);
+          mbar_arrive_expect_tx(araw_full + 8u * ra.i, a_bytes);
+          tma_load_2d(smem_base + (uint32_t)ra.i * a_bytes, &tm_x, kc * BK2, row0, araw_full + 8u * ra.i);
+          ra.next();
+        }
+      }
+    }
+  } else if (warp == SK2_BPROD_WARP) {
+    // ===== TMA producer: Om^T hi / lo tiles (L2 resident, same for every row tile) =====
+    if (lane == 0) {
+      Ring rb(p.rb);
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.num_k; ++kc) {
+          mbar_wait(b_empty + 8u * rb.i, rb.ph ^ 1u);
+          const uint32_t dst = b_base + (uint32_t)rb.i * b_bytes;
+          mbar_arrive_expect_tx(b_full + 8u * rb.i, b_bytes);
+          tma_load_2d(dst, &tm_ohi, kc * BK2, 0, b_full + 8u * rb.i);
+          tma_load_2d(dst + b_half, &tm_olo, kc * BK2, 0, b_full + 8u * rb.i);
+          rb.next();
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: A (hi / lo) from TMEM, B (Om^T hi / lo) from smem =====
     const uint32_t idesc = make_idesc_tf32(BM2, p.npad, 0, 0);
-    int s = 0; uint32_t ph = 0;
-    int ab = 0; uint32_t aph = 0;
-    int buf = 0; uint32_t tph = 0;
+    Ring rb(p.rb), at(AT_RING), acc(2);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar(buf), tph ^ 1u);
+      mbar_wait(tempty + 8u * acc.i, acc.ph ^ 1u);
       tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)buf * acc_cols;
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc.i * acc_cols;
       for (int kc = 0; kc < p.num_k; ++kc) {
-        mbar_wait(full_bar(s), ph);          // B tiles landed (and the raw A tile)
-        mbar_wait(aready_bar(ab), aph);      // A hi / lo stored to TMEM by the transform warps
+        mbar_wait(b_full + 8u * rb.i, rb.ph);
+        mbar_wait(at_ready + 8u * at.i, at.ph);
         tcgen05_fence_after();
         if (lane == 0) {
-          const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-          const uint32_t a_hi = tmem_base + a_col0 + (uint32_t)ab * A_COLS;
+          const uint32_t bs = b_base + (uint32_t)rb.i * b_bytes;
+          const uint32_t a_hi = tmem_base + at_col0 + (uint32_t)at.i * AT_COLS;
           const uint32_t a_lo = a_hi + 32;
 #pragma unroll
           for (int kk = 0; kk < BK2 / UK2; ++kk) {
             const uint32_t koff = kk * UK2 * 4;
-            const uint64_t b_hi = make_smem_desc(st + a_bytes + koff, 16, 1024);
-            const uint64_t b_lo = make_smem_desc(st + a_bytes + b_bytes + koff, 16, 1024);
+            const uint64_t b_hi = make_smem_desc(bs + koff, 16, 1024);
+            const uint64_t b_lo = make_smem_desc(bs + b_half + koff, 16, 1024);
             umma_tf32_ts(d_tmem, a_lo + kk * UK2, b_hi, idesc, (kc | kk) != 0);
             umma_tf32_ts(d_tmem, a_hi + kk * UK2, b_lo, idesc, 1);
             umma_tf32_ts(d_tmem, a_hi + kk * UK2, b_hi, idesc, 1);
           }
-          umma_commit(empty_bar(s));
-          umma_commit(aempty_bar(ab));
-          if (kc == p.num_k - 1) umma_commit(tfull_bar(buf));
+          umma_commit(b_empty + 8u * rb.i);
+          umma_commit(at_empty + 8u * at.i);
+          if (kc == p.num_k - 1) umma_commit(tfull + 8u * acc.i);
         }
         __syncwarp();
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
-        if (++ab == A_RING) { ab = 0; aph ^= 1u; }
+        rb.next();
+        at.next();
       }
-      if (++buf == 2) { buf = 0; tph ^= 1u; }
+      acc.next();
     }
   } else if (warp < SK2_EPI_WARP0) {
     // ===== transform: raw X tile (smem, 128 B swizzle) -> hi / lo -> TMEM (lane = row) =====
     const int q = warp % 4;
     const int grp = (warp - 2) / 4;                    // this group handles chunks with (count & 1) == grp
     const int r = q * 32 + lane;                       // row of the tile == TMEM lane
-    int s = 0; uint32_t ph = 0;
-    int ab = 0; uint32_t aph = 0;
+    Ring ra(p.ra), at(AT_RING);
     uint32_t cnt = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < p.num_k; ++kc, ++cnt) {
-        if ((cnt & 1u) != (uint32_t)grp) {
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
-          if (++ab == A_RING) { ab = 0; aph ^= 1u; }
-          continue;
-        }
-        mbar_wait(full_bar(s), ph);
-        mbar_wait(aempty_bar(ab), aph ^ 1u);           // MMAs that read this TMEM buffer have retired
-        tcgen05_fence_after();
-        const uint32_t row_addr = smem_base + (uint32_t)s * stage_bytes + (uint32_t)r * 128u;
-        const uint32_t t_hi = tmem_base + a_col0 + (uint32_t)ab * A_COLS + ((uint32_t)(q * 32) << 16);
+        if ((cnt & 1u) == (uint32_t)grp) {
+          mbar_wait(araw_full + 8u * ra.i, ra.ph);
+          const uint32_t row_addr = smem_base + (uint32_t)ra.i * a_bytes + (uint32_t)r * 128u;
+          float4 v[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int chunk = half * 4 + c;            // 16-byte chunk of the 128-byte row
-            float4 v;
+          for (int c = 0; c < 8; ++c)                  // 16-byte chunk c of the 128-byte row, un-swizzled
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(row_addr + (uint32_t)((chunk ^ (r & 7)) << 4)));
-            // truncation split (1 LOP + 1 FADD per element): hi = x with the low 13 mantissa bits cleared,
-            // lo = x - hi exact, |lo| < 2^-10 |x|
-            const float h0 = tf32_trunc(v.x), h1 = tf32_trunc(v.y), h2 = tf32_trunc(v.z), h3 = tf32_trunc(v.w);
-            hi[4 * c + 0] = __float_as_uint(h0); lo[4 * c + 0] = __float_as_uint(v.x - h0);
-            hi[4 * c + 1] = __float_as_uint(h1); lo[4 * c + 1] = __float_as_uint(v.y - h1);
-            hi[4 * c + 2] = __float_as_uint(h2); lo[4 * c + 2] = __float_as_uint(v.z - h2);
-            hi[4 * c + 3] = __float_as_uint(h3); lo[4 * c + 3] = __float_as_uint(v.w - h3);
+                         : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
+                         : "r"(row_addr + (uint32_t)((c ^ (r & 7)) << 4)));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(araw_empty + 8u * ra.i);    // slot free for the next HBM tile
+          mbar_wait(at_empty + 8u * at.i, at.ph ^ 1u);           // MMAs that read this TMEM buffer have retired
+          tcgen05_fence_after();
+          const uint32_t t_hi = tmem_base + at_col0 + (uint32_t)at.i * AT_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // truncation split (1 LOP + 1 FADD per element): hi = x with the low 13 mantissa bits
+              // cleared, lo = x - hi exact, |lo| < 2^-10 |x|
+              const float4 x = v[half * 4 + c];
+              const float h0 = tf32_trunc(x.x), h1 = tf32_trunc(x.y), h2 = tf32_trunc(x.z), h3 = tf32_trunc(x.w);
+              hi[4 * c + 0] = __float_as_uint(h0); lo[4 * c + 0] = __float_as_uint(x.x - h0);
+              hi[4 * c + 1] = __float_as_uint(h1); lo[4 * c + 1] = __float_as_uint(x.y - h1);
+              hi[4 * c + 2] = __float_as_uint(h2); lo[4 * c + 2] = __float_as_uint(x.z - h2);
+              hi[4 * c + 3] = __float_as_uint(h3); lo[4 * c + 3] = __float_as_uint(x.w - h3);
+            }
+            tmem_st16(t_hi + half * 16, hi);
+            tmem_st16(t_hi + 32 + half * 16, lo);
           }
-          tmem_st16(t_hi + half * 16, hi);
-          tmem_st16(t_hi + 32 + half * 16, lo);
+          tmem_wait_st();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(at_ready + 8u * at.i);
         }
-        tmem_wait_st();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(aready_bar(ab));
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
-        if (++ab == A_RING) { ab = 0; aph ^= 1u; }
+        ra.next();
+        at.next();
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global (Y, Y_hi, Y_lo) =====
     const int q = warp % 4;
-    int buf = 0; uint32_t tph = 0;
+    Ring acc(2);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(tfull_bar(buf), tph);
+      mbar_wait(tfull + 8u * acc.i, acc.ph);
       tcgen05_fence_after();
       const int64_t row = tile * BM2 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)acc.i * acc_cols + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.npad; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c0, v);
@@ -227,8 +256,8 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
-      if (++buf == 2) { buf = 0; tph ^= 1u; }
+      if (lane == 0) mbar_arrive(tempty + 8u * acc.i);
+      acc.next();
     }
   }
   tcgen05_fence_before();
@@ -269,12 +298,14 @@ int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const d
   p.npad = npad;
   p.Y = Y; p.Yhi = Yhi; p.Ylo = Ylo;
   p.ldy = ldy;
-  const size_t stage_bytes = (size_t)tc::BM2 * tc::BK2 * 4 + 2 * (size_t)npad * tc::BK2 * 4;
+  // shared memory: B ring of 4 slots (L2 latency), the rest for the raw-A ring (HBM latency), up to 8 slots
+  const size_t a_bytes = (size_t)tc::BM2 * tc::BK2 * 4, b_bytes = 2 * (size_t)npad * tc::BK2 * 4;
   const size_t budget = 227 * 1024 - 1024 - 512;
-  p.stages = (int)(budget / stage_bytes);
-  if (p.stages > 6) p.stages = 6;
-  ERA5SVD_REQUIRE(p.stages >= 2, "sketch_tf32x3: not enough shared memory for two stages");
-  const size_t smem = p.stages * stage_bytes + 1024 + 512;
+  p.rb = 4;
+  p.ra = (int)((budget - p.rb * b_bytes) / a_bytes);
+  if (p.ra > 8) p.ra = 8;
+  ERA5SVD_REQUIRE(p.ra >= 2, "sketch_tf32x3: not enough shared memory");
+  const size_t smem = p.ra * a_bytes + p.rb * b_bytes + 1024 + 512;
   ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   tc::sketch_tc2_kernel<<<(unsigned)grid, tc::SK2_THREADS, smem, st>>>(tm_x, tm_ohi, tm_olo, p);
