@@ -27,6 +27,11 @@ int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const d
                       int64_t ldo, float* Y, float* Yhi, float* Ylo, int64_t ldy, void* workspace,
                       cudaStream_t st);
 
+int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Yhi, const float* Ylo,
+                       int64_t l, int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st);
+size_t project_tf32x3_raw_workspace_bytes(int64_t m, int64_t n, int64_t l);
+
 // from gemm_simt.cu
 void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
                                 int64_t ldz, int accumulate, cudaStream_t st);
@@ -552,7 +557,8 @@ int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l) {
   using namespace era5svd;
   if (m <= 0 || n <= 0 || l <= 0) return 0;
-  return pj_plan(m, n + 3, l).bytes;
+  const size_t a = pj_plan(m, n + 3, l).bytes, b = project_tf32x3_raw_workspace_bytes(m, n, l);
+  return a > b ? a : b;
 }
 
 int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
@@ -560,13 +566,16 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
                            int64_t ldz, int accumulate, void* workspace, size_t workspace_bytes,
                            void* stream) {
   using namespace era5svd;
-  ERA5SVD_REQUIRE(Xhi && Xlo && Yhi && Ylo && Z, "project_tf32x3: null pointer");
+  ERA5SVD_REQUIRE(Xhi && Yhi && Ylo && Z, "project_tf32x3: null pointer");
   ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldy >= l && ldz >= l, "project_tf32x3: bad shape");
   if (l > 128) {
     set_error("project_tf32x3: l = %lld > 128 is not supported by the tensor-core path", (long long)l);
     return ERA5SVD_ERR_UNSUPPORTED;
   }
   ERA5SVD_REQUIRE(m < ((int64_t)1 << 31), "project_tf32x3: m too large for TMA coordinates");
+  if (!Xlo)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu)
+    return project_tf32x3_raw(Xhi, m, n, ldx, Yhi, Ylo, l, ldy, Z, ldz, accumulate, workspace, workspace_bytes,
+                              as_stream(stream));
   // plan for the widest window (xshift <= 3) so that the workspace query needs no pointer
   const PjPlan pl = pj_plan(m, n + 3, l);
   if (!workspace || workspace_bytes < pl.bytes) {

@@ -16,6 +16,10 @@
 #include "tc_common.cuh"
 
 namespace era5svd {
+
+void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
+                                int64_t ldz, int accumulate, cudaStream_t st);
+
 namespace tc {
 
 int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
@@ -265,6 +269,219 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// project v2:  Z[n x l] += X^T Y over a row split, X split on chip.
+//   A = X^T tile in TMEM (lane = time within a 128-wide tile, columns = rows of the slot, K-major)
+//   B = Y tile (hi / lo, pre-split by the sketch epilogue) from smem, N-major (32 B-granule swizzle)
+//   D = [128 time lanes x 128 sketch columns] per time tile, two time tiles (256 time columns) per CTA,
+//       accumulated in TMEM over the CTA's whole row split, then written as a float32 partial tile.
+// grid = (ceil(n / 256), splits); one slot = 16 rows x 256 time values (16 KB of X).
+// ---------------------------------------------------------------------------------------------
+struct Project2Params {
+  int64_t m, n;
+  int l;
+  int xshift;
+  int ra, rb;
+  int64_t rows_per_split;
+  float* part;        // [splits][n][l]
+};
+
+constexpr int PJ2_THREADS = 480;
+constexpr int PJ2_KS = 16;                 // rows per slot
+constexpr int PJ2_TT = 2;                  // time tiles per CTA
+constexpr int PJ2_NC = PJ2_TT * 128;       // time columns per CTA
+constexpr uint32_t PJ2_AT_COLS = PJ2_TT * 2 * PJ2_KS;   // 64 TMEM columns per A slot
+
+__global__ void __launch_bounds__(PJ2_THREADS, 1)
+project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_yhi,
+                   const __grid_constant__ CUtensorMap tm_ylo, const Project2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t box_bytes = PJ2_KS * BK2 * 4;                  // [16 rows x 32 floats] = 2 KB
+  const uint32_t a_bytes = (PJ2_NC / BK2) * box_bytes;          // 8 boxes = 16 KB
+  const uint32_t y_half = 4 * box_bytes;                        // 128 sketch columns, hi (or lo)
+  const uint32_t b_bytes = 2 * y_half;
+  const uint32_t b_base = smem_base + (uint32_t)p.ra * a_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)p.rb * b_bytes;
+  int nb = 0;
+  const uint32_t araw_full = bar_base + 8u * nb;  nb += p.ra;
+  const uint32_t araw_empty = bar_base + 8u * nb; nb += p.ra;
+  const uint32_t b_full = bar_base + 8u * nb;     nb += p.rb;
+  const uint32_t b_empty = bar_base + 8u * nb;    nb += p.rb;
+  const uint32_t at_ready = bar_base + 8u * nb;   nb += AT_RING;
+  const uint32_t at_empty = bar_base + 8u * nb;   nb += AT_RING;
+  const uint32_t tfull = bar_base + 8u * nb;      nb += 1;
+  const uint32_t tmem_slot = bar_base + 8u * nb;
+  const uint32_t at_col0 = 256;                                  // [0,256): two accumulators, [256,512): A ring
+
+  const int64_t t0 = (int64_t)blockIdx.x * PJ2_NC;
+  const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
+  const int64_t r_end = min(p.m, r_begin + p.rows_per_split);
+  const int num_k = (int)((r_end - r_begin + PJ2_KS - 1) / PJ2_KS);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.ra; ++i) {
+      mbar_init(araw_full + 8u * i, 1);
+      mbar_init(araw_empty + 8u * i, 8);      // all eight transform warps read every slot
+    }
+    for (int i = 0; i < p.rb; ++i) {
+      mbar_init(b_full + 8u * i, 1);
+      mbar_init(b_empty + 8u * i, 1);
+    }
+    for (int i = 0; i < AT_RING; ++i) {
+      mbar_init(at_ready + 8u * i, 8);
+      mbar_init(at_empty + 8u * i, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_x);
+  if (warp == SK2_BPROD_WARP && lane == 0) { tma_prefetch_desc(&tm_yhi); tma_prefetch_desc(&tm_ylo); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===== TMA producer: raw X slots (HBM stream), 8 boxes of [16 rows x 32 time] =====
+    if (lane == 0) {
+      Ring ra(p.ra);
+      for (int kc = 0; kc < num_k; ++kc) {
+        mbar_wait(araw_empty + 8u * ra.i, ra.ph ^ 1u);
+        const uint32_t dst = smem_base + (uint32_t)ra.i * a_bytes;
+        const int32_t row0 = (int32_t)(r_begin + (int64_t)kc * PJ2_KS);
+        mbar_arrive_expect_tx(araw_full + 8u * ra.i, a_bytes);
+        for (int c = 0; c < PJ2_NC / BK2; ++c)
+          tma_load_2d(dst + c * box_bytes, &tm_x, (int32_t)(t0 + c * BK2), row0, araw_full + 8u * ra.i);
+        ra.next();
+      }
+    }
+  } else if (warp == SK2_BPROD_WARP) {
+    // ===== TMA producer: Y hi / lo slots, 4 + 4 boxes of [16 rows x 32 columns] =====
+    if (lane == 0) {
+      Ring rb(p.rb);
+      for (int kc = 0; kc < num_k; ++kc) {
+        mbar_wait(b_empty + 8u * rb.i, rb.ph ^ 1u);
+        const uint32_t dst = b_base + (uint32_t)rb.i * b_bytes;
+        const int32_t row0 = (int32_t)(r_begin + (int64_t)kc * PJ2_KS);
+        mbar_arrive_expect_tx(b_full + 8u * rb.i, b_bytes);
+        for (int c = 0; c < 4; ++c) {
+          tma_load_2d(dst + c * box_bytes, &tm_yhi, c * BK2, row0, b_full + 8u * rb.i);
+          tma_load_2d(dst + y_half + c * box_bytes, &tm_ylo, c * BK2, row0, b_full + 8u * rb.i);
+        }
+        rb.next();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_tf32(128, 128, 0, 1);      // A K-major (TMEM), B MN-major
+    Ring rb(p.rb), at(AT_RING);
+    for (int kc = 0; kc < num_k; ++kc) {
+      mbar_wait(b_full + 8u * rb.i, rb.ph);
+      mbar_wait(at_ready + 8u * at.i, at.ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t bs = b_base + (uint32_t)rb.i * b_bytes;
+        const uint32_t a0 = tmem_base + at_col0 + (uint32_t)at.i * PJ2_AT_COLS;
+#pragma unroll
+        for (int tt = 0; tt < PJ2_TT; ++tt) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)tt * 128;
+#pragma unroll
+          for (int ks = 0; ks < PJ2_KS / UK2; ++ks) {
+            const uint32_t a_hi = a0 + (uint32_t)tt * 2 * PJ2_KS + ks * UK2;
+            const uint32_t a_lo = a_hi + PJ2_KS;
+            const uint32_t koff = (uint32_t)ks * UK2 * 128;      // 8 K rows = two 4-row swizzle atoms
+            const uint64_t b_hi = make_smem_desc(bs + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
+            const uint64_t b_lo = make_smem_desc(bs + y_half + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
+            umma_tf32_ts(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
+            umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1);
+            umma_tf32_ts(d_tmem, a_hi, b_hi, idesc, 1);
+          }
+        }
+        umma_commit(b_empty + 8u * rb.i);
+        umma_commit(at_empty + 8u * at.i);
+        if (kc == num_k - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      rb.next();
+      at.next();
+    }
+  } else if (warp < SK2_EPI_WARP0) {
+    // ===== transform: X slot (smem [row][time]) -> hi / lo of X^T -> TMEM (lane = time, column = row) =====
+    const int q = warp % 4;
+    const int tt = (warp - 2) / 4;                       // time tile handled by this group of four warps
+    const int tl = q * 32 + lane;                        // time index within the tile == TMEM lane
+    const int box = (tt * 128 + tl) / BK2;               // which [16 x 32] box holds this time column
+    const int col = tl % BK2;                            // float index inside the 128-byte box row
+    Ring ra(p.ra), at(AT_RING);
+    for (int kc = 0; kc < num_k; ++kc) {
+      mbar_wait(araw_full + 8u * ra.i, ra.ph);
+      const uint32_t base = smem_base + (uint32_t)ra.i * a_bytes + (uint32_t)box * box_bytes;
+      float x[PJ2_KS];
+#pragma unroll
+      for (int k = 0; k < PJ2_KS; ++k) {                 // row k of the box: 128 B, 16-byte chunks XOR-swizzled by (k & 7)
+        const uint32_t addr = base + (uint32_t)k * 128u + (uint32_t)((((col >> 2) ^ (k & 7)) << 4) | ((col & 3) << 2));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[k]) : "r"(addr));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(araw_empty + 8u * ra.i);
+      mbar_wait(at_empty + 8u * at.i, at.ph ^ 1u);
+      tcgen05_fence_after();
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int k = 0; k < PJ2_KS; ++k) {
+        const float h = tf32_trunc(x[k]);
+        hi[k] = __float_as_uint(h);
+        lo[k] = __float_as_uint(x[k] - h);
+      }
+      const uint32_t t_hi = tmem_base + at_col0 + (uint32_t)at.i * PJ2_AT_COLS + (uint32_t)tt * 2 * PJ2_KS +
+                            ((uint32_t)(q * 32) << 16);
+      tmem_st16(t_hi, hi);
+      tmem_st16(t_hi + PJ2_KS, lo);
+      tmem_wait_st();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(at_ready + 8u * at.i);
+      ra.next();
+      at.next();
+    }
+  } else {
+    // ===== epilogue: accumulators -> float32 partial tile part[split][time][column] =====
+    const int q = warp % 4;
+    float* out = p.part + (int64_t)blockIdx.y * p.n * p.l;
+    if (num_k > 0) {
+      mbar_wait(tfull, 0);
+      tcgen05_fence_after();
+    }
+    for (int tt = 0; tt < PJ2_TT; ++tt) {
+      const int64_t t = t0 + tt * 128 + q * 32 + lane - p.xshift;     // window-relative time index of this lane
+      const uint32_t taddr = tmem_base + (uint32_t)tt * 128 + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.l; c0 += 16) {
+        uint32_t v[16];
+        if (num_k > 0) {
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (t >= 0 && t < p.n) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.l) out[t * p.l + c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace tc
 
 static int round_up2(int64_t a, int64_t b) { return (int)(ceil_div(a, b) * b); }
@@ -310,6 +527,66 @@ int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const d
   int64_t grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   tc::sketch_tc2_kernel<<<(unsigned)grid, tc::SK2_THREADS, smem, st>>>(tm_x, tm_ohi, tm_olo, p);
   return check_launch("sketch_tc2_kernel");
+}
+
+
+struct Pj2Plan {
+  int nchunks;
+  int64_t splits, rows_per_split;
+  size_t bytes;
+};
+
+static Pj2Plan pj2_plan(int64_t m, int64_t n, int64_t l) {
+  Pj2Plan pl;
+  pl.nchunks = (int)ceil_div(n, tc::PJ2_NC);
+  const int sms = sm_count();
+  int64_t splits = ceil_div(m, 4096);
+  int64_t ctas = ceil_div(splits * pl.nchunks, sms) * sms;      // whole waves
+  splits = ceil_div(ctas, pl.nchunks);
+  const int64_t cap = ((int64_t)512 << 20) / (n * l * 4 > 0 ? n * l * 4 : 1);
+  if (splits > cap) splits = cap > 0 ? cap : 1;
+  if (splits > 65535) splits = 65535;
+  int64_t rps = ceil_div(ceil_div(m, splits), tc::PJ2_KS) * tc::PJ2_KS;
+  pl.splits = ceil_div(m, rps);
+  pl.rows_per_split = rps;
+  pl.bytes = (size_t)(pl.splits * n * l * 4);
+  return pl;
+}
+
+size_t project_tf32x3_raw_workspace_bytes(int64_t m, int64_t n, int64_t l) { return pj2_plan(m, n + 3, l).bytes; }
+
+// Z (+)= X^T Y with X a plain float32 matrix (split on chip), Y given as (Yhi, Ylo).
+int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Yhi, const float* Ylo,
+                       int64_t l, int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  CUtensorMap tm_x, tm_yhi, tm_ylo;
+  int xs = 0, ys = 0, ys2 = 0, rc;
+  if ((rc = tc::make_tmap(&tm_x, X, n, m, ldx, tc::BK2, tc::PJ2_KS, &xs, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = tc::make_tmap(&tm_yhi, Yhi, l, m, ldy, tc::BK2, tc::PJ2_KS, &ys, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = tc::make_tmap(&tm_ylo, Ylo, l, m, ldy, tc::BK2, tc::PJ2_KS, &ys2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  ERA5SVD_REQUIRE(ys == 0 && ys2 == 0, "project_tf32x3: Yhi / Ylo must be 16-byte aligned");
+  const Pj2Plan pl = pj2_plan(m, n + xs, l);
+  const size_t need = (size_t)(pl.splits * n * l * 4);
+  if (!workspace || workspace_bytes < need) {
+    set_error("project_tf32x3: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return ERA5SVD_ERR_WORKSPACE;
+  }
+  tc::Project2Params p;
+  p.m = m; p.n = n; p.l = (int)l;
+  p.xshift = xs;
+  p.rows_per_split = pl.rows_per_split;
+  p.part = (float*)workspace;
+  const size_t a_bytes = (size_t)(tc::PJ2_NC / tc::BK2) * tc::PJ2_KS * tc::BK2 * 4;   // 16 KB
+  const size_t b_bytes = 2 * 4 * (size_t)tc::PJ2_KS * tc::BK2 * 4;                    // 16 KB
+  p.rb = 4;
+  p.ra = 8;
+  const size_t smem = p.ra * a_bytes + p.rb * b_bytes + 1024 + 512;
+  ERA5SVD_CUDA(cudaFuncSetAttribute(tc::project_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)pl.nchunks, (unsigned)pl.splits);
+  tc::project_tc2_kernel<<<grid, tc::PJ2_THREADS, smem, st>>>(tm_x, tm_yhi, tm_ylo, p);
+  if ((rc = check_launch("project_tc2_kernel"))) return rc;
+  launch_reduce_partials_f32(p.part, pl.splits, n, l, Z, ldz, accumulate, st);
+  return check_launch("reduce_partials_kernel");
 }
 
 }  // namespace era5svd

@@ -237,7 +237,8 @@ class CudaOps:
         if Z is None:
             Z = self.empty((n, l), torch.float64)
             accumulate = False
-        hp, hld = _mat(Xhi, "Xhi"); lp, lld = _mat(Xlo, "Xlo")
+        hp, hld = _mat(Xhi, "Xhi")
+        lp, lld = _mat(Xlo, "Xlo") if Xlo is not None else (None, hld)   # None: plain float32 X, split on chip
         yhp, yhld = _mat(Yhi, "Yhi"); ylp, ylld = _mat(Ylo, "Ylo"); zp, zld = _mat(Z, "Z")
         if hld != lld or yhld != ylld:
             raise ValueError("project_tf32x3: hi/lo operands must share their row pitch")

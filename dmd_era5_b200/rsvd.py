@@ -137,7 +137,9 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
             raise TypeError("precision 'tf32x3' needs a float32 snapshot matrix")
         if l > 128:
             raise ValueError(f"precision 'tf32x3' supports sketch widths up to 128, got l = {l}")
-        Xhi, Xlo = split if split is not None else ops.split_tf32(X)
+        # pre-split images if the caller has them (gemm_tc.cu), else the plain matrix, split on chip
+        # (gemm_tc2.cu: X crosses HBM once per pass)
+        Xhi, Xlo = split if split is not None else (X, None)
         ldy = ops.tf32_ldy(l)
         Y = ops.empty((m0 * d, ldy), tall)[:, :l]
         Yhi = ops.empty((m0 * d, ldy), tall)[:, :l]
@@ -151,7 +153,7 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         if use_tc:
             for j in range(d):
                 rows = slice(j * m0, (j + 1) * m0)
-                xh, xl = Xhi[:, j : j + n], Xlo[:, j : j + n]
+                xh, xl = Xhi[:, j : j + n], (Xlo[:, j : j + n] if Xlo is not None else None)
                 ops.sketch_tf32x3(xh, xl, Omega64, Y[rows] if keep_y else None, Yhi[rows], Ylo[rows])
                 Z = ops.project_tf32x3(xh, xl, Yhi[rows], Ylo[rows], Z, accumulate=j > 0)
         else:

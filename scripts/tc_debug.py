@@ -43,21 +43,25 @@ def run_sketch(m, n, l, seed=0, off=0, raw=False):
     return ok
 
 
-def run_project(m, n, l, seed=0, onehot=False):
+def run_project(m, n, l, seed=0, onehot=False, raw=False, off=0):
     rng = np.random.RandomState(seed)
-    Xh = rng.standard_normal((m, n)).astype(np.float32)
+    Xfull = rng.standard_normal((m, n + off)).astype(np.float32)
+    Xh = Xfull[:, off:]
     Yh = rng.standard_normal((m, l)).astype(np.float32)
     if onehot:
         Yh[:] = 0
         Yh[5, 3] = 1.0
     ldy = ops.tf32_ldy(l)
     Yb = torch.zeros((m, ldy), device="cuda"); Yb[:, :l] = dev(Yh)
-    xhi, xlo = ops.split_tf32(dev(Xh))
     yhi, ylo = ops.split_tf32(Yb)
-    Z = ops.project_tf32x3(xhi, xlo, yhi[:, :l], ylo[:, :l])
+    if raw:
+        Z = ops.project_tf32x3(dev(Xfull)[:, off:], None, yhi[:, :l], ylo[:, :l])
+    else:
+        xhi, xlo = ops.split_tf32(dev(Xfull))
+        Z = ops.project_tf32x3(xhi[:, off:], xlo[:, off:], yhi[:, :l], ylo[:, :l])
     torch.cuda.synchronize()
     ref = Xh.astype(np.float64).T @ Yh.astype(np.float64)
-    return report(f"project m={m} n={n} l={l} onehot={onehot}", Z.cpu().numpy(), ref, np.sqrt(m) if not onehot else 1.0)
+    return report(f"project{'-raw' if raw else ''} m={m} n={n} l={l} onehot={onehot} off={off}", Z.cpu().numpy(), ref, np.sqrt(m) if not onehot else 1.0)
 
 
 if __name__ == "__main__":
@@ -75,6 +79,24 @@ if __name__ == "__main__":
         ok &= run_project(1000, 744, 110)
         ok &= run_project(50000, 1460, 110)
         ok &= run_project(4097, 25, 20)
+    if which in ("all", "rawp"):
+        ok &= run_project(16, 32, 16, onehot=True, raw=True)
+        ok &= run_project(64, 32, 32, raw=True)
+        ok &= run_project(1000, 744, 110, raw=True)
+        ok &= run_project(50000, 1460, 110, raw=True)
+        ok &= run_project(4097, 25, 20, raw=True)
+        ok &= run_project(3000, 742, 110, raw=True, off=2)
+        X = torch.randn((1038240, 744), device="cuda")
+        ldy = ops.tf32_ldy(110)
+        Yb = torch.randn((1038240, ldy), device="cuda"); yhi, ylo = ops.split_tf32(Yb)
+        hi, lo = ops.split_tf32(X)
+        for name, a, b in (("v1 (hi/lo in HBM)", hi, lo), ("v2 (on-chip split)", X, None)):
+            for _ in range(2): ops.project_tf32x3(a, b, yhi[:, :110], ylo[:, :110])
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5): ops.project_tf32x3(a, b, yhi[:, :110], ylo[:, :110])
+            e1.record(); torch.cuda.synchronize()
+            print(f"project {name}: {e0.elapsed_time(e1) / 5:.3f} ms per pass (c2 shape)")
     if which in ("all", "raw"):
         ok &= run_sketch(128, 32, 16, raw=True)
         ok &= run_sketch(128, 64, 110, raw=True)
