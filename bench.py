@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=os.environ.get("ERA5SVD_PRECISION", "tf32x3"), choices=["native", "tf32x3"],
                     help="tf32x3 (default, headline): tcgen05 3xTF32 passes; native: FP32 FMA passes on the CUDA cores")
+    ap.add_argument("--tc-split", default="onchip", choices=["onchip", "hbm"])
     ap.add_argument("--rows", type=int, default=0, help="override points per rank (debug only; invalidates the number)")
     ap.add_argument("--cpu-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -208,7 +209,9 @@ def main():
 
     def step(src_dev, timer=None):
         ops.timer = timer
-        tc = args.precision == "tf32x3"
+        # tf32x3: "onchip" reads the plain matrix and splits it on chip (gemm_tc2.cu); "hbm" streams
+        # pre-split hi / lo images written by the build kernel (gemm_tc.cu)
+        tc = args.precision == "tf32x3" and args.tc_split == "hbm"
         built = build_matrix_device(ops, [src_dev], mean_center=True, scale=False, split=tc, keep_x=not tc)
         U, s, V = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=1, precision=args.precision,
                              comm=comm, row_offset=row_offset, m0_global=m_global,
@@ -301,7 +304,7 @@ def main():
                 roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": gbs / pk["hbm_gbs"], "traffic": None}
             roofline["note"] = (f"3xTF32 tcgen05 pass; tensor: 3*2mnl flops vs 1/2 sustained bf16 peak; hbm: algorithmic "
-                                f"m*n*4 + m*l*4 bytes (the pre-split hi/lo images double the real X traffic); {pk['source']}")
+                                f"m*n*4 + m*l*4 bytes (tc_split=hbm: the pre-split hi/lo images double the real X traffic); {pk['source']}")
             roofline["hbm_frac_algorithmic"] = gbs / pk["hbm_gbs"]
             roofline["tensor_frac"] = tfl / peak_tf32
         else:
@@ -326,7 +329,7 @@ def main():
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "native" else "tf32x3", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "rows_per_rank": S, "snapshots": T, "k": k, "l": k + 10,
-                       "n_iter": q, "mean_center": True, "precision": args.precision,
+                       "n_iter": q, "mean_center": True, "precision": args.precision, "tc_split": args.tc_split,
                        "l2": "inputs larger than L2 (matrix shard >= 3 GB vs 126 MB)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "sigma_1": s_first,

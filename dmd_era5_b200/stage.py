@@ -216,12 +216,11 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
             w_rows = np.tile(np.tile(np.repeat(w, O), L), len(variables))
             weights = torch.from_numpy(w_rows.astype(np.float32 if blocks[0].dtype == torch.float32 else np.float64)).to(ops.device)
         built = build_matrix_device(ops, blocks, mean_center=mean_center, scale=scale, weights=weights,
-                                    check_finite=True, split=tc, keep_x=True)
+                                    check_finite=True)
         label = "standard" if parsed_config["svd_type"] == "standard" else "randomized"
         log_and_print(logger, f"Performing {label} SVD...")
         U, s, V = svd_device(ops, built.X, svd_type=parsed_config["svd_type"], n_components=parsed_config["n_components"],
-                             delay=d, seed=parsed_config.get("random_seed"), precision=precision if tc else "native",
-                             split=(built.Xhi, built.Xlo) if tc else None)
+                             delay=d, seed=parsed_config.get("random_seed"), precision=precision if tc else "native")
         log_and_print(logger, f"{label.capitalize()} SVD complete.")
         if int(built.nonfinite.item()):
             raise ValueError("Input contains NaN or infinity.")          # sklearn check_array (extmath.py:546)

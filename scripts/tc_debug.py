@@ -55,7 +55,9 @@ def run_project(m, n, l, seed=0, onehot=False, raw=False, off=0):
     Yb = torch.zeros((m, ldy), device="cuda"); Yb[:, :l] = dev(Yh)
     yhi, ylo = ops.split_tf32(Yb)
     if raw:
-        Z = ops.project_tf32x3(dev(Xfull)[:, off:], None, yhi[:, :l], ylo[:, :l])
+        ldp = -(-(n + off) // 4) * 4
+        Xp = torch.zeros((m, ldp), device="cuda"); Xp[:, :n + off] = dev(Xfull)
+        Z = ops.project_tf32x3(Xp[:, off:off + n], None, yhi[:, :l], ylo[:, :l])
     else:
         xhi, xlo = ops.split_tf32(dev(Xfull))
         Z = ops.project_tf32x3(xhi[:, off:], xlo[:, off:], yhi[:, :l], ylo[:, :l])
