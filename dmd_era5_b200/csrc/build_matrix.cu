@@ -118,6 +118,104 @@ transpose_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t 
   }
 }
 
+// Single-read variant: one CTA keeps a [T x PB] tile of the native array (PB = 32 points, every
+// snapshot) in shared memory, computes the per-point statistics from it and writes the PB finished
+// rows of X.  HBM traffic = read m*n*b + write m*n*b: the algorithmic minimum of the build.
+//   load : warp w reads snapshots w, w + 8, ... ; a warp-load is 32 consecutive points (128 B for fp32)
+//   stats: warp w owns points w, w + 8, ... ; lanes stride over time, float64 warp reduction
+//   store: same ownership; a warp writes one row of X with lanes along time (fully coalesced)
+// The tile row pitch PB + 1 keeps both the column walks (stats / store) and the row fills conflict free.
+constexpr int FB_PB = 32;
+constexpr int FB_THREADS = 512;
+constexpr int FB_UNROLL = 8;     // independent 128-byte loads in flight per warp
+
+template <typename Ts, typename Tx>
+__global__ void __launch_bounds__(FB_THREADS)
+fused_build_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t P,
+                   Tx* __restrict__ X, int64_t ldx, Tx* __restrict__ mean_out, Tx* __restrict__ std_out,
+                   const Tx* __restrict__ weights, int center, int do_scale, int check_finite,
+                   int* __restrict__ nonfinite_flag, float* __restrict__ Xhi, float* __restrict__ Xlo) {
+  extern __shared__ unsigned char fb_smem[];
+  Ts* tile = reinterpret_cast<Ts*>(fb_smem);                  // [T][PB + 1]
+  constexpr int LD = FB_PB + 1;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = FB_THREADS / 32;
+  const int64_t p0 = (int64_t)blockIdx.x * FB_PB;
+  const int64_t p = p0 + lane;
+  int bad = 0;
+  for (int64_t tb = warp; tb < T; tb += (int64_t)nwarps * FB_UNROLL) {
+    Ts v[FB_UNROLL];
+#pragma unroll
+    for (int i = 0; i < FB_UNROLL; ++i) {
+      const int64_t t = tb + (int64_t)i * nwarps;
+      v[i] = (t < T && p < P) ? src[t * src_ld + p] : Ts(0);
+    }
+#pragma unroll
+    for (int i = 0; i < FB_UNROLL; ++i) {
+      const int64_t t = tb + (int64_t)i * nwarps;
+      if (t < T) {
+        if (check_finite && !isfinite((double)v[i])) bad = 1;
+        tile[t * LD + lane] = v[i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int pp = warp; pp < FB_PB; pp += nwarps) {
+    const int64_t gp = p0 + pp;
+    if (gp >= P) break;
+    Tx mean_x = Tx(0), std_x = Tx(1);
+    if (center) {
+      double s = 0.0;
+      int cnt = 0;
+      for (int64_t t = lane; t < T; t += 32) {
+        const double v = (double)tile[t * LD + pp];
+        if (v == v) { s += v; ++cnt; }
+      }
+      s = warp_sum(s);
+      cnt = warp_sum(cnt);
+      const double mean = cnt > 0 ? s / (double)cnt : __longlong_as_double(0x7ff8000000000000LL);
+      mean_x = (Tx)mean;
+      if (do_scale) {
+        double a = 0.0, q = 0.0;
+        for (int64_t t = lane; t < T; t += 32) {
+          const Ts raw = tile[t * LD + pp];
+          if (raw == raw) {
+            const double xc = (double)centre<Ts, Tx>(raw, mean_x);
+            a += xc;
+            q += xc * xc;
+          }
+        }
+        a = warp_sum(a);
+        q = warp_sum(q);
+        const double m2 = cnt > 0 ? a / (double)cnt : 0.0;
+        double var = cnt > 0 ? q / (double)cnt - m2 * m2 : __longlong_as_double(0x7ff8000000000000LL);
+        if (var < 0.0) var = 0.0;
+        std_x = (Tx)sqrt(var);
+      }
+      if (lane == 0) {
+        mean_out[gp] = mean_x;
+        if (do_scale) std_out[gp] = std_x;
+      }
+    }
+    const Tx w = weights ? weights[gp] : Tx(1);
+    for (int64_t t = lane; t < T; t += 32) {
+      const Ts raw = tile[t * LD + pp];
+      Tx v = center ? centre<Ts, Tx>(raw, mean_x) : (Tx)raw;
+      if (do_scale) v = v / std_x;
+      if (weights) v = v * w;
+      if (X) X[gp * ldx + t] = v;
+      if (Xhi) {
+        const float h = tc::tf32_hi((float)v);
+        Xhi[gp * ldx + t] = h;
+        Xlo[gp * ldx + t] = (float)v - h;
+      }
+    }
+  }
+  if (check_finite) {
+    int any = __syncthreads_or(bad);
+    if (any && threadIdx.x == 0) atomicExch(nonfinite_flag, 1);
+  }
+}
+
 template <typename Ts, typename Tx>
 int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void* X, int64_t ldx,
                     void* mean_out, void* std_out, const void* weights, unsigned flags,
@@ -125,6 +223,16 @@ int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void*
   const bool center = flags & ERA5SVD_BUILD_MEAN_CENTER;
   const bool scale = flags & ERA5SVD_BUILD_SCALE;
   const bool check = (flags & ERA5SVD_BUILD_CHECK_FINITE) && nonfinite_flag;
+  // single-read fused kernel whenever the [T x 32] tile fits in shared memory (T <= ~1700 for fp32)
+  const size_t tile_bytes = (size_t)T * (FB_PB + 1) * sizeof(Ts);
+  if (tile_bytes <= 220 * 1024) {
+    auto kern = fused_build_kernel<Ts, Tx>;
+    ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+    kern<<<(unsigned)ceil_div(P, FB_PB), FB_THREADS, tile_bytes, st>>>(
+        (const Ts*)src, T, src_ld, P, (Tx*)X, ldx, (Tx*)mean_out, (Tx*)std_out, (const Tx*)weights, center ? 1 : 0,
+        (center && scale) ? 1 : 0, check ? 1 : 0, nonfinite_flag, Xhi, Xlo);
+    return check_launch("fused_build_kernel");
+  }
   if (center) {
     int threads = 128;
     int64_t blocks = ceil_div(P, threads);

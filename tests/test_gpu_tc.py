@@ -102,7 +102,9 @@ def test_fused_build_split_pipeline(ops):
     U1, s1, V1 = svd_device(ops, ref.X, svd_type="randomized", n_components=20, seed=2, precision="tf32x3")
     U2, s2, V2 = svd_device(ops, None, svd_type="randomized", n_components=20, seed=2, precision="tf32x3",
                             split=(only.Xhi, only.Xlo))
-    assert torch.equal(s1, s2) and torch.equal(U1, U2)            # same kernels, same bits
+    # U1: plain X, tf32 split on chip (gemm_tc2.cu); U2: hi / lo images from HBM (gemm_tc.cu)
+    assert float(((s1 - s2).abs() / s2).max()) < 1e-5
+    assert float((U1.double() - U2.double()).abs().max()) < 1e-4
     U0, s0, V0 = randomized_svd_ref(ref.X.double().cpu().numpy(), 20, 2)
     assert sigma_rel_err(s2.cpu().numpy(), s0) < 1e-4
 
