@@ -128,7 +128,13 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         n_iter = n_iter_auto(m_global, n, k)
     tall = blocks.X.dtype
     rel_tol = 1e-13 if tall == torch.float64 else 1e-6
-    Omega = _orth(ops, ops.to_device(om, non_blocking=False).clone(), 1e-13)
+    # A Gaussian n x l block is already well conditioned (cond ~ (1 + sqrt(l/n)) / (1 - sqrt(l/n))): like the
+    # reference, Omega_0 is used as drawn (column-normalised); when l is close to n it is orthonormalised.
+    Omega = ops.to_device(om, non_blocking=False).clone()
+    if 4 * l > n:
+        Omega = _orth(ops, Omega, 1e-13)
+    else:
+        ops.col_normalize(Omega)
 
     use_tc = precision == PREC_TF32X3
     if use_tc:
