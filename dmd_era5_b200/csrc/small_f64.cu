@@ -202,8 +202,6 @@ syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restric
 // Cholesky G = R^T R (upper R) + explicit inverse, one CTA (32 x 32 threads).  Working copies in
 // shared memory when they fit (l <= 118), else in the caller's R / Rinv buffers.
 // ---------------------------------------------------------------------------------------------
-constexpr int CHOL_XREG = 8;   // register-resident solution entries per lane: columns up to l = 256
-
 __global__ void __launch_bounds__(1024, 1)
 chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __restrict__ R,
                 int64_t ldr, double* __restrict__ Rinv, int64_t ldri, double rel_tol, int use_smem) {
@@ -254,39 +252,22 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
     }
   }
   __syncthreads();
-  // inverse, one warp per column c of Rinv: solve R x = e_c by column-oriented back substitution.
-  // Lane k (+32 j) keeps x_k in a register; step i finalises x_i = x_i / r_ii (reciprocal precomputed,
-  // broadcast by shuffle) and every lane subtracts r_ki x_i from its own entries: no reductions.
+  // inverse, one warp per column c of Rinv: solve R x = e_c by column-oriented back substitution:
+  // step i finalises x_i = x_i / r_ii (reciprocal precomputed) and the lanes subtract r_ki x_i from the
+  // entries k < i: no reductions, no divisions in the loop.
   for (int j = t; j < l; j += 1024) scale[j] = 1.0 / Rw[j * ld_r + j];      // reuse: reciprocal diagonal
   __syncthreads();
-  if (l <= 32 * CHOL_XREG) {
-    for (int c = ty; c < l; c += 32) {
-      double x[CHOL_XREG];
-#pragma unroll
-      for (int j = 0; j < CHOL_XREG; ++j) x[j] = (tx + 32 * j == c) ? 1.0 : 0.0;
-      for (int i = c; i >= 0; --i) {
-        double mine = 0.0;
-#pragma unroll
-        for (int j = 0; j < CHOL_XREG; ++j)
-          if (j == i / 32) mine = x[j];
-        const double xi = __shfl_sync(0xffffffffu, mine, i % 32) * scale[i];
-        if (tx == i % 32) Iw[i * ld_i + c] = xi;
-#pragma unroll
-        for (int j = 0; j < CHOL_XREG; ++j) {
-          const int k = tx + 32 * j;
-          if (k < i) x[j] = fma(-Rw[k * ld_r + i], xi, x[j]);
-        }
-      }
-    }
-  } else {
-    for (int c = ty; c < l; c += 32) {
-      for (int i = c; i >= 0; --i) {
-        double sum = 0.0;
-        for (int k = i + 1 + tx; k <= c; k += 32) sum += Rw[i * ld_r + k] * Iw[k * ld_i + c];
-        sum = warp_sum(sum);
-        if (tx == 0) Iw[i * ld_i + c] = ((i == c ? 1.0 : 0.0) - sum) * scale[i];
-        __syncwarp();
-      }
+  // x lives in column c of Iw itself (zero-initialised above; stride ld_i is odd in shared memory, so the
+  // column walk is conflict free)
+  for (int c = ty; c < l; c += 32) {
+    if (tx == 0) Iw[c * ld_i + c] = 1.0;
+    __syncwarp();
+    for (int i = c; i >= 0; --i) {
+      const double xi = Iw[i * ld_i + c] * scale[i];
+      __syncwarp();
+      if (tx == 0) Iw[i * ld_i + c] = xi;
+      for (int k = tx; k < i; k += 32) Iw[k * ld_i + c] = fma(-Rw[k * ld_r + i], xi, Iw[k * ld_i + c]);
+      __syncwarp();
     }
   }
   if (use_smem) {
