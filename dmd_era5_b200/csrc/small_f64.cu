@@ -100,7 +100,7 @@ __device__ __forceinline__ void jacobi_pair(int step, int i, int n_pad, int& p, 
 
 __global__ void __launch_bounds__(JAC_THREADS, 1)
 syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restrict__ W,
-             double* __restrict__ V, int64_t ldv, int max_sweeps, double* __restrict__ ws,
+             double* __restrict__ V, int64_t ldv, int max_sweeps, double tol_in, double* __restrict__ ws,
              int use_smem) {
   extern __shared__ double smem[];
   const int t = threadIdx.x;
@@ -122,7 +122,7 @@ syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restric
   __syncthreads();
 
   // relative off-diagonal threshold |a_pq| <= tol * sqrt(|a_pp a_qq|), tol = eps * sqrt(n) (cf. xGESVJ)
-  const double tol = 2.220446049250313e-16 * sqrt((double)n);
+  const double tol = tol_in > 0.0 ? tol_in : 2.220446049250313e-16 * sqrt((double)n);
   const double tol2 = tol * tol;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     int did = 0;
@@ -374,7 +374,7 @@ size_t era5svd_syevj_workspace_bytes(int64_t n) {
 }
 
 int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
-                      int max_sweeps, void* workspace, size_t workspace_bytes, void* stream) {
+                      int max_sweeps, double tol, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace era5svd;
   ERA5SVD_REQUIRE(A && W && V, "syevj: null pointer");
   ERA5SVD_REQUIRE(n > 0 && n <= 16384 && lda >= n && ldv >= n, "syevj: bad shape n=%lld", (long long)n);
@@ -391,7 +391,7 @@ int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, i
     }
   }
   ERA5SVD_CUDA(cudaFuncSetAttribute(syevj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-  syevj_kernel<<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, (double*)workspace, use_smem);
+  syevj_kernel<<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, (double*)workspace, use_smem);
   return check_launch("syevj_kernel");
 }
 

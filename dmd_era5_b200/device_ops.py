@@ -269,7 +269,7 @@ class CudaOps:
                                         self._stream()), "era5svd_gemm_f64")
         return C
 
-    def syevj(self, A: torch.Tensor, max_sweeps: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+    def syevj(self, A: torch.Tensor, max_sweeps: int = 0, tol: float = 0.0) -> tuple[torch.Tensor, torch.Tensor]:
         """Eigen-decomposition of symmetric A (destroyed).  Returns (W descending, V columns)."""
         n = A.shape[0]
         ap, ald = _mat(A, "A")
@@ -277,7 +277,7 @@ class CudaOps:
         V = self.empty((n, n), torch.float64)
         nbytes = int(self.lib.era5svd_syevj_workspace_bytes(n))
         ws = self._workspace("syevj", nbytes)
-        check(self.lib.era5svd_syevj_f64(ap, n, ald, W.data_ptr(), V.data_ptr(), n, max_sweeps, ws.data_ptr(),
+        check(self.lib.era5svd_syevj_f64(ap, n, ald, W.data_ptr(), V.data_ptr(), n, max_sweeps, tol, ws.data_ptr(),
                                          ws.numel(), self._stream()), "era5svd_syevj_f64")
         return W, V
 

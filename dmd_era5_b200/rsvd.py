@@ -128,6 +128,10 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         n_iter = n_iter_auto(m_global, n, k)
     tall = blocks.X.dtype
     rel_tol = 1e-13 if tall == torch.float64 else 1e-6
+    # Jacobi stopping thresholds (relative off-diagonal size): full precision for float64 data; for
+    # float32 data the factors carry ~1e-7 anyway, so 1e-10 changes sigma by < 1e-12 relative
+    rr_tol = 0.0 if tall == torch.float64 else 1e-8
+    eig_tol = 0.0 if tall == torch.float64 else 1e-10
     # A Gaussian n x l block is already well conditioned (cond ~ (1 + sqrt(l/n)) / (1 - sqrt(l/n))): like the
     # reference, Omega_0 is used as drawn (column-normalised); when l is close to n it is orthonormalised.
     Omega = ops.to_device(om, non_blocking=False).clone()
@@ -180,7 +184,7 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
             # the columns of X (Z W) come out nearly orthogonal and graded (~ sigma_j u_j) and the Gram
             # matrix of the stored float32 Y is well conditioned after diagonal scaling.
             T = ops.gemm(Omega, Z, transA=True)
-            _, W = ops.syevj(T)
+            _, W = ops.syevj(T, tol=rr_tol)                # only has to decouple the columns
             Z = ops.gemm(Z, W)
         # cond(Z) ~ kappa(X)^2 after the random start (shifted CholeskyQR3), <~ kappa(X) afterwards
         Omega = _orth(ops, Z, 1e-13, shifted=(it == 0 and n_iter > 1))
@@ -192,7 +196,7 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     _, Rinv = ops.chol_inv(G, rel_tol)
     B = ops.gemm(Rinv, Zp, transA=True, transB=True)   # l x n  = R^-T Z'^T = Q^T X
     BBt = ops.gemm(B, B, transB=True)                  # l x l
-    lam, Uh = ops.syevj(BBt)
+    lam, Uh = ops.syevj(BBt, tol=eig_tol)
     s, inv_s = ops.sigma_from_eig(lam)
     Vt = ops.gemm(Uh, B, transA=True)                  # l x n
     ops.scale_rows(Vt, inv_s)

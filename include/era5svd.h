@@ -149,10 +149,11 @@ int era5svd_gemm_f64(int transA, int transB, int64_t M, int64_t N, int64_t K, do
  * W[n] = eigenvalues in DESCENDING order, V[n x n] = eigenvectors in columns (same order).
  * Replaces the small dense solves of scipy.linalg.svd(B, gesdd) (extmath.py:615) and the
  * eigensolve behind the Gram-route standard SVD (np.linalg.svd, era5_svd.py:251).
- * max_sweeps <= 0 selects the default (30); iteration stops early at convergence. */
+ * max_sweeps <= 0 selects the default (30); iteration stops early at convergence, i.e. when a whole
+ * sweep finds every |a_pq| <= tol * sqrt(|a_pp a_qq|); tol <= 0 selects eps * sqrt(n). */
 size_t era5svd_syevj_workspace_bytes(int64_t n);
 int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
-                      int max_sweeps, void* workspace, size_t workspace_bytes, void* stream);
+                      int max_sweeps, double tol, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Cholesky G = R^T R (R upper triangular) of a symmetric positive (semi-)definite l x l matrix and
  * the explicit inverse Rinv = R^{-1} (upper triangular), one CTA.  Replaces scipy qr / lu

@@ -59,7 +59,7 @@ class FakeOps:
         C.copy_(out + beta * C)
         return C
 
-    def syevj(self, A, max_sweeps=0):
+    def syevj(self, A, max_sweeps=0, tol=0.0):
         self._count("syevj")
         w, v = np.linalg.eigh(0.5 * (A.numpy() + A.numpy().T))
         return torch.from_numpy(w[::-1].copy()), torch.from_numpy(np.ascontiguousarray(v[:, ::-1]))
