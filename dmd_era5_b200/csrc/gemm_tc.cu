@@ -164,7 +164,7 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
                  const SketchParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform
   const uint32_t a_bytes = BM * BK * 4;                 // 16 KB
   const uint32_t b_bytes = (uint32_t)p.npad * BK * 4;   // npad x 128 B
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
@@ -201,7 +201,7 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0; uint32_t ph = 0;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int32_t row0 = (int32_t)(tile * BM);
@@ -229,7 +229,7 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
       for (int kc = 0; kc < p.num_k; ++kc) {
         mbar_wait(full_bar(s), ph);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
@@ -313,7 +313,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
                   const ProjectParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform
   const uint32_t box_bytes = (uint32_t)p.ks * BK * 4;       // one [ks rows x 32] box (2 KB for ks = 16)
   const uint32_t y_bytes = 4 * box_bytes;                   // 128 sketch columns
   const uint32_t x_bytes = (uint32_t)p.ncc * box_bytes;
@@ -351,7 +351,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0; uint32_t ph = 0;
       for (int kc = 0; kc < num_k; ++kc) {
         mbar_wait(empty_bar(s), ph ^ 1u);
@@ -377,7 +377,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
     for (int kc = 0; kc < num_k; ++kc) {
       mbar_wait(full_bar(s), ph);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
         for (int ks = 0; ks < p.ks / UMMA_K; ++ks) {
           const uint32_t koff = (uint32_t)ks * UMMA_K * 128;       // next 8 K rows (two 4-row swizzle atoms)

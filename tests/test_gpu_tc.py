@@ -64,6 +64,53 @@ def test_project_tf32x3(ops, m, n, l):
     assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
 
 
+@pytest.mark.parametrize("m,n,l,off", [(128, 32, 16, 0), (1000, 744, 110, 0), (300, 100, 128, 0), (129, 40, 112, 0),
+                                       (5000, 1460, 110, 0), (2000, 742, 110, 2), (77, 25, 20, 1), (40000, 744, 100, 3)])
+def test_sketch_tf32x3_onchip_split(ops, m, n, l, off):
+    """Xlo = None: the plain float32 matrix is split on chip (gemm_tc2.cu; merged-N kernel for l <= 112)."""
+    rng = np.random.RandomState(m + n + 1)
+    Xfull = (rng.standard_normal((m, n + off)) * np.exp(rng.uniform(-3, 3, size=(m, 1)))).astype(np.float32)
+    Om = rng.standard_normal((n, l))
+    ld = (n + off + 7) // 8 * 8
+    Xb = torch.zeros((m, ld), device="cuda")
+    Xb[:, : n + off] = dev(Xfull)
+    ldy = ops.tf32_ldy(l)
+    Y = torch.zeros((m, ldy), device="cuda")[:, :l]
+    Yh = torch.zeros((m, ldy), device="cuda")[:, :l]
+    Yl = torch.zeros((m, ldy), device="cuda")[:, :l]
+    ops.sketch_tf32x3(Xb[:, off:off + n], None, dev(Om), Y, Yh, Yl)
+    ref = Xfull[:, off:].astype(np.float64) @ Om
+    bound = TC_REL * np.linalg.norm(Xfull[:, off:], axis=1)[:, None] * np.linalg.norm(Om, axis=0)[None, :]
+    assert np.all(np.abs(Y.cpu().numpy() - ref) <= bound + 1e-30)
+    assert np.array_equal((Yh + Yl).cpu().numpy(), Y.cpu().numpy())
+    # only the plain output (the U = Y M pass)
+    Y2 = torch.zeros((m, ldy), device="cuda")[:, :l]
+    ops.sketch_tf32x3(Xb[:, off:off + n], None, dev(Om), Y2, None, None)
+    assert torch.equal(Y2, Y)
+
+
+@pytest.mark.parametrize("m,n,l,off", [(16, 32, 16, 0), (1000, 744, 110, 0), (50000, 1460, 110, 0), (4097, 25, 20, 1),
+                                       (333, 600, 128, 0), (20000, 742, 112, 2), (9000, 130, 100, 3)])
+def test_project_tf32x3_onchip_split(ops, m, n, l, off):
+    """Xlo = None: Z = X^T Y with the plain float32 X split on chip; column windows X[:, off:] included."""
+    rng = np.random.RandomState(m + l + 1)
+    Xfull = (rng.standard_normal((m, n + off)) * np.exp(rng.uniform(-3, 3, size=(m, 1)))).astype(np.float32)
+    Yh = rng.standard_normal((m, l)).astype(np.float32)
+    ld = (n + off + 7) // 8 * 8
+    Xb = torch.zeros((m, ld), device="cuda")
+    Xb[:, : n + off] = dev(Xfull)
+    ldy = ops.tf32_ldy(l)
+    Yb = torch.zeros((m, ldy), device="cuda")
+    Yb[:, :l] = dev(Yh)
+    yhi, ylo = ops.split_tf32(Yb)
+    Z = ops.project_tf32x3(Xb[:, off:off + n], None, yhi[:, :l], ylo[:, :l])
+    ref = Xfull[:, off:].astype(np.float64).T @ Yh.astype(np.float64)
+    bound = TC_REL * np.linalg.norm(Xfull[:, off:], axis=0)[:, None] * np.linalg.norm(Yh, axis=0)[None, :]
+    assert np.all(np.abs(Z.cpu().numpy() - ref) <= bound)
+    Z2 = ops.project_tf32x3(Xb[:, off:off + n], None, yhi[:, :l], ylo[:, :l], Z.clone(), accumulate=True)
+    assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
+
+
 @pytest.mark.parametrize("d", [1, 2])
 def test_randomized_tf32x3_vs_oracle(d):
     """float32 storage, tensor-core passes: sigma within 1e-4 of the float64 oracle on the same data."""
