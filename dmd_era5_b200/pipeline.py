@@ -83,6 +83,26 @@ def build_matrix_device(ops: CudaOps, var_blocks: list[torch.Tensor], *, mean_ce
     return BuiltMatrix(X=X, Xhi=Xhi, Xlo=Xlo, mean=mean, std=std, row_offset=0, m0_global=m0, nonfinite=flag)
 
 
+_OMEGA_CACHE: dict = {}
+
+
+def _omega_on_device(ops: CudaOps, n: int, k: int, seed: int | None, dtype: torch.dtype):
+    """Test matrix for the randomized SVD.  Unseeded (the reference's behaviour, quirk Q6) it is drawn from NumPy's
+    global RandomState at every call.  With a seed it is a pure function of (n, k, seed, dtype), so the device copy
+    is cached: repeated calls (SvdStageStream) then issue no small host -> device copy, which would otherwise queue
+    behind the multi-GB slice transfer on the same copy engine and stall the compute stream."""
+    if seed is None:
+        return draw_omega(n, k, None, dtype)
+    key = (str(ops.device), n, k, int(seed), dtype)
+    om = _OMEGA_CACHE.get(key)
+    if om is None:
+        om = ops.to_device(torch.from_numpy(draw_omega(n, k, seed, dtype)), non_blocking=False)
+        if len(_OMEGA_CACHE) > 16:
+            _OMEGA_CACHE.clear()
+        _OMEGA_CACHE[key] = om
+    return om
+
+
 def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_components: int, delay: int = 1,
                seed: int | None = None, precision: str = "native", comm=None, row_offset: int = 0,
                m0_global: int | None = None, n_iter: int | None = None, stats: dict | None = None,
@@ -97,7 +117,7 @@ def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_compone
             X = split[0] + split[1]
         return standard_svd_device(ops, X, n_components, delay=delay, comm=comm)
     if svd_type == "randomized":
-        omega0 = draw_omega(n, n_components, seed, ref.dtype)
+        omega0 = _omega_on_device(ops, n, n_components, seed, ref.dtype)
         return randomized_svd_device(ops, X, n_components, omega0, n_iter=n_iter, delay=delay,
                                      precision=PRECISIONS[precision], comm=comm, row_offset=row_offset,
                                      m0_global=m0_global, stats=stats, split=split)

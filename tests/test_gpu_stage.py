@@ -119,3 +119,32 @@ def test_standardize_data_gpu():
     out3, _, _ = st.standardize_data(ds, dim="level")     # test_02:180-212
     assert np.allclose(out3["u_component_of_wind"].values.mean(axis=1), 0, atol=1e-6)
     assert np.allclose(out3["u_component_of_wind"].values.std(axis=1), 1, atol=1e-6)
+
+
+def test_stage_stream_matches_one_shot():
+    """SvdStageStream (H2D | compute | D2H overlapped, buffers reused) returns, slice by slice, exactly what the
+    one-shot path returns for the same slice."""
+    import torch
+
+    from dmd_era5_b200.era5_svd import get_ops
+    from dmd_era5_b200.pipeline import build_matrix_device, svd_device
+    from dmd_era5_b200.stage_stream import SvdStageStream
+    from dmd_era5_b200.synthetic import synthetic_field
+
+    ops = get_ops()
+    T, S, k = 96, 20000, 12
+    hosts = []
+    for i in range(5):
+        f = synthetic_field(T, S, device="cuda", seed=40 + i, rank=30, rho=0.8)
+        h = torch.empty((T, S), dtype=torch.float32, pin_memory=True)
+        h.copy_(f)
+        hosts.append(h)
+    torch.cuda.synchronize()
+    got = {}
+    st = SvdStageStream(ops, T, S, n_components=k, precision="tf32x3", seed=5)
+    n = st.run(hosts, consume=lambda i, U, s, V: got.__setitem__(i, (U.clone(), s.clone(), V.clone())))
+    assert n == 5 and sorted(got) == [0, 1, 2, 3, 4]
+    for i, h in enumerate(hosts):
+        built = build_matrix_device(ops, [h.cuda()], mean_center=True, scale=False)
+        U, s, V = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=5, precision="tf32x3")
+        assert torch.equal(got[i][1], s.cpu()) and torch.equal(got[i][2], V.cpu()) and torch.equal(got[i][0], U.cpu())
