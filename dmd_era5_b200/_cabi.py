@@ -36,6 +36,12 @@ PROTOTYPES = {
     "era5svd_gemm_f64": (_int, [_int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64, _vp]),
     "era5svd_syevj_workspace_bytes": (_sz, [_i64]),
     "era5svd_syevj_f64": (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _int, _dbl, _vp, _sz, _vp]),
+    "era5svd_tridiag_reduce_workspace_bytes": (_sz, [_i64]),
+    "era5svd_tridiag_reduce_f64": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "era5svd_tridiag_eig_topk_workspace_bytes": (_sz, [_i64, _i64]),
+    "era5svd_tridiag_eig_topk_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "era5svd_tridiag_apply_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "era5svd_tridiag_backtransform_f64": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "era5svd_chol_inv_f64": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _vp]),
     "era5svd_col_normalize_f64": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "era5svd_sigma_from_eig_f64": (_int, [_vp, _i64, _vp, _vp, _vp]),

@@ -281,6 +281,48 @@ class CudaOps:
                                          ws.numel(), self._stream()), "era5svd_syevj_f64")
         return W, V
 
+    # -- time-sized symmetric eigensolver (csrc/eig_tridiag.cu) -------------------------------
+    def tridiag_reduce(self, A: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Householder tridiagonalisation of symmetric A in place (A then holds the reflectors).
+        Returns (d (n,), e (n,), tau (n,))."""
+        n = A.shape[0]
+        ap, ald = _mat(A, "A")
+        d = self.empty((n,), torch.float64); e = self.empty((n,), torch.float64); tau = self.empty((n,), torch.float64)
+        ws = self._workspace("tridiag", int(self.lib.era5svd_tridiag_reduce_workspace_bytes(n)))
+        end = self.timer.start("tridiag_reduce", bytes=8.0 * n ** 3, flops=4.0 / 3.0 * n ** 3) if self.timer else None
+        check(self.lib.era5svd_tridiag_reduce_f64(ap, n, ald, d.data_ptr(), e.data_ptr(), tau.data_ptr(), ws.data_ptr(),
+                                                  ws.numel(), self._stream()), "era5svd_tridiag_reduce_f64")
+        if end is not None:
+            end.record()
+        return d, e, tau
+
+    def tridiag_eig_topk(self, d: torch.Tensor, e: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """k largest eigenvalues (descending) and (unorthogonalised) eigenvectors Z (n, k) of T = tridiag(e, d, e)."""
+        n = d.shape[0]
+        W = self.empty((k,), torch.float64)
+        Z = self.empty((n, k), torch.float64)
+        ws = self._workspace("tridiag_eig", int(self.lib.era5svd_tridiag_eig_topk_workspace_bytes(n, k)))
+        check(self.lib.era5svd_tridiag_eig_topk_f64(d.data_ptr(), e.data_ptr(), n, k, W.data_ptr(), Z.data_ptr(), k,
+                                                    ws.data_ptr(), ws.numel(), self._stream()),
+              "era5svd_tridiag_eig_topk_f64")
+        return W, Z
+
+    def tridiag_apply(self, d: torch.Tensor, e: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+        n, k = Z.shape
+        zp, zld = _mat(Z, "Z")
+        Y = self.empty((n, k), torch.float64)
+        check(self.lib.era5svd_tridiag_apply_f64(d.data_ptr(), e.data_ptr(), n, k, zp, zld, Y.data_ptr(), k,
+                                                 self._stream()), "era5svd_tridiag_apply_f64")
+        return Y
+
+    def tridiag_backtransform(self, A: torch.Tensor, tau: torch.Tensor, Z: torch.Tensor) -> torch.Tensor:
+        n, k = Z.shape
+        ap, ald = _mat(A, "A"); zp, zld = _mat(Z, "Z")
+        V = self.empty((n, k), torch.float64)
+        check(self.lib.era5svd_tridiag_backtransform_f64(ap, n, ald, tau.data_ptr(), k, zp, zld, V.data_ptr(), k,
+                                                         self._stream()), "era5svd_tridiag_backtransform_f64")
+        return V
+
     def chol_inv(self, G: torch.Tensor, rel_tol: float) -> tuple[torch.Tensor, torch.Tensor]:
         l = G.shape[0]
         gp, gld = _mat(G, "G")

@@ -4,24 +4,90 @@ Replaces ``np.linalg.svd(X, full_matrices=False)`` + truncation
 (src/dmd_era5/era5_svd/era5_svd.py:249-254; LAPACK gesdd, O(m n^2) on the host and an m x n
 temporary U).  For the tall-skinny snapshot matrix:
 
-    G = X^T X          (n x n, float64; tall pass, all-reduced over row shards)
-    G = V L V^T        (Jacobi eigensolver)         s = sqrt(L)
-    U_k = X V_k S_k^-1 (tall pass)                  Vt_k = V_k^T
+    G = X^T X          (n x n, float64; tall passes, all-reduced over row shards)
+    G = V L V^T        k largest eigenpairs only (the reference truncates to n_components):
+                         n <= 118 : one-CTA Jacobi (small_f64.cu)
+                         larger n : Householder tridiagonalisation on all SMs + bisection / inverse iteration
+                                    + one Rayleigh-Ritz step + back-transformation (eig_tridiag.cu)
+    s = sqrt(L);  U_k = X V_k S_k^-1 (tall pass);  Vt_k = V_k^T
 
 Only k columns of U are ever formed.  Like the reference, no sign normalisation is applied
 (LAPACK's signs are arbitrary too); parity is up to a per-pair sign.  The Gram matrix squares the
 condition number: sigma_i is accurate to ~ eps * (sigma_1 / sigma_i)^2, i.e. 1e-6 down to
-sigma_i ~ 1e-5 sigma_1 in float64.
+sigma_i ~ 1e-5 sigma_1 in float64; with precision "tf32x3" (float32 data) eps is the
+~1e-6 of the tensor-core Gram, so only the leading components (sigma_i >~ 0.1 sigma_1) reach 1e-4.
 """
 from __future__ import annotations
 
 import torch
 
-from ._cabi import PREC_NATIVE
+from ._cabi import PREC_NATIVE, PREC_TF32X3
 from .dist import LocalComm
 
+JACOBI_MAX_N = 118      # largest n whose working copies fit one CTA's shared memory (syevj_kernel)
+TC_BLOCK = 112          # sketch-width block of the tensor-core project kernel
 
-def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int = 1, comm=None):
+
+def _orth2(ops, Z: torch.Tensor) -> torch.Tensor:
+    """Two CholeskyQR sweeps: orthonormal basis of span(Z) for a well-conditioned n x k float64 Z."""
+    for _ in range(2):
+        G = ops.gemm(Z, Z, transA=True)
+        _, Rinv = ops.chol_inv(G, 1e-14)
+        Z = ops.gemm(Z, Rinv)
+    return Z
+
+
+def sym_eig_topk(ops, G: torch.Tensor, k: int, refine: bool = True) -> tuple[torch.Tensor, torch.Tensor]:
+    """k largest eigenpairs of the symmetric float64 matrix G (n x n; not modified).
+    Returns (lam (k,) descending, V (n, k) orthonormal columns)."""
+    n = G.shape[0]
+    k = min(int(k), n)
+    if n <= JACOBI_MAX_N:
+        lam, V = ops.syevj(G.clone())
+        return lam[:k].contiguous(), V[:, :k].contiguous()
+    A = (0.5 * (G + G.t())).contiguous()                 # both triangles are read; destroyed by the reduction
+    d, e, tau = ops.tridiag_reduce(A)
+    kk = min(n, k + min(8, n - k))                        # a few guard vectors resolve a cluster cut by the k-th value
+    W, Z = ops.tridiag_eig_topk(d, e, kk)
+    Z = _orth2(ops, Z)
+    if refine:
+        # Rayleigh-Ritz in the tridiagonal basis: decouples vectors of close eigenvalues (inverse iteration leaves
+        # them mixed) and returns Ritz values consistent with the orthonormalised vectors
+        H = ops.gemm(Z, ops.tridiag_apply(d, e, Z), transA=True)
+        lam, Wh = sym_eig_topk(ops, H, kk, refine=False)
+        Z = ops.gemm(Z, Wh)
+    else:
+        lam = W
+    V = ops.tridiag_backtransform(A, tau, Z[:, :k].contiguous())
+    return lam[:k].contiguous(), V
+
+
+def gram_device(ops, X: torch.Tensor, n: int, delay: int, precision: int) -> torch.Tensor:
+    """G = sum_j X_j^T X_j over the delay windows X_j = X[:, j : j + n] (float64, this rank's rows only)."""
+    G = None
+    if precision == PREC_TF32X3:
+        if X.dtype != torch.float32:
+            raise TypeError("precision 'tf32x3' needs a float32 snapshot matrix")
+        G = ops.empty((n, n), torch.float64)
+        for j in range(delay):
+            Xj = X[:, j : j + n]
+            for c0 in range(0, n, TC_BLOCK):
+                c1 = min(n, c0 + TC_BLOCK)
+                hi, lo = ops.split_tf32(Xj[:, c0:c1])      # the (Y_hi, Y_lo) operand of the project kernel
+                Z = ops.project_tf32x3(Xj, None, hi, lo)   # (n, c1 - c0) float64
+                if j == 0:
+                    G[:, c0:c1] = Z
+                else:
+                    G[:, c0:c1] += Z
+        return G
+    for j in range(delay):
+        Xj = X[:, j : j + n]
+        G = ops.project(Xj, Xj, G, accumulate=j > 0, precision=PREC_NATIVE)
+    return G
+
+
+def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int = 1, comm=None,
+                        precision: int = PREC_NATIVE):
     """X: this rank's base rows (m0_local, T).  Returns (U_local (m0_local*delay, k), s (k,), Vt (k, n))."""
     comm = comm or LocalComm()
     m0, T = X.shape
@@ -30,18 +96,22 @@ def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int =
     if n < 1:
         raise ValueError("delay embedding larger than the number of snapshots")
     k = min(int(n_components), n)
-    G = None
-    for j in range(d):
-        Xj = X[:, j : j + n]
-        G = ops.project(Xj, Xj, G, accumulate=j > 0, precision=PREC_NATIVE)
+    use_tc = precision == PREC_TF32X3 and X.dtype == torch.float32 and k <= 128
+    G = gram_device(ops, X, n, d, PREC_TF32X3 if use_tc else PREC_NATIVE)
     comm.allreduce_sum_(G)
-    lam, V = ops.syevj(G)
+    lam, V = sym_eig_topk(ops, G, k)
     s, inv_s = ops.sigma_from_eig(lam)
-    Vk = V[:, :k].t().contiguous()              # (k, n): rows = right singular vectors, descending
+    Vk = V.t().contiguous()                     # (k, n): rows = right singular vectors, descending
     M = Vk.clone()
-    ops.scale_rows(M, inv_s[:k].contiguous())   # S_k^-1 V_k^T
-    Mt = ops.convert(M.t().contiguous(), X.dtype)   # (n, k) = V_k S_k^-1 in the tall dtype
-    U = ops.empty((m0 * d, k), X.dtype)
-    for j in range(d):
-        ops.sketch(X[:, j : j + n], Mt, U[j * m0 : (j + 1) * m0], PREC_NATIVE)
-    return U, s[:k], Vk
+    ops.scale_rows(M, inv_s.contiguous())       # S_k^-1 V_k^T
+    Mt = M.t().contiguous()                     # (n, k) = V_k S_k^-1
+    if use_tc:
+        U = ops.empty((m0 * d, ops.tf32_ldy(k)), X.dtype)[:, :k]
+        for j in range(d):
+            ops.sketch_tf32x3(X[:, j : j + n], None, Mt, U[j * m0 : (j + 1) * m0], None, None)
+    else:
+        Mt = ops.convert(Mt, X.dtype)
+        U = ops.empty((m0 * d, k), X.dtype)
+        for j in range(d):
+            ops.sketch(X[:, j : j + n], Mt, U[j * m0 : (j + 1) * m0], PREC_NATIVE)
+    return U, s, Vk

@@ -155,6 +155,27 @@ size_t era5svd_syevj_workspace_bytes(int64_t n);
 int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
                       int max_sweeps, double tol, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Symmetric eigensolver for time-sized matrices, k largest eigenpairs (the eigensolve behind the Gram-route
+ * standard SVD: np.linalg.svd(X, full_matrices=False) followed by the [:k] truncation, era5_svd.py:249-254).
+ *   tridiag_reduce        : A (n x n symmetric, both triangles, row-major) = Q T Q^T.  On return d[n], e[n] (e[n-1] = 0)
+ *                           hold T, tau[n] the reflector scalars and row j of A (columns j+1..) the Householder vector
+ *                           of column j (v[0] = 1 stored); the rest of A is destroyed.  Multi-CTA, memory bound.
+ *   tridiag_eig_topk      : the k largest eigenvalues of T (W, descending; bisection on Sturm counts) and vectors
+ *                           Z (n x k, columns; inverse iteration).  Vectors of close eigenvalues are independent but
+ *                           not orthogonal: the caller orthonormalises and applies one Rayleigh-Ritz step (Y = T Z
+ *                           via tridiag_apply).
+ *   tridiag_backtransform : V (n x k) = Q Z. */
+size_t era5svd_tridiag_reduce_workspace_bytes(int64_t n);
+int era5svd_tridiag_reduce_f64(double* A, int64_t n, int64_t lda, double* d, double* e, double* tau,
+                               void* workspace, size_t workspace_bytes, void* stream);
+size_t era5svd_tridiag_eig_topk_workspace_bytes(int64_t n, int64_t k);
+int era5svd_tridiag_eig_topk_f64(const double* d, const double* e, int64_t n, int64_t k, double* W, double* Z,
+                                 int64_t ldz, void* workspace, size_t workspace_bytes, void* stream);
+int era5svd_tridiag_apply_f64(const double* d, const double* e, int64_t n, int64_t k, const double* Z, int64_t ldz,
+                              double* Y, int64_t ldy, void* stream);
+int era5svd_tridiag_backtransform_f64(const double* A, int64_t n, int64_t lda, const double* tau, int64_t k,
+                                      const double* Z, int64_t ldz, double* V, int64_t ldv, void* stream);
+
 /* Cholesky G = R^T R (R upper triangular) of a symmetric positive (semi-)definite l x l matrix and
  * the explicit inverse Rinv = R^{-1} (upper triangular), one CTA.  Replaces scipy qr / lu
  * normalisers (extmath.py:371-383) in CholeskyQR form.  A pivot that falls below
