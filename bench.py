@@ -329,6 +329,11 @@ def main():
                         "frac": gbs / pk["hbm_gbs"], "traffic": None,
                         "note": f"FP32-FMA (CUDA-core) pass, algorithmic bytes m*n*4 + m*l*4 per launch; {pk['source']}"}
         roofline["avg_launch_ms"] = avg_ms
+        try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload)
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                roofline["traffic"] = json.load(f).get(args.workload, {}).get(dom)
+        except Exception:
+            pass
     kernels = {n: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps} for n, v in ksum.items()}
 
     # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------
