@@ -528,14 +528,16 @@ int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const d
   p.npad = npad;
   p.Y = Y; p.Yhi = Yhi; p.Ylo = Ylo;
   p.ldy = ldy;
-  // shared memory: B ring of 5 slots (the MMA warp otherwise waits ~25 % of its time for Om^T tiles coming from
-  // L2), the rest for the raw-A ring (HBM latency), up to 8 slots
+  // shared memory: B ring of 4 slots (L2 latency), the rest for the raw-A ring (HBM latency), up to 8 slots.
+  // The raw-A depth must be EVEN: the two transform groups take alternate chunks, so with an even depth every slot
+  // always belongs to the same group.  With an odd depth a group meets a slot only every other use and its parity wait
+  // can be satisfied by the use it skipped (seen as a race and, eventually, a hung barrier at depth 5).
   const size_t a_bytes = (size_t)tc::BM2 * tc::BK2 * 4, b_bytes = 2 * (size_t)npad * tc::BK2 * 4;
   const size_t budget = 227 * 1024 - 1024 - 512;
-  p.rb = 5;
+  p.rb = 4;
   p.ra = (int)((budget - p.rb * b_bytes) / a_bytes);
-  if (p.ra < 4) { p.rb = 4; p.ra = (int)((budget - p.rb * b_bytes) / a_bytes); }
   if (p.ra > 8) p.ra = 8;
+  p.ra &= ~1;
   ERA5SVD_REQUIRE(p.ra >= 2, "sketch_tf32x3: not enough shared memory");
   const size_t smem = p.ra * a_bytes + p.rb * b_bytes + 1024 + 512;
   ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -42,6 +42,34 @@ def test_build_rows(ops, dtype, tol, flags):
     assert float(buf[:, T:].abs().max()) == 0.0       # padding untouched
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 2e-6)])
+@pytest.mark.parametrize("T,P,ld_src", [(744, 1000, 1000), (1460, 333, 336), (2920, 200, 200), (5000, 64, 64), (744, 130, 131)])
+def test_build_rows_long_series(ops, dtype, tol, T, P, ld_src):
+    """Long time axes: the single-read smem-tile kernel (T up to ~1700 for float32) and the two-kernel path beyond it,
+    aligned and misaligned source pitches, NaN skipping, scaling."""
+    rng = np.random.RandomState(T + P)
+    src = (rng.rand(T, ld_src) * 30 + 250 + 5 * np.sin(np.arange(T))[:, None]).astype(dtype)
+    src[T // 3, 7] = np.nan                      # skipped by mean / std like xarray does
+    d_src = dev(src)[:, :P]
+    X = torch.zeros((P, T + (-T) % 8), dtype=d_src.dtype, device="cuda")[:, :T]
+    mean = torch.zeros(P, dtype=d_src.dtype, device="cuda")
+    std = torch.zeros(P, dtype=d_src.dtype, device="cuda")
+    ops.build_rows(d_src, X, mean, std, None, BUILD_MEAN_CENTER | BUILD_SCALE, None)
+    # float64 statement of the same operations on the same (float32 or float64) data: the kernel accumulates the
+    # statistics in float64 and rounds once, so it must agree with this to the rounding of the matrix dtype ...
+    ref, mu, sd = standardize_np(src[:, :P].astype(np.float64), scale=True)
+    assert np.allclose(mean.cpu().numpy(), mu, rtol=tol / 10, atol=0)
+    assert np.allclose(std.cpu().numpy(), sd, rtol=10 * tol, atol=0)
+    got = X.cpu().numpy()
+    ok = ~np.isnan(ref.T)
+    assert np.array_equal(np.isnan(got), ~ok)
+    assert np.max(np.abs(got[ok] - ref.T[ok])) <= (1e-12 if dtype == np.float64 else 5e-6)
+    # ... and with the reference-dtype oracle (NumPy sums float32 means row after row, so its own mean drifts ~T * eps)
+    ref32, mu32, sd32 = standardize_np(src[:, :P], scale=True)
+    assert np.allclose(mean.cpu().numpy(), mu32, rtol=max(tol, 2e-9 * T), atol=0)
+    assert np.max(np.abs(got[ok] - ref32.T[ok])) <= (20 * tol if dtype == np.float64 else max(1e-4, 1e-7 * T))
+
+
 def test_build_rows_nan_and_flag(ops):
     src = np.random.RandomState(1).rand(16, 64)
     src[3, 5] = np.nan

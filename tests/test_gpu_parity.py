@@ -135,3 +135,38 @@ def test_invariants_at_bench_shape_reduced_rows(ops):
     # spectrum of the generator: sigma_i ~ 100 * 0.93**i
     expect = 100.0 * 0.93 ** torch.arange(k, device="cuda", dtype=torch.float64)
     assert float(((s64 - expect).abs() / expect).max()) < 0.15
+
+
+def test_invariants_at_full_c2_size_tf32x3(ops):
+    """BASELINE configs[1] at FULL size (1 038 240 x 744 float32, k = 100) on the tensor-core path; the CPU oracle
+    cannot run this in test time, so size-independent properties are checked: descending sigma, orthonormal U / V,
+    X^T U = V^T S, linearity (scaling X by 4 scales sigma by 4 exactly and leaves U, V unchanged bit for bit),
+    run-to-run bitwise reproducibility, and agreement of sigma with the FP32-FMA path (different kernels, same data)."""
+    from dmd_era5_b200.synthetic import synthetic_field
+
+    T, S, k = 744, 721 * 1440, 100
+    field = synthetic_field(T, S, device="cuda", seed=1000)
+    built = build_matrix_device(ops, [field], mean_center=True, scale=False)
+    del field
+    X = built.X
+    U, s, V = svd_device(ops, X, svd_type="randomized", n_components=k, seed=1, precision="tf32x3")
+    U2, s2, V2 = svd_device(ops, X, svd_type="randomized", n_components=k, seed=1, precision="tf32x3")
+    assert torch.equal(s, s2) and torch.equal(V, V2) and torch.equal(U, U2)
+    eye = torch.eye(k, device="cuda", dtype=torch.float64)
+    assert torch.all(s[:-1] >= s[1:])
+    UtU = torch.zeros((k, k), device="cuda", dtype=torch.float64)
+    XtU = torch.zeros((T, k), device="cuda", dtype=torch.float64)
+    for r0 in range(0, S, 1 << 17):                      # float64 reductions in row chunks (bounded temporaries)
+        Uc = U[r0 : r0 + (1 << 17)].double()
+        UtU += Uc.t() @ Uc
+        XtU += X[r0 : r0 + (1 << 17)].double().t() @ Uc
+    assert float((UtU - eye).abs().max()) < 5e-5
+    assert float((V @ V.t() - eye).abs().max()) < 5e-5
+    assert float((XtU - V.t() * s).norm() / s.norm()) < 1e-4
+    # scaling by a power of two is exact in every kernel of the path
+    X.mul_(4.0)
+    U4, s4, V4 = svd_device(ops, X, svd_type="randomized", n_components=k, seed=1, precision="tf32x3")
+    assert torch.equal(s4, 4.0 * s) and torch.equal(V4, V) and torch.equal(U4, U)
+    X.mul_(0.25)
+    Un, sn, Vn = svd_device(ops, X, svd_type="randomized", n_components=k, seed=1, precision="native")
+    assert float(((s - sn).abs() / sn).max()) < 1e-4
