@@ -42,6 +42,9 @@ PROTOTYPES = {
     "era5svd_tridiag_eig_topk_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _sz, _vp]),
     "era5svd_tridiag_apply_f64": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp]),
     "era5svd_tridiag_backtransform_f64": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "era5svd_bop_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
+    "era5svd_bop_iterate_f64": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _vp, _dbl, _dbl, _int, _vp, _sz, _vp]),
     "era5svd_chol_inv_f64": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _dbl, _vp]),
     "era5svd_col_normalize_f64": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "era5svd_sigma_from_eig_f64": (_int, [_vp, _i64, _vp, _vp, _vp]),

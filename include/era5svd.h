@@ -197,6 +197,26 @@ int era5svd_convert(const void* src, int dtype_src, int64_t lds, void* dst, int 
                     int64_t ldd, int64_t rows, int64_t cols, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (d') Optimized DMD / BOP-DMD on the SVD-projected coefficients, batched over bagging trials.  NOT in the reference
+ * (it only cites the method, README.md:85, :139); named by BASELINE.json (north_star (d), configs[4]).  Variable
+ * projection + Levenberg-Marquardt (Askham & Kutz 2018), restated in oracle/bopdmd_np.py.
+ *
+ * H (n_time x N, row-major, ldh) : projected coefficients, row i = snapshot at time t[i]  (= (diag(s) V)^T of the SVD)
+ * idx (K x p int32)              : time-ordered snapshot subset of every trial (K = 1 with idx = 0..n_time-1: full fit)
+ * alpha, alpha_try (K x r complex128, interleaved re/im): accepted eigenvalues / candidate evaluated by this call;
+ *                                  before the first call alpha_try holds the initial guess, rho = +inf, lam = lam0, done = 0
+ * rho, lam (K), JhJ (K x r x r complex), rhs (K x r complex), Bout (K x r x N complex: B of the accepted point,
+ * mode j = Bout[j, :] in the coordinates of H's columns), done (K int32: 1 once converged / failed).
+ * One call = one LM iteration of every trial with done == 0:  Psi = [Re Phi | Im Phi] -> batched FP64 Gram GEMMs ->
+ * one CTA per trial (complex Cholesky, B, rho, accept / reject, J^H J, rhs, next candidate).  first != 0 also
+ * computes the per-trial ||H[idx]||_F^2. */
+size_t era5svd_bop_workspace_bytes(int64_t K, int64_t p, int64_t r, int64_t N);
+int era5svd_bop_iterate_f64(const double* H, int64_t n_time, int64_t N, int64_t ldh, const double* t, const int* idx,
+                            int64_t K, int64_t p, int64_t r, double* alpha, double* alpha_try, double* rho,
+                            double* lam, double* JhJ, double* rhs, double* Bout, int* done, double nu, double tol,
+                            int first, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * svd_flip (extmath.py:964-972, u-based): per column of U the FIRST row holding max |U[:, j]|.
  * col_absmax writes, per column j < k: absmax[j], row[j] = row_offset + local row (lowest on ties),
  * sign[j] = sign of that entry (+1 / -1 / 0).  combine reduces R stacked candidate sets
