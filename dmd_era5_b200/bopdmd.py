@@ -42,7 +42,7 @@ def draw_subsets(n_time: int, trial_size: int, n_trials: int, seed: int | None) 
 
 
 def optdmd_device(ops, H: torch.Tensor, t: torch.Tensor, idx: torch.Tensor, alpha0: torch.Tensor, *, max_iter: int = 30,
-                  tol: float = 1e-12, lam0: float = 1.0, nu: float = 3.0):
+                  tol: float = 1e-9, lam0: float = 1.0, nu: float = 3.0):
     """Batched optimized DMD.  H (n_time, N) float64, t (n_time,) float64, idx (K, p) int32, alpha0 (K, r) or (r,)
     complex128, all on the device.  Returns (alpha (K, r), B (K, r, N), rho (K,), done (K,), iterations)."""
     dev = ops.device
@@ -78,7 +78,7 @@ def optdmd_device(ops, H: torch.Tensor, t: torch.Tensor, idx: torch.Tensor, alph
 
 
 def bopdmd_device(ops, H, t, *, n_trials: int, trial_size: int, r: int | None = None, seed: int | None = 0,
-                  max_iter: int = 30, tol: float = 1e-12, alpha0=None) -> dict:
+                  max_iter: int = 30, tol: float = 1e-9, alpha0=None) -> dict:
     """BOP-DMD: full fit, then `n_trials` refits of random `trial_size`-snapshot subsets started from the full fit.
     H: (n_time, N) projected coefficients (NumPy or tensor), t: (n_time,) times, r: number of DMD modes (default N).
     Returns tensors on the device:

@@ -276,8 +276,9 @@ bop_step_kernel(const StepParams q) {
     } else {
       const double l = q.lam[k] * q.nu;
       q.lam[k] = l;
-      // no accepted point yet (singular start) or the damping has run away: stop this trial
-      finished = (l > 1e12) || !(rho_old < 1e300);
+      // no accepted point yet (singular start), runaway damping, or stagnation (the candidate is within tol of the
+      // accepted objective: converged): stop this trial
+      finished = (l > 1e12) || !(rho_old < 1e300) || (ok && rho_try - rho_old <= q.tol * rho_old);
     }
   }
   __syncthreads();

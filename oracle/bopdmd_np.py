@@ -81,11 +81,13 @@ def dense_jacobian(alpha: np.ndarray, t: np.ndarray, H: np.ndarray):
     return J, Res.ravel()
 
 
-def optdmd(H: np.ndarray, t: np.ndarray, alpha0: np.ndarray, max_iter: int = 30, tol: float = 1e-12,
+def optdmd(H: np.ndarray, t: np.ndarray, alpha0: np.ndarray, max_iter: int = 30, tol: float = 1e-9,
            lam0: float = 1.0, nu: float = 3.0):
     """Levenberg-Marquardt on alpha.  Fixed control flow shared with the device driver: every iteration evaluates
     the candidate alpha_try; a decrease of rho accepts it (lambda /= nu), otherwise lambda *= nu; the next candidate
-    is alpha + delta(lambda) from the normal equations of the last accepted point."""
+    is alpha + delta(lambda) from the normal equations of the last accepted point.  A trial stops when an accepted
+    step gains less than tol * rho, or a rejected candidate is within tol * rho of the accepted objective (rho is
+    formed as ||H||^2 - tr(C^H B), so its own rounding is ~1e-16 ||H||^2: tol below ~1e-10 is meaningless)."""
     H = np.asarray(H, dtype=np.float64)
     alpha = np.array(alpha0, dtype=np.complex128)
     rho = np.inf
@@ -103,7 +105,8 @@ def optdmd(H: np.ndarray, t: np.ndarray, alpha0: np.ndarray, max_iter: int = 30,
                 done = converged
             else:
                 lam = lam * nu
-                if lam > 1e12:
+                # stagnation (the candidate is no worse than tol): converged; runaway damping: give up
+                if lam > 1e12 or (np.isfinite(rho) and rho_t - rho <= tol * rho):
                     done = True
             if not done:
                 Areg = JhJ + lam * np.diag(np.real(np.diag(JhJ)))
@@ -118,7 +121,7 @@ def subsets(n_time: int, trial_size: int, n_trials: int, seed: int) -> np.ndarra
 
 
 def bopdmd(H: np.ndarray, t: np.ndarray, r: int, n_trials: int, trial_size: int, seed: int = 0, max_iter: int = 30,
-           tol: float = 1e-12, alpha0: np.ndarray | None = None):
+           tol: float = 1e-9, alpha0: np.ndarray | None = None):
     """Returns dict(alpha_full, alpha_mean, alpha_std, amp_mean, amp_std, alphas (n_trials, r))."""
     H = np.asarray(H, dtype=np.float64)
     a0 = initial_eigenvalues(H, t, r) if alpha0 is None else np.asarray(alpha0, dtype=np.complex128)
