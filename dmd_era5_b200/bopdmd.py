@@ -78,12 +78,19 @@ def optdmd_device(ops, H: torch.Tensor, t: torch.Tensor, idx: torch.Tensor, alph
 
 
 def bopdmd_device(ops, H, t, *, n_trials: int, trial_size: int, r: int | None = None, seed: int | None = 0,
-                  max_iter: int = 30, tol: float = 1e-9, alpha0=None) -> dict:
+                  max_iter: int = 30, tol: float = 1e-9, alpha0=None, comm=None) -> dict:
     """BOP-DMD: full fit, then `n_trials` refits of random `trial_size`-snapshot subsets started from the full fit.
     H: (n_time, N) projected coefficients (NumPy or tensor), t: (n_time,) times, r: number of DMD modes (default N).
-    Returns tensors on the device:
-    alpha_full (r,), B_full (r, N), alphas (n_trials, r), amps (n_trials, r), alpha_mean, alpha_std, amp_mean, amp_std,
-    mode_mean (r, N) / mode_std (r, N) of the unit-norm rows of B, and the subsets used."""
+    With a multi-rank `comm` the TRIALS are partitioned over the ranks (they are independent: no data-path collective);
+    the per-trial eigenvalues / amplitudes are all-gathered and the mode statistics all-reduced, so every rank returns
+    the same dictionary.  Returns tensors on the device: alpha_full (r,), B_full (r, N), alphas (n_trials, r), amps
+    (n_trials, r), alpha_mean, alpha_std, amp_mean, amp_std, mode_mean (r, N) / mode_std (r, N) of the unit-norm rows
+    of B, and the subsets used."""
+    from .dist import LocalComm
+
+    comm = comm or LocalComm()
+    if comm.world > 1 and seed is None:
+        raise ValueError("bopdmd_device: a seed is required when the trials are partitioned over several ranks")
     dev = ops.device
     H_h = H.detach().cpu().numpy() if torch.is_tensor(H) else np.asarray(H)
     t_h = t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
@@ -97,23 +104,48 @@ def bopdmd_device(ops, H, t, *, n_trials: int, trial_size: int, r: int | None = 
         full_idx = torch.arange(n_time, dtype=torch.int32, device=dev).unsqueeze(0)
         a_full, B_full, rho_full, _, it_full = optdmd_device(ops, Hd, td, full_idx, torch.from_numpy(a0).to(dev),
                                                              max_iter=max_iter, tol=tol)
-        idx_h = draw_subsets(n_time, trial_size, n_trials, seed)
-        idx = torch.from_numpy(idx_h).to(dev)
-        alphas, Bs, rhos, done, iters = optdmd_device(ops, Hd, td, idx, a_full[0], max_iter=max_iter, tol=tol)
-        amps = torch.linalg.vector_norm(Bs, dim=2)                         # (K, r)
-        modes = Bs / amps.clamp_min(1e-300).unsqueeze(-1)
-        # fix the phase of every trial's mode to the full fit's before averaging
+        idx_h = draw_subsets(n_time, trial_size, n_trials, seed)             # identical on every rank (seeded)
+        per = -(-n_trials // comm.world)
+        k0, k1 = min(n_trials, comm.rank * per), min(n_trials, (comm.rank + 1) * per)
+        nr = a_full.shape[1]
         ref = B_full[0] / torch.linalg.vector_norm(B_full[0], dim=1, keepdim=True).clamp_min(1e-300)
-        ph = (modes * ref.conj().unsqueeze(0)).sum(dim=2)
-        modes = modes * (ph.conj() / ph.abs().clamp_min(1e-300)).unsqueeze(-1)
+        alphas = torch.zeros((per, nr), dtype=torch.complex128, device=dev)
+        amps = torch.zeros((per, nr), dtype=torch.float64, device=dev)
+        rhos = torch.zeros((per,), dtype=torch.float64, device=dev)
+        done = torch.zeros((per,), dtype=torch.int32, device=dev)
+        msum = torch.zeros((2, nr, N), dtype=torch.complex128, device=dev)   # sum of modes, sum of |mode|^2
+        iters = 0
+        if k1 > k0:
+            idx = torch.from_numpy(idx_h[k0:k1]).to(dev)
+            al, Bs, rh, dn, iters = optdmd_device(ops, Hd, td, idx, a_full[0], max_iter=max_iter, tol=tol)
+            am = torch.linalg.vector_norm(Bs, dim=2)                         # (k1 - k0, r)
+            modes = Bs / am.clamp_min(1e-300).unsqueeze(-1)
+            # fix the phase of every trial's mode to the full fit's before averaging
+            ph = (modes * ref.conj().unsqueeze(0)).sum(dim=2)
+            modes = modes * (ph.conj() / ph.abs().clamp_min(1e-300)).unsqueeze(-1)
+            alphas[: k1 - k0], amps[: k1 - k0], rhos[: k1 - k0], done[: k1 - k0] = al, am, rh, dn
+            msum[0] = modes.sum(dim=0)
+            msum[1] = modes.abs().pow(2).sum(dim=0).to(torch.complex128)
+        if comm.world > 1:
+            alphas = torch.view_as_complex(comm.allgather(torch.view_as_real(alphas)).reshape(-1, nr, 2))[:n_trials]
+            amps = comm.allgather(amps).reshape(-1, nr)[:n_trials]
+            rhos = comm.allgather(rhos).reshape(-1)[:n_trials]
+            done = comm.allgather(done).reshape(-1)[:n_trials]
+            ms = torch.view_as_real(msum).contiguous()
+            comm.allreduce_sum_(ms)
+            msum = torch.view_as_complex(ms)
+        else:
+            alphas, amps, rhos, done = alphas[:n_trials], amps[:n_trials], rhos[:n_trials], done[:n_trials]
+        mode_mean = msum[0] / n_trials
+        mode_var = (msum[1].real / n_trials - mode_mean.abs().pow(2)).clamp_min(0.0)
         return {
             "alpha_full": a_full[0], "B_full": B_full[0], "rho_full": rho_full[0], "iterations_full": it_full,
             "alphas": alphas, "amps": amps, "rhos": rhos, "done": done, "iterations": iters,
             "alpha_mean": alphas.mean(dim=0),
             "alpha_std": torch.sqrt(alphas.real.var(dim=0, unbiased=False) + alphas.imag.var(dim=0, unbiased=False)),
             "amp_mean": amps.mean(dim=0), "amp_std": amps.std(dim=0, unbiased=False),
-            "mode_mean": modes.mean(dim=0), "mode_std": torch.sqrt((modes - modes.mean(dim=0)).abs().pow(2).mean(dim=0)),
-            "subsets": idx,
+            "mode_mean": mode_mean, "mode_std": torch.sqrt(mode_var),
+            "subsets": torch.from_numpy(idx_h).to(dev),
         }
 
 

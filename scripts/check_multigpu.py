@@ -59,6 +59,37 @@ def main():
                               "signs_agree": signs_agree(Ufull, U0)}
             out[precision]["pass"] = bool(out[precision]["sigma_rel_err"] < tol and out[precision]["signs_agree"]
                                           and out[precision]["angle_U_max"] < 2e-2)
+    # standard SVD (Gram route: the n x n Gram matrix is the only collective), float64, against np.linalg.svd
+    from oracle.svd_ref import standard_svd_ref
+
+    X64 = lowrank_field_np(4096 * world + 33, 200, r=60, rho=0.9, seed=12)
+    a0, a1 = shard_rows(X64.shape[0], world, rank)
+    U, s, V = svd_device(ops, torch.from_numpy(X64[a0:a1].copy()).cuda(), svd_type="standard", n_components=16, comm=comm,
+                         row_offset=a0, m0_global=X64.shape[0])
+    if rank == 0:
+        U0, s0, V0 = standard_svd_ref(X64, 16)
+        out["standard_fp64"] = {"sigma_rel_err": sigma_rel_err(s.cpu().numpy(), s0),
+                                "angle_V_max": float(vector_angles(V.cpu().numpy().T, V0.T).max()),
+                                "angle_U_shard0_max": float(vector_angles(U.cpu().numpy(), U0[a0:a1]).max())}
+        out["standard_fp64"]["pass"] = bool(out["standard_fp64"]["sigma_rel_err"] < 1e-6 and out["standard_fp64"]["angle_V_max"] < 1e-5)
+    # BOP-DMD: trials partitioned over the ranks must reproduce the single-rank ensemble
+    from dmd_era5_b200.bopdmd import bopdmd_device
+
+    rng = np.random.RandomState(1)
+    om = np.sort(rng.uniform(0.2, 3.0, 4)) + 0.15 * np.arange(4)
+    al = np.concatenate([-rng.uniform(0, 0.05, 4) + 1j * om, -rng.uniform(0, 0.05, 4) - 1j * om])
+    al[4:] = al[:4].conj()
+    Bh = rng.standard_normal((4, 10)) + 1j * rng.standard_normal((4, 10))
+    tt = np.linspace(0, 20, 400)
+    Hh = (np.exp(np.outer(tt, al)) @ np.concatenate([Bh, Bh.conj()])).real + 0.05 * rng.standard_normal((400, 10))
+    sharded = bopdmd_device(ops, Hh, tt, n_trials=41, trial_size=320, r=8, seed=3, comm=comm)
+    if rank == 0:
+        single = bopdmd_device(ops, Hh, tt, n_trials=41, trial_size=320, r=8, seed=3)
+        out["bopdmd_trials_sharded"] = {
+            "alphas_max_diff": float((sharded["alphas"] - single["alphas"]).abs().max()),
+            "alpha_std_max_diff": float((sharded["alpha_std"] - single["alpha_std"]).abs().max()),
+            "mode_mean_max_diff": float((sharded["mode_mean"] - single["mode_mean"]).abs().max())}
+        out["bopdmd_trials_sharded"]["pass"] = bool(max(out["bopdmd_trials_sharded"].values()) < 1e-12)
     if rank == 0:
         out["world"] = world
         print(json.dumps(out))
