@@ -74,12 +74,16 @@ tridiag_symv_kernel(const double* __restrict__ A, int64_t lda, int n, int j, dou
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   for (int i = blockIdx.x * TD_WARPS + warp; i < r; i += gridDim.x * TD_WARPS) {
     const double* row = A + (int64_t)(j + 1 + i) * lda + j + 1;
-    double s = 0.0;
-    for (int c = lane; c < r; c += 32) {
-      const double vc = c == 0 ? 1.0 : x[c] * h.scale;
-      s = fma(row[c], vc, s);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int c = lane;
+    for (; c + 96 < r; c += 128) {          // four independent 256-byte loads in flight per warp
+      const double a0 = row[c], a1 = row[c + 32], a2 = row[c + 64], a3 = row[c + 96];
+      const double v0 = c == 0 ? 1.0 : x[c] * h.scale, v1 = x[c + 32] * h.scale, v2 = x[c + 64] * h.scale,
+                   v3 = x[c + 96] * h.scale;
+      s0 = fma(a0, v0, s0); s1 = fma(a1, v1, s1); s2 = fma(a2, v2, s2); s3 = fma(a3, v3, s3);
     }
-    s = warp_sum(s);
+    for (; c < r; c += 32) s0 = fma(row[c], c == 0 ? 1.0 : x[c] * h.scale, s0);
+    const double s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) pbuf[i] = h.tau * s;
   }
 }
@@ -99,7 +103,15 @@ tridiag_rank2_kernel(double* __restrict__ A, int64_t lda, int n, int j, const do
   for (int i = blockIdx.x * TD_WARPS + warp; i < r; i += gridDim.x * TD_WARPS) {
     double* row = A + (int64_t)(j + 1 + i) * lda + j + 1;
     const double vi = vbuf[i], wi = pbuf[i] - coef * vi;
-    for (int c = lane; c < r; c += 32) {
+    int c = lane;
+    for (; c + 96 < r; c += 128) {          // four independent read-modify-writes in flight per warp
+      double a[4], vc[4], pc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = row[c + 32 * u]; vc[u] = vbuf[c + 32 * u]; pc[u] = pbuf[c + 32 * u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) row[c + 32 * u] = a[u] - fma(vi, pc[u] - coef * vc[u], wi * vc[u]);
+    }
+    for (; c < r; c += 32) {
       const double vc = vbuf[c], wc = pbuf[c] - coef * vc;
       row[c] -= fma(vi, wc, wi * vc);
     }
@@ -336,7 +348,7 @@ int era5svd_tridiag_reduce_f64(double* A, int64_t n, int64_t lda, double* d, dou
   for (int j = 0; j + 2 < (int)n; ++j) {
     const int r = (int)n - j - 1;
     int grid = (int)ceil_div(r, TD_WARPS);
-    if (grid > 4 * sms) grid = 4 * sms;
+    if (grid > 8 * sms) grid = 8 * sms;      // 64 resident warps per SM: one row per warp up to n ~ 9.5 k
     tridiag_symv_kernel<<<grid, TD_THREADS, 0, st>>>(A, lda, (int)n, j, vbuf, pbuf, d, e, tau);
     tridiag_rank2_kernel<<<grid, TD_THREADS, 0, st>>>(A, lda, (int)n, j, vbuf, pbuf, tau);
     count_launch(2);
