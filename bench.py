@@ -103,6 +103,33 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Multi-rank runs: keep this rank's threads (and therefore its first-touched pinned host buffers) on the NUMA node
+    the GPU hangs off, so that the H2D / D2H copies of the e2e leg do not cross the socket interconnect.  Best effort:
+    any failure (no sysfs, restricted cpuset) leaves the affinity untouched."""
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if len(allowed) >= 2:
+            os.sched_setaffinity(0, allowed)
+            return {"node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_run(rows: int, T: int, k: int, seed: int, threads: int):
     """The reference's own numerics on the host cores for a bounded row sample of the workload:
     NumPy restatement of the build (oracle) + sklearn.utils.extmath.randomized_svd, exactly the
@@ -187,6 +214,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
 
@@ -295,7 +323,8 @@ def main():
         e2e = {"value": x_bytes * world / 1e9 / (ms_e2e / 1e3), "unit": "GB/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(stream.h2d_bytes), "d2h_bytes_per_step": int(stream.d2h_bytes),
                "mode": f"SvdStageStream over {n_e2e} host slices: H2D(i+1) | build+SVD(i) | D2H(i-1), 2 device input buffers",
-               "single_shot": {"value": x_bytes * world / 1e9 / (ms_single / 1e3), "ms_per_step": ms_single}}
+               "single_shot": {"value": x_bytes * world / 1e9 / (ms_single / 1e3), "ms_per_step": ms_single},
+               "numa_binding": numa}
         del host, stream
 
     # ---------------- roofline of the dominant kernel ----------------
