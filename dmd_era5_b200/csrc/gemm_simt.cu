@@ -188,7 +188,15 @@ reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, in
   int64_t total = n * l;
   if (idx >= total) return;
   double s = 0.0;
-  for (int64_t k = 0; k < splits; ++k) s += (double)part[k * total + idx];
+  int64_t k = 0;
+  for (; k + 8 <= splits; k += 8) {       // eight independent loads in flight, summed in the same fixed order
+    T v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = part[(k + u) * total + idx];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += (double)v[u];
+  }
+  for (; k < splits; ++k) s += (double)part[k * total + idx];
   int64_t r = idx / l, c = idx % l;
   double* z = Z + r * ldz + c;
   *z = accumulate ? (*z + s) : s;
