@@ -1,11 +1,12 @@
-// (b) Tall GEMM passes, native-precision path (FP64 DFMA / FP32 FFMA on the CUDA cores).
+// (b) Tall GEMM passes, native-precision path: float64 on the FP64 tensor cores (mma.sync m8n8k4 DMMA),
+// float32 by FFMA on the CUDA cores.
 //
 //   sketch :  Y[m x l]  = X[m x n] * Om[n x l]              (`A @ Q`,   sklearn/utils/extmath.py:378,383)
 //   project:  Z[n x l] += X[m x n]^T * Y[m x l]  (float64)  (`A.T @ Q`, extmath.py:379; `Q.T @ M`, :606)
 //
 // This is the accuracy-first path (FP64 parity mode, and the checker for the tcgen05 path in
-// gemm_tc.cu); it is a register-tiled 128 x (16*TN) x 16 SIMT GEMM, 256 threads, 8 x TN outputs per
-// thread, register prefetch of the next k-tile.  Both passes share one inner product core because
+// gemm_tc.cu); a 128 x (16*TN) x 16 tiled GEMM, 256 threads, register prefetch of the next k-tile; the float32
+// variant is register-tiled SIMT (8 x TN outputs per thread), the float64 variant feeds the same staged tiles to DMMA.  Both passes share one inner product core because
 // both stage their operands k-major in shared memory:
 //   sketch : As[k][row]  <- X[row][k]   (transposed on the way in)   Bs[k][col] <- Om[k][col]
 //   project: As[k][time] <- X[k=row][time] (straight copy)           Bs[k][col] <- Y[k=row][col]
@@ -24,8 +25,29 @@ template <typename T, int TN>
 struct Tile {
   static constexpr int BN = 16 * TN;
   T As[BK][BM + PAD];
-  T Bs[BK][BN];
+  T Bs[BK][BN + PAD];     // the pad keeps the DMMA fragment loads (4 k-rows x 8 columns per warp) conflict free
 };
+
+// FP64 tensor-core product of one staged tile (float64 operands only): mma.sync.m8n8k4.f64.  Warp w owns rows
+// [16 w, 16 w + 16) of the 128-row tile and every 8-column tile; per k4-step it loads 2 A and 2 TN B fragments
+// (one double each) and issues 4 TN DMMAs.  Fragment layout (PTX ISA, m8n8k4 .f64): g = lane / 4, tig = lane % 4;
+// a = A[g][tig], b = B[tig][g], c = C[g][2 tig + {0, 1}].
+template <int TN>
+__device__ __forceinline__ void dmma_tile(const Tile<double, TN>& s, double (&acc)[2][2 * TN][2], int warp, int lane) {
+  const int g = lane / 4, tig = lane % 4;
+#pragma unroll
+  for (int k0 = 0; k0 < BK; k0 += 4) {
+    const double a0 = s.As[k0 + tig][warp * 16 + g], a1 = s.As[k0 + tig][warp * 16 + 8 + g];
+#pragma unroll
+    for (int nt = 0; nt < 2 * TN; ++nt) {
+      const double b = s.Bs[k0 + tig][nt * 8 + g];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(acc[0][nt][0]), "+d"(acc[0][nt][1]) : "d"(a0), "d"(b));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(acc[1][nt][0]), "+d"(acc[1][nt][1]) : "d"(a1), "d"(b));
+    }
+  }
+}
 
 template <typename T, int TN>
 __device__ __forceinline__ void mma_tile(const Tile<T, TN>& s, T (&acc)[8][TN], int ty, int tx) {
@@ -180,6 +202,131 @@ project_kernel(const T* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FP64 on the tensor cores (DMMA): same staging as sketch_kernel / project_kernel<double>, product by dmma_tile.
+// ---------------------------------------------------------------------------------------------
+template <int TN>
+__global__ void __launch_bounds__(NTHREADS)
+sketch_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const double* __restrict__ Om,
+                   int64_t l, int64_t ldo, double* __restrict__ Y, int64_t ldy) {
+  __shared__ Tile<double, TN> s;
+  constexpr int BN = 16 * TN;
+  const int t = threadIdx.x, warp = t / 32, lane = t % 32;
+  const int tx = t % 16;
+  const int64_t row0 = (int64_t)blockIdx.x * BM;
+  const int64_t col0 = (int64_t)blockIdx.y * BN;
+  const int a_row = t % BM, a_k0 = (t / BM) * 8;
+  const int64_t g_row = row0 + a_row;
+  const double* a_ptr = X + (g_row < m ? g_row : 0) * ldx;
+  const int b_k = t / 16;
+  double a_reg[8], b_reg[TN];
+  double acc[2][2 * TN][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2 * TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  auto load = [&](int64_t k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t k = k0 + a_k0 + i;
+      a_reg[i] = (g_row < m && k < n) ? a_ptr[k] : 0.0;
+    }
+    int64_t kb = k0 + b_k;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int64_t c = col0 + tx + 16 * j;
+      b_reg[j] = (kb < n && c < l) ? Om[kb * ldo + c] : 0.0;
+    }
+  };
+  load(0);
+  for (int64_t k0 = 0; k0 < n; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.As[a_k0 + i][a_row] = a_reg[i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) s.Bs[b_k][tx + 16 * j] = b_reg[j];
+    __syncthreads();
+    if (k0 + BK < n) load(k0 + BK);
+    dmma_tile<TN>(s, acc, warp, lane);
+    __syncthreads();
+  }
+  const int g = lane / 4, tig = lane % 4;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int64_t r = row0 + warp * 16 + mt * 8 + g;
+    if (r < m) {
+#pragma unroll
+      for (int nt = 0; nt < 2 * TN; ++nt) {
+        const int64_t c = col0 + nt * 8 + 2 * tig;
+        if (c < l) Y[r * ldy + c] = acc[mt][nt][0];
+        if (c + 1 < l) Y[r * ldy + c + 1] = acc[mt][nt][1];
+      }
+    }
+  }
+}
+
+template <int TN>
+__global__ void __launch_bounds__(NTHREADS)
+project_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const double* __restrict__ Y,
+                    int64_t l, int64_t ldy, double* __restrict__ part, int64_t rows_per_split) {
+  __shared__ Tile<double, TN> s;
+  constexpr int BN = 16 * TN;
+  const int t = threadIdx.x, warp = t / 32, lane = t % 32;
+  const int tx = t % 16;
+  const int64_t t0 = (int64_t)blockIdx.x * BM;     // time tile
+  const int64_t col0 = (int64_t)blockIdx.y * BN;   // sketch-column tile
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
+  const int64_t r_end = min(m, r_begin + rows_per_split);
+  const int a_k = t / 16, a_i0 = (t % 16) * 8;
+  double a_reg[8], b_reg[TN];
+  double acc[2][2 * TN][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2 * TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  auto load = [&](int64_t r0) {
+    int64_t r = r0 + a_k;
+    const double* xr = X + (r < r_end ? r : r_begin) * ldx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t tt = t0 + a_i0 + i;
+      a_reg[i] = (r < r_end && tt < n) ? xr[tt] : 0.0;
+    }
+    const double* yr = Y + (r < r_end ? r : r_begin) * ldy;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int64_t c = col0 + tx + 16 * j;
+      b_reg[j] = (r < r_end && c < l) ? yr[c] : 0.0;
+    }
+  };
+  if (r_begin < r_end) {
+    load(r_begin);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += BK) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s.As[a_k][a_i0 + i] = a_reg[i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) s.Bs[a_k][tx + 16 * j] = b_reg[j];
+      __syncthreads();
+      if (r0 + BK < r_end) load(r0 + BK);
+      dmma_tile<TN>(s, acc, warp, lane);
+      __syncthreads();
+    }
+  }
+  double* out = part + (int64_t)blockIdx.z * n * l;
+  const int g = lane / 4, tig = lane % 4;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int64_t tt = t0 + warp * 16 + mt * 8 + g;
+    if (tt < n) {
+#pragma unroll
+      for (int nt = 0; nt < 2 * TN; ++nt) {
+        const int64_t c = col0 + nt * 8 + 2 * tig;
+        if (c < l) out[tt * l + c] = acc[mt][nt][0];
+        if (c + 1 < l) out[tt * l + c + 1] = acc[mt][nt][1];
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, int64_t l,
@@ -234,6 +381,16 @@ static bool use_tn7(int64_t l) { return ceil_div(l, 112) * 112 <= ceil_div(l, 12
 template <typename T>
 int sketch_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void* Om, int64_t l,
                   int64_t ldo, void* Y, int64_t ldy, cudaStream_t st) {
+  if constexpr (sizeof(T) == 8) {      // float64: FP64 tensor cores (mma.sync m8n8k4)
+    if (use_tn7(l)) {
+      dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, 112));
+      sketch_dmma_kernel<7><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Om, l, ldo, (double*)Y, ldy);
+    } else {
+      dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, 128));
+      sketch_dmma_kernel<8><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Om, l, ldo, (double*)Y, ldy);
+    }
+    return check_launch("sketch_dmma_kernel");
+  }
   if (use_tn7(l)) {
     dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, 112));
     sketch_kernel<T, 7><<<grid, NTHREADS, 0, st>>>((const T*)X, m, n, ldx, (const T*)Om, l, ldo, (T*)Y, ldy);
@@ -248,6 +405,19 @@ template <typename T>
 int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void* Y, int64_t l,
                    int64_t ldy, double* Z, int64_t ldz, int accumulate, void* ws,
                    const ProjectPlan& plan, cudaStream_t st) {
+  if constexpr (sizeof(T) == 8) {      // float64: FP64 tensor cores (mma.sync m8n8k4)
+    if (use_tn7(l)) {
+      dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 112), (unsigned)plan.splits);
+      project_dmma_kernel<7><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Y, l, ldy, (double*)ws, plan.rows_per_split);
+    } else {
+      dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 128), (unsigned)plan.splits);
+      project_dmma_kernel<8><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Y, l, ldy, (double*)ws, plan.rows_per_split);
+    }
+    int rc = check_launch("project_dmma_kernel");
+    if (rc) return rc;
+    reduce_partials_kernel<double><<<(unsigned)ceil_div(n * l, 256), 256, 0, st>>>((const double*)ws, plan.splits, n, l, Z, ldz, accumulate);
+    return check_launch("reduce_partials_kernel");
+  }
   if (use_tn7(l)) {
     dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 112), (unsigned)plan.splits);
     project_kernel<T, 7><<<grid, NTHREADS, 0, st>>>((const T*)X, m, n, ldx, (const T*)Y, l, ldy, (T*)ws, plan.rows_per_split);
