@@ -9,7 +9,8 @@ Opt-in extension keys read from ``parsed_config`` (all default to the reference'
 the reference's parser ignores unknown keys):
     random_seed : int | None   - None draws Omega from NumPy's global RandomState exactly like the
                                  unseeded reference call (quirk Q6)
-    precision   : "native" (FP64 for float64 X, FP32 FMA for float32 X) | "tf32x3"
+    precision   : "auto" (default: "tf32x3" for float32 X when the sketch fits one tensor-core tile, else "native") |
+                  "native" (FP64 DMMA for float64 X, FP32 FMA for float32 X) | "tf32x3"
     device      : torch device (default "cuda:0")
 """
 from __future__ import annotations
@@ -84,7 +85,7 @@ def svd_on_era5(da, parsed_config: dict) -> tuple[np.ndarray, np.ndarray, np.nda
         Xd = host_to_device_matrix(ops, X)
         U, s, V = svd_device(ops, Xd, svd_type=svd_type, n_components=n_components,
                              seed=parsed_config.get("random_seed"),
-                             precision=parsed_config.get("precision", "native"))
+                             precision=parsed_config.get("precision", "auto"))
         out_dtype = Xd.dtype
         U_h = U.to(out_dtype).cpu().numpy()
         s_h = s.to(out_dtype).cpu().numpy()

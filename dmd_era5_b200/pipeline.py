@@ -104,7 +104,7 @@ def _omega_on_device(ops: CudaOps, n: int, k: int, seed: int | None, dtype: torc
 
 
 def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_components: int, delay: int = 1,
-               seed: int | None = None, precision: str = "native", comm=None, row_offset: int = 0,
+               seed: int | None = None, precision: str = "auto", comm=None, row_offset: int = 0,
                m0_global: int | None = None, n_iter: int | None = None, stats: dict | None = None,
                split: tuple[torch.Tensor, torch.Tensor] | None = None):
     """SVD of the (virtual) delay-embedded matrix whose base rows are X (device, tall dtype).
@@ -112,6 +112,11 @@ def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_compone
     Dispatch and error text follow svd_on_era5 (era5_svd.py:247-262)."""
     ref = X if X is not None else split[0]
     n = ref.shape[1] - delay + 1
+    if precision == "auto":
+        # float32 data: tensor-core 3xTF32 passes whenever the sketch / component count fits one MMA tile (<= 128);
+        # float64 data (and anything wider): the native path (FP64 DMMA / FP32 FMA)
+        width = min(int(n_components) + 10, n) if svd_type == "randomized" else min(int(n_components), n)
+        precision = "tf32x3" if (ref.dtype == torch.float32 and width <= 128) else "native"
     if svd_type == "standard":
         if X is None:
             X = split[0] + split[1]

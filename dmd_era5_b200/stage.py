@@ -204,10 +204,9 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
     mean_center = bool(parsed_config["mean_center"])
     scale = bool(parsed_config["scale"]) and mean_center                 # quirk Q4 (:389-395)
     ops = get_ops(parsed_config.get("device", "cuda:0"))
-    precision = parsed_config.get("precision", "native")
+    precision = parsed_config.get("precision", "auto")
     with torch.cuda.device(ops.device):
         blocks, S = _to_blocks(ds, variables, ops)
-        tc = precision == "tf32x3" and blocks[0].dtype == torch.float32 and parsed_config["svd_type"] == "randomized"
         weights = None
         if parsed_config.get("area_weighting"):                          # opt-in extension (absent in the reference)
             lat = np.deg2rad(np.asarray(ds.coord("latitude"), dtype=np.float64))
@@ -220,7 +219,7 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
         label = "standard" if parsed_config["svd_type"] == "standard" else "randomized"
         log_and_print(logger, f"Performing {label} SVD...")
         U, s, V = svd_device(ops, built.X, svd_type=parsed_config["svd_type"], n_components=parsed_config["n_components"],
-                             delay=d, seed=parsed_config.get("random_seed"), precision=precision if tc else "native")
+                             delay=d, seed=parsed_config.get("random_seed"), precision=precision)
         log_and_print(logger, f"{label.capitalize()} SVD complete.")
         if int(built.nonfinite.item()):
             raise ValueError("Input contains NaN or infinity.")          # sklearn check_array (extmath.py:546)
