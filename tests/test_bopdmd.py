@@ -95,3 +95,24 @@ def test_device_bopdmd_r100_scale(ops):
     assert match(af, alpha) < 1e-3
     assert float(out["alpha_std"].max()) < 1e-2
     assert match(out["alpha_mean"].cpu().numpy(), alpha) < 1e-3
+
+
+@pytest.mark.gpu
+def test_device_bopdmd_on_svd_output_of_noise_like_data(ops):
+    """Coefficients that are NOT sums of exponentials (random orthonormal temporal patterns, as in the bench's
+    synthetic field): the fit is poor, but every trial must end in a finite accepted state or be flagged, never NaN."""
+    import torch
+
+    from dmd_era5_b200.bopdmd import bopdmd_on_svd
+
+    rng = np.random.RandomState(0)
+    k, n = 20, 300
+    V = np.linalg.qr(rng.standard_normal((n, k)))[0].T
+    s = 100.0 * 0.9 ** np.arange(k)
+    out = bopdmd_on_svd(ops, s, V, np.arange(n, dtype=np.float64), n_trials=16, trial_size=240, seed=2, max_iter=15)
+    assert out["alphas"].shape == (16, k)
+    assert bool(torch.isfinite(torch.view_as_real(out["alphas"])).all())
+    assert bool(torch.isfinite(out["amps"]).all()) and bool(torch.isfinite(out["rhos"]).all())
+    # the objective never exceeds the energy of the data it fits
+    H = (V * s[:, None]).T
+    assert float(out["rho_full"]) <= float((H * H).sum()) * (1 + 1e-9)
