@@ -142,9 +142,10 @@ bop_hnorm_kernel(const double* __restrict__ H, int64_t ldh, const int* __restric
   }
 }
 
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 1024;
+constexpr int ST_SPLIT = 4;            // threads per right-hand side in the triangular solves
 
-__device__ double block_sum_256(double v, double* red) {
+__device__ double block_sum_st(double v, double* red) {
   v = warp_sum(v);
   __syncthreads();
   if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = v;
@@ -155,9 +156,8 @@ __device__ double block_sum_256(double v, double* red) {
   return s;
 }
 
-// In-place complex Cholesky A = L L^H of a Hermitian positive definite r x r matrix held column-major-by-row as
-// L[i * ld + j] (lower triangle used).  Returns 0 in *ok (shared) on a non-positive pivot.  Right-looking, one barrier
-// per column.
+// In-place complex Cholesky A = L L^H of a Hermitian positive definite r x r matrix, L[i * ld + j], lower triangle.
+// *ok (shared) becomes 0 on a non-positive pivot.  Right-looking, two barriers per column.
 __device__ void chol_lower(cd* L, int r, int ld, int* ok) {
   for (int j = 0; j < r; ++j) {
     __syncthreads();
@@ -168,11 +168,9 @@ __device__ void chol_lower(cd* L, int r, int ld, int* ok) {
       return;
     }
     const double inv = rsqrt(djj);
-    // scale column j (rows > j) -- each thread its own rows; column j is read by the update below after a barrier
     for (int i = j + 1 + threadIdx.x; i < r; i += ST_THREADS) L[i * ld + j] = cscale(L[i * ld + j], inv);
     __syncthreads();
     if (threadIdx.x == 0) L[j * ld + j] = {sqrt(djj), 0.0};   // after the barrier: every thread has read d_jj above
-    // trailing update: A[i][c] -= L[i][j] conj(L[c][j]) for j < c <= i
     const int m = r - j - 1;
     for (int e = threadIdx.x; e < m * m; e += ST_THREADS) {
       const int i = j + 1 + e / m, c = j + 1 + e % m;
@@ -182,19 +180,38 @@ __device__ void chol_lower(cd* L, int r, int ld, int* ok) {
   __syncthreads();
 }
 
-// X <- (L L^H)^-1 X for nrhs right-hand sides stored as X[col * ldx + row] (one thread per right-hand side)
-__device__ void chol_solve(const cd* L, int r, int ld, cd* X, int ldx, int nrhs) {
-  for (int c = threadIdx.x; c < nrhs; c += ST_THREADS) {
-    cd* x = X + (int64_t)c * ldx;
+// X <- (L L^H)^-1 X for the ncol columns of the ROW-MAJOR matrix X[row * ldx + col] (global memory).  ST_SPLIT adjacent
+// lanes share one column: each takes every ST_SPLIT-th term of the substitution sum (independent, coalesced loads of
+// X rows; L broadcast from shared memory) and the partial sums meet through shuffles.
+__device__ void chol_solve_rows(const cd* L, int r, int ld, cd* X, int ldx, int ncol) {
+  const int part = threadIdx.x % ST_SPLIT;
+  const int ngrp = ST_THREADS / ST_SPLIT;
+  for (int c0 = 0; c0 < ncol; c0 += ngrp) {
+    const int c = c0 + threadIdx.x / ST_SPLIT;
+    const bool on = c < ncol;
     for (int i = 0; i < r; ++i) {             // L y = b
-      cd s = x[i];
-      for (int q = 0; q < i; ++q) s = csub(s, cmul(L[i * ld + q], x[q]));
-      x[i] = cscale(s, 1.0 / L[i * ld + i].x);
+      cd s = {0.0, 0.0};
+      if (on)
+        for (int q = part; q < i; q += ST_SPLIT) s = cadd(s, cmul(L[i * ld + q], X[(int64_t)q * ldx + c]));
+#pragma unroll
+      for (int o = ST_SPLIT / 2; o > 0; o >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+      }
+      if (on && part == 0) X[(int64_t)i * ldx + c] = cscale(csub(X[(int64_t)i * ldx + c], s), 1.0 / L[i * ld + i].x);
+      __syncwarp();
     }
     for (int i = r - 1; i >= 0; --i) {        // L^H z = y
-      cd s = x[i];
-      for (int q = i + 1; q < r; ++q) s = csub(s, cconjmul(L[q * ld + i], x[q]));
-      x[i] = cscale(s, 1.0 / L[i * ld + i].x);
+      cd s = {0.0, 0.0};
+      if (on)
+        for (int q = i + 1 + part; q < r; q += ST_SPLIT) s = cadd(s, cconjmul(L[q * ld + i], X[(int64_t)q * ldx + c]));
+#pragma unroll
+      for (int o = ST_SPLIT / 2; o > 0; o >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+        s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+      }
+      if (on && part == 0) X[(int64_t)i * ldx + c] = cscale(csub(X[(int64_t)i * ldx + c], s), 1.0 / L[i * ld + i].x);
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -213,7 +230,8 @@ struct StepParams {
   cd* rhs;              // [K][r]
   cd* Bout;             // [K][r][N] amplitudes / modes of the accepted point
   int* done;            // [K]
-  cd* scratch;          // [K][ (N + 2r) * r ]  right-hand sides (transposed) + work
+  cd* scratch;          // per trial: X = [C | F] -> [B | P] (r x (N + r), row-major), F (r x r), W (r x r), E (r x N)[, L]
+  int64_t scratch_stride;   // complex elements per trial
   double nu, tol;
   int use_smem;
 };
@@ -225,12 +243,15 @@ bop_step_kernel(const StepParams q) {
   __shared__ int ok, accept, finished;
   const int k = blockIdx.x;
   if (q.done[k]) return;
-  const int r = q.r, N = q.N, r2 = 2 * r;
+  const int r = q.r, N = q.N, r2 = 2 * r, M = N + r;
   const int ld = r + 1;
-  cd* XB = q.scratch + (int64_t)k * ((int64_t)(N + 2 * r) * r + (q.use_smem ? 0 : (int64_t)r * ld));
-  cd* XP = XB + (int64_t)N * r;                       // P = G^-1 F, transposed: XP[c * r + i]
-  cd* Wk = XP + (int64_t)r * r;                       // r x r work (B B^H, then the LM matrix when not in smem)
-  cd* L = q.use_smem ? reinterpret_cast<cd*>(st_smem) : Wk + (int64_t)r * r;
+  cd* X = q.scratch + (int64_t)k * q.scratch_stride;    // [B | P] after the solve
+  cd* Fm = X + (int64_t)r * M;                           // F = Phi^H T Phi, row-major
+  cd* Wk = Fm + (int64_t)r * r;                          // B B^H, then F^H P
+  cd* Ek = Wk + (int64_t)r * r;                          // F^H B  (r x N)
+  cd* rowF = reinterpret_cast<cd*>(st_smem);             // staged row m of F (r) and of [B | P] (M)
+  cd* rowX = rowF + r;
+  cd* L = q.use_smem ? rowX + M : Ek + (int64_t)r * N;
   const double* S0 = q.S + (int64_t)k * 3 * r2 * r2;
   const double* S1 = S0 + (int64_t)r2 * r2;
   const double* S2 = S1 + (int64_t)r2 * r2;
@@ -246,25 +267,22 @@ bop_step_kernel(const StepParams q) {
   for (int e = threadIdx.x; e < r * r; e += ST_THREADS) {
     const int i = e / r, j = e % r;
     L[i * ld + j] = herm(S0, i, j);
-    XP[(int64_t)j * r + i] = herm(S1, i, j);          // column j of F
+    const cd f = herm(S1, i, j);
+    Fm[e] = f;
+    X[(int64_t)i * M + N + j] = f;
   }
-  for (int e = threadIdx.x; e < r * N; e += ST_THREADS) {
-    const int i = e / N, n = e % N;
-    XB[(int64_t)n * r + i] = rect(R0, i, n);          // column n of C
-  }
+  for (int e = threadIdx.x; e < r * N; e += ST_THREADS) X[(int64_t)(e / N) * M + e % N] = rect(R0, e / N, e % N);
   __syncthreads();
   chol_lower(L, r, ld, &ok);
   double rho_try = __longlong_as_double(0x7ff0000000000000LL);
   if (ok) {
-    chol_solve(L, r, ld, XB, r, N + r);               // XB and XP are contiguous: N + r right-hand sides
-    // rho = ||H||^2 - Re tr(C^H B)
-    double s = 0.0;
+    chol_solve_rows(L, r, ld, X, M, M);
+    double s = 0.0;                                       // rho = ||H||^2 - Re tr(C^H B)
     for (int e = threadIdx.x; e < r * N; e += ST_THREADS) {
-      const int i = e / N, n = e % N;
-      const cd c = rect(R0, i, n), b = XB[(int64_t)n * r + i];
+      const cd c = rect(R0, e / N, e % N), b = X[(int64_t)(e / N) * M + e % N];
       s += c.x * b.x + c.y * b.y;
     }
-    rho_try = q.hn2[k] - block_sum_256(s, red);
+    rho_try = q.hn2[k] - block_sum_st(s, red);
   }
   const double rho_old = q.rho[k];
   if (threadIdx.x == 0) {
@@ -286,32 +304,72 @@ bop_step_kernel(const StepParams q) {
     // accepted: alpha <- alpha_try, store B, J^H J and rhs of this point
     for (int j = threadIdx.x; j < r; j += ST_THREADS) q.alpha[(int64_t)k * r + j] = q.alpha_try[(int64_t)k * r + j];
     cd* Bk = q.Bout + (int64_t)k * r * N;
-    for (int e = threadIdx.x; e < r * N; e += ST_THREADS) Bk[e] = XB[(int64_t)(e % N) * r + e / N];
-    // Wk = B B^H
-    for (int e = threadIdx.x; e < r * r; e += ST_THREADS) {
-      const int j = e / r, l = e % r;
-      cd s = {0.0, 0.0};
-      for (int n = 0; n < N; ++n) s = cadd(s, cmulc(XB[(int64_t)n * r + j], XB[(int64_t)n * r + l]));
-      Wk[e] = s;
+    for (int e = threadIdx.x; e < r * N; e += ST_THREADS) Bk[e] = X[(int64_t)(e / N) * M + e % N];
+    // Wk = B B^H: column n of B staged in shared memory per step; 8 outputs per thread and pass (registers)
+    constexpr int CH = 8;
+    for (int e0 = 0; e0 < r * r; e0 += CH * ST_THREADS) {
+      cd acc[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) acc[u] = {0.0, 0.0};
+      for (int n = 0; n < N; ++n) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < r; j += ST_THREADS) rowF[j] = X[(int64_t)j * M + n];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int e = e0 + threadIdx.x + u * ST_THREADS;
+          if (e < r * r) acc[u] = cadd(acc[u], cmulc(rowF[e / r], rowF[e % r]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int e = e0 + threadIdx.x + u * ST_THREADS;
+        if (e < r * r) Wk[e] = acc[u];
+      }
     }
     __syncthreads();
+    // [F^H B | F^H P]: rows m of F and of [B | P] staged per step; thread owns outputs (j, c), c fastest.
+    // J^H J = (E2 - F^H P) o conj(B B^H);   E = Ct - F^H B
     cd* Jk = q.JhJ + (int64_t)k * r * r;
-    for (int e = threadIdx.x; e < r * r; e += ST_THREADS) {
-      const int j = e / r, l = e % r;
-      // A1[j][l] = E2[j][l] - sum_m conj(F[m][j]) P[m][l]
-      cd s = herm(S2, j, l);
-      for (int m = 0; m < r; ++m) s = csub(s, cconjmul(herm(S1, m, j), XP[(int64_t)l * r + m]));
-      const cd w = Wk[e];
-      Jk[e] = cmul(s, {w.x, -w.y});                   // A1 o conj(B B^H)
-    }
-    for (int j = threadIdx.x; j < r; j += ST_THREADS) {
-      cd s = {0.0, 0.0};
-      for (int n = 0; n < N; ++n) {
-        cd e = rect(R1, j, n);                        // Ct[j][n] - sum_m conj(F[m][j]) B[m][n]
-        for (int m = 0; m < r; ++m) e = csub(e, cconjmul(herm(S1, m, j), XB[(int64_t)n * r + m]));
-        s = cadd(s, cconjmul(XB[(int64_t)n * r + j], e));
+    for (int e0 = 0; e0 < r * M; e0 += CH * ST_THREADS) {
+      cd acc[CH];
+#pragma unroll
+      for (int u = 0; u < CH; ++u) acc[u] = {0.0, 0.0};
+      for (int m = 0; m < r; ++m) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < r; j += ST_THREADS) rowF[j] = Fm[(int64_t)m * r + j];
+        for (int c = threadIdx.x; c < M; c += ST_THREADS) rowX[c] = X[(int64_t)m * M + c];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+          const int e = e0 + threadIdx.x + u * ST_THREADS;
+          if (e < r * M) acc[u] = cadd(acc[u], cconjmul(rowF[e / M], rowX[e % M]));
+        }
       }
-      q.rhs[(int64_t)k * r + j] = s;
+#pragma unroll
+      for (int u = 0; u < CH; ++u) {
+        const int e = e0 + threadIdx.x + u * ST_THREADS;
+        if (e < r * M) {
+          const int j = e / M, c = e % M;
+          if (c < N) {
+            Ek[(int64_t)j * N + c] = csub(rect(R1, j, c), acc[u]);
+          } else {
+            const int l = c - N;
+            const cd a1 = csub(herm(S2, j, l), acc[u]);
+            const cd w = Wk[(int64_t)j * r + l];
+            Jk[(int64_t)j * r + l] = cmul(a1, {w.x, -w.y});
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // rhs_j = sum_n conj(B[j][n]) E[j][n]: one warp per row j
+    for (int j = threadIdx.x / 32; j < r; j += ST_THREADS / 32) {
+      cd s = {0.0, 0.0};
+      for (int n = threadIdx.x % 32; n < N; n += 32) s = cadd(s, cconjmul(X[(int64_t)j * M + n], Ek[(int64_t)j * N + n]));
+      s.x = warp_sum(s.x);
+      s.y = warp_sum(s.y);
+      if (threadIdx.x % 32 == 0) q.rhs[(int64_t)k * r + j] = s;
     }
     __syncthreads();
   }
@@ -328,7 +386,7 @@ bop_step_kernel(const StepParams q) {
     if (i == j) v.x += lam * v.x;
     L[i * ld + j] = v;
   }
-  cd* dl = XB;                                          // delta, length r
+  cd* dl = X;                                           // delta as a one-column row-major matrix (ldx = 1)
   for (int j = threadIdx.x; j < r; j += ST_THREADS) dl[j] = q.rhs[(int64_t)k * r + j];
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
@@ -337,7 +395,7 @@ bop_step_kernel(const StepParams q) {
     if (threadIdx.x == 0) q.done[k] = 1;
     return;
   }
-  chol_solve(L, r, ld, dl, r, 1);
+  chol_solve_rows(L, r, ld, dl, 1, 1);
   for (int j = threadIdx.x; j < r; j += ST_THREADS) q.alpha_try[(int64_t)k * r + j] = cadd(q.alpha[(int64_t)k * r + j], dl[j]);
 }
 
@@ -346,12 +404,16 @@ bop_step_kernel(const StepParams q) {
 
 extern "C" {
 
+static size_t bop_scratch_elems(int64_t r, int64_t N) {
+  // [B | P] r x (N + r), F r x r, W r x r, E r x N, and L r x (r + 1) when it does not fit shared memory
+  return (size_t)(r * (N + r) + 2 * r * r + r * N + r * (r + 1));
+}
+
 size_t era5svd_bop_workspace_bytes(int64_t K, int64_t p, int64_t r, int64_t N) {
   if (K <= 0 || p <= 0 || r <= 0 || N <= 0) return 0;
   const size_t psi = (size_t)K * p * 2 * r * 8;
   const size_t S = (size_t)K * 3 * 4 * r * r * 8, R = (size_t)K * 2 * 2 * r * N * 8;
-  const size_t scratch = (size_t)K * ((size_t)(N + 2 * r) * r + (size_t)r * (r + 1)) * 16;
-  return psi + S + R + scratch + (size_t)K * 8 + 256;
+  return psi + S + R + (size_t)K * bop_scratch_elems(r, N) * 16 + (size_t)K * 8 + 256;
 }
 
 // One Levenberg-Marquardt iteration for every trial that is not done (see the file header).
@@ -361,7 +423,7 @@ int era5svd_bop_iterate_f64(const double* H, int64_t n_time, int64_t N, int64_t 
                             int first, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace era5svd;
   ERA5SVD_REQUIRE(H && t && idx && alpha && alpha_try && rho && lam && JhJ && rhs && Bout && done, "bop_iterate: null pointer");
-  ERA5SVD_REQUIRE(K > 0 && p > 0 && r > 0 && N > 0 && ldh >= N && p <= n_time && K <= 65535 && r <= 4096,
+  ERA5SVD_REQUIRE(K > 0 && p > 0 && r > 0 && N > 0 && ldh >= N && p <= n_time && K <= 65535 && r <= 128 && N <= 128,
                   "bop_iterate: bad shape K=%lld p=%lld r=%lld N=%lld", (long long)K, (long long)p, (long long)r, (long long)N);
   const size_t need = era5svd_bop_workspace_bytes(K, p, r, N);
   if (!workspace || workspace_bytes < need) {
@@ -393,9 +455,11 @@ int era5svd_bop_iterate_f64(const double* H, int64_t n_time, int64_t N, int64_t 
   q.S = S; q.R = R; q.hn2 = hn2; q.K = (int)K; q.r = (int)r; q.N = (int)N;
   q.alpha = (cd*)alpha; q.alpha_try = (cd*)alpha_try; q.rho = rho; q.lam = lam; q.JhJ = (cd*)JhJ; q.rhs = (cd*)rhs;
   q.Bout = (cd*)Bout; q.done = done; q.scratch = scratch; q.nu = nu; q.tol = tol;
+  q.scratch_stride = (int64_t)bop_scratch_elems(r, N);
+  const size_t rows = (size_t)(2 * r + N) * 16;                 // staged rows of F and [B | P]
   const size_t lbytes = (size_t)r * (r + 1) * 16;
-  q.use_smem = lbytes <= 200 * 1024;
-  const size_t smem = q.use_smem ? lbytes : 0;
+  q.use_smem = rows + lbytes <= 200 * 1024;
+  const size_t smem = rows + (q.use_smem ? lbytes : 0);
   ERA5SVD_CUDA(cudaFuncSetAttribute(bop_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   bop_step_kernel<<<(unsigned)K, ST_THREADS, smem, st>>>(q);
   return check_launch("bop_step_kernel");
