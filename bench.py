@@ -76,9 +76,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """Summary of the samples that arrived inside [t0, t1] (host clock), i.e. DURING the timed region; the
+        sampler itself is started before the warm-up because nvidia-smi needs a few hundred ms to produce its first line."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -88,7 +90,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        inside = [ln for (ts, ln) in self.samples if (t0 is None or ts >= t0) and (t1 is None or ts <= t1)]
+        if not inside:                       # very short region: fall back to the samples nearest to it
+            inside = [ln for (_, ln) in self.samples[-3:]]
+        for s in inside:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -229,6 +234,9 @@ def main():
         S = args.rows
     k = K_COMPONENTS
     ops = CudaOps(device)
+    sampler = ClockSampler(local_rank)      # started now: nvidia-smi needs a few hundred ms before its first sample
+    if rank == 0:
+        sampler.start()
     field = synthetic_field(T, S, device=device, seed=1000 + rank)          # native (T, S) f32, outside the timed region
     m_global = S * world
     row_offset = rank * S
@@ -256,10 +264,8 @@ def main():
     for _ in range(args.warmup):
         step(field)
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     timer = KernelTimer()
+    t_region0 = time.perf_counter()
     launches0 = _cabi.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -268,7 +274,7 @@ def main():
     e1.record()
     sync_all()
     launches = _cabi.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
