@@ -161,3 +161,35 @@ def test_svd_on_era5_tf32x3_api():
     U0, s0, V0 = randomized_svd_ref(X.astype(np.float64), 20, 4)
     U, s, V = svd_on_era5(X, {"svd_type": "randomized", "n_components": 20, "random_seed": 4, "precision": "tf32x3"})
     assert U.dtype == np.float32 and sigma_rel_err(s, s0) < 1e-4 and signs_agree(U, U0)
+
+
+@pytest.mark.parametrize("m,n,l", [(129, 40, 20), (1000, 744, 110), (4097, 130, 100)])
+def test_tc_kernels_write_only_their_outputs(ops, m, n, l):
+    """Poor man's memcheck (compute-sanitizer is not available on the pool): outputs are views into larger buffers
+    filled with a canary; rows after the last tile row, the columns right of the padded width and the memory around Z
+    must come back untouched, for both the on-chip-split and the pre-split kernels."""
+    rng = np.random.RandomState(m)
+    X = dev(rng.standard_normal((m, n)).astype(np.float32))
+    ld = (n + 7) // 8 * 8
+    Xb = torch.zeros((m, ld), device="cuda"); Xb[:, :n] = X
+    Om = dev(rng.standard_normal((n, l)))
+    ldy = ops.tf32_ldy(l)
+    CAN = 12345.0
+    # outputs at the documented pitch (ldy) with 200 guard rows below them
+    exact = [torch.full((m + 200, ldy), CAN, device="cuda") for _ in range(3)]
+    Ye, Yhe, Yle = (b[:m, :l] for b in exact)
+    ops.sketch_tf32x3(Xb[:, :n], None, Om, Ye, Yhe, Yle)
+    for b in exact:
+        assert bool((b[m:] == CAN).all()), "rows below the matrix were written"
+        assert bool(torch.isfinite(b[:m]).all())
+    hi, lo = ops.split_tf32(Xb[:, :n])
+    exact2 = [torch.full((m + 200, ldy), CAN, device="cuda") for _ in range(3)]
+    ops.sketch_tf32x3(hi, lo, Om, *(b[:m, :l] for b in exact2))
+    for b in exact2:
+        assert bool((b[m:] == CAN).all())
+    Zbuf = torch.full((n + 64, l), CAN, dtype=torch.float64, device="cuda")
+    Z = Zbuf[32 : 32 + n]
+    ops.project_tf32x3(Xb[:, :n], None, Yhe, Yle, Z, accumulate=False)
+    assert bool((Zbuf[:32] == CAN).all()) and bool((Zbuf[32 + n :] == CAN).all())
+    ref = X.double().t() @ (Yhe.double() + Yle.double())
+    assert float((Z - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
