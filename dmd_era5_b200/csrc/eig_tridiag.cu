@@ -2,9 +2,9 @@
 // SVD (np.linalg.svd(X, full_matrices=False) + [:k] truncation, src/dmd_era5/era5_svd/era5_svd.py:249-254; LAPACK
 // gesdd on the host).  Only the k LARGEST eigenpairs are ever used (the reference truncates to n_components), so:
 //
-//   1. era5svd_tridiag_reduce_f64     A = Q T Q^T  Householder tridiagonalisation, all SMs, memory bound:
-//                                     per column one symv pass (read the trailing block) and one rank-2 update
-//                                     pass (read + write it); 24 B per trailing element and column, 8 n^3 B total
+//   1. era5svd_tridiag_reduce_f64     A = Q T Q^T  Householder tridiagonalisation, all SMs, memory bound: ONE fused
+//                                     pass per column (rank-2 update of the trailing block + symv of the next
+//                                     column on the updated values): 16 B per trailing element and column
 //   2. era5svd_tridiag_eig_topk_f64   k largest eigenvalues of T by bisection on Sturm counts (one thread each),
 //                                     vectors by inverse iteration (tridiagonal LU with partial pivoting)
 //   3. era5svd_tridiag_apply_f64      Y = T Z   (for the Rayleigh-Ritz clean-up of close eigenvalues, done by the
@@ -57,81 +57,141 @@ __device__ House householder(const double* __restrict__ x, int r, double* red) {
   return h;
 }
 
-// pass A of column j:  p = tau * A22 v   (A22 = trailing r x r block, r = n - j - 1), one warp per row.
-// CTA 0 also publishes v, tau, d[j], e[j].
-__global__ void __launch_bounds__(TD_THREADS)
-tridiag_symv_kernel(const double* __restrict__ A, int64_t lda, int n, int j, double* __restrict__ vbuf,
-                    double* __restrict__ pbuf, double* __restrict__ d, double* __restrict__ e,
-                    double* __restrict__ tau) {
-  __shared__ double red[TD_WARPS];
-  const int r = n - j - 1;
-  const double* x = A + (int64_t)j * lda + j + 1;
-  const House h = householder(x, r, red);
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < r; c += TD_THREADS) vbuf[c] = c == 0 ? 1.0 : x[c] * h.scale;
-    if (threadIdx.x == 0) { tau[j] = h.tau; e[j] = h.beta; d[j] = A[(int64_t)j * lda + j]; }
-  }
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  for (int i = blockIdx.x * TD_WARPS + warp; i < r; i += gridDim.x * TD_WARPS) {
-    const double* row = A + (int64_t)(j + 1 + i) * lda + j + 1;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int c = lane;
-    for (; c + 96 < r; c += 128) {          // four independent 256-byte loads in flight per warp
-      const double a0 = row[c], a1 = row[c + 32], a2 = row[c + 64], a3 = row[c + 96];
-      const double v0 = c == 0 ? 1.0 : x[c] * h.scale, v1 = x[c + 32] * h.scale, v2 = x[c + 64] * h.scale,
-                   v3 = x[c + 96] * h.scale;
-      s0 = fma(a0, v0, s0); s1 = fma(a1, v1, s1); s2 = fma(a2, v2, s2); s3 = fma(a3, v3, s3);
-    }
-    for (; c < r; c += 32) s0 = fma(row[c], c == 0 ? 1.0 : x[c] * h.scale, s0);
-    const double s = warp_sum((s0 + s1) + (s2 + s3));
-    if (lane == 0) pbuf[i] = h.tau * s;
-  }
-}
+// Fused pass for column j: rank-2 update of the trailing block with (v_j, w_j) AND the symv of column j + 1 on the
+// updated values, 16 B of HBM traffic per trailing element instead of 24 B in two launches.
+//   A22 = A[j+1:, j+1:] (r x r).  w = p - (tau/2)(p^T v) v.  Row 0 of the updated block gives the next Householder
+//   vector v' (every CTA recomputes beta', tau', scale' from a_0c - v_0 w_c - w_0 v_c: three r-long vector reads),
+//   rows i >= 1 are updated in place and dotted with v':  p'_{i-1} = tau' sum_{c>=1} a'_ic v'_{c-1}.
+// A warp owns TD_ROWS rows; v, w, v' are staged chunk by chunk in shared memory, so an element costs one global load,
+// one global store and three shared-memory reads.  has_update == 0 (first call, j = -1): symv only.
+constexpr int TD_ROWS = 2;          // rows per warp
+constexpr int TD_CHUNK = 1024;      // staged columns per step
 
-// pass B of column j:  w = p - (tau/2)(p^T v) v ;  A22 -= v w^T + w v^T ; CTA 0 stores v into row j of A.
 __global__ void __launch_bounds__(TD_THREADS)
-tridiag_rank2_kernel(double* __restrict__ A, int64_t lda, int n, int j, const double* __restrict__ vbuf,
-                     const double* __restrict__ pbuf, const double* __restrict__ tau) {
+tridiag_fused_kernel(double* __restrict__ A, int64_t lda, int n, int j, int has_update, const double* __restrict__ vbuf,
+                     const double* __restrict__ pbuf, double* __restrict__ vnext, double* __restrict__ pnext,
+                     double* __restrict__ d, double* __restrict__ e, double* __restrict__ tau) {
   __shared__ double red[TD_WARPS];
-  const int r = n - j - 1;
-  const double t = tau[j];
-  if (t == 0.0) return;                       // H = I: nothing to update (row j already holds v = e_1 pattern)
-  double s = 0.0;
-  for (int c = threadIdx.x; c < r; c += TD_THREADS) s = fma(pbuf[c], vbuf[c], s);
-  const double coef = 0.5 * t * block_sum(s, red);
+  __shared__ double sv[TD_CHUNK], sw[TD_CHUNK], sn[TD_CHUNK];
+  const int r = n - j - 1;                      // order of the trailing block A22 (rows / columns j+1 .. n-1)
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  for (int i = blockIdx.x * TD_WARPS + warp; i < r; i += gridDim.x * TD_WARPS) {
-    double* row = A + (int64_t)(j + 1 + i) * lda + j + 1;
-    const double vi = vbuf[i], wi = pbuf[i] - coef * vi;
-    int c = lane;
-    for (; c + 96 < r; c += 128) {          // four independent read-modify-writes in flight per warp
-      double a[4], vc[4], pc[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = row[c + 32 * u]; vc[u] = vbuf[c + 32 * u]; pc[u] = pbuf[c + 32 * u]; }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) row[c + 32 * u] = a[u] - fma(vi, pc[u] - coef * vc[u], wi * vc[u]);
-    }
-    for (; c < r; c += 32) {
+  double* A22 = A + (int64_t)(j + 1) * lda + (j + 1);
+  const double t = has_update ? tau[j] : 0.0;
+  double coef = 0.0;
+  if (t != 0.0) {
+    double s = 0.0;
+    for (int c = threadIdx.x; c < r; c += TD_THREADS) s = fma(pbuf[c], vbuf[c], s);
+    coef = 0.5 * t * block_sum(s, red);
+  }
+  const double v0 = t != 0.0 ? vbuf[0] : 0.0, w0 = t != 0.0 ? pbuf[0] - coef * v0 : 0.0;
+  auto new_row0 = [&](int c) -> double {        // updated A22[0][c]
+    double a = A22[c];
+    if (t != 0.0) {
       const double vc = vbuf[c], wc = pbuf[c] - coef * vc;
-      row[c] -= fma(vi, wc, wi * vc);
+      a -= fma(v0, wc, w0 * vc);
+    }
+    return a;
+  };
+  // Householder vector of the next column from x' = A22'[0, 1:] (length r - 1); nothing to do when r - 1 < 2
+  const int rn = r - 1;
+  const bool do_next = rn >= 2;
+  double beta = 0.0, tnext = 0.0, scale = 0.0;
+  if (do_next) {
+    double s = 0.0;
+    for (int c = 2 + threadIdx.x; c < r; c += TD_THREADS) { const double x = new_row0(c); s = fma(x, x, s); }
+    const double sigma = block_sum(s, red);
+    const double x0 = new_row0(1);
+    if (sigma == 0.0) {
+      beta = x0; tnext = 0.0; scale = 0.0;
+    } else {
+      const double nrm = sqrt(fma(x0, x0, sigma));
+      beta = x0 >= 0.0 ? -nrm : nrm;
+      tnext = (beta - x0) / beta;
+      scale = 1.0 / (x0 - beta);
+    }
+    if (blockIdx.x == 0) {
+      for (int c = 1 + threadIdx.x; c < r; c += TD_THREADS) vnext[c - 1] = c == 1 ? 1.0 : new_row0(c) * scale;
+      if (threadIdx.x == 0) { tau[j + 1] = tnext; e[j + 1] = beta; }
     }
   }
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) d[j + 1] = new_row0(0);   // row 0 of the block is never written back
+  if (blockIdx.x == 0 && has_update) {          // reflector j goes to its final place: row j, columns j+1..
     double* x = A + (int64_t)j * lda + j + 1;
     for (int c = threadIdx.x; c < r; c += TD_THREADS) x[c] = vbuf[c];
   }
+  if (t == 0.0 && !do_next) return;
+  // rows 1 .. r-1 of A22: warp owns TD_ROWS consecutive rows
+  const int row_first = 1 + (blockIdx.x * TD_WARPS + warp) * TD_ROWS;
+  double vi[TD_ROWS], wi[TD_ROWS], acc[TD_ROWS];
+#pragma unroll
+  for (int u = 0; u < TD_ROWS; ++u) {
+    const int i = row_first + u;
+    vi[u] = (t != 0.0 && i < r) ? vbuf[i] : 0.0;
+    wi[u] = (t != 0.0 && i < r) ? pbuf[i] - coef * vi[u] : 0.0;
+    acc[u] = 0.0;
+  }
+  for (int c0 = 0; c0 < r; c0 += TD_CHUNK) {
+    const int cn = min(TD_CHUNK, r - c0);
+    __syncthreads();
+    for (int c = threadIdx.x; c < cn; c += TD_THREADS) {
+      const int gc = c0 + c;
+      const double vc = t != 0.0 ? vbuf[gc] : 0.0;
+      sv[c] = vc;
+      sw[c] = t != 0.0 ? pbuf[gc] - coef * vc : 0.0;
+      sn[c] = (do_next && gc >= 1) ? (gc == 1 ? 1.0 : new_row0(gc) * scale) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < TD_ROWS; ++u) {
+      const int i = row_first + u;
+      if (i >= r) continue;
+      double* row = A22 + (int64_t)i * lda + c0;
+      int c = lane;
+      for (; c + 96 < cn; c += 128) {          // four independent read-modify-writes in flight
+        double a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = row[c + 32 * q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cc = c + 32 * q;
+          a[q] -= fma(vi[u], sw[cc], wi[u] * sv[cc]);
+          acc[u] = fma(a[q], sn[cc], acc[u]);
+        }
+        if (t != 0.0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) row[c + 32 * q] = a[q];
+        }
+      }
+      for (; c < cn; c += 32) {
+        const double a = row[c] - fma(vi[u], sw[c], wi[u] * sv[c]);
+        acc[u] = fma(a, sn[c], acc[u]);
+        if (t != 0.0) row[c] = a;
+      }
+    }
+  }
+  if (do_next) {
+#pragma unroll
+    for (int u = 0; u < TD_ROWS; ++u) {
+      const int i = row_first + u;
+      const double s = warp_sum(acc[u]);
+      if (lane == 0 && i < r) pnext[i - 1] = tnext * s;
+    }
+  }
 }
 
+// last 2 x 2 block: d[n-2] was written by the final fused call (n >= 3); the off-diagonal and d[n-1] are read from the
+// updated last ROW (the fused kernel does not write row 0 of a block back)
 __global__ void tridiag_tail_kernel(const double* __restrict__ A, int64_t lda, int n, double* __restrict__ d,
                                     double* __restrict__ e, double* __restrict__ tau) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (n >= 2) {
-    d[n - 2] = A[(int64_t)(n - 2) * lda + n - 2];
-    e[n - 2] = A[(int64_t)(n - 2) * lda + n - 1];
+    if (n == 2) d[0] = A[0];
+    e[n - 2] = A[(int64_t)(n - 1) * lda + n - 2];
     tau[n - 2] = 0.0;
   }
   d[n - 1] = A[(int64_t)(n - 1) * lda + n - 1];
-  if (n >= 1) { e[n - 1] = 0.0; tau[n - 1] = 0.0; }
+  e[n - 1] = 0.0;
+  tau[n - 1] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -336,28 +396,28 @@ int era5svd_tridiag_reduce_f64(double* A, int64_t n, int64_t lda, double* d, dou
   using namespace era5svd;
   ERA5SVD_REQUIRE(A && d && e && tau, "tridiag_reduce: null pointer");
   ERA5SVD_REQUIRE(n > 0 && n <= 32768 && lda >= n, "tridiag_reduce: bad shape n=%lld", (long long)n);
-  const size_t need = (size_t)(2 * n) * sizeof(double);
+  const size_t need = (size_t)(4 * n) * sizeof(double);
   if (!workspace || workspace_bytes < need) {
     set_error("tridiag_reduce: workspace too small (%zu < %zu)", workspace_bytes, need);
     return ERA5SVD_ERR_WORKSPACE;
   }
   cudaStream_t st = as_stream(stream);
-  double* vbuf = (double*)workspace;
-  double* pbuf = vbuf + n;
-  const int sms = sm_count();
-  for (int j = 0; j + 2 < (int)n; ++j) {
+  double* vb[2] = {(double*)workspace, (double*)workspace + n};
+  double* pb[2] = {(double*)workspace + 2 * n, (double*)workspace + 3 * n};
+  // call j = -1 computes the reflector and the symv of column 0; call j >= 0 applies reflector j and prepares j + 1
+  for (int j = -1; j + 2 < (int)n; ++j) {
     const int r = (int)n - j - 1;
-    int grid = (int)ceil_div(r, TD_WARPS);
-    if (grid > 8 * sms) grid = 8 * sms;      // 64 resident warps per SM: one row per warp up to n ~ 9.5 k
-    tridiag_symv_kernel<<<grid, TD_THREADS, 0, st>>>(A, lda, (int)n, j, vbuf, pbuf, d, e, tau);
-    tridiag_rank2_kernel<<<grid, TD_THREADS, 0, st>>>(A, lda, (int)n, j, vbuf, pbuf, tau);
-    count_launch(2);
+    const int cur = (j + 2) & 1, nxt = cur ^ 1;
+    const int grid = (int)ceil_div(r > 1 ? r - 1 : 1, TD_WARPS * TD_ROWS);
+    tridiag_fused_kernel<<<grid, TD_THREADS, 0, st>>>(A, lda, (int)n, j, j >= 0 ? 1 : 0, vb[cur], pb[cur], vb[nxt], pb[nxt],
+                                                       d, e, tau);
+    count_launch(1);
   }
   tridiag_tail_kernel<<<1, 32, 0, st>>>(A, lda, (int)n, d, e, tau);
   return check_launch("tridiag_reduce");
 }
 
-size_t era5svd_tridiag_reduce_workspace_bytes(int64_t n) { return n > 0 ? (size_t)(2 * n) * sizeof(double) : 0; }
+size_t era5svd_tridiag_reduce_workspace_bytes(int64_t n) { return n > 0 ? (size_t)(4 * n) * sizeof(double) : 0; }
 
 size_t era5svd_tridiag_eig_topk_workspace_bytes(int64_t n, int64_t k) {
   if (n <= 0 || k <= 0) return 0;
