@@ -68,18 +68,18 @@ def gram_device(ops, X: torch.Tensor, n: int, delay: int, precision: int) -> tor
     if precision == PREC_TF32X3:
         if X.dtype != torch.float32:
             raise TypeError("precision 'tf32x3' needs a float32 snapshot matrix")
-        G = ops.empty((n, n), torch.float64)
+        # symmetric: block column [c0, c1) is computed for the time rows t >= c0 only (the column window X[:, c0:]
+        # is the X operand) and mirrored, which halves the passes over X
+        G = ops.zeros((n, n), torch.float64)
         for j in range(delay):
             Xj = X[:, j : j + n]
             for c0 in range(0, n, TC_BLOCK):
                 c1 = min(n, c0 + TC_BLOCK)
-                hi, lo = ops.split_tf32(Xj[:, c0:c1])      # the (Y_hi, Y_lo) operand of the project kernel
-                Z = ops.project_tf32x3(Xj, None, hi, lo)   # (n, c1 - c0) float64
-                if j == 0:
-                    G[:, c0:c1] = Z
-                else:
-                    G[:, c0:c1] += Z
-        return G
+                hi, lo = ops.split_tf32(Xj[:, c0:c1])             # the (Y_hi, Y_lo) operand of the project kernel
+                Z = ops.project_tf32x3(Xj[:, c0:], None, hi, lo)  # (n - c0, c1 - c0) float64 = G[c0:, c0:c1]
+                G[c0:, c0:c1] += Z
+        low = torch.tril(G, -1)
+        return torch.tril(G) + low.t()                             # the diagonal blocks' upper parts come from the mirror
     for j in range(delay):
         Xj = X[:, j : j + n]
         G = ops.project(Xj, Xj, G, accumulate=j > 0, precision=PREC_NATIVE)
