@@ -54,58 +54,115 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples SM clocks / clock-event (throttle) reasons DURING the timed region.  NVML is polled from a thread every
+    ~5 ms (nvidia_ml_py: the library `nvidia-smi` itself sits on); `nvidia-smi -lms` is the fallback when NVML cannot
+    be loaded — it needs up to a second before its first line, too slow for a 0.3 s timed region on its own."""
 
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, uuid: str | None = None):
         self.index = index
-        self.samples = []
+        self.uuid = uuid
+        self.samples = []                    # (host time, sm MHz, max sm MHz, set of reasons)
         self.proc = None
+        self.thread = None
+        self.source = None
+        self._stop = threading.Event()
+
+    # ---- NVML ----
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        if self.uuid:
+            for u in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    return pynvml, pynvml.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                except Exception:
+                    pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            ent = vis.split(",")[self.index].strip()
+            if ent.isdigit():
+                idx = int(ent)
+            else:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(ent.encode())
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+
+    def _poll_nvml(self, pynvml, h):
+        bits = [(pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        try:
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self._stop.is_set():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((time.perf_counter(), sm, mx, {nm for b, nm in bits if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    # ---- nvidia-smi fallback ----
+    def _poll_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            self.samples.append((time.perf_counter(), sm, mx,
+                                 {nm for nm, val in zip(self.NAMES, f[2:6]) if val.lower().startswith("active")}))
 
     def start(self):
+        try:
+            pynvml, h = self._nvml_handle()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(pynvml, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._poll_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.perf_counter(), line.strip()))
-
     def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
-        """Summary of the samples that arrived inside [t0, t1] (host clock), i.e. DURING the timed region; the
-        sampler itself is started before the warm-up because nvidia-smi needs a few hundred ms to produce its first line."""
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [ln for (ts, ln) in self.samples if (t0 is None or ts >= t0) and (t1 is None or ts <= t1)]
-        if not inside:                       # very short region: fall back to the samples nearest to it
-            inside = [ln for (_, ln) in self.samples[-3:]]
-        for s in inside:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
+        """Summary of the samples taken inside [t0, t1] (host clock), i.e. DURING the timed region."""
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        self.thread.join(timeout=2)
+        inside = [x for x in self.samples if (t0 is None or x[0] >= t0) and (t1 is None or x[0] <= t1)]
+        where = "timed region"
+        if not inside:                       # very short region: fall back to the samples nearest to it
+            inside, where = self.samples[-3:], "nearest to the timed region"
+        sm = [x[1] for x in inside]
+        mx = [x[2] for x in inside if x[2] is not None]
+        reasons = set().union(*[x[3] for x in inside]) if inside else set()
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source, "window": where}
 
 
 def bind_to_gpu_numa_node(local_rank: int):
@@ -234,7 +291,7 @@ def main():
         S = args.rows
     k = K_COMPONENTS
     ops = CudaOps(device)
-    sampler = ClockSampler(local_rank)      # started now: nvidia-smi needs a few hundred ms before its first sample
+    sampler = ClockSampler(local_rank, uuid=str(torch.cuda.get_device_properties(local_rank).uuid))
     if rank == 0:
         sampler.start()
     field = synthetic_field(T, S, device=device, seed=1000 + rank)          # native (T, S) f32, outside the timed region

@@ -5,7 +5,8 @@ same literal types, same derived names and paths, same error texts the reference
 (tests/test_03_era5_svd.py:104-150).  Table-driven restatement, not a copy.
 
 Opt-in extension keys (absent = reference behaviour; the reference's parser ignores unknown keys):
-    precision ("native" | "tf32x3"), random_seed (int | None), area_weighting (bool), device (str).
+    precision ("native" | "tf32x3"), random_seed (int | None), area_weighting (bool), device (str),
+    matrix_dtype ("float32" | "float64": the build kernel casts while it stacks; north_star "float cast").
 """
 from __future__ import annotations
 
@@ -26,7 +27,7 @@ REQUIRED = {
 }
 _DELTA_UNITS = {"h": lambda x: timedelta(hours=x), "d": lambda x: timedelta(days=x), "w": lambda x: timedelta(weeks=x),
                 "m": lambda x: timedelta(days=x * 365 // 12), "y": lambda x: timedelta(days=x * 365)}
-EXTENSION_KEYS = ("precision", "random_seed", "area_weighting", "device")
+EXTENSION_KEYS = ("precision", "random_seed", "area_weighting", "device", "matrix_dtype")
 
 
 def project_root() -> str:

@@ -214,8 +214,17 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
             L, O = len(ds.coord("level")), len(ds.coord("longitude"))
             w_rows = np.tile(np.tile(np.repeat(w, O), L), len(variables))
             weights = torch.from_numpy(w_rows.astype(np.float32 if blocks[0].dtype == torch.float32 else np.float64)).to(ops.device)
+        # opt-in extension (north_star "float cast"; absent in the reference): matrix_dtype = "float32" stores the
+        # snapshot matrix in float32 whatever the slice's dtype (the cast happens inside the build kernel, statistics
+        # still accumulate in float64), which halves the memory and enables the tensor-core passes for float64 slices
+        mdt = parsed_config.get("matrix_dtype")
+        if mdt not in (None, "float32", "float64"):
+            raise ValueError(f"matrix_dtype {mdt} is not supported.")
+        xdtype = None if mdt is None else (torch.float32 if mdt == "float32" else torch.float64)
+        if weights is not None and xdtype is not None:
+            weights = weights.to(xdtype)
         built = build_matrix_device(ops, blocks, mean_center=mean_center, scale=scale, weights=weights,
-                                    check_finite=True)
+                                    check_finite=True, dtype=xdtype)
         label = "standard" if parsed_config["svd_type"] == "standard" else "randomized"
         log_and_print(logger, f"Performing {label} SVD...")
         U, s, V = svd_device(ops, built.X, svd_type=parsed_config["svd_type"], n_components=parsed_config["n_components"],

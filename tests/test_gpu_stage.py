@@ -91,6 +91,27 @@ def test_main_end_to_end(tmp_path, monkeypatch, svd_type, d, mc, sc):
     assert np.array_equal(back["U"].values, res["U"].values)
 
 
+def test_main_matrix_dtype_cast(tmp_path, monkeypatch):
+    """Opt-in float cast (north_star (a); absent in the reference): float64 mock slice, float32 snapshot matrix written
+    by the build kernel, tensor-core passes; sigma within the FP32-split tolerance (1e-4) of the float64 oracle."""
+    from dmd_era5_b200.era5_svd import main
+
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    cfg = base_config(delay_embedding=1, matrix_dtype="float32")
+    m, parsed = make_slice(tmp_path, cfg)
+    res, _, _ = main(cfg)
+    X, _, _ = oracle_matrix(m, cfg)
+    U0, s0, V0 = randomized_svd_ref(X, 6, 3)
+    assert res["U"].values.dtype == np.float32 and res["X"].values.dtype == np.float32
+    assert np.max(np.abs(res["X"].values - X)) <= 2e-7 * np.max(np.abs(X))
+    assert sigma_rel_err(res["s"].values, s0) < 1e-4
+    ref = recon_rel_err(X, U0, s0, V0)
+    assert abs(recon_rel_err(X, res["U"].values.astype(np.float64), res["s"].values.astype(np.float64),
+                             res["V"].values.astype(np.float64)) - ref) <= 0.01 * ref
+    with pytest.raises(Exception, match="matrix_dtype"):
+        main(base_config(delay_embedding=1, matrix_dtype="float16"))
+
+
 def test_main_phase_errors(tmp_path, monkeypatch):
     from dmd_era5_b200.era5_svd import main
 
