@@ -216,6 +216,197 @@ fused_build_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_
   }
 }
 
+// TMA variant of the single-read build for float32 sources (the real ERA5 dtype).  The register-staged loads of
+// fused_build_kernel keep only 16 x 8 x 128 B = 16 KB per CTA in flight, which is what bounds it (c2: 3.2 TB/s,
+// c3 with one resident CTA: 2.0 TB/s).  Here ONE thread issues the whole [T x 32 points] tile as 2-D TMA boxes
+// (32 points x 64 snapshots, 8 KB each), so the complete tile (95 KB at T = 744, 187 KB at T = 1460) is in flight
+// at once and no registers are spent on staging.
+//   smem tile : [Tpad][32] float32, 128-byte rows, TMA SWIZZLE_128B: 16-byte chunk c of row t sits at chunk
+//               c ^ (t & 7), so a quarter-warp reading chunk c of 8 consecutive snapshots hits 8 distinct
+//               16-byte bank groups -> the transposing column reads are conflict free WITHOUT padding.
+//   warp w    : points 4 (w % 8) .. + 3 (one 16-byte chunk), time half w / 8; lane = snapshot.
+//   stats     : float64 partial sums per (warp, point), combined across the two time halves through smem.
+//   store     : four 128-byte coalesced row stores per warp iteration (one per point of the chunk).
+constexpr int TB_THREADS = 512;
+constexpr int TB_BOX_T = 64;
+
+__device__ __forceinline__ float4 tb_ld_chunk(uint32_t tile, int t, int c) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(tile + (uint32_t)t * 128u + (uint32_t)((c ^ (t & 7)) << 4)));
+  return v;
+}
+
+template <typename Tx>
+__global__ void __launch_bounds__(TB_THREADS)
+fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_t P, int col_shift,
+                       Tx* __restrict__ X, int64_t ldx, Tx* __restrict__ mean_out, Tx* __restrict__ std_out,
+                       const Tx* __restrict__ weights, int center, int do_scale, int check_finite,
+                       int* __restrict__ nonfinite_flag, float* __restrict__ Xhi, float* __restrict__ Xlo) {
+  extern __shared__ unsigned char fb_smem[];
+  __shared__ double part_a[2][FB_PB], part_q[2][FB_PB];
+  __shared__ int part_n[2][FB_PB];
+  __shared__ __align__(8) uint64_t bar_storage;
+  const uint32_t tile = (tc::smem_u32(fb_smem) + 1023u) & ~1023u;
+  const uint32_t bar = tc::smem_u32(&bar_storage);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int c = warp % 8, h = warp / 8;
+  const int64_t p0 = (int64_t)blockIdx.x * FB_PB;
+  const int nbox = (T + TB_BOX_T - 1) / TB_BOX_T;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(bar, 1);
+    tc::fence_barrier_init();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::mbar_arrive_expect_tx(bar, (uint32_t)nbox * (uint32_t)(TB_BOX_T * 128));
+    for (int b = 0; b < nbox; ++b)
+      tc::tma_load_2d(tile + (uint32_t)b * (uint32_t)(TB_BOX_T * 128), &tm_src, (int32_t)p0, b * TB_BOX_T, bar);
+  }
+  __syncthreads();                 // barrier initialised before anyone polls it
+  // time range of this warp: halves split on a multiple of 32 snapshots
+  const int t_half = ((T + 63) / 64) * 32;
+  const int t_begin = h == 0 ? 0 : t_half;
+  const int t_end = h == 0 ? (t_half < T ? t_half : T) : T;
+  // a source whose base is not 16-byte aligned is mapped from the aligned address below it (boxes under the 128-byte
+  // swizzle must start on 16-byte boundaries): tile column x holds point p0 + x - col_shift
+  const int64_t gp0 = p0 + 4 * c - col_shift;
+  bool valid[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) valid[e] = gp0 + e >= 0 && gp0 + e < P;
+  Tx w4[4] = {Tx(1), Tx(1), Tx(1), Tx(1)};
+  if (weights)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (valid[e]) w4[e] = weights[gp0 + e];
+  tc::mbar_wait(bar, 0);
+
+  int bad = 0;
+  Tx mean_x[4] = {Tx(0), Tx(0), Tx(0), Tx(0)}, std_x[4] = {Tx(1), Tx(1), Tx(1), Tx(1)};
+  if (center) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    int cnt[4] = {0, 0, 0, 0};
+    for (int t = t_begin + lane; t < t_end; t += 32) {
+      const float4 v4 = tb_ld_chunk(tile, t, c);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (v[e] == v[e]) { s[e] += (double)v[e]; ++cnt[e]; }
+        if (check_finite && valid[e] && !isfinite(v[e])) bad = 1;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s[e] = warp_sum(s[e]);
+      cnt[e] = warp_sum(cnt[e]);
+    }
+    if (lane == 0)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { part_a[h][4 * c + e] = s[e]; part_n[h][4 * c + e] = cnt[e]; }
+    __syncthreads();
+    int n_valid[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      n_valid[e] = part_n[0][4 * c + e] + part_n[1][4 * c + e];
+      const double tot = part_a[0][4 * c + e] + part_a[1][4 * c + e];
+      const double mean = n_valid[e] > 0 ? tot / (double)n_valid[e] : __longlong_as_double(0x7ff8000000000000LL);
+      mean_x[e] = (Tx)mean;
+    }
+    if (do_scale) {
+      __syncthreads();             // part_a is reused below
+      double a[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int t = t_begin + lane; t < t_end; t += 32) {
+        const float4 v4 = tb_ld_chunk(tile, t, c);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (v[e] == v[e]) {
+            const double xc = (double)centre<float, Tx>(v[e], mean_x[e]);
+            a[e] += xc;
+            q[e] += xc * xc;
+          }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        a[e] = warp_sum(a[e]);
+        q[e] = warp_sum(q[e]);
+      }
+      if (lane == 0)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { part_a[h][4 * c + e] = a[e]; part_q[h][4 * c + e] = q[e]; }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double at = part_a[0][4 * c + e] + part_a[1][4 * c + e];
+        const double qt = part_q[0][4 * c + e] + part_q[1][4 * c + e];
+        const double m2 = n_valid[e] > 0 ? at / (double)n_valid[e] : 0.0;
+        double var = n_valid[e] > 0 ? qt / (double)n_valid[e] - m2 * m2 : __longlong_as_double(0x7ff8000000000000LL);
+        if (var < 0.0) var = 0.0;
+        std_x[e] = (Tx)sqrt(var);
+      }
+    }
+    if (h == 0 && lane < 4 && gp0 + lane >= 0 && gp0 + lane < P) {
+      // lane e publishes point e (static register indexing kept by the unrolled select)
+      Tx mv = mean_x[0], sv = std_x[0];
+#pragma unroll
+      for (int e = 1; e < 4; ++e)
+        if (lane == e) { mv = mean_x[e]; sv = std_x[e]; }
+      mean_out[gp0 + lane] = mv;
+      if (do_scale) std_out[gp0 + lane] = sv;
+    }
+  }
+  for (int t = t_begin + lane; t < t_end; t += 32) {
+    const float4 v4 = tb_ld_chunk(tile, t, c);
+    const float raw[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (!center && check_finite && valid[e] && !isfinite(raw[e])) bad = 1;
+      if (valid[e]) {
+        Tx v = center ? centre<float, Tx>(raw[e], mean_x[e]) : (Tx)raw[e];
+        if (do_scale) v = v / std_x[e];
+        if (weights) v = v * w4[e];
+        const int64_t off = (gp0 + e) * ldx + t;
+        if (X) X[off] = v;
+        if (Xhi) {
+          const float hh = tc::tf32_hi((float)v);
+          Xhi[off] = hh;
+          Xlo[off] = (float)v - hh;
+        }
+      }
+    }
+  }
+  if (check_finite) {
+    int any = __syncthreads_or(bad);
+    if (any && threadIdx.x == 0) atomicExch(nonfinite_flag, 1);
+  }
+}
+
+namespace tc {
+int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer, int64_t ld,
+              uint32_t box_inner, uint32_t box_outer, int* col_shift, CUtensorMapSwizzle swizzle);
+}
+
+// float32 source, tile fits in shared memory, 16-byte row pitch: the TMA kernel.  Returns 1 when it ran,
+// 0 when the shape does not qualify (caller falls back), < 0 on error.
+template <typename Tx>
+int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, Tx* X, int64_t ldx, Tx* mean_out,
+                       Tx* std_out, const Tx* weights, bool center, bool scale, bool check, int* nonfinite_flag,
+                       cudaStream_t st, float* Xhi, float* Xlo) {
+  const int64_t tpad = ceil_div(T, (int64_t)TB_BOX_T) * TB_BOX_T;
+  const size_t tile_bytes = (size_t)tpad * 128 + 1024;
+  if (tile_bytes > 224 * 1024 || (src_ld * 4) % 16 != 0 || P + 4 >= (int64_t)1 << 31) return 0;
+  CUtensorMap tm;
+  int shift = 0;
+  int rc = tc::make_tmap(&tm, src, P, T, src_ld, FB_PB, TB_BOX_T, &shift, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  auto kern = fused_build_tma_kernel<Tx>;
+  ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+  kern<<<(unsigned)ceil_div(P + shift, (int64_t)FB_PB), TB_THREADS, tile_bytes, st>>>(
+      tm, (int)T, P, shift, X, ldx, mean_out, std_out, weights, center ? 1 : 0, (center && scale) ? 1 : 0,
+      check ? 1 : 0, nonfinite_flag, Xhi, Xlo);
+  rc = check_launch("fused_build_tma_kernel");
+  return rc ? rc : 1;
+}
+
 template <typename Ts, typename Tx>
 int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void* X, int64_t ldx,
                     void* mean_out, void* std_out, const void* weights, unsigned flags,
@@ -223,6 +414,13 @@ int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void*
   const bool center = flags & ERA5SVD_BUILD_MEAN_CENTER;
   const bool scale = flags & ERA5SVD_BUILD_SCALE;
   const bool check = (flags & ERA5SVD_BUILD_CHECK_FINITE) && nonfinite_flag;
+  if constexpr (sizeof(Ts) == 4) {
+    if (!(flags & ERA5SVD_BUILD_NO_TMA)) {
+      int rc = try_build_rows_tma<Tx>((const float*)src, T, src_ld, P, (Tx*)X, ldx, (Tx*)mean_out, (Tx*)std_out,
+                                      (const Tx*)weights, center, scale, check, nonfinite_flag, st, Xhi, Xlo);
+      if (rc != 0) return rc < 0 ? rc : ERA5SVD_OK;
+    }
+  }
   // single-read fused kernel whenever the [T x 32] tile fits in shared memory (T <= ~1700 for fp32)
   const size_t tile_bytes = (size_t)T * (FB_PB + 1) * sizeof(Ts);
   if (tile_bytes <= 220 * 1024) {

@@ -55,6 +55,7 @@ typedef enum {
 #define ERA5SVD_BUILD_MEAN_CENTER 1u
 #define ERA5SVD_BUILD_SCALE 2u
 #define ERA5SVD_BUILD_CHECK_FINITE 4u
+#define ERA5SVD_BUILD_NO_TMA 8u /* diagnostics: float32 sources take the register-staged kernel instead of the TMA one */
 
 int era5svd_version(void);
 const char* era5svd_last_error(void);

@@ -70,6 +70,61 @@ def test_build_rows_long_series(ops, dtype, tol, T, P, ld_src):
     assert np.max(np.abs(got[ok] - ref32.T[ok])) <= (20 * tol if dtype == np.float64 else max(1e-4, 1e-7 * T))
 
 
+@pytest.mark.parametrize("no_tma", [0, 8])
+@pytest.mark.parametrize("T,P,off,xdt", [(744, 70, 1, torch.float32), (100, 1000, 3, torch.float64), (64, 33, 0, torch.float32),
+                                         (1460, 97, 2, torch.float32), (1700, 40, 0, torch.float32), (9, 5, 1, torch.float32)])
+def test_build_rows_tma_views(ops, T, P, off, xdt, no_tma):
+    """float32 sources take the TMA kernel (whole [T x 32] tile in flight, swizzled smem tile); column-offset views
+    (base not 16-byte aligned -> shifted tensor map), ragged point tails, the float64 cast, weights, no centring with
+    the finiteness flag, and the same calls through the register-staged kernel (flag 8 = ERA5SVD_BUILD_NO_TMA)."""
+    rng = np.random.RandomState(T * 7 + P)
+    ld_src = ((off + P + 3) // 4) * 4 + 4
+    src = (rng.rand(T, ld_src) * 30 + 250 + 3 * np.cos(np.arange(T) / 5.0)[:, None]).astype(np.float32)
+    src[T // 2, off + 3] = np.nan
+    d_src = dev(src)[:, off:off + P]
+    w = (rng.rand(P) + 0.5).astype(np.float32 if xdt == torch.float32 else np.float64)
+    a = src[:, off:off + P].astype(np.float64)
+    ref, mu, sd = standardize_np(a, scale=True)
+    ok = ~np.isnan(ref.T)
+    tol = 5e-6 if xdt == torch.float32 else 1e-12
+    for flags, wt in [(BUILD_MEAN_CENTER | BUILD_SCALE, None), (BUILD_MEAN_CENTER, w), (0, None)]:
+        X = torch.full((P, T + (-T) % 8 + 8), -7.0, dtype=xdt, device="cuda")
+        mean = torch.zeros(P, dtype=xdt, device="cuda"); std = torch.zeros(P, dtype=xdt, device="cuda")
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.build_rows(d_src, X[:, :T], mean if flags & 1 else None, std if flags & 2 else None,
+                       dev(wt) if wt is not None else None, flags | BUILD_CHECK_FINITE | no_tma, flag)
+        got = X[:, :T].cpu().numpy().astype(np.float64)
+        assert float((X[:, T:] + 7.0).abs().max()) == 0.0                   # padding untouched
+        assert int(flag.item()) == 1                                        # the NaN is reported
+        assert np.array_equal(np.isnan(got), ~ok)
+        if flags == 0:
+            assert np.array_equal(got[ok], a.T[ok])                         # plain transpose (+ exact cast)
+            continue
+        assert np.allclose(mean.cpu().numpy(), mu, rtol=1e-7 if xdt == torch.float32 else 1e-14, atol=0)
+        if flags & 2:
+            assert np.allclose(std.cpu().numpy(), sd, rtol=2e-5, atol=0)
+            assert np.max(np.abs(got[ok] - ref.T[ok])) <= (5e-5 if xdt == torch.float32 else 1e-5)
+        else:
+            want = (a - mu).T * wt[:, None].astype(np.float64)
+            # float32 matrix: the mean is rounded to float32 first (it is what mean_out stores): 300 K * 6e-8
+            assert np.max(np.abs(got[ok] - want[ok])) <= (6e-5 if xdt == torch.float32 else 1e-10)
+
+
+def test_build_rows_split_tma(ops):
+    """hi / lo images from the TMA kernel: Xhi + Xlo == X exactly, Xhi is a tf32 value."""
+    rng = np.random.RandomState(5)
+    T, P = 200, 75
+    src = (rng.rand(T, 76) * 30 + 250).astype(np.float32)
+    d_src = dev(src)[:, :P]
+    X, Xhi, Xlo = (torch.zeros((P, 200), dtype=torch.float32, device="cuda") for _ in range(3))
+    mean = torch.zeros(P, dtype=torch.float32, device="cuda")
+    ops.build_rows_split(d_src, X, Xhi, Xlo, mean, None, None, BUILD_MEAN_CENTER, None)
+    assert torch.equal(Xhi + Xlo, X)
+    assert int((Xhi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    ref, mu, _ = standardize_np(src[:, :P].astype(np.float64), scale=False)
+    assert np.max(np.abs(X.cpu().numpy() - ref.T)) <= 6e-5
+
+
 def test_build_rows_nan_and_flag(ops):
     src = np.random.RandomState(1).rand(16, 64)
     src[3, 5] = np.nan

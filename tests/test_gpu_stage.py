@@ -103,7 +103,9 @@ def test_main_matrix_dtype_cast(tmp_path, monkeypatch):
     X, _, _ = oracle_matrix(m, cfg)
     U0, s0, V0 = randomized_svd_ref(X, 6, 3)
     assert res["U"].values.dtype == np.float32 and res["X"].values.dtype == np.float32
-    assert np.max(np.abs(res["X"].values - X)) <= 2e-7 * np.max(np.abs(X))
+    # the time mean is held in the matrix dtype (it is what X_mean stores): one float32 rounding of a ~300 K mean
+    raw_max = max(float(np.max(np.abs(v))) for v in m["vars"].values())
+    assert np.max(np.abs(res["X"].values - X)) <= 1.2e-7 * raw_max
     assert sigma_rel_err(res["s"].values, s0) < 1e-4
     ref = recon_rel_err(X, U0, s0, V0)
     assert abs(recon_rel_err(X, res["U"].values.astype(np.float64), res["s"].values.astype(np.float64),
