@@ -31,6 +31,8 @@ PROTOTYPES = {
     "era5svd_split_tf32": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp]),
     "era5svd_sketch_tf32x3_workspace_bytes": (_sz, [_i64, _i64]),
     "era5svd_sketch_tf32x3": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "era5svd_sketch_tf32x2": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "era5svd_round_tf32_f64": (_int, [_vp, _i64, _i64, _i64, _vp]),
     "era5svd_project_tf32x3_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "era5svd_project_tf32x3": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _int, _vp, _sz, _vp]),
     "era5svd_gemm_f64": (_int, [_int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64, _vp]),

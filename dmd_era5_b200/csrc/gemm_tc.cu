@@ -25,7 +25,7 @@ namespace era5svd {
 // from gemm_tc2.cu: on-chip split variants (X given as one plain float32 matrix)
 int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
                       int64_t ldo, float* Y, float* Yhi, float* Ylo, int64_t ldy, void* workspace,
-                      cudaStream_t st);
+                      cudaStream_t st, int om_tf32);
 
 int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Yhi, const float* Ylo,
                        int64_t l, int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
@@ -494,9 +494,9 @@ size_t era5svd_sketch_tf32x3_workspace_bytes(int64_t n, int64_t l) {
   return (size_t)2 * round_up(l, 16) * round_up(n + 3, 4) * sizeof(float);
 }
 
-int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
-                          const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
-                          int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
+static int sketch_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                           const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
+                           int64_t ldy, void* workspace, size_t workspace_bytes, void* stream, int om_tf32) {
   using namespace era5svd;
   ERA5SVD_REQUIRE(Xhi && Om, "sketch_tf32x3: null pointer");
   ERA5SVD_REQUIRE(Y || Yhi, "sketch_tf32x3: no output requested");
@@ -519,7 +519,8 @@ int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t
   ERA5SVD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "sketch_tf32x3: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (!Xlo)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu), X read from HBM once
-    return sketch_tf32x3_raw(Xhi, m, n, ldx, Om, l, ldo, Y, Yhi, Ylo, ldy, workspace, st);
+    return sketch_tf32x3_raw(Xhi, m, n, ldx, Om, l, ldo, Y, Yhi, Ylo, ldy, workspace, st, om_tf32);
+  ERA5SVD_REQUIRE(!om_tf32, "sketch_tf32x2: needs the plain float32 matrix (Xlo == NULL, on-chip split)");
   CUtensorMap tm_xhi, tm_xlo, tm_ohi, tm_olo;
   int xs = 0, xs2 = 0, os = 0, os2 = 0, rc;
   if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, tc::BM, &xs))) return rc;
@@ -552,6 +553,38 @@ int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t
   int64_t grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   tc::sketch_tc_kernel<<<(unsigned)grid, tc::SK_THREADS, smem, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, p);
   return check_launch("sketch_tc_kernel");
+}
+
+int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                          const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
+                          int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
+  return sketch_tf32_impl(Xhi, Xlo, m, n, ldx, Om, l, ldo, Y, Yhi, Ylo, ldy, workspace, workspace_bytes, stream, 0);
+}
+
+int era5svd_sketch_tf32x2(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
+                          int64_t ldo, float* Y, float* Yhi, float* Ylo, int64_t ldy, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return sketch_tf32_impl(X, nullptr, m, n, ldx, Om, l, ldo, Y, Yhi, Ylo, ldy, workspace, workspace_bytes, stream, 1);
+}
+
+namespace era5svd {
+namespace tc {
+__global__ void __launch_bounds__(256)
+round_tf32_f64_kernel(double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int64_t r = idx / cols, c = idx - r * cols;
+  A[r * lda + c] = (double)tf32_hi((float)A[r * lda + c]);
+}
+}  // namespace tc
+}  // namespace era5svd
+
+int era5svd_round_tf32_f64(double* A, int64_t rows, int64_t cols, int64_t lda, void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(A, "round_tf32: null pointer");
+  ERA5SVD_REQUIRE(rows > 0 && cols > 0 && lda >= cols, "round_tf32: bad shape");
+  tc::round_tf32_f64_kernel<<<(unsigned)ceil_div(rows * cols, (int64_t)256), 256, 0, as_stream(stream)>>>(A, rows, cols, lda);
+  return check_launch("round_tf32_f64_kernel");
 }
 
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l) {

@@ -46,6 +46,7 @@ struct Sketch2Params {
   int npad;
   int ra;          // raw-A ring depth
   int rb;          // B ring depth
+  int use_lo;      // 1: Om = hi + lo (three MMAs per k-step); 0: Om is tf32-exact, lo tile neither loaded nor multiplied
   float* Y;
   float* Yhi;
   float* Ylo;
@@ -78,7 +79,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform
   const uint32_t a_bytes = BM2 * BK2 * 4;                   // raw A slot
   const uint32_t b_half = (uint32_t)p.npad * BK2 * 4;       // Om^T hi (or lo) tile
-  const uint32_t b_bytes = 2 * b_half;                      // B slot
+  const uint32_t b_bytes = p.use_lo ? 2 * b_half : b_half;  // B slot
   const uint32_t b_base = smem_base + (uint32_t)p.ra * a_bytes;
   const uint32_t bar_base = b_base + (uint32_t)p.rb * b_bytes;
   int nb = 0;
@@ -147,7 +148,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const uint32_t dst = b_base + (uint32_t)rb.i * b_bytes;
           mbar_arrive_expect_tx(b_full + 8u * rb.i, b_bytes);
           tma_load_2d(dst, &tm_ohi, kc * BK2, 0, b_full + 8u * rb.i);
-          tma_load_2d(dst + b_half, &tm_olo, kc * BK2, 0, b_full + 8u * rb.i);
+          if (p.use_lo) tma_load_2d(dst + b_half, &tm_olo, kc * BK2, 0, b_full + 8u * rb.i);
           rb.next();
         }
       }
@@ -155,6 +156,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   } else if (warp == 1) {
     // ===== MMA issuer: A (hi / lo) from TMEM, B (Om^T hi / lo) from smem =====
     const uint32_t idesc = make_idesc_tf32(BM2, p.npad, 0, 0);
+    const bool use_lo = p.use_lo != 0;            // kernel parameter: uniform, so the issue loop stays branch-free per chunk
     Ring rb(p.rb), at(AT_RING), acc(2);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(tempty + 8u * acc.i, acc.ph ^ 1u);
@@ -174,7 +176,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const uint64_t b_hi = make_smem_desc(bs + koff, 16, 1024);
             const uint64_t b_lo = make_smem_desc(bs + b_half + koff, 16, 1024);
             umma_tf32_ts(d_tmem, a_lo + kk * UK2, b_hi, idesc, (kc | kk) != 0);
-            umma_tf32_ts(d_tmem, a_hi + kk * UK2, b_lo, idesc, 1);
+            if (use_lo) umma_tf32_ts(d_tmem, a_hi + kk * UK2, b_lo, idesc, 1);
             umma_tf32_ts(d_tmem, a_hi + kk * UK2, b_hi, idesc, 1);
           }
           umma_commit(b_empty + 8u * rb.i);
@@ -500,9 +502,12 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 static int round_up2(int64_t a, int64_t b) { return (int)(ceil_div(a, b) * b); }
 
 // Y = X Om with X a plain float32 matrix (split on chip).  Called by era5svd_sketch_tf32x3 when Xlo == NULL.
+// om_tf32 != 0: Y = X tf32(Om) - the small factor is taken rounded to tf32 (for a factor that already holds
+// tf32-representable values, era5svd_round_tf32_f64, this is exact), so its lo image vanishes: two MMAs per k-step
+// instead of three and half the Om^T tile traffic.
 int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
                       int64_t ldo, float* Y, float* Yhi, float* Ylo, int64_t ldy, void* workspace,
-                      cudaStream_t st) {
+                      cudaStream_t st, int om_tf32) {
   const int npad = round_up2(l, 16);
   if (npad > 128) {
     set_error("sketch_tf32x3 (on-chip split): l = %lld > 128 is not supported", (long long)l);
@@ -532,9 +537,10 @@ int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const d
   // The raw-A depth must be EVEN: the two transform groups take alternate chunks, so with an even depth every slot
   // always belongs to the same group.  With an odd depth a group meets a slot only every other use and its parity wait
   // can be satisfied by the use it skipped (seen as a race and, eventually, a hung barrier at depth 5).
-  const size_t a_bytes = (size_t)tc::BM2 * tc::BK2 * 4, b_bytes = 2 * (size_t)npad * tc::BK2 * 4;
+  p.use_lo = om_tf32 ? 0 : 1;
+  const size_t a_bytes = (size_t)tc::BM2 * tc::BK2 * 4, b_bytes = (p.use_lo ? 2 : 1) * (size_t)npad * tc::BK2 * 4;
   const size_t budget = 227 * 1024 - 1024 - 512;
-  p.rb = 4;
+  p.rb = p.use_lo ? 4 : 6;
   p.ra = (int)((budget - p.rb * b_bytes) / a_bytes);
   if (p.ra > 8) p.ra = 8;
   p.ra &= ~1;

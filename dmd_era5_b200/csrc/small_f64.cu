@@ -224,18 +224,68 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
   for (int j = t; j < l; j += 1024) gdiag[j] = G[(int64_t)j * ldg + j];
   // Right-looking Cholesky with the row scaling deferred: one barrier per step.  At step j the
   // (unscaled) pivot row is final; trailing rows get  R[i][c] -= R[j][i] R[j][c] / d_j.
-  for (int j = 0; j < l; ++j) {
+  if (l <= 128) {
+    // Small factor (the sketch width): every thread owns at most 4 x 4 trailing entries per step.  The pivot-row
+    // values and the row entries are loaded as one batch before any store (a plain read-modify-write loop is
+    // serialised: the compiler cannot prove that the stores do not alias the next loads), and the reciprocal pivot
+    // is computed ONCE, by the thread that has just finished updating it, instead of by all 1024 threads.
+    __shared__ double s_inv[2];
     __syncthreads();
-    const double d = Rw[j * ld_r + j];
-    // dependent (or non-positive) pivot: the direction is dropped (no update, zero row), never NaN
-    const double inv_d = (d > rel_tol * gdiag[j] && d > 0.0) ? 1.0 / d : 0.0;
-    const double* prow = Rw + j * ld_r;
-    for (int i = j + 1 + ty; i < l; i += 32) {
-      const double f = prow[i] * inv_d;
-      double* row = Rw + i * ld_r;
-      // columns c >= i only, lanes strided: first column handled by lane ((i - j - 1) % 32)
-      for (int c = j + 1 + tx; c < l; c += 32)
-        if (c >= i) row[c] = fma(-f, prow[c], row[c]);
+    if (t == 0) {
+      const double d0 = Rw[0];
+      s_inv[0] = (d0 > rel_tol * gdiag[0] && d0 > 0.0) ? 1.0 / d0 : 0.0;
+    }
+    for (int j = 0; j < l; ++j) {
+      __syncthreads();
+      const double inv_d = s_inv[j & 1];
+      const double* prow = Rw + j * ld_r;
+      double pc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = j + 1 + tx + 32 * k;
+        pc[k] = c < l ? prow[c] : 0.0;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int i = j + 1 + ty + 32 * rr;
+        if (i < l) {
+          const double f = prow[i] * inv_d;
+          double* row = Rw + i * ld_r;
+          double v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = j + 1 + tx + 32 * k;
+            if (c < l && c >= i) v[k] = row[c];
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = j + 1 + tx + 32 * k;
+            if (c < l && c >= i) {
+              v[k] = fma(-f, pc[k], v[k]);
+              row[c] = v[k];
+            }
+          }
+          if (rr == 0 && t == 0) {       // thread 0 has just produced the next pivot R[j+1][j+1]
+            const double dn = v[0];
+            s_inv[(j + 1) & 1] = (dn > rel_tol * gdiag[j + 1] && dn > 0.0) ? 1.0 / dn : 0.0;
+          }
+        }
+      }
+    }
+  } else {
+    for (int j = 0; j < l; ++j) {
+      __syncthreads();
+      const double d = Rw[j * ld_r + j];
+      // dependent (or non-positive) pivot: the direction is dropped (no update, zero row), never NaN
+      const double inv_d = (d > rel_tol * gdiag[j] && d > 0.0) ? 1.0 / d : 0.0;
+      const double* prow = Rw + j * ld_r;
+      for (int i = j + 1 + ty; i < l; i += 32) {
+        const double f = prow[i] * inv_d;
+        double* row = Rw + i * ld_r;
+        // columns c >= i only, lanes strided: first column handled by lane ((i - j - 1) % 32)
+        for (int c = j + 1 + tx; c < l; c += 32)
+          if (c >= i) row[c] = fma(-f, prow[c], row[c]);
+      }
     }
   }
   __syncthreads();
@@ -259,15 +309,57 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
   __syncthreads();
   // x lives in column c of Iw itself (zero-initialised above; stride ld_i is odd in shared memory, so the
   // column walk is conflict free)
-  for (int c = ty; c < l; c += 32) {
-    if (tx == 0) Iw[c * ld_i + c] = 1.0;
-    __syncwarp();
-    for (int i = c; i >= 0; --i) {
-      const double xi = Iw[i * ld_i + c] * scale[i];
+  if (l <= 128) {
+    // register-resident variant: the warp solves its (up to four) columns ty, ty + 32, ... TOGETHER; lane tx holds
+    // rows tx + 32 m of each.  One step = four conflict-free column loads of R shared by the four solves, one
+    // shuffle broadcast and four DFMAs per column; the four dependency chains interleave.
+    double x[4][4];
+    int c_hi = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ck = ty + 32 * k;
+      if (ck < l) c_hi = ck;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) x[k][m] = (tx + 32 * m == ck && ck < l) ? 1.0 : 0.0;
+    }
+    for (int i = c_hi; i >= 0; --i) {
+      const int owner = i & 31, slot = i >> 5;
+      const double sc = scale[i];
+      double rk[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int row = tx + 32 * m;
+        rk[m] = row < i ? Rw[row * ld_r + i] : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double xo = slot == 0 ? x[k][0] : (slot == 1 ? x[k][1] : (slot == 2 ? x[k][2] : x[k][3]));
+        const double xi = __shfl_sync(0xffffffffu, xo, owner) * sc;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) x[k][m] = (tx + 32 * m == i) ? xi : fma(-rk[m], xi, x[k][m]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ck = ty + 32 * k;
+      if (ck < l)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int row = tx + 32 * m;
+          if (row <= ck) Iw[row * ld_i + ck] = x[k][m];
+        }
+    }
+  } else {
+    for (int c = ty; c < l; c += 32) {
+      if (tx == 0) Iw[c * ld_i + c] = 1.0;
       __syncwarp();
-      if (tx == 0) Iw[i * ld_i + c] = xi;
-      for (int k = tx; k < i; k += 32) Iw[k * ld_i + c] = fma(-Rw[k * ld_r + i], xi, Iw[k * ld_i + c]);
-      __syncwarp();
+      for (int i = c; i >= 0; --i) {
+        const double xi = Iw[i * ld_i + c] * scale[i];
+        __syncwarp();
+        if (tx == 0) Iw[i * ld_i + c] = xi;
+        for (int k = tx; k < i; k += 32) Iw[k * ld_i + c] = fma(-Rw[k * ld_r + i], xi, Iw[k * ld_i + c]);
+        __syncwarp();
+      }
     }
   }
   if (use_smem) {

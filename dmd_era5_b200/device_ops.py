@@ -201,10 +201,20 @@ class CudaOps:
         """Row pitch the tensor-core sketch needs for its outputs: round_up(l, 16)."""
         return -(-l // 16) * 16
 
+    def round_tf32_(self, A: torch.Tensor) -> torch.Tensor:
+        """A <- tf32(A) in place (float64 small factor): the values the tensor core reads exactly."""
+        if A.dtype != torch.float64:
+            raise ValueError("round_tf32_: float64 small factor expected")
+        ap, ald = _mat(A, "A")
+        check(self.lib.era5svd_round_tf32_f64(ap, A.shape[0], A.shape[1], ald, self._stream()), "era5svd_round_tf32_f64")
+        return A
+
     def sketch_tf32x3(self, Xhi: torch.Tensor, Xlo: torch.Tensor, Om: torch.Tensor, Y: torch.Tensor | None,
-                      Yhi: torch.Tensor | None, Ylo: torch.Tensor | None) -> None:
+                      Yhi: torch.Tensor | None, Ylo: torch.Tensor | None, om_tf32: bool = False) -> None:
         """Y (and/or the split pair Yhi, Ylo) = X @ Om; Om is the float64 (n, l) small factor.
-        Outputs are (m, l) views of buffers whose row pitch is tf32_ldy(l)."""
+        Outputs are (m, l) views of buffers whose row pitch is tf32_ldy(l).
+        om_tf32: Om holds tf32-representable values (round_tf32_): two tensor-core products per k-step instead of
+        three (era5svd_sketch_tf32x2; plain float32 X only)."""
         m, n = Xhi.shape
         l = Om.shape[1]
         if Om.dtype != torch.float64 or Om.shape[0] != n:
@@ -223,10 +233,16 @@ class CudaOps:
         ws = self._workspace("sketch_tc", nbytes)
         end = self.timer.start("sketch_tc" if n > 2 * l else "apply_basis_tc", bytes=4.0 * (m * n + m * l + n * l),
                                flops=2.0 * m * n * l) if self.timer else None
-        check(self.lib.era5svd_sketch_tf32x3(hp, lp, m, n, hld, op, l, old, Y.data_ptr() if Y is not None else None,
-                                             Yhi.data_ptr() if Yhi is not None else None,
-                                             Ylo.data_ptr() if Ylo is not None else None, ldy, ws.data_ptr(), ws.numel(),
-                                             self._stream()), "era5svd_sketch_tf32x3")
+        outp = (Y.data_ptr() if Y is not None else None, Yhi.data_ptr() if Yhi is not None else None,
+                Ylo.data_ptr() if Ylo is not None else None)
+        if om_tf32:
+            if Xlo is not None:
+                raise ValueError("sketch_tf32x3: om_tf32 needs the plain float32 matrix (Xlo=None)")
+            check(self.lib.era5svd_sketch_tf32x2(hp, m, n, hld, op, l, old, *outp, ldy, ws.data_ptr(), ws.numel(),
+                                                 self._stream()), "era5svd_sketch_tf32x2")
+        else:
+            check(self.lib.era5svd_sketch_tf32x3(hp, lp, m, n, hld, op, l, old, *outp, ldy, ws.data_ptr(), ws.numel(),
+                                                 self._stream()), "era5svd_sketch_tf32x3")
         if end is not None:
             end.record()
 

@@ -15,7 +15,8 @@ there for floating-point stability only.  The device schedule th
 same Omega_0, q and flip rule but never factorises a TALL matrix inside the power iterations:
 
     Omega = orth(Omega_0)                                   (n x l, float64, CholeskyQR2)
-    q x { Y = X Omega            [tall pass, not normalised]
+    q x { Y = X Omega            [tall pass, not normalised; Omega held in tf32-representable values on the
+                                  tensor-core path: 2 instead of 3 products per k-step, see below]
           Z = X^T Y              [tall pass -> n x l float64, all-reduce over row shards]
           last iteration only: T = Omega^T Z = Y^T Y = W L W^T (l x l Jacobi), Z <- Z W   (Rayleigh-Ritz)
           Omega = orth(Z)        }  (CholeskyQR2; shifted CholeskyQR3 after the random start)
@@ -141,6 +142,12 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         ops.col_normalize(Omega)
 
     use_tc = precision == PREC_TF32X3
+    # On-chip split path: the basis Omega is ours to choose (any well-conditioned basis of the same span serves), so
+    # it is kept in tf32-representable values - every formula below uses the SAME rounded Omega, so nothing is
+    # approximated - and the sketch needs two tensor-core products per k-step instead of three (Omega_lo = 0).
+    om_tf32 = use_tc and split is None
+    if om_tf32:
+        ops.round_tf32_(Omega)
     if use_tc:
         # tensor-core path: operands pre-split into tf32 hi / lo images (see csrc/gemm_tc.cu)
         if tall != torch.float32:
@@ -164,7 +171,7 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
             for j in range(d):
                 rows = slice(j * m0, (j + 1) * m0)
                 xh, xl = Xhi[:, j : j + n], (Xlo[:, j : j + n] if Xlo is not None else None)
-                ops.sketch_tf32x3(xh, xl, Omega64, Y[rows] if keep_y else None, Yhi[rows], Ylo[rows])
+                ops.sketch_tf32x3(xh, xl, Omega64, Y[rows] if keep_y else None, Yhi[rows], Ylo[rows], om_tf32=om_tf32)
                 Z = ops.project_tf32x3(xh, xl, Yhi[rows], Ylo[rows], Z, accumulate=j > 0)
         else:
             Om_t = ops.convert(Omega64, tall)
@@ -188,6 +195,8 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
             Z = ops.gemm(Z, W)
         # cond(Z) ~ kappa(X)^2 after the random start (shifted CholeskyQR3), <~ kappa(X) afterwards
         Omega = _orth(ops, Z, 1e-13, shifted=(it == 0 and n_iter > 1))
+        if om_tf32:
+            ops.round_tf32_(Omega)
 
     Zp = tall_pass(Omega, keep_y=not use_tc)           # n x l
     # l x l Gram matrix of the STORED (rounded) Y, so that Q = Y R^-1 is orthonormal for the Y we keep

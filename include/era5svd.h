@@ -131,6 +131,18 @@ size_t era5svd_sketch_tf32x3_workspace_bytes(int64_t n, int64_t l);
 int era5svd_sketch_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
                           const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
                           int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+/* The small factor of the range finder is OURS to choose (any well-conditioned basis of the same span serves the
+ * power iteration, extmath.py:371-383 normalises only for stability), so the driver keeps it in tf32-representable
+ * values: its lo image is then zero and the sketch needs two tensor-core products per k-step instead of three, and
+ * half the Om^T tile traffic.
+ * era5svd_round_tf32_f64 : A <- tf32(A) in place (float64 storage, round to nearest, 10 explicit mantissa bits).
+ * era5svd_sketch_tf32x2  : Y = X * tf32(Om), X the plain float32 matrix (split hi/lo on chip), l <= 128; same
+ *                          outputs, pitches and workspace as era5svd_sketch_tf32x3.  Exact (to the fp32 accumulate)
+ *                          for a factor that went through era5svd_round_tf32_f64. */
+int era5svd_round_tf32_f64(double* A, int64_t rows, int64_t cols, int64_t lda, void* stream);
+int era5svd_sketch_tf32x2(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
+                          int64_t ldo, float* Y, float* Yhi, float* Ylo, int64_t ldy, void* workspace,
+                          size_t workspace_bytes, void* stream);
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l);
 int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
                            const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,

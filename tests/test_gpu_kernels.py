@@ -72,10 +72,12 @@ def test_build_rows_long_series(ops, dtype, tol, T, P, ld_src):
 
 @pytest.mark.parametrize("no_tma", [0, 8])
 @pytest.mark.parametrize("T,P,off,xdt", [(744, 70, 1, torch.float32), (100, 1000, 3, torch.float64), (64, 33, 0, torch.float32),
-                                         (1460, 97, 2, torch.float32), (1700, 40, 0, torch.float32), (9, 5, 1, torch.float32)])
+                                         (1460, 97, 2, torch.float32), (1700, 40, 0, torch.float32), (9, 5, 1, torch.float32),
+                                         (70, 40000, 1, torch.float32), (300, 33000, 0, torch.float32)])
 def test_build_rows_tma_views(ops, T, P, off, xdt, no_tma):
     """float32 sources take the TMA kernel (whole [T x 32] tile in flight, swizzled smem tile); column-offset views
-    (base not 16-byte aligned -> shifted tensor map), ragged point tails, the float64 cast, weights, no centring with
+    (base not 16-byte aligned -> shifted tensor map), ragged point tails, more tiles than resident CTAs (persistent loop,
+    box-by-box refill), the float64 cast, weights, no centring with
     the finiteness flag, and the same calls through the register-staged kernel (flag 8 = ERA5SVD_BUILD_NO_TMA)."""
     rng = np.random.RandomState(T * 7 + P)
     ld_src = ((off + P + 3) // 4) * 4 + 4

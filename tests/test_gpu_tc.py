@@ -89,6 +89,39 @@ def test_sketch_tf32x3_onchip_split(ops, m, n, l, off):
     assert torch.equal(Y2, Y)
 
 
+@pytest.mark.parametrize("m,n,l,off", [(128, 32, 16, 0), (1000, 744, 110, 0), (300, 100, 128, 0), (5000, 1460, 110, 0),
+                                       (2000, 742, 110, 2), (77, 25, 20, 1), (40000, 744, 100, 3)])
+def test_sketch_tf32x2_rounded_omega(ops, m, n, l, off):
+    """The driver keeps the small factor in tf32-representable values (era5svd_round_tf32_f64), so its lo image is
+    zero and the sketch issues two tensor-core products per k-step (era5svd_sketch_tf32x2): Y = X tf32(Om) to the same
+    bound as the three-product kernel, which it must reproduce on the rounded factor."""
+    rng = np.random.RandomState(m + n + 2)
+    Xfull = (rng.standard_normal((m, n + off)) * np.exp(rng.uniform(-3, 3, size=(m, 1)))).astype(np.float32)
+    Om = dev(rng.standard_normal((n, l)))
+    Om0 = Om.clone()
+    ops.round_tf32_(Om)
+    omr = Om.cpu().numpy()
+    assert np.array_equal(omr.astype(np.float32).astype(np.float64), omr)                 # float32-exact ...
+    assert int((torch.from_numpy(omr.astype(np.float32)).view(torch.int32) & 0x1FFF).abs().max()) == 0   # ... tf32-exact
+    assert float(((Om - Om0).abs() / Om0.abs()).max()) <= 2.0 ** -11 * (1 + 1e-6)         # round to nearest
+    ld = (n + off + 7) // 8 * 8
+    Xb = torch.zeros((m, ld), device="cuda")
+    Xb[:, : n + off] = dev(Xfull)
+    ldy = ops.tf32_ldy(l)
+    Y, Yh, Yl, Y3 = (torch.zeros((m, ldy), device="cuda")[:, :l] for _ in range(4))
+    ops.sketch_tf32x3(Xb[:, off:off + n], None, Om, Y, Yh, Yl, om_tf32=True)
+    ref = Xfull[:, off:].astype(np.float64) @ omr
+    bound = TC_REL * np.linalg.norm(Xfull[:, off:], axis=1)[:, None] * np.linalg.norm(omr, axis=0)[None, :]
+    assert np.all(np.abs(Y.cpu().numpy() - ref) <= bound + 1e-30)
+    assert np.array_equal((Yh + Yl).cpu().numpy(), Y.cpu().numpy())
+    ops.sketch_tf32x3(Xb[:, off:off + n], None, Om, Y3, None, None)                      # three products, lo image = 0
+    assert torch.equal(Y3, Y)
+    # an unrounded factor is taken as tf32(Om): same result as rounding first
+    Y4 = torch.zeros((m, ldy), device="cuda")[:, :l]
+    ops.sketch_tf32x3(Xb[:, off:off + n], None, Om0, Y4, None, None, om_tf32=True)
+    assert torch.equal(Y4, Y)
+
+
 @pytest.mark.parametrize("m,n,l,off", [(16, 32, 16, 0), (1000, 744, 110, 0), (50000, 1460, 110, 0), (4097, 25, 20, 1),
                                        (333, 600, 128, 0), (20000, 742, 112, 2), (9000, 130, 100, 3)])
 def test_project_tf32x3_onchip_split(ops, m, n, l, off):
