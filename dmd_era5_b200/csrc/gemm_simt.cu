@@ -327,26 +327,44 @@ project_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t 
   }
 }
 
+// 64 outputs x 4 split groups per CTA: group g sums its contiguous quarter of the splits (eight independent loads
+// in flight), the four group sums are added through shared memory in a fixed order (deterministic).  One thread
+// per output walking all ~300 splits alone was latency bound (~37 dependent rounds of HBM latency).
+constexpr int RP_OUT = 64;
+constexpr int RP_GROUPS = 4;
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RP_OUT * RP_GROUPS)
 reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, int64_t l,
                        double* __restrict__ Z, int64_t ldz, int accumulate) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = n * l;
-  if (idx >= total) return;
+  __shared__ double sm[RP_GROUPS][RP_OUT];
+  const int o = threadIdx.x % RP_OUT, g = threadIdx.x / RP_OUT;
+  const int64_t idx = (int64_t)blockIdx.x * RP_OUT + o;
+  const int64_t total = n * l;
+  const int64_t per = (splits + RP_GROUPS - 1) / RP_GROUPS;
+  const int64_t k_end = (g + 1) * per < splits ? (g + 1) * per : splits;
   double s = 0.0;
-  int64_t k = 0;
-  for (; k + 8 <= splits; k += 8) {       // eight independent loads in flight, summed in the same fixed order
-    T v[8];
+  if (idx < total) {
+    int64_t k = g * per;
+    for (; k + 8 <= k_end; k += 8) {
+      T v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = part[(k + u) * total + idx];
+      for (int u = 0; u < 8; ++u) v[u] = part[(k + u) * total + idx];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s += (double)v[u];
+      for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; k < k_end; ++k) s += (double)part[k * total + idx];
   }
-  for (; k < splits; ++k) s += (double)part[k * total + idx];
-  int64_t r = idx / l, c = idx % l;
-  double* z = Z + r * ldz + c;
-  *z = accumulate ? (*z + s) : s;
+  sm[g][o] = s;
+  __syncthreads();
+  if (g == 0 && idx < total) {
+    double t = sm[0][o];
+#pragma unroll
+    for (int j = 1; j < RP_GROUPS; ++j) t += sm[j][o];
+    const int64_t r = idx / l, c = idx % l;
+    double* z = Z + r * ldz + c;
+    *z = accumulate ? (*z + t) : t;
+  }
 }
 
 struct ProjectPlan {
@@ -415,7 +433,7 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
     }
     int rc = check_launch("project_dmma_kernel");
     if (rc) return rc;
-    reduce_partials_kernel<double><<<(unsigned)ceil_div(n * l, 256), 256, 0, st>>>((const double*)ws, plan.splits, n, l, Z, ldz, accumulate);
+    reduce_partials_kernel<double><<<(unsigned)ceil_div(n * l, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const double*)ws, plan.splits, n, l, Z, ldz, accumulate);
     return check_launch("reduce_partials_kernel");
   }
   if (use_tn7(l)) {
@@ -428,14 +446,14 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
   int rc = check_launch("project_kernel");
   if (rc) return rc;
   int64_t total = n * l;
-  reduce_partials_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>((const T*)ws, plan.splits, n, l, Z, ldz, accumulate);
+  reduce_partials_kernel<T><<<(unsigned)ceil_div(total, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const T*)ws, plan.splits, n, l, Z, ldz, accumulate);
   return check_launch("reduce_partials_kernel");
 }
 
 // shared with the tcgen05 path (gemm_tc.cu): float32 partial tiles -> float64 sum
 void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
                                 int64_t ldz, int accumulate, cudaStream_t st) {
-  reduce_partials_kernel<float><<<(unsigned)ceil_div(n * l, 256), 256, 0, st>>>(part, splits, n, l, Z, ldz, accumulate);
+  reduce_partials_kernel<float><<<(unsigned)ceil_div(n * l, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>(part, splits, n, l, Z, ldz, accumulate);
 }
 
 }  // namespace era5svd

@@ -131,7 +131,9 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     rel_tol = 1e-13 if tall == torch.float64 else 1e-6
     # Jacobi stopping thresholds (relative off-diagonal size): full precision for float64 data; for
     # float32 data the factors carry ~1e-7 anyway, so 1e-10 changes sigma by < 1e-12 relative
-    rr_tol = 0.0 if tall == torch.float64 else 1e-8
+    # (the Rayleigh-Ritz rotation is a choice of basis, not a result: it only has to leave the columns of Y graded and
+    # the scaled Gram matrix well conditioned, for which |cos(y_p, y_q)| <= 1e-4 is ample)
+    rr_tol = 0.0 if tall == torch.float64 else 1e-4
     eig_tol = 0.0 if tall == torch.float64 else 1e-10
     # A Gaussian n x l block is already well conditioned (cond ~ (1 + sqrt(l/n)) / (1 - sqrt(l/n))): like the
     # reference, Omega_0 is used as drawn (column-normalised); when l is close to n it is orthonormalised.
