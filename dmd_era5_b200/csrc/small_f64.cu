@@ -4,6 +4,8 @@
 // Gram-route standard SVD (np.linalg.svd, src/dmd_era5/era5_svd/era5_svd.py:251).
 // They are latency-bound, replicated on every GPU, and run as one CTA (the solvers) or a handful of
 // CTAs (the small GEMM).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace era5svd {
@@ -103,7 +105,11 @@ __device__ __forceinline__ void jacobi_pair(int step, int i, int n_pad, int& p, 
 template <bool SMEM>
 __global__ void __launch_bounds__(JAC_THREADS, 1)
 syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restrict__ W,
-             double* __restrict__ V, int64_t ldv, int max_sweeps, double tol_in, double* __restrict__ ws) {
+             double* __restrict__ V, int64_t ldv, int max_sweeps, double tol_in, double* __restrict__ ws,
+             const int* __restrict__ run_if) {
+  // run_if != NULL: this launch is the fallback of syev_chol_jacobi_kernel and runs only if that reported a
+  // dropped pivot (*run_if == 1)
+  if (run_if && *run_if == 0) return;
   extern __shared__ double smem[];
   const int t = threadIdx.x;
   const int g = t / JAC_GROUP, gl = t % JAC_GROUP;
@@ -200,6 +206,196 @@ syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restric
   __syncthreads();
   for (int r = t / 32; r < n; r += JAC_THREADS / 32)
     for (int c = t % 32; c < n; c += 32) V[(int64_t)r * ldv + rank[c]] = Vw[r * ldw + c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Symmetric POSITIVE DEFINITE eigensolver for the sketch-sized factors (n <= 128): Cholesky G = R^T R followed by
+// ONE-SIDED Jacobi on the rows of R (Veselic / Hari).  Row rotations R <- J^T R leave R^T R = G unchanged and
+// drive the rows to mutual orthogonality; at convergence R = Lambda^(1/2) U^T, i.e. eigenvalue j = |row j|^2 and
+// eigenvector j = row j / |row j|.  Compared with the two-sided kernel above (columns of A, columns of V, rows of
+// A: 580 KB of shared-memory traffic per step, two barriers) a step reads and writes each row once (194 KB, one
+// barrier) and needs no eigenvector accumulation; the two-sided kernel is shared-memory-bandwidth bound (ncu: 79 %
+// of the LSU wavefront peak).  One 16-lane group owns one (p, q) pair per step: its lanes hold the two rows in
+// registers, form the three dot products (butterfly shuffles), rotate and store.
+// A dropped Cholesky pivot (G numerically singular, e.g. a sketch wider than the rank) sets *status = 1 and leaves
+// the outputs untouched: the caller then runs the two-sided kernel, which needs no definiteness.
+// ---------------------------------------------------------------------------------------------
+constexpr int J1_MAXN = 128;
+constexpr int J1_PER_LANE = J1_MAXN / JAC_GROUP;     // 8 row elements per lane
+
+__device__ __forceinline__ double group16_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 16);
+  return v;
+}
+
+__global__ void __launch_bounds__(JAC_THREADS, 1)
+syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restrict__ W,
+                        double* __restrict__ V, int64_t ldv, int max_sweeps, double tol_in, double pivot_tol,
+                        int* __restrict__ status) {
+  extern __shared__ double smem[];
+  __shared__ double prow[2][J1_MAXN];
+  __shared__ double s_inv[2];
+  __shared__ double gdiag[J1_MAXN];
+  __shared__ double lam[J1_MAXN];
+  __shared__ int rank[J1_MAXN];
+  const int t = threadIdx.x, tx = t % 32, ty = t / 32;
+  const int ldw = n + (n & 1);                  // even pitch: 16-byte aligned rows, contiguous row access
+  double* Rw = smem;                            // [n][ldw]
+  for (int r = ty; r < n; r += 32)
+    for (int c = tx; c < ldw; c += 32)
+      Rw[r * ldw + c] = (c >= r && c < n) ? 0.5 * (A[(int64_t)r * lda + c] + A[(int64_t)c * lda + r]) : 0.0;
+  for (int j = t; j < n; j += JAC_THREADS) gdiag[j] = A[(int64_t)j * lda + j];
+  __syncthreads();
+  // ---- register-tiled right-looking Cholesky (see chol_inv_kernel) ----
+  int dropped = 0;
+  {
+    double r[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = ty + 32 * a, c = tx + 32 * b;
+        r[a][b] = (i < n && c < n && c >= i) ? Rw[i * ldw + c] : 0.0;
+      }
+    if (ty == 0) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (tx + 32 * b < n) prow[0][tx + 32 * b] = r[0][b];
+      if (tx == 0) s_inv[0] = (r[0][0] > pivot_tol * gdiag[0] && r[0][0] > 0.0) ? 1.0 / r[0][0] : 0.0;
+    }
+    for (int j = 0; j < n; ++j) {
+      __syncthreads();
+      const double inv_d = s_inv[j & 1];
+      if (inv_d == 0.0) dropped = 1;           // uniform: every thread reads the same value
+      const double* pw = prow[j & 1];
+      double pc[4], pr[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) pc[b] = (tx + 32 * b < n) ? pw[tx + 32 * b] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = ty + 32 * a;
+        pr[a] = (i > j && i < n) ? pw[i] * inv_d : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (tx + 32 * b >= ty + 32 * a) r[a][b] = fma(-pr[a], pc[b], r[a][b]);
+      const int jn = j + 1;
+      if (jn < n && ty == (jn & 31)) {
+        const int an = jn >> 5;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c = tx + 32 * b;
+          const double v = an == 0 ? r[0][b] : (an == 1 ? r[1][b] : (an == 2 ? r[2][b] : r[3][b]));
+          if (c < n && c >= jn) prow[jn & 1][c] = v;
+          if (c == jn) s_inv[jn & 1] = (v > pivot_tol * gdiag[jn] && v > 0.0) ? 1.0 / v : 0.0;
+        }
+      }
+    }
+    if (dropped) {                              // uniform over the CTA
+      if (t == 0) *status = 1;
+      return;
+    }
+    // R = D^(-1/2) * (unscaled rows); the diagonal owner of row i publishes the scale
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (ty == tx && ty + 32 * a < n) lam[ty + 32 * a] = rsqrt(r[a][a]);
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = ty + 32 * a, c = tx + 32 * b;
+        if (i < n && c < n && c >= i) Rw[i * ldw + c] = r[a][b] * lam[i];
+      }
+  }
+  if (t == 0) *status = 0;
+  __syncthreads();
+
+  // ---- one-sided Jacobi on the rows of R ----
+  const int g = t / JAC_GROUP, gl = t % JAC_GROUP;
+  const unsigned gmask = 0xFFFFu << (16 * (g & 1));
+  const int n_pad = n + (n & 1);
+  const int npairs = n_pad / 2;
+  const double tol = tol_in > 0.0 ? tol_in : 2.220446049250313e-16 * sqrt((double)n);
+  const double tol2 = tol * tol;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    int did = 0;
+    for (int step = 0; step < n_pad - 1; ++step) {
+      if (g < npairs) {
+        int p, q;
+        jacobi_pair(step, g, n_pad, p, q);
+        if (q < n) {
+          double x[J1_PER_LANE], y[J1_PER_LANE];
+          double app = 0.0, aqq = 0.0, apq = 0.0;
+#pragma unroll
+          for (int k = 0; k < J1_PER_LANE; ++k) {
+            const int c = gl + JAC_GROUP * k;
+            x[k] = c < n ? Rw[p * ldw + c] : 0.0;
+            y[k] = c < n ? Rw[q * ldw + c] : 0.0;
+            app = fma(x[k], x[k], app);
+            aqq = fma(y[k], y[k], aqq);
+            apq = fma(x[k], y[k], apq);
+          }
+          app = group16_sum(app, gmask);
+          aqq = group16_sum(aqq, gmask);
+          apq = group16_sum(apq, gmask);
+          if (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300) {
+            // rotation that orthogonalises rows p, q (same angle as the two-sided rotation of the 2 x 2 Gram block);
+            // tan(theta) from fast float32 ops, c and s completed in float64 (exactly orthogonal rotation)
+            const float dq = (float)(aqq - app), ap2 = 2.0f * (float)apq;
+            double t64;
+            if (fabsf(ap2) > 1e-30f && fabsf(dq) < 1e30f) {
+              const float tau = __fdividef(dq, ap2);
+              const float tf = __fdividef(copysignf(1.0f, tau), fabsf(tau) + sqrtf(fmaf(tau, tau, 1.0f)));
+              t64 = (double)tf;
+            } else {
+              const double tau = (aqq - app) / (2.0 * apq);
+              t64 = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            }
+            const double cs = rsqrt(fma(t64, t64, 1.0));
+            const double sn = t64 * cs;
+            did = 1;
+#pragma unroll
+            for (int k = 0; k < J1_PER_LANE; ++k) {
+              const int c = gl + JAC_GROUP * k;
+              if (c < n) {
+                Rw[p * ldw + c] = cs * x[k] - sn * y[k];
+                Rw[q * ldw + c] = sn * x[k] + cs * y[k];
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(did)) break;
+  }
+  // ---- eigenvalues = squared row norms, eigenvectors = normalised rows; descending order ----
+  for (int i = g; i < n; i += JAC_GROUPS) {
+    double s = 0.0;
+    for (int c = gl; c < n; c += JAC_GROUP) s = fma(Rw[i * ldw + c], Rw[i * ldw + c], s);
+    s = group16_sum(s, gmask);
+    if (gl == 0) lam[i] = s;
+  }
+  __syncthreads();
+  for (int j = t; j < n; j += JAC_THREADS) {
+    const double wj = lam[j];
+    int rk = 0;
+    for (int i = 0; i < n; ++i) {
+      const double wi = lam[i];
+      rk += (wi > wj) || (wi == wj && i < j);
+    }
+    W[rk] = wj;
+    rank[j] = rk;
+  }
+  __syncthreads();
+  for (int r = ty; r < n; r += 32) {           // r = component, c = eigenvector (row of R)
+    for (int c = tx; c < n; c += 32) V[(int64_t)r * ldv + rank[c]] = Rw[c * ldw + r] * rsqrt(lam[c]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,6 +683,12 @@ int era5svd_gemm_f64(int transA, int transB, int64_t M, int64_t N, int64_t K, do
   return check_launch("gemm_f64_kernel");
 }
 
+// bit 0: force the two-sided kernel (ERA5SVD_SYEVJ_TWOSIDED=1; diagnostics and tests)
+static unsigned syevj_flags() {
+  const char* e = getenv("ERA5SVD_SYEVJ_TWOSIDED");
+  return (e && e[0] == '1') ? 1u : 0u;
+}
+
 static size_t syevj_small_smem_doubles(int64_t n) {
   int64_t npairs = (n + (n & 1)) / 2;
   return (size_t)(2 * npairs + (n + 1) / 2);
@@ -497,7 +699,7 @@ static size_t syevj_smem_bytes(int64_t n) {
 
 size_t era5svd_syevj_workspace_bytes(int64_t n) {
   if (n <= 0) return 0;
-  return (size_t)(2 * n * (n | 1)) * sizeof(double);
+  return (size_t)(2 * n * (n | 1)) * sizeof(double) + 16;     // + the status word of the positive-definite fast path
 }
 
 int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
@@ -506,6 +708,19 @@ int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, i
   ERA5SVD_REQUIRE(A && W && V, "syevj: null pointer");
   ERA5SVD_REQUIRE(n > 0 && n <= 16384 && lda >= n && ldv >= n, "syevj: bad shape n=%lld", (long long)n);
   if (max_sweeps <= 0) max_sweeps = 30;
+  // Sketch-sized factors (Gram matrices: positive definite unless the sketch is wider than the rank): Cholesky +
+  // one-sided Jacobi.  It reports a dropped pivot through a status word; the two-sided kernel below then runs
+  // (it returns at once when the fast path has succeeded).
+  int* status = nullptr;
+  if (n <= J1_MAXN && n >= 2 && workspace && workspace_bytes >= era5svd_syevj_workspace_bytes(n) &&
+      !(syevj_flags() & 1)) {
+    status = reinterpret_cast<int*>(static_cast<char*>(workspace) + (size_t)(2 * n * (n | 1)) * sizeof(double));
+    const size_t sm1 = (size_t)n * (n + (n & 1)) * sizeof(double);
+    ERA5SVD_CUDA(cudaFuncSetAttribute(syev_chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    syev_chol_jacobi_kernel<<<1, JAC_THREADS, sm1, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, 1e-13, status);
+    int rc = check_launch("syev_chol_jacobi_kernel");
+    if (rc) return rc;
+  }
   const size_t full = syevj_smem_bytes(n);
   const size_t limit = 227 * 1024;
   int use_smem = full <= limit;
@@ -520,9 +735,9 @@ int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, i
   ERA5SVD_CUDA(cudaFuncSetAttribute(syevj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   ERA5SVD_CUDA(cudaFuncSetAttribute(syevj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
   if (use_smem)
-    syevj_kernel<true><<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, (double*)workspace);
+    syevj_kernel<true><<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, (double*)workspace, status);
   else
-    syevj_kernel<false><<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, (double*)workspace);
+    syevj_kernel<false><<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, (double*)workspace, status);
   return check_launch("syevj_kernel");
 }
 

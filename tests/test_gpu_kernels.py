@@ -217,6 +217,33 @@ def test_syevj(ops, n):
     assert np.max(np.abs(A @ V - V * W)) < 1e-12 * w[0] * n
 
 
+@pytest.mark.parametrize("n", [3, 25, 110, 128])
+def test_syevj_fast_path_and_fallback(ops, n, monkeypatch):
+    """n <= 128: Cholesky + one-sided Jacobi on the factor (positive definite input); a singular or indefinite matrix
+    drops a pivot and the two-sided kernel takes over.  Both paths against numpy.linalg.eigh, and against each other."""
+    rng = np.random.RandomState(100 + n)
+    B = rng.standard_normal((2 * n, n)) * (0.9 ** np.arange(n))
+    A = B.T @ B
+    ref = np.linalg.eigvalsh(A)[::-1]
+    W1, V1 = (x.cpu().numpy() for x in ops.syevj(dev(A)))
+    monkeypatch.setenv("ERA5SVD_SYEVJ_TWOSIDED", "1")
+    W2, V2 = (x.cpu().numpy() for x in ops.syevj(dev(A)))
+    monkeypatch.delenv("ERA5SVD_SYEVJ_TWOSIDED")
+    for W, V in ((W1, V1), (W2, V2)):
+        assert np.max(np.abs(W - ref) / ref) < 1e-9
+        assert np.max(np.abs(V.T @ V - np.eye(n))) < 1e-13 * n
+        assert np.max(np.abs(A @ V - V * W)) < 1e-12 * ref[0] * n
+    assert np.max(np.abs(np.abs(np.sum(V1 * V2, axis=0)) - 1.0)) < 1e-8        # same eigenvectors up to sign
+    # singular (rank n - 1) and indefinite inputs: the pivot test rejects them, two-sided Jacobi answers
+    Bs = B.copy(); Bs[:, -1] = Bs[:, 0]
+    for M in (Bs.T @ Bs, A - 0.5 * ref[0] * np.eye(n)):
+        W, V = (x.cpu().numpy() for x in ops.syevj(dev(M)))
+        refm = np.linalg.eigvalsh(M)[::-1]
+        assert np.max(np.abs(W - refm)) < 1e-12 * np.abs(refm).max() * n
+        assert np.max(np.abs(V.T @ V - np.eye(n))) < 1e-13 * n
+        assert np.max(np.abs(M @ V - V * W)) < 1e-12 * np.abs(refm).max() * n
+
+
 def test_syevj_psd_relative_accuracy(ops):
     # graded PSD matrix: Jacobi keeps small eigenvalues to high relative accuracy
     rng = np.random.RandomState(3)
