@@ -326,8 +326,11 @@ def main():
     launches0 = _cabi.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        U, s, V = step(field, timer)
+    # per-launch CUDA events (KernelTimer) ride on every 4th timed step: two event records around each of the ~13
+    # timed ops cost ~0.4 ms of a 14 ms step when every step carries them
+    sampled = [i for i in range(args.steps) if i % 4 == 0]
+    for i in range(args.steps):
+        U, s, V = step(field, timer if i % 4 == 0 else None)
     e1.record()
     sync_all()
     launches = _cabi.launch_count() - launches0
@@ -429,7 +432,9 @@ def main():
                 roofline["traffic"] = json.load(f).get(args.workload, {}).get(dom)
         except Exception:
             pass
-    kernels = {n: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps} for n, v in ksum.items()}
+    kernels = {n: {"calls_per_step": v["calls"] / len(sampled), "ms_per_step": v["ms"] / len(sampled)} for n, v in ksum.items()}
+    if roofline is not None:
+        roofline["timed_launches"] = f"per-launch CUDA events on {len(sampled)} of the {args.steps} timed steps (every 4th)"
 
     # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------
     cpu = None
