@@ -163,7 +163,12 @@ int era5svd_gemm_f64(int transA, int transB, int64_t M, int64_t N, int64_t K, do
  * Replaces the small dense solves of scipy.linalg.svd(B, gesdd) (extmath.py:615) and the
  * eigensolve behind the Gram-route standard SVD (np.linalg.svd, era5_svd.py:251).
  * max_sweeps <= 0 selects the default (30); iteration stops early at convergence, i.e. when a whole
- * sweep finds every |a_pq| <= tol * sqrt(|a_pp a_qq|); tol <= 0 selects eps * sqrt(n). */
+ * sweep finds every |a_pq| <= tol * sqrt(|a_pp a_qq|); tol <= 0 selects eps * sqrt(n).
+ * n <= 128 (the sketch-sized Gram matrices): Cholesky A = R^T R followed by ONE-SIDED Jacobi on the rows of R
+ * (eigenvalue = squared row norm, eigenvector = normalised row; a third of the shared-memory traffic of the
+ * two-sided iteration).  A dropped pivot (A numerically singular or indefinite) falls back to the two-sided
+ * iteration inside the same call, so the contract above holds for any symmetric A.  The workspace
+ * (era5svd_syevj_workspace_bytes, required for n <= 128) also carries the 4-byte status word of that hand-over. */
 size_t era5svd_syevj_workspace_bytes(int64_t n);
 int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
                       int max_sweeps, double tol, void* workspace, size_t workspace_bytes, void* stream);

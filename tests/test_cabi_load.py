@@ -34,7 +34,7 @@ def test_argument_validation_without_gpu():
     rc = lib.era5svd_sketch(None, 0, 1, 1, 1, None, 1, 1, None, 1, 0, None)
     assert rc == -1 and b"null" in lib.era5svd_last_error()
     assert lib.era5svd_project_workspace_bytes(0, 1038240, 744, 110, 0) > 0
-    assert lib.era5svd_syevj_workspace_bytes(110) == 2 * 110 * 111 * 8   # odd leading dimension
+    assert lib.era5svd_syevj_workspace_bytes(110) == 2 * 110 * 111 * 8 + 16   # odd leading dimension + status word
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
