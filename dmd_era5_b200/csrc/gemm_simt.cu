@@ -335,12 +335,13 @@ constexpr int RP_GROUPS = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(RP_OUT * RP_GROUPS)
-reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, int64_t l,
+reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, int64_t l, int64_t lp,
                        double* __restrict__ Z, int64_t ldz, int accumulate) {
+  // part[split][n][lp]: lp >= l is the column pitch of a partial tile (columns l..lp-1 are padding)
   __shared__ double sm[RP_GROUPS][RP_OUT];
   const int o = threadIdx.x % RP_OUT, g = threadIdx.x / RP_OUT;
   const int64_t idx = (int64_t)blockIdx.x * RP_OUT + o;
-  const int64_t total = n * l;
+  const int64_t total = n * lp;
   const int64_t per = (splits + RP_GROUPS - 1) / RP_GROUPS;
   const int64_t k_end = (g + 1) * per < splits ? (g + 1) * per : splits;
   double s = 0.0;
@@ -361,9 +362,11 @@ reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, in
     double t = sm[0][o];
 #pragma unroll
     for (int j = 1; j < RP_GROUPS; ++j) t += sm[j][o];
-    const int64_t r = idx / l, c = idx % l;
-    double* z = Z + r * ldz + c;
-    *z = accumulate ? (*z + t) : t;
+    const int64_t r = idx / lp, c = idx % lp;
+    if (c < l) {
+      double* z = Z + r * ldz + c;
+      *z = accumulate ? (*z + t) : t;
+    }
   }
 }
 
@@ -433,7 +436,7 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
     }
     int rc = check_launch("project_dmma_kernel");
     if (rc) return rc;
-    reduce_partials_kernel<double><<<(unsigned)ceil_div(n * l, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const double*)ws, plan.splits, n, l, Z, ldz, accumulate);
+    reduce_partials_kernel<double><<<(unsigned)ceil_div(n * l, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const double*)ws, plan.splits, n, l, l, Z, ldz, accumulate);
     return check_launch("reduce_partials_kernel");
   }
   if (use_tn7(l)) {
@@ -446,14 +449,14 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
   int rc = check_launch("project_kernel");
   if (rc) return rc;
   int64_t total = n * l;
-  reduce_partials_kernel<T><<<(unsigned)ceil_div(total, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const T*)ws, plan.splits, n, l, Z, ldz, accumulate);
+  reduce_partials_kernel<T><<<(unsigned)ceil_div(total, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const T*)ws, plan.splits, n, l, l, Z, ldz, accumulate);
   return check_launch("reduce_partials_kernel");
 }
 
 // shared with the tcgen05 path (gemm_tc.cu): float32 partial tiles -> float64 sum
-void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
+void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
                                 int64_t ldz, int accumulate, cudaStream_t st) {
-  reduce_partials_kernel<float><<<(unsigned)ceil_div(n * l, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>(part, splits, n, l, Z, ldz, accumulate);
+  reduce_partials_kernel<float><<<(unsigned)ceil_div(n * lp, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>(part, splits, n, l, lp, Z, ldz, accumulate);
 }
 
 }  // namespace era5svd

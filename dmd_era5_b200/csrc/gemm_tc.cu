@@ -33,7 +33,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
 size_t project_tf32x3_raw_workspace_bytes(int64_t m, int64_t n, int64_t l);
 
 // from gemm_simt.cu
-void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
+void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
                                 int64_t ldz, int accumulate, cudaStream_t st);
 
 namespace tc {
@@ -645,7 +645,7 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
   dim3 grid((unsigned)pl.nchunks, (unsigned)pl.splits);
   tc::project_tc_kernel<<<grid, tc::PJ_THREADS, smem, st>>>(tm_xhi, tm_xlo, tm_yhi, tm_ylo, p);
   if ((rc = check_launch("project_tc_kernel"))) return rc;
-  launch_reduce_partials_f32(p.part, pl.splits, n, l, Z, ldz, accumulate, st);
+  launch_reduce_partials_f32(p.part, pl.splits, n, l, l, Z, ldz, accumulate, st);
   return check_launch("reduce_partials_kernel");
 }
 

@@ -24,7 +24,7 @@
 
 namespace era5svd {
 
-void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, double* Z,
+void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
                                 int64_t ldz, int accumulate, cudaStream_t st);
 
 namespace tc {
@@ -298,7 +298,8 @@ struct Project2Params {
   int xshift;
   int ra, rb;
   int64_t rows_per_split;
-  float* part;        // [splits][n][l]
+  int lp;             // column pitch of a partial tile: l rounded up to 16 (pad columns hold the zeros the MMA produced)
+  float* part;        // [splits][n][lp]
 };
 
 constexpr int PJ2_THREADS = 480;
@@ -467,7 +468,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   } else {
     // ===== epilogue: accumulators -> float32 partial tile part[split][time][column] =====
     const int q = warp % 4;
-    float* out = p.part + (int64_t)blockIdx.y * p.n * p.l;
+    float* out = p.part + (int64_t)blockIdx.y * p.n * p.lp;
     if (num_k > 0) {
       mbar_wait(tfull, 0);
       tcgen05_fence_after();
@@ -485,9 +486,12 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
         if (t >= 0 && t < p.n) {
+          // 16-byte aligned rows of the partial tile: four 16-byte stores per lane instead of sixteen scalar ones
+          float4* dst = reinterpret_cast<float4*>(out + t * p.lp + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < p.l) out[t * p.l + c0 + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
         }
       }
     }
@@ -572,13 +576,14 @@ static Pj2Plan pj2_plan(int64_t m, int64_t n, int64_t l) {
   int64_t ctas = ceil_div(splits * pl.nchunks, sms) * sms;      // whole waves
   splits = ctas / pl.nchunks;                                    // never more CTAs than whole waves
   if (splits < 1) splits = 1;
-  const int64_t cap = ((int64_t)512 << 20) / (n * l * 4 > 0 ? n * l * 4 : 1);
+  const int64_t lp = ceil_div(l, (int64_t)16) * 16;            // column pitch of a partial tile (16-byte aligned rows)
+  const int64_t cap = ((int64_t)512 << 20) / (n * lp * 4 > 0 ? n * lp * 4 : 1);
   if (splits > cap) splits = cap > 0 ? cap : 1;
   if (splits > 65535) splits = 65535;
   int64_t rps = ceil_div(ceil_div(m, splits), tc::PJ2_KS) * tc::PJ2_KS;
   pl.splits = ceil_div(m, rps);
   pl.rows_per_split = rps;
-  pl.bytes = (size_t)(pl.splits * n * l * 4);
+  pl.bytes = (size_t)(pl.splits * n * lp * 4);
   return pl;
 }
 
@@ -600,7 +605,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
     return ERA5SVD_ERR_WORKSPACE;
   }
   tc::Project2Params p;
-  p.m = m; p.n = n; p.l = (int)l;
+  p.m = m; p.n = n; p.l = (int)l; p.lp = round_up2(l, 16);
   p.xshift = xs;
   p.rows_per_split = pl.rows_per_split;
   p.part = (float*)workspace;
@@ -613,7 +618,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
   dim3 grid((unsigned)ceil_div(n + xs, tc::PJ2_NC), (unsigned)pl.splits);
   tc::project_tc2_kernel<<<grid, tc::PJ2_THREADS, smem, st>>>(tm_x, tm_yhi, tm_ylo, p);
   if ((rc = check_launch("project_tc2_kernel"))) return rc;
-  launch_reduce_partials_f32(p.part, pl.splits, n, l, Z, ldz, accumulate, st);
+  launch_reduce_partials_f32(p.part, pl.splits, n, l, round_up2(l, 16), Z, ldz, accumulate, st);
   return check_launch("reduce_partials_kernel");
 }
 
