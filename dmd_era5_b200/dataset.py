@@ -15,12 +15,58 @@ from __future__ import annotations
 import numpy as np
 
 
+class LazyTake:
+    """A pending ``np.take`` along one or more axes of a host array.  ``slice_era5_dataset`` / ``resample_era5_dataset``
+    (index selections along time and level, slice_tools.py:20-141) return these instead of copies: the SVD stage
+    gathers the selected planes straight into its pinned staging buffers (stage.stage_blocks), so a slice is read once
+    on its way to the device instead of being copied once per selection step.  Anything else that touches
+    ``DataArray.values`` gets the materialised ndarray (same values as the eager ``np.take`` chain)."""
+
+    def __init__(self, base: np.ndarray, index: dict | None = None):
+        self.base = base
+        self.index = dict(index or {})          # axis -> 1-D integer index array (absent = the whole axis)
+
+    @property
+    def shape(self):
+        return tuple(len(self.index[ax]) if ax in self.index else n for ax, n in enumerate(self.base.shape))
+
+    @property
+    def ndim(self):
+        return self.base.ndim
+
+    @property
+    def dtype(self):
+        return self.base.dtype
+
+    def take(self, idx, axis: int) -> "LazyTake":
+        idx = np.asarray(idx, dtype=np.int64)
+        n = self.shape[axis]
+        if idx.size and (idx.min() < -n or idx.max() >= n):
+            raise IndexError(f"index out of bounds for axis {axis} with size {n}")
+        idx = np.where(idx < 0, idx + n, idx)
+        new = dict(self.index)
+        new[axis] = new[axis][idx] if axis in new else idx
+        if len(new[axis]) == self.base.shape[axis] and np.array_equal(new[axis], np.arange(self.base.shape[axis])):
+            del new[axis]                       # identity selection: nothing pending
+        return LazyTake(self.base, new)
+
+    def materialise(self) -> np.ndarray:
+        a = self.base
+        for ax in sorted(self.index):
+            a = np.take(a, self.index[ax], axis=ax)
+        return a
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialise()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+
 class DataArray:
     def __init__(self, values, dims, coords: dict | None = None, attrs: dict | None = None, name: str | None = None):
-        self.values = values if hasattr(values, "shape") else np.asarray(values)
+        self._values = values if hasattr(values, "shape") else np.asarray(values)
         self.dims = tuple(dims)
-        if len(self.dims) != self.values.ndim:
-            raise ValueError(f"dims {self.dims} do not match a {self.values.ndim}-D array")
+        if len(self.dims) != self._values.ndim:
+            raise ValueError(f"dims {self.dims} do not match a {self._values.ndim}-D array")
         # coords: name -> (dims tuple, 1-D ndarray)
         self.coords: dict[str, tuple[tuple[str, ...], np.ndarray]] = {}
         for k, v in (coords or {}).items():
@@ -30,8 +76,26 @@ class DataArray:
         self.name = name
 
     @property
+    def values(self):
+        """The data as an ndarray (a pending selection is carried out on first access and kept)."""
+        if isinstance(self._values, LazyTake):
+            self._values = self._values.materialise()
+        return self._values
+
+    @values.setter
+    def values(self, v):
+        self._values = v if hasattr(v, "shape") else np.asarray(v)
+
+    def lazy(self) -> LazyTake:
+        """The data as a pending selection on its host array, without materialising it."""
+        v = self._values
+        if isinstance(v, LazyTake):
+            return v
+        return LazyTake(v if isinstance(v, np.ndarray) else np.asarray(v))
+
+    @property
     def shape(self):
-        return tuple(self.values.shape)
+        return tuple(self._values.shape)
 
     @property
     def sizes(self):
@@ -85,6 +149,7 @@ class Dataset:
 # NetCDF I/O
 # ------------------------------------------------------------------------------------------------
 _EPOCH = np.datetime64("1970-01-01T00:00:00", "s")
+LAZY_READ_BYTES = 32 << 20      # read_netcdf: numeric variables at least this large stay memory-mapped (NetCDF-3 path)
 
 
 def _have_xarray() -> bool:
@@ -158,6 +223,10 @@ def write_netcdf(ds: Dataset, path: str) -> str:
                     arr = arr.astype(np.int32)
                 if arr.dtype == np.bool_:
                     arr = arr.astype(np.int8)
+                if arr.nbytes >= 2 ** 31:
+                    raise ValueError(f"variable {name!r} ({arr.nbytes / 2 ** 30:.1f} GiB) exceeds the 2 GiB per-variable limit of "
+                                     "the NetCDF-3 fallback writer (scipy); install xarray + netCDF4 for the reference's "
+                                     "NETCDF4 output (era5_svd.py:434)")
                 var = f.createVariable(name, arr.dtype, tuple(dims))
                 var[:] = arr
             for k, v in {**(attrs or {}), **extra}.items():
@@ -183,8 +252,10 @@ def _decode_attr(k, v):
     return v
 
 
-def read_netcdf(path: str) -> Dataset:
-    """Read a file written by ``write_netcdf`` (or any NetCDF the available backend can open)."""
+def read_netcdf(path: str, lazy: bool = False) -> Dataset:
+    """Read a file written by ``write_netcdf`` (or any NetCDF the available backend can open).
+    lazy (NetCDF-3 path): large numeric variables come back memory-mapped (read-only, on-disk byte order) instead of
+    being read; for INPUT files only - the mapping must not outlive a rewrite of the file."""
     if _have_xarray():
         import xarray as xr
 
@@ -192,16 +263,36 @@ def read_netcdf(path: str) -> Dataset:
         dv = {k: DataArray(v.values, v.dims, attrs=dict(v.attrs)) for k, v in x.data_vars.items()}
         co = {k: (tuple(v.dims), v.values) for k, v in x.coords.items()}
         return Dataset(dv, co, dict(x.attrs))
-    with _netcdf3(path, "r", mmap=False) as f:
+    # NetCDF-3 through scipy.  Large numeric variables (the slice itself: GBs) are NOT read here: they come back as
+    # read-only np.memmap views of the file in its on-disk (big-endian) byte order, so that the only pass over the
+    # data is the staging copy into pinned memory (stage.stage_blocks), which converts the byte order on the way.
+    # Everything small (coordinates, attributes, results) is decoded eagerly to native arrays as before.
+    import warnings
+
+    big = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        f = _netcdf3(path, "r", mmap=True)
+    try:
         attrs = {k: _decode_attr(k, v) for k, v in f._attributes.items()}
         coord_names = set(str(attrs.pop("coordinates_hint", "")).split())
         dv, co = {}, {}
-        for name, var in f.variables.items():
-            arr = np.array(var[:])
-            if arr.dtype.byteorder == ">":                      # NetCDF-3 is big-endian on disk
-                arr = arr.astype(arr.dtype.newbyteorder("="))
+        base_addr = f._mm_buf.__array_interface__["data"][0] if getattr(f, "_mm_buf", None) is not None else None
+        for name in list(f.variables):
+            var = f.variables[name]
             dims = tuple(var.dimensions)
             vattrs = {k: _decode_attr(k, v) for k, v in var._attributes.items()}
+            data = var.data
+            lazy_ok = (lazy and base_addr is not None and not var.isrec and data.dtype.kind in "fiu" and
+                       data.nbytes >= LAZY_READ_BYTES and not str(vattrs.get("units", "")).startswith("seconds since"))
+            if lazy_ok:
+                big[name] = (data.__array_interface__["data"][0] - base_addr, data.dtype, tuple(data.shape), dims, vattrs)
+                del data, var
+                continue
+            arr = np.array(data)
+            del data, var
+            if arr.dtype.byteorder == ">":                      # NetCDF-3 is big-endian on disk
+                arr = arr.astype(arr.dtype.newbyteorder("="))
             if arr.dtype.kind == "S" and dims and dims[-1].startswith("string"):
                 arr = np.array([b"".join(row).decode().rstrip("\x00") for row in arr.reshape(-1, arr.shape[-1])],
                                dtype=object).reshape(arr.shape[:-1])
@@ -215,4 +306,15 @@ def read_netcdf(path: str) -> Dataset:
                 co[name] = (dims, arr)
             else:
                 dv[name] = DataArray(arr, dims, attrs=vattrs)
+    finally:
+        f.variables = {}                                        # no views of the mapping are left: close() is clean
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            f.close()
+    for name, (offset, dt, shape, dims, vattrs) in big.items():
+        arr = np.memmap(path, dtype=dt, mode="r", offset=offset, shape=shape)
+        if name in coord_names or dims == (name,):
+            co[name] = (dims, np.asarray(arr).astype(dt.newbyteorder("=")))
+        else:
+            dv[name] = DataArray(arr, dims, attrs=vattrs)
     return Dataset(dv, co, attrs)

@@ -59,7 +59,7 @@ def host_to_device_matrix(ops: CudaOps, X: np.ndarray) -> torch.Tensor:
     """Copy a host (m, n) matrix into a padded device buffer (rows 32-byte aligned); returns the
     (m, n) view.  Pinned staging + async copy on the current stream."""
     m, n = X.shape
-    t = torch.from_numpy(np.ascontiguousarray(X))
+    t = torch.from_numpy(np.ascontiguousarray(X, dtype=X.dtype.newbyteorder("=")))     # memory-mapped NetCDF-3 data is big-endian
     ld = padded_ld(n, t.dtype)
     buf = ops.empty((m, ld), t.dtype)
     view = buf[:, :n]

@@ -34,7 +34,8 @@ def _subset(ds: Dataset, dim: str, index: np.ndarray, new_coord: np.ndarray | No
     dv = {}
     for name, da in ds.data_vars.items():
         ax = da.dims.index(dim)
-        dv[name] = DataArray(np.take(da.values, index, axis=ax), da.dims, attrs=da.attrs)
+        # pending selection (dataset.LazyTake): carried out when .values is read, or fused into the staging copy
+        dv[name] = DataArray(da.lazy().take(index, ax), da.dims, attrs=da.attrs)
     coords = dict(ds.coords)
     coords[dim] = ((dim,), ds.coord(dim)[index] if new_coord is None else new_coord)
     return Dataset(dv, coords, ds.attrs)
@@ -107,7 +108,7 @@ def standardize_data(data: Dataset, dim: str = "time", scale: bool = True):
             a = np.moveaxis(np.asarray(da.values), ax, 0)
             rest_dims = tuple(d for d in da.dims if d != dim)
             T, rest = a.shape[0], a.shape[1:]
-            src = torch.from_numpy(np.ascontiguousarray(a.reshape(T, -1))).to(ops.device)
+            src = torch.from_numpy(np.ascontiguousarray(a.reshape(T, -1), dtype=a.dtype.newbyteorder("="))).to(ops.device)
             P = src.shape[1]
             X = ops.empty((P, T), src.dtype)
             mu = ops.empty((P,), src.dtype)

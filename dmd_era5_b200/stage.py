@@ -66,7 +66,7 @@ def retrieve_era5_slice(parsed_config: dict, use_dvc: bool = False):
     path = parsed_config["era5_slice_path"]
     if os.path.exists(path):
         log_and_print(logger, "ERA5 slice found in working directory.")
-        ds = read_netcdf(path)
+        ds = read_netcdf(path, lazy=True)        # input file: the variables stay memory-mapped until they are staged
         a = ds.attrs
         ok = (sorted(parsed_config["variables"]) == sorted(set(_as_str_list(a["variables"])) & set(parsed_config["variables"]))
               and sorted(parsed_config["levels"]) == sorted(set(_as_int_list(a["levels"])) & set(parsed_config["levels"]))
@@ -134,16 +134,125 @@ def combine_svd_results(U, s, V, coords: dict, **kwargs) -> Dataset:
     return Dataset(dv, all_coords)
 
 
-def _to_blocks(ds: Dataset, variables: list[str], ops) -> tuple[list[torch.Tensor], int]:
-    """Host (T, L, A, O) arrays of the selected variables -> device (T, S) native-layout blocks."""
+_NATIVE_DIMS = ("time", "level", "latitude", "longitude")
+_STAGING: dict = {}            # (device, bytes) -> two pinned host buffers, reused across calls
+
+
+def _pinned_ring(device, nbytes: int):
+    key = (str(device), int(nbytes))
+    if key not in _STAGING:
+        _STAGING.clear()       # one ring per process is enough; do not accumulate pinned memory across sizes
+        _STAGING[key] = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    return _STAGING[key]
+
+
+def _gather_chunk(base: np.ndarray, t_idx, l_idx, c0: int, c1: int, host: np.ndarray) -> None:
+    """host[...] = base[time selection c0:c1][:, level selection] in ONE pass over the source where NumPy allows it
+    (contiguous time range or a native-byte-order gather); byte-order conversion rides on the same copy."""
+    native = base.dtype.isnative
+    if l_idx is None:
+        if t_idx is None:
+            np.copyto(host, base[c0:c1])                               # view -> pinned buffer
+        elif native:
+            np.take(base, t_idx[c0:c1], axis=0, out=host, mode="clip")  # indices validated by LazyTake.take
+        else:
+            np.copyto(host, base[t_idx[c0:c1]])
+        return
+    rows = base[c0:c1] if t_idx is None else base[t_idx[c0:c1]]
+    if native:
+        np.take(rows, l_idx, axis=1, out=host, mode="clip")
+    else:
+        np.copyto(host, np.take(rows, l_idx, axis=1))
+
+
+_POOL = None
+
+
+def _gather_chunk_mt(base: np.ndarray, t_idx, l_idx, c0: int, c1: int, host: np.ndarray) -> None:
+    """_gather_chunk over a few host threads (NumPy releases the GIL inside large copies): the host-side gather, not
+    PCIe, bounds the upload of a slice that is not pinned yet."""
+    global _POOL
+    n = c1 - c0
+    threads = min(8, len(os.sched_getaffinity(0)), n)
+    if threads <= 1 or host.nbytes < (8 << 20):
+        return _gather_chunk(base, t_idx, l_idx, c0, c1, host)
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="era5svd-stage")
+    step = -(-n // threads)
+    futs = [_POOL.submit(_gather_chunk, base, t_idx, l_idx, c0 + a, min(c1, c0 + a + step), host[a : a + step])
+            for a in range(0, n, step)]
+    for f in futs:
+        f.result()
+
+
+def stage_blocks(ds: Dataset, variables: list[str], ops, chunk_bytes: int | None = None) -> tuple[list[torch.Tensor], int]:
+    """Host slice -> device blocks in the native (T, S = L*A*O) time-major layout, one per variable
+    (what era5_svd.py:384-388 hands to the matrix build, era5_download.py:36-42 being the file layout).
+
+    The pending time / level selections of ``slice_era5_dataset`` and ``resample_era5_dataset`` (dataset.LazyTake) are
+    carried out HERE, while the data is copied into a ring of two pinned staging buffers (``chunk_bytes`` each,
+    default 128 MiB, $ERA5SVD_STAGE_CHUNK_MB): chunk i + 1 is gathered on the host while chunk i crosses PCIe on a
+    copy stream.  A slice is therefore read ONCE on its way to the device (any byte-order or dtype-preserving layout
+    fix-up happens in that same pass) instead of once per selection step plus a pinning copy."""
+    if chunk_bytes is None:
+        chunk_bytes = int(os.environ.get("ERA5SVD_STAGE_CHUNK_MB", "128")) << 20
+    dev = ops.device
+    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream.wait_stream(torch.cuda.current_stream(dev))
     blocks = []
+    ring = None
+    ring_events = [None, None]
+    slot = 0
     for v in variables:
         da = ds[v]
-        a = np.transpose(np.asarray(da.values), [da.dims.index(dm) for dm in ("time", "level", "latitude", "longitude")])
-        T = a.shape[0]
-        t = torch.from_numpy(np.ascontiguousarray(a.reshape(T, -1)))
-        blocks.append(t.pin_memory().to(ops.device, non_blocking=True) if t.numel() >= 1 << 16 else t.to(ops.device))
+        lz = da.lazy()
+        if da.dims != _NATIVE_DIMS:
+            # any other dimension order: materialise and transpose on the host (not what era5_download writes)
+            a = np.transpose(np.asarray(da.values), [da.dims.index(dm) for dm in _NATIVE_DIMS])
+            lz = type(lz)(np.ascontiguousarray(a))
+        base = lz.base
+        T, L, A, O = lz.shape
+        t_idx, l_idx = lz.index.get(0), lz.index.get(1)
+        if 2 in lz.index or 3 in lz.index:
+            base = np.take(np.take(base, lz.index.get(2, np.arange(base.shape[2])), axis=2),
+                           lz.index.get(3, np.arange(base.shape[3])), axis=3)
+        tdt = torch.from_numpy(np.empty(0, dtype=base.dtype.newbyteorder("="))).dtype
+        row_bytes = L * A * O * base.dtype.itemsize
+        block = torch.empty((T, L * A * O), dtype=tdt, device=dev)
+        if T * row_bytes < (1 << 16):
+            # tiny slice (the mock configuration): one pageable copy
+            block.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(lz), dtype=base.dtype.newbyteorder("=")).reshape(T, -1)))
+            blocks.append(block)
+            continue
+        rows = max(1, min(T, chunk_bytes // row_bytes))
+        need = rows * row_bytes
+        if ring is None or ring[0].numel() < need:
+            ring = _pinned_ring(dev, max(need, chunk_bytes if row_bytes <= chunk_bytes else need))
+            ring_events = [None, None]
+        for c0 in range(0, T, rows):
+            c1 = min(T, c0 + rows)
+            buf = ring[slot]
+            if ring_events[slot] is not None:
+                ring_events[slot].synchronize()          # the previous upload from this buffer has finished
+            host = buf[: (c1 - c0) * row_bytes].view(tdt).view(c1 - c0, L, A, O).numpy()
+            _gather_chunk_mt(base, t_idx, l_idx, c0, c1, host)
+            with torch.cuda.stream(copy_stream):
+                block[c0:c1].copy_(buf[: (c1 - c0) * row_bytes].view(tdt).view(c1 - c0, L * A * O), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            ring_events[slot] = ev
+            slot ^= 1
+        blocks.append(block)
+    torch.cuda.current_stream(dev).wait_stream(copy_stream)
+    for b in blocks:
+        b.record_stream(copy_stream)
     return blocks, blocks[0].shape[1]
+
+
+def _to_blocks(ds: Dataset, variables: list[str], ops) -> tuple[list[torch.Tensor], int]:
+    return stage_blocks(ds, variables, ops)
 
 
 def main(config: dict | None = None, write_to_netcdf: bool = False, use_dvc: bool = False):

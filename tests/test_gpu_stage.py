@@ -171,3 +171,28 @@ def test_stage_stream_matches_one_shot():
         built = build_matrix_device(ops, [h.cuda()], mean_center=True, scale=False)
         U, s, V = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=5, precision="tf32x3")
         assert torch.equal(got[i][1], s.cpu()) and torch.equal(got[i][2], V.cpu()) and torch.equal(got[i][0], U.cpu())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, ">f4"])
+def test_stage_blocks_chunked_upload(dtype):
+    """Pinned-ring staging: many small chunks, pending time (resample) and level selections fused into the copy,
+    native and big-endian sources, several variables: the device blocks equal the materialised host selection."""
+    from datetime import timedelta
+
+    from dmd_era5_b200 import slice_tools as st
+    from dmd_era5_b200.era5_svd import get_ops
+    from dmd_era5_b200.stage import stage_blocks
+
+    m = mock_era5_np(49, VARS, LEVELS, seed=2)
+    dv = {k: DataArray(v.astype(dtype), ("time", "level", "latitude", "longitude")) for k, v in m["vars"].items()}
+    ds = Dataset(dv, {"time": m["time"], "level": m["level"], "latitude": m["latitude"], "longitude": m["longitude"]})
+    ops = get_ops("cuda:0")
+    for sel in (ds, st.slice_era5_dataset(ds, levels=[500, 1000]),
+                st.resample_era5_dataset(st.slice_era5_dataset(ds, levels=[850]), timedelta(hours=6))):
+        want = {v: np.asarray(sel[v].lazy().materialise()).astype(np.dtype(dtype).newbyteorder("=")) for v in VARS}
+        for chunk in (50_000, 1 << 20, None):
+            blocks, S = stage_blocks(sel, VARS, ops, chunk_bytes=chunk)
+            for v, b in zip(VARS, blocks):
+                T = want[v].shape[0]
+                assert S == want[v][0].size and tuple(b.shape) == (T, S)
+                assert np.array_equal(b.cpu().numpy(), want[v].reshape(T, -1))

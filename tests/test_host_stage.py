@@ -147,3 +147,64 @@ def test_netcdf_round_trip(tmp_path):
     from dmd_era5_b200.stage import _as_int_list, _as_str_list
     assert _as_str_list(back.attrs["variables"]) == ["temperature", "u_component_of_wind"]
     assert _as_int_list(back.attrs["levels"]) == [1000, 850]
+
+
+def test_lazy_selection_matches_eager_take():
+    """slice / resample return pending selections (dataset.LazyTake); reading .values gives exactly the eager np.take
+    chain, identity selections leave nothing pending, and the chunk gather used by the staging copy reproduces it for
+    contiguous ranges, index arrays, level subsets and big-endian (NetCDF-3) sources."""
+    from dmd_era5_b200.dataset import LazyTake
+    from dmd_era5_b200.stage import _gather_chunk
+
+    rng = np.random.RandomState(0)
+    base = rng.standard_normal((25, 4, 6, 8)).astype(np.float32)
+    lz = LazyTake(base)
+    assert lz.take(np.arange(25), 0).index == {} and lz.take(np.arange(25), 0).materialise() is base
+    t_idx = np.array([0, 6, 12, 18, 24]); l_idx = np.array([2, 0])
+    sel = lz.take(t_idx, 0).take(l_idx, 1)
+    want = np.take(np.take(base, t_idx, axis=0), l_idx, axis=1)
+    assert sel.shape == want.shape and np.array_equal(sel.materialise(), want) and np.array_equal(np.asarray(sel), want)
+    again = sel.take(np.array([4, 1]), 0)                                   # composition of selections along one axis
+    assert np.array_equal(again.materialise(), want[[4, 1]])
+    with pytest.raises(IndexError):
+        lz.take(np.array([25]), 0)
+    for src in (base, base.astype(">f4")):
+        for ti, li in ((None, None), (t_idx, None), (None, l_idx), (t_idx, l_idx)):
+            full = src.astype(np.float32)
+            ref = full if ti is None else full[ti]
+            ref = ref if li is None else ref[:, li]
+            T = ref.shape[0]
+            got = np.empty(ref.shape, dtype=np.float32)
+            for c0 in range(0, T, 2):
+                _gather_chunk(src, ti, li, c0, min(T, c0 + 2), got[c0:c0 + 2])
+            assert np.array_equal(got, ref)
+    # through the Dataset API: the selection stays pending until .values is read
+    ds = mock_dataset(25)
+    out = st.resample_era5_dataset(st.slice_era5_dataset(ds, levels=[850]), __import__("datetime").timedelta(hours=6))
+    da = out["temperature"]
+    assert isinstance(da._values, LazyTake) and da.shape == (5, 1, 36, 72)
+    assert np.array_equal(da.values, ds["temperature"].values[::6, 1:2])
+    assert isinstance(da._values, np.ndarray)
+
+
+def test_netcdf_lazy_read(tmp_path, monkeypatch):
+    """read_netcdf(lazy=True): large numeric variables come back memory-mapped in the file's byte order, small ones and
+    coordinates are decoded eagerly; values equal the eager read; the file can be deleted only after the views are gone."""
+    import dmd_era5_b200.dataset as dsm
+
+    monkeypatch.setattr(dsm, "LAZY_READ_BYTES", 4096)
+    if dsm._have_xarray():
+        pytest.skip("NetCDF-3 fallback path only")
+    ds = mock_dataset(25)
+    path = str(tmp_path / "slice.nc")
+    write_netcdf(ds, path)
+    eager, lazy = read_netcdf(path), read_netcdf(path, lazy=True)
+    for v in ("temperature", "u_component_of_wind"):
+        a = lazy[v]._values
+        assert isinstance(a, np.memmap) and not a.flags.writeable and a.dtype.byteorder == ">"
+        assert isinstance(eager[v]._values, np.ndarray) and not isinstance(eager[v]._values, np.memmap)
+        assert np.array_equal(np.asarray(a), eager[v].values) and np.array_equal(eager[v].values, ds[v].values)
+    assert np.array_equal(lazy.coord("time"), ds.coord("time")) and lazy.coord("latitude").dtype.isnative
+    # selections on the mapped data stay pending and give the right planes
+    out = st.slice_era5_dataset(lazy, levels=[850])
+    assert np.array_equal(out["temperature"].values, ds["temperature"].values[:, 1:2])
