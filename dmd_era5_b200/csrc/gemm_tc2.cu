@@ -131,7 +131,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int32_t row0 = (int32_t)(tile * BM2);
         for (int kc = 0; kc < p.num_k; ++kc) {
-          mbar_wait(araw_empty + 8u * ra.i, ra.ph ^ 1u);
+          mbar_wait_hint(araw_empty + 8u * ra.i, ra.ph ^ 1u, 2000u);
           mbar_arrive_expect_tx(araw_full + 8u * ra.i, a_bytes);
           tma_load_2d(smem_base + (uint32_t)ra.i * a_bytes, &tm_x, kc * BK2, row0, araw_full + 8u * ra.i);
           ra.next();
@@ -199,7 +199,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < p.num_k; ++kc, ++cnt) {
         if ((cnt & 1u) == (uint32_t)grp) {
-          mbar_wait(araw_full + 8u * ra.i, ra.ph);
+          mbar_wait_hint(araw_full + 8u * ra.i, ra.ph, 2000u);
           const uint32_t row_addr = smem_base + (uint32_t)ra.i * a_bytes + (uint32_t)r * 128u;
           float4 v[8];
 #pragma unroll
@@ -207,7 +207,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(v[c].x), "=f"(v[c].y), "=f"(v[c].z), "=f"(v[c].w)
                          : "r"(row_addr + (uint32_t)((c ^ (r & 7)) << 4)));
-          mbar_wait(at_empty + 8u * at.i, at.ph ^ 1u);           // MMAs that read this TMEM buffer have retired
+          mbar_wait_hint(at_empty + 8u * at.i, at.ph ^ 1u, 2000u);   // MMAs that read this TMEM buffer have retired
           tcgen05_fence_after();
           const uint32_t t_hi = tmem_base + at_col0 + (uint32_t)at.i * AT_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -248,7 +248,7 @@ sketch_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int q = warp % 4;
     Ring acc(2);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      mbar_wait(tfull + 8u * acc.i, acc.ph);
+      mbar_wait_hint(tfull + 8u * acc.i, acc.ph, 20000u);
       tcgen05_fence_after();
       const int64_t row = tile * BM2 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t)acc.i * acc_cols + ((uint32_t)(q * 32) << 16);
@@ -434,7 +434,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int col = tl % BK2;                            // float index inside the 128-byte box row
     Ring ra(p.ra), at(AT_RING);
     for (int kc = 0; kc < num_k; ++kc) {
-      mbar_wait(araw_full + 8u * ra.i, ra.ph);
+      mbar_wait_hint(araw_full + 8u * ra.i, ra.ph, 2000u);
       const uint32_t base = smem_base + (uint32_t)ra.i * a_bytes + (uint32_t)box * box_bytes;
       float x[PJ2_KS];
 #pragma unroll
@@ -442,7 +442,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const uint32_t addr = base + (uint32_t)k * 128u + (uint32_t)((((col >> 2) ^ (k & 7)) << 4) | ((col & 3) << 2));
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[k]) : "r"(addr));
       }
-      mbar_wait(at_empty + 8u * at.i, at.ph ^ 1u);
+      mbar_wait_hint(at_empty + 8u * at.i, at.ph ^ 1u, 2000u);
       tcgen05_fence_after();
       uint32_t hi[16], lo[16];
 #pragma unroll
@@ -470,7 +470,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int q = warp % 4;
     float* out = p.part + (int64_t)blockIdx.y * p.n * p.lp;
     if (num_k > 0) {
-      mbar_wait(tfull, 0);
+      mbar_wait_hint(tfull, 0, 50000u);
       tcgen05_fence_after();
     }
     for (int tt = 0; tt < PJ2_TT; ++tt) {

@@ -322,6 +322,12 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
   const int npairs = n_pad / 2;
   const double tol = tol_in > 0.0 ? tol_in : 2.220446049250313e-16 * sqrt((double)n);
   const double tol2 = tol * tol;
+  // Early stop for a caller-given tolerance (float32 data paths): the iteration converges quadratically, so a sweep
+  // that met no pair above sqrt(tol / 100) leaves every pair below tol (the factor 100 covers relative gaps down
+  // to ~1 %); the usual extra sweep that only verifies convergence is then skipped.  With tol_in <= 0 (float64
+  // parity) the sweep-without-rotation rule stays.
+  const bool early = tol_in > 0.0;
+  const double tol_early = tol * 0.01;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     int did = 0;
     for (int step = 0; step < n_pad - 1; ++step) {
@@ -343,6 +349,7 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
           app = group16_sum(app, gmask);
           aqq = group16_sum(aqq, gmask);
           apq = group16_sum(apq, gmask);
+          if (early ? (apq * apq > tol_early * app * aqq) : (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300)) did = 1;
           if (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300) {
             // rotation that orthogonalises rows p, q (same angle as the two-sided rotation of the 2 x 2 Gram block);
             // tan(theta) from fast float32 ops, c and s completed in float64 (exactly orthogonal rotation)
@@ -358,7 +365,6 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
             }
             const double cs = rsqrt(fma(t64, t64, 1.0));
             const double sn = t64 * cs;
-            did = 1;
 #pragma unroll
             for (int k = 0; k < J1_PER_LANE; ++k) {
               const int c = gl + JAC_GROUP * k;

@@ -41,6 +41,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same wait for barriers that are expected to complete much later (the epilogue's "accumulator full", a ring slot
+// several stages ahead): try_wait takes a suspend-time hint, so the hardware parks the thread for up to `hint_ns`
+// instead of the short system default and still resumes it the moment the phase completes.  The tall kernels run
+// against the 1000 W power cap (SM clock ~1.55 GHz while they run, 1.9 GHz otherwise), and ~30 % of the warp
+// instructions they executed were these polling loops (ncu source view, profiles/r01_ncu_full_s3.md).
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    if (!done && spins > (1u << 24)) __trap();
+  }
+}
+
 // ---- fences ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
