@@ -14,6 +14,8 @@
 //                       writes coalesced along time, applies (x - mean) / std * w and the cast.
 // Algorithmic bytes per element: read 4 (stats) [+4 second stats pass when scaling] + read 4 +
 // write 4 (f32).  See DESIGN.md for the single-read fused variant.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -230,43 +232,53 @@ fused_build_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_
 constexpr int TB_THREADS = 512;
 constexpr int TB_BOX_T = 64;
 
+// PB = 32: 128-byte rows under SWIZZLE_128B (chunk c of row t at c ^ (t & 7)); PB = 16: 64-byte rows under SWIZZLE_64B
+// (address bits [4,6) XOR bits [7,9): chunk c of row t at c ^ ((t >> 1) & 3)).  Either way a quarter-warp reading one
+// chunk of eight consecutive snapshots touches eight distinct 16-byte bank groups.
+template <int PB>
 __device__ __forceinline__ float4 tb_ld_chunk(uint32_t tile, int t, int c) {
   float4 v;
+  const uint32_t sw = PB == 32 ? (uint32_t)(c ^ (t & 7)) : (uint32_t)(c ^ ((t >> 1) & 3));
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "r"(tile + (uint32_t)t * 128u + (uint32_t)((c ^ (t & 7)) << 4)));
+               : "r"(tile + (uint32_t)t * (uint32_t)(PB * 4) + (sw << 4)));
   return v;
 }
 
-template <typename Tx>
+// PB = points per tile: 32 (128-byte source segments) while two [T x 32] tiles fit one SM; 16 (64-byte segments) for
+// longer series (T = 1460: 94 KB per tile), so that TWO CTAs stay resident and one CTA's loads overlap the other's
+// statistics / stores - with a single resident CTA the load and store phases alternate and HBM idles half the time.
+// Warp w: chunk w % (PB / 4), time part w / (PB / 4) (2 parts for PB = 32, 4 for PB = 16).
+template <typename Tx, int PB>
 __global__ void __launch_bounds__(TB_THREADS)
 fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_t P, int col_shift,
                        Tx* __restrict__ X, int64_t ldx, Tx* __restrict__ mean_out, Tx* __restrict__ std_out,
                        const Tx* __restrict__ weights, int center, int do_scale, int check_finite,
                        int* __restrict__ nonfinite_flag, float* __restrict__ Xhi, float* __restrict__ Xlo) {
   extern __shared__ unsigned char fb_smem[];
-  __shared__ double part_a[2][FB_PB], part_q[2][FB_PB];
-  __shared__ int part_n[2][FB_PB];
+  constexpr int NCH = PB / 4, NP = (TB_THREADS / 32) / NCH, ROWB = PB * 4;
+  __shared__ double part_a[NP][PB], part_q[NP][PB];
+  __shared__ int part_n[NP][PB];
   __shared__ __align__(8) uint64_t bar_storage;
   const uint32_t tile = (tc::smem_u32(fb_smem) + 1023u) & ~1023u;
   const uint32_t bar = tc::smem_u32(&bar_storage);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int c = warp % 8, h = warp / 8;
-  const int64_t p0 = (int64_t)blockIdx.x * FB_PB;
+  const int c = warp % NCH, h = warp / NCH;
+  const int64_t p0 = (int64_t)blockIdx.x * PB;
   const int nbox = (T + TB_BOX_T - 1) / TB_BOX_T;
   if (threadIdx.x == 0) {
     tc::mbar_init(bar, 1);
     tc::fence_barrier_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc::mbar_arrive_expect_tx(bar, (uint32_t)nbox * (uint32_t)(TB_BOX_T * 128));
+    tc::mbar_arrive_expect_tx(bar, (uint32_t)nbox * (uint32_t)(TB_BOX_T * ROWB));
     for (int b = 0; b < nbox; ++b)
-      tc::tma_load_2d(tile + (uint32_t)b * (uint32_t)(TB_BOX_T * 128), &tm_src, (int32_t)p0, b * TB_BOX_T, bar);
+      tc::tma_load_2d(tile + (uint32_t)b * (uint32_t)(TB_BOX_T * ROWB), &tm_src, (int32_t)p0, b * TB_BOX_T, bar);
   }
   __syncthreads();                 // barrier initialised before anyone polls it
-  // time range of this warp: halves split on a multiple of 32 snapshots
-  const int t_half = ((T + 63) / 64) * 32;
-  const int t_begin = h == 0 ? 0 : t_half;
-  const int t_end = h == 0 ? (t_half < T ? t_half : T) : T;
+  // time range of this warp: NP parts split on multiples of 32 snapshots
+  const int t_part = ((T + 32 * NP - 1) / (32 * NP)) * 32;
+  const int t_begin = h * t_part < T ? h * t_part : T;
+  const int t_end = (h + 1) * t_part < T ? (h + 1) * t_part : T;
   // a source whose base is not 16-byte aligned is mapped from the aligned address below it (boxes under the 128-byte
   // swizzle must start on 16-byte boundaries): tile column x holds point p0 + x - col_shift
   const int64_t gp0 = p0 + 4 * c - col_shift;
@@ -286,7 +298,7 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
     double s[4] = {0.0, 0.0, 0.0, 0.0};
     int cnt[4] = {0, 0, 0, 0};
     for (int t = t_begin + lane; t < t_end; t += 32) {
-      const float4 v4 = tb_ld_chunk(tile, t, c);
+      const float4 v4 = tb_ld_chunk<PB>(tile, t, c);
       const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -306,8 +318,10 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
     int n_valid[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      n_valid[e] = part_n[0][4 * c + e] + part_n[1][4 * c + e];
-      const double tot = part_a[0][4 * c + e] + part_a[1][4 * c + e];
+      n_valid[e] = 0;
+      double tot = 0.0;
+#pragma unroll
+      for (int hh = 0; hh < NP; ++hh) { n_valid[e] += part_n[hh][4 * c + e]; tot += part_a[hh][4 * c + e]; }
       const double mean = n_valid[e] > 0 ? tot / (double)n_valid[e] : __longlong_as_double(0x7ff8000000000000LL);
       mean_x[e] = (Tx)mean;
     }
@@ -315,7 +329,7 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
       __syncthreads();             // part_a is reused below
       double a[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
       for (int t = t_begin + lane; t < t_end; t += 32) {
-        const float4 v4 = tb_ld_chunk(tile, t, c);
+        const float4 v4 = tb_ld_chunk<PB>(tile, t, c);
         const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -336,8 +350,9 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
       __syncthreads();
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const double at = part_a[0][4 * c + e] + part_a[1][4 * c + e];
-        const double qt = part_q[0][4 * c + e] + part_q[1][4 * c + e];
+        double at = 0.0, qt = 0.0;
+#pragma unroll
+        for (int hh = 0; hh < NP; ++hh) { at += part_a[hh][4 * c + e]; qt += part_q[hh][4 * c + e]; }
         const double m2 = n_valid[e] > 0 ? at / (double)n_valid[e] : 0.0;
         double var = n_valid[e] > 0 ? qt / (double)n_valid[e] - m2 * m2 : __longlong_as_double(0x7ff8000000000000LL);
         if (var < 0.0) var = 0.0;
@@ -355,7 +370,7 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
     }
   }
   for (int t = t_begin + lane; t < t_end; t += 32) {
-    const float4 v4 = tb_ld_chunk(tile, t, c);
+    const float4 v4 = tb_ld_chunk<PB>(tile, t, c);
     const float raw[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -387,22 +402,44 @@ int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer,
 
 // float32 source, tile fits in shared memory, 16-byte row pitch: the TMA kernel.  Returns 1 when it ran,
 // 0 when the shape does not qualify (caller falls back), < 0 on error.
+// bit 0: ERA5SVD_BUILD_PB32=1 keeps 32-point tiles for long series too (diagnostics: scripts/time_build.py)
+static unsigned build_debug_flags() {
+  const char* e = getenv("ERA5SVD_BUILD_PB32");
+  const char* f = getenv("ERA5SVD_BUILD_PB16");       // bit 1: 16-point tiles for short series as well
+  return ((e && e[0] == '1') ? 1u : 0u) | ((f && f[0] == '1') ? 2u : 0u);
+}
+
 template <typename Tx>
 int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, Tx* X, int64_t ldx, Tx* mean_out,
                        Tx* std_out, const Tx* weights, bool center, bool scale, bool check, int* nonfinite_flag,
                        cudaStream_t st, float* Xhi, float* Xlo) {
   const int64_t tpad = ceil_div(T, (int64_t)TB_BOX_T) * TB_BOX_T;
-  const size_t tile_bytes = (size_t)tpad * 128 + 1024;
-  if (tile_bytes > 224 * 1024 || (src_ld * 4) % 16 != 0 || P + 4 >= (int64_t)1 << 31) return 0;
+  if ((src_ld * 4) % 16 != 0 || P + 4 >= (int64_t)1 << 31) return 0;
+  // 32-point tiles while two of them fit one SM (T <= ~850), else 16-point tiles (two resident CTAs up to T ~ 1750)
+  const size_t tile32 = (size_t)tpad * 128 + 1024, tile16 = (size_t)tpad * 64 + 1024;
+  const size_t two_resident = 112 * 1024;
+  const unsigned dbg = build_debug_flags();
+  const bool pb16 = ((tile32 > two_resident && tile16 <= two_resident) || (dbg & 2)) && !(dbg & 1);
+  const size_t tile_bytes = pb16 ? tile16 : tile32;
+  if (tile_bytes > 225 * 1024) return 0;
+  const int pb = pb16 ? 16 : 32;
   CUtensorMap tm;
   int shift = 0;
-  int rc = tc::make_tmap(&tm, src, P, T, src_ld, FB_PB, TB_BOX_T, &shift, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = tc::make_tmap(&tm, src, P, T, src_ld, (uint32_t)pb, TB_BOX_T, &shift,
+                         pb16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  auto kern = fused_build_tma_kernel<Tx>;
-  ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
-  kern<<<(unsigned)ceil_div(P + shift, (int64_t)FB_PB), TB_THREADS, tile_bytes, st>>>(
-      tm, (int)T, P, shift, X, ldx, mean_out, std_out, weights, center ? 1 : 0, (center && scale) ? 1 : 0,
-      check ? 1 : 0, nonfinite_flag, Xhi, Xlo);
+  const unsigned grid = (unsigned)ceil_div(P + shift, (int64_t)pb);
+  if (pb16) {
+    auto kern = fused_build_tma_kernel<Tx, 16>;
+    ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+    kern<<<grid, TB_THREADS, tile_bytes, st>>>(tm, (int)T, P, shift, X, ldx, mean_out, std_out, weights, center ? 1 : 0,
+                                               (center && scale) ? 1 : 0, check ? 1 : 0, nonfinite_flag, Xhi, Xlo);
+  } else {
+    auto kern = fused_build_tma_kernel<Tx, 32>;
+    ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+    kern<<<grid, TB_THREADS, tile_bytes, st>>>(tm, (int)T, P, shift, X, ldx, mean_out, std_out, weights, center ? 1 : 0,
+                                               (center && scale) ? 1 : 0, check ? 1 : 0, nonfinite_flag, Xhi, Xlo);
+  }
   rc = check_launch("fused_build_tma_kernel");
   return rc ? rc : 1;
 }
