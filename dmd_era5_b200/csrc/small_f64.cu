@@ -238,6 +238,7 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
   __shared__ double s_inv[2];
   __shared__ double gdiag[J1_MAXN];
   __shared__ double lam[J1_MAXN];
+  __shared__ double nrm2[J1_MAXN];
   __shared__ int rank[J1_MAXN];
   const int t = threadIdx.x, tx = t % 32, ty = t / 32;
   const int ldw = n + (n & 1);                  // even pitch: 16-byte aligned rows, contiguous row access
@@ -330,24 +331,31 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
   const double tol_early = tol * 0.01;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     int did = 0;
+    // squared row norms, recomputed once per sweep and then carried through the rotations (a'_pp = a_pp - t a_pq,
+    // a'_qq = a_qq + t a_pq): they only steer the angle and the convergence test, so a step needs ONE dot product
+    // (a_pq) instead of three - the kernel is bound by the float64 pipe.  The eigenvalues come from fresh norms below.
+    for (int i = g; i < n; i += JAC_GROUPS) {
+      double sq = 0.0;
+      for (int c = gl; c < n; c += JAC_GROUP) sq = fma(Rw[i * ldw + c], Rw[i * ldw + c], sq);
+      sq = group16_sum(sq, gmask);
+      if (gl == 0) nrm2[i] = sq;
+    }
+    __syncthreads();
     for (int step = 0; step < n_pad - 1; ++step) {
       if (g < npairs) {
         int p, q;
         jacobi_pair(step, g, n_pad, p, q);
         if (q < n) {
           double x[J1_PER_LANE], y[J1_PER_LANE];
-          double app = 0.0, aqq = 0.0, apq = 0.0;
+          const double app = nrm2[p], aqq = nrm2[q];
+          double apq = 0.0;
 #pragma unroll
           for (int k = 0; k < J1_PER_LANE; ++k) {
             const int c = gl + JAC_GROUP * k;
             x[k] = c < n ? Rw[p * ldw + c] : 0.0;
             y[k] = c < n ? Rw[q * ldw + c] : 0.0;
-            app = fma(x[k], x[k], app);
-            aqq = fma(y[k], y[k], aqq);
             apq = fma(x[k], y[k], apq);
           }
-          app = group16_sum(app, gmask);
-          aqq = group16_sum(aqq, gmask);
           apq = group16_sum(apq, gmask);
           if (early ? (apq * apq > tol_early * app * aqq) : (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300)) did = 1;
           if (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300) {
@@ -365,6 +373,7 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
             }
             const double cs = rsqrt(fma(t64, t64, 1.0));
             const double sn = t64 * cs;
+            if (gl == 0) { nrm2[p] = app - t64 * apq; nrm2[q] = aqq + t64 * apq; }
 #pragma unroll
             for (int k = 0; k < J1_PER_LANE; ++k) {
               const int c = gl + JAC_GROUP * k;
