@@ -599,7 +599,8 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
                            int64_t ldz, int accumulate, void* workspace, size_t workspace_bytes,
                            void* stream) {
   using namespace era5svd;
-  ERA5SVD_REQUIRE(Xhi && Yhi && Ylo && Z, "project_tf32x3: null pointer");
+  ERA5SVD_REQUIRE(Xhi && Yhi && Z, "project_tf32x3: null pointer");
+  ERA5SVD_REQUIRE(Ylo || !Xlo, "project_tf32x3: a plain Y (Ylo == NULL) needs the on-chip split path (Xlo == NULL too)");
   ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldy >= l && ldz >= l, "project_tf32x3: bad shape");
   if (l > 128) {
     set_error("project_tf32x3: l = %lld > 128 is not supported by the tensor-core path", (long long)l);

@@ -298,6 +298,7 @@ struct Project2Params {
   int xshift;
   int ra, rb;
   int64_t rows_per_split;
+  int split_y;        // 1: tm_yhi maps the PLAIN float32 Y; its lo image is formed on chip by the (otherwise idle) epilogue warps
   int lp;             // column pitch of a partial tile: l rounded up to 16 (pad columns hold the zeros the MMA produced)
   float* part;        // [splits][n][lp]
 };
@@ -328,6 +329,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const uint32_t at_ready = bar_base + 8u * nb;   nb += AT_RING;
   const uint32_t at_empty = bar_base + 8u * nb;   nb += AT_RING;
   const uint32_t tfull = bar_base + 8u * nb;      nb += 1;
+  const uint32_t b_raw = bar_base + 8u * nb;      nb += p.rb;    // split_y: raw Y tile landed (TMA) -> epilogue warps
   const uint32_t tmem_slot = bar_base + 8u * nb;
   const uint32_t at_col0 = 256;                                  // [0,256): two accumulators, [256,512): A ring
 
@@ -342,8 +344,9 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_init(araw_empty + 8u * i, 8);      // all eight transform warps read every slot
     }
     for (int i = 0; i < p.rb; ++i) {
-      mbar_init(b_full + 8u * i, 1);
+      mbar_init(b_full + 8u * i, p.split_y ? 4 : 1);   // split_y: the four warps that wrote the lo image arrive
       mbar_init(b_empty + 8u * i, 1);
+      mbar_init(b_raw + 8u * i, 1);
     }
     for (int i = 0; i < AT_RING; ++i) {
       mbar_init(at_ready + 8u * i, 8);
@@ -383,10 +386,15 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         mbar_wait(b_empty + 8u * rb.i, rb.ph ^ 1u);
         const uint32_t dst = b_base + (uint32_t)rb.i * b_bytes;
         const int32_t row0 = (int32_t)(r_begin + (int64_t)kc * PJ2_KS);
-        mbar_arrive_expect_tx(b_full + 8u * rb.i, b_bytes);
-        for (int c = 0; c < 4; ++c) {
-          tma_load_2d(dst + c * box_bytes, &tm_yhi, c * BK2, row0, b_full + 8u * rb.i);
-          tma_load_2d(dst + y_half + c * box_bytes, &tm_ylo, c * BK2, row0, b_full + 8u * rb.i);
+        if (p.split_y) {
+          mbar_arrive_expect_tx(b_raw + 8u * rb.i, y_half);
+          for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * box_bytes, &tm_yhi, c * BK2, row0, b_raw + 8u * rb.i);
+        } else {
+          mbar_arrive_expect_tx(b_full + 8u * rb.i, b_bytes);
+          for (int c = 0; c < 4; ++c) {
+            tma_load_2d(dst + c * box_bytes, &tm_yhi, c * BK2, row0, b_full + 8u * rb.i);
+            tma_load_2d(dst + y_half + c * box_bytes, &tm_ylo, c * BK2, row0, b_full + 8u * rb.i);
+          }
         }
         rb.next();
       }
@@ -469,6 +477,30 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ===== epilogue: accumulators -> float32 partial tile part[split][time][column] =====
     const int q = warp % 4;
     float* out = p.part + (int64_t)blockIdx.y * p.n * p.lp;
+    if (p.split_y) {
+      // Y arrives as ONE plain float32 image (the sketch then writes, and this pass reads, m*l*4 bytes instead of
+      // twice that).  The tensor core truncates its operands to tf32, so the raw tile already serves as the hi
+      // operand; these warps (idle until the accumulators are complete) form lo = y - trunc(y) next to it.  The
+      // tile layout (32-byte-granule swizzle) does not matter: the split is elementwise, same offsets in both tiles.
+      Ring rb(p.rb);
+      const uint32_t e = (uint32_t)(q * 32 + lane);            // 128 threads x 4 chunks of 16 bytes = y_half (8 KB)
+      for (int kc = 0; kc < num_k; ++kc) {
+        mbar_wait_hint(b_raw + 8u * rb.i, rb.ph, 2000u);
+        const uint32_t src = b_base + (uint32_t)rb.i * b_bytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = (e + 128u * c) << 4;
+          float4 y;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w) : "r"(src + off));
+          const float4 w = make_float4(y.x - tf32_trunc(y.x), y.y - tf32_trunc(y.y), y.z - tf32_trunc(y.z), y.w - tf32_trunc(y.w));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(src + y_half + off), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_full + 8u * rb.i);
+        rb.next();
+      }
+    }
     if (num_k > 0) {
       mbar_wait_hint(tfull, 0, 50000u);
       tcgen05_fence_after();
@@ -597,7 +629,8 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
   int xs = 0, ys = 0, ys2 = 0, rc;
   if ((rc = tc::make_tmap(&tm_x, X, n, m, ldx, tc::BK2, tc::PJ2_KS, &xs, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = tc::make_tmap(&tm_yhi, Yhi, l, m, ldy, tc::BK2, tc::PJ2_KS, &ys, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-  if ((rc = tc::make_tmap(&tm_ylo, Ylo, l, m, ldy, tc::BK2, tc::PJ2_KS, &ys2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  // Ylo == NULL: Yhi is the plain float32 Y, split on chip
+  if ((rc = tc::make_tmap(&tm_ylo, Ylo ? Ylo : Yhi, l, m, ldy, tc::BK2, tc::PJ2_KS, &ys2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   ERA5SVD_REQUIRE(ys == 0 && ys2 == 0, "project_tf32x3: Yhi / Ylo must be 16-byte aligned");
   const Pj2Plan pl = pj2_plan(m, n, l);
   if (!workspace || workspace_bytes < pl.bytes) {
@@ -606,6 +639,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
   }
   tc::Project2Params p;
   p.m = m; p.n = n; p.l = (int)l; p.lp = round_up2(l, 16);
+  p.split_y = Ylo ? 0 : 1;
   p.xshift = xs;
   p.rows_per_split = pl.rows_per_split;
   p.part = (float*)workspace;
@@ -613,7 +647,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
   const size_t b_bytes = 2 * 4 * (size_t)tc::PJ2_KS * tc::BK2 * 4;                    // 16 KB
   p.rb = 4;
   p.ra = 8;
-  const size_t smem = p.ra * a_bytes + p.rb * b_bytes + 1024 + 512;
+  const size_t smem = p.ra * a_bytes + p.rb * b_bytes + 1024 + 512;     // 512 B hold the (2 ra + 3 rb + 2 AT_RING + 2) barriers
   ERA5SVD_CUDA(cudaFuncSetAttribute(tc::project_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(n + xs, tc::PJ2_NC), (unsigned)pl.splits);
   tc::project_tc2_kernel<<<grid, tc::PJ2_THREADS, smem, st>>>(tm_x, tm_yhi, tm_ylo, p);

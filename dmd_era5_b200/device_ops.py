@@ -255,7 +255,11 @@ class CudaOps:
             accumulate = False
         hp, hld = _mat(Xhi, "Xhi")
         lp, lld = _mat(Xlo, "Xlo") if Xlo is not None else (None, hld)   # None: plain float32 X, split on chip
-        yhp, yhld = _mat(Yhi, "Yhi"); ylp, ylld = _mat(Ylo, "Ylo"); zp, zld = _mat(Z, "Z")
+        yhp, yhld = _mat(Yhi, "Yhi"); zp, zld = _mat(Z, "Z")
+        # Ylo None (with Xlo None): Yhi is the plain float32 Y of the sketch, split on chip as well
+        ylp, ylld = _mat(Ylo, "Ylo") if Ylo is not None else (None, yhld)
+        if Ylo is None and Xlo is not None:
+            raise ValueError("project_tf32x3: a plain Y (Ylo=None) needs the plain X path (Xlo=None)")
         if hld != lld or yhld != ylld:
             raise ValueError("project_tf32x3: hi/lo operands must share their row pitch")
         nbytes = int(self.lib.era5svd_project_tf32x3_workspace_bytes(m, n, l))

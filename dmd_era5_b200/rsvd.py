@@ -166,13 +166,19 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     else:
         Y = ops.empty((m0 * d, l), tall)
 
-    def tall_pass(Omega64: torch.Tensor, keep_y: bool = False) -> torch.Tensor:
-        """Y = X_d Omega (kept in the preallocated buffers), returns Z = X_d^T Y (all-reduced)."""
+    def tall_pass(Omega64: torch.Tensor, keep_y: bool = False, final: bool = False) -> torch.Tensor:
+        """Y = X_d Omega (kept in the preallocated buffers), returns Z = X_d^T Y (all-reduced).
+        On the on-chip-split path the power iterations keep Y as ONE plain float32 image (split again on chip by the
+        projection); only the final pass writes the hi / lo pair that the Gram and U = Y M kernels consume."""
         Z = None
         if use_tc:
             for j in range(d):
                 rows = slice(j * m0, (j + 1) * m0)
                 xh, xl = Xhi[:, j : j + n], (Xlo[:, j : j + n] if Xlo is not None else None)
+                if xl is None and not final:
+                    ops.sketch_tf32x3(xh, None, Omega64, Y[rows], None, None, om_tf32=om_tf32)
+                    Z = ops.project_tf32x3(xh, None, Y[rows], None, Z, accumulate=j > 0)
+                    continue
                 ops.sketch_tf32x3(xh, xl, Omega64, Y[rows] if keep_y else None, Yhi[rows], Ylo[rows], om_tf32=om_tf32)
                 Z = ops.project_tf32x3(xh, xl, Yhi[rows], Ylo[rows], Z, accumulate=j > 0)
         else:
@@ -200,7 +206,7 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         if om_tf32:
             ops.round_tf32_(Omega)
 
-    Zp = tall_pass(Omega, keep_y=not use_tc)           # n x l
+    Zp = tall_pass(Omega, keep_y=not use_tc, final=True)           # n x l
     # l x l Gram matrix of the STORED (rounded) Y, so that Q = Y R^-1 is orthonormal for the Y we keep
     G = ops.project_tf32x3(Yhi, Ylo, Yhi, Ylo) if use_tc else ops.project(Y, Y, precision=PREC_NATIVE)
     comm.allreduce_sum_(G)

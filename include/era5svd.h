@@ -121,7 +121,9 @@ int era5svd_project(const void* X, int dtype, int64_t m, int64_t n, int64_t ldx,
  *                           float32) and the pair (Yhi, Ylo) for a following project; all share ldy,
  *                           which must be >= round_up(l, 16) and a multiple of 4 (pad columns get 0).
  * era5svd_project_tf32x3  : Z (float64, n x l) (+)= X^T Y from (Xhi, Xlo), (Yhi, Ylo); l <= 128.  Xlo == NULL:
- *                           Xhi is the plain float32 matrix, split on chip.
+ *                           Xhi is the plain float32 matrix, split on chip; then Ylo == NULL is allowed as well: Yhi is
+ *                           the plain float32 Y (the sketch's Y output), split on chip too, so that the tall factor
+ *                           crosses HBM once per pass instead of as two images.
  * Pointers may carry a column offset (delay-embedded window X + j): only 4-byte alignment of the
  * tall operands is required, row pitches must be multiples of 4 floats.
  */

@@ -23,4 +23,6 @@ def timeit(fn, reps=10):
 print(os.environ.get("ERA5SVD_SK_DBG", "0"), os.environ.get("ERA5SVD_PJ_DBG", "0"),
       "sketch %.3f ms" % timeit(lambda: ops.sketch_tf32x3(X, None, Om, None, Yh, Yl)),
       "sketch x2 (tf32 Omega) %.3f ms" % timeit(lambda: ops.sketch_tf32x3(X, None, Om, None, Yh, Yl, om_tf32=True)),
-      "project %.3f ms" % timeit(lambda: ops.project_tf32x3(X, None, Yh, Yl)))
+      "project %.3f ms" % timeit(lambda: ops.project_tf32x3(X, None, Yh, Yl)),
+      "project plain-Y %.3f ms" % timeit(lambda: ops.project_tf32x3(X, None, Yh, None)),
+      "sketch x2 one image %.3f ms" % timeit(lambda: ops.sketch_tf32x3(X, None, Om, Yh, None, None, om_tf32=True)))

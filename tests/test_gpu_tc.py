@@ -142,6 +142,12 @@ def test_project_tf32x3_onchip_split(ops, m, n, l, off):
     assert np.all(np.abs(Z.cpu().numpy() - ref) <= bound)
     Z2 = ops.project_tf32x3(Xb[:, off:off + n], None, yhi[:, :l], ylo[:, :l], Z.clone(), accumulate=True)
     assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
+    # Ylo = None: the plain float32 Y is split on chip as well (one image of the tall factor crosses HBM)
+    Z3 = ops.project_tf32x3(Xb[:, off:off + n], None, Yb[:, :l], None)
+    assert np.all(np.abs(Z3.cpu().numpy() - ref) <= bound)
+    Z4 = ops.project_tf32x3(Xb[:, off:off + n], None, Yb[:, :l], None, Z3.clone(), accumulate=True)
+    assert np.allclose(Z4.cpu().numpy(), 2 * Z3.cpu().numpy(), rtol=1e-12)
+    assert torch.equal(ops.project_tf32x3(Xb[:, off:off + n], None, Yb[:, :l], None), Z3)      # reproducible
 
 
 @pytest.mark.parametrize("d", [1, 2])
