@@ -5,8 +5,9 @@ output layout (README.md:97-119): data_vars U (space, components), s (components
 time), optional X, X_mean, X_std; coords space, components, time, original_variable, delay, level,
 latitude, longitude.
 
-DVC plumbing (dvc_tools.py) is out of scope for this build: ``use_dvc=True`` logs a warning and
-behaves like the reference when its DVC retrieval fails (falls through to compute / no add).
+DVC plumbing: ``dvc_tools.py`` of this package (same calls as the reference's); where ``dvc`` / ``GitPython`` are not
+installed a retrieval behaves like the reference's failed retrieval (warning, falls through to computing) and adding
+results raises the reference's "Error adding SVD results to DVC" error.
 """
 from __future__ import annotations
 
@@ -56,8 +57,20 @@ def _as_int_list(obj) -> list[int]:
     return [int(x) for x in arr.ravel().tolist()]
 
 
-def _dvc_unavailable(what: str):
-    log_and_print(logger, f"Could not retrieve {what} from DVC: DVC plumbing is not part of this build", "warning")
+def _retrieve_from_dvc(parsed_config: dict, data_type: str, what: str, path_key: str, lazy: bool):
+    """The ``retrieve_from_dvc`` closures of era5_svd.py:116-129 / 190-203: check the matching version out of DVC and
+    open it; a failed retrieval (nothing logged, nothing matching, no cache / remote, or no dvc installation) is a
+    warning and ``None``, never an error."""
+    from . import dvc_tools
+
+    log_and_print(logger, f"Attempting to retrieve {what} from DVC...")
+    try:
+        dvc_tools.retrieve_data_from_dvc(parsed_config, data_type=data_type)
+        log_and_print(logger, f"{what} retrieved from DVC: {parsed_config[path_key]}")
+        return read_netcdf(parsed_config[path_key], lazy=lazy)
+    except (FileNotFoundError, ValueError) as e:
+        log_and_print(logger, f"Could not retrieve {what} from DVC: {e}", "warning")
+        return None
 
 
 def retrieve_era5_slice(parsed_config: dict, use_dvc: bool = False):
@@ -76,13 +89,14 @@ def retrieve_era5_slice(parsed_config: dict, use_dvc: bool = False):
             return ds, False
         log_and_print(logger, "ERA5 slice does not match configuration.")
         if use_dvc:
-            _dvc_unavailable("ERA5 slice")
-        else:
-            log_and_print(logger, "ERA5 slice in working directory does not match configuration.", "warning")
+            ds = _retrieve_from_dvc(parsed_config, "era5_slice", "ERA5 slice", "era5_slice_path", lazy=True)
+            return (ds, True) if ds is not None else (None, False)
+        log_and_print(logger, "ERA5 slice in working directory does not match configuration.", "warning")
         return None, False
     log_and_print(logger, "ERA5 slice not found in working directory.", "warning")
     if use_dvc:
-        _dvc_unavailable("ERA5 slice")
+        ds = _retrieve_from_dvc(parsed_config, "era5_slice", "ERA5 slice", "era5_slice_path", lazy=True)
+        return (ds, True) if ds is not None else (None, False)
     return None, False
 
 
@@ -104,13 +118,14 @@ def retrieve_svd_results(parsed_config: dict, use_dvc: bool = False):
             return ds, False
         log_and_print(logger, "SVD results do not match configuration.")
         if use_dvc:
-            _dvc_unavailable("SVD results")
-        else:
-            log_and_print(logger, "SVD results in working directory do not match configuration.", "warning")
+            ds = _retrieve_from_dvc(parsed_config, "era5_svd", "SVD results", "save_path", lazy=False)
+            return (ds, True) if ds is not None else (None, False)
+        log_and_print(logger, "SVD results in working directory do not match configuration.", "warning")
         return None, False
     log_and_print(logger, "SVD results not found in working directory.", "warning")
     if use_dvc:
-        _dvc_unavailable("SVD results")
+        ds = _retrieve_from_dvc(parsed_config, "era5_svd", "SVD results", "save_path", lazy=False)
+        return (ds, True) if ds is not None else (None, False)
     return None, False
 
 
@@ -299,8 +314,18 @@ def main(config: dict | None = None, write_to_netcdf: bool = False, use_dvc: boo
                 msg = f"Error writing SVD results to NetCDF: {e}"
                 log_and_print(logger, msg, "error")
                 raise Exception(msg) from e
-            if use_dvc:
-                log_and_print(logger, "DVC plumbing is not part of this build: results were not added to DVC.", "warning")
+            if use_dvc:                                                  # era5_svd.py:442-451
+                try:
+                    from . import dvc_tools
+
+                    log_and_print(logger, "Adding SVD results to DVC...")
+                    dvc_tools.add_data_to_dvc(parsed_config["save_path"], svd_results.attrs)
+                    log_and_print(logger, "SVD results added to DVC.")
+                    added_to_dvc = True
+                except Exception as e:
+                    msg = f"Error adding SVD results to DVC: {e}"
+                    log_and_print(logger, msg, "error")
+                    raise Exception(msg) from e
     return svd_results, added_to_dvc, retrieved_from_dvc
 
 

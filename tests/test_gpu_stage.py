@@ -196,3 +196,21 @@ def test_stage_blocks_chunked_upload(dtype):
                 T = want[v].shape[0]
                 assert S == want[v][0].size and tuple(b.shape) == (T, S)
                 assert np.array_equal(b.cpu().numpy(), want[v].reshape(T, -1))
+
+
+def test_main_use_dvc_without_dvc(tmp_path, monkeypatch):
+    """use_dvc=True where dvc / GitPython are not installed: retrieval attempts end in the reference's warnings and the
+    stage computes (era5_svd.py:116-154, 190-227); adding the written result to DVC fails with the reference's error
+    wrapper (:442-451).  With dvc installed this path is the reference's docker-marked test (test_05_dvc_era5_svd.py)."""
+    from dmd_era5_b200 import dvc_tools
+    from dmd_era5_b200.era5_svd import main
+
+    if dvc_tools.dvc_available():
+        pytest.skip("dvc is installed: covered by the reference's own DVC tests")
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    cfg = base_config(delay_embedding=1)
+    make_slice(tmp_path, cfg)
+    res, added, retrieved = main(cfg, write_to_netcdf=False, use_dvc=True)        # nothing to add: no error
+    assert added is False and retrieved is False and res["s"].shape == (6,)
+    with pytest.raises(Exception, match="Error adding SVD results to DVC"):
+        main(base_config(delay_embedding=1, n_components=5), write_to_netcdf=True, use_dvc=True)

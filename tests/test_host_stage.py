@@ -208,3 +208,51 @@ def test_netcdf_lazy_read(tmp_path, monkeypatch):
     # selections on the mapped data stay pending and give the right planes
     out = st.slice_era5_dataset(lazy, levels=[850])
     assert np.array_equal(out["temperature"].values, ds["temperature"].values[:, 1:2])
+
+
+def test_dvc_side_log_and_version_matching(tmp_path, monkeypatch):
+    """DVC plumbing without a DVC installation (reference dvc_tools.py:11-47, 119-207, tests/test_05_dvc_era5_svd.py):
+    the YAML side-log format, the matching rules (superset match for slices, order-sensitive equality for results,
+    svd_type / save_data_matrix not compared, most recent entry wins) and the error contract of the retrieval."""
+    import yaml
+
+    from dmd_era5_b200 import dvc_tools
+
+    data = tmp_path / "2019-01-01T00_2019-01-02T00_1h.nc"
+    data.write_bytes(b"x")
+    (tmp_path / (data.name + ".dvc")).write_text("outs:\n- md5: 0123456789abcdef0123456789abcdef\n  size: 1\n  path: x.nc\n")
+    attrs = {"source_path": "gs://mock", "variables": ["temperature", "u_component_of_wind"], "levels": [1000, 850],
+             "n_components": 6, "mean_center": 1, "scale": 0, "delay_embedding": 2, "svd_type": "randomized",
+             "save_data_matrix": 1, "date_processed": datetime(2024, 5, 1, 12, 0, 0)}
+    dvc_tools.add_config_to_dvc_log(str(data) + ".dvc", str(data), attrs)
+    (tmp_path / (data.name + ".dvc")).write_text("outs:\n- md5: ffffffffffffffffffffffffffffffff\n  size: 1\n  path: x.nc\n")
+    dvc_tools.add_config_to_dvc_log(str(data) + ".dvc", str(data), {**attrs, "date_processed": datetime(2024, 6, 1), "svd_type": "standard"})
+    log = yaml.safe_load((tmp_path / (data.name + ".yaml")).read_text())
+    assert list(log) == ["0123456789abcdef0123456789abcdef", "f" * 32]
+    assert log["f" * 32]["variables"] == attrs["variables"] and log["f" * 32]["date_processed"] == datetime(2024, 6, 1)
+    want = {"source_path": "gs://mock", "variables": ["temperature", "u_component_of_wind"], "levels": [1000, 850],
+            "n_components": 6, "mean_center": True, "scale": False, "delay_embedding": 2, "svd_type": "randomized"}
+    assert dvc_tools.select_logged_version(log, want, "era5_svd") == "f" * 32          # most recent; svd_type ignored (Q5)
+    assert dvc_tools.select_logged_version(log, {**want, "variables": want["variables"][::-1]}, "era5_svd") is None   # order (Q2)
+    assert dvc_tools.select_logged_version(log, {**want, "n_components": 7}, "era5_svd") is None
+    slice_log = {"aa": {"variables": ["temperature", "u_component_of_wind"], "levels": [1000, 850, 500], "source_path": "gs://mock",
+                        "date_downloaded": datetime(2024, 1, 1)},
+                 "bb": {"variables": ["temperature"], "levels": [1000], "source_path": "gs://mock", "date_downloaded": datetime(2024, 2, 1)}}
+    req = {"variables": ["temperature"], "levels": [1000], "source_path": "gs://mock"}
+    assert dvc_tools.select_logged_version(slice_log, req, "era5_slice") == "bb"        # both cover it: newest
+    assert dvc_tools.select_logged_version(slice_log, {**req, "levels": [850, 1000]}, "era5_slice") == "aa"   # superset match
+    assert dvc_tools.select_logged_version(slice_log, {**req, "levels": [300]}, "era5_slice") is None
+    # retrieval error contract
+    cfg = {**want, "era5_svd_path": str(tmp_path / "missing.nc"), "era5_slice_path": str(tmp_path / "missing_slice.nc")}
+    with pytest.raises(FileNotFoundError, match="DVC file or log file does not exist."):
+        dvc_tools.retrieve_data_from_dvc(cfg, "era5_svd")
+    with pytest.raises(ValueError, match="Data type not supported"):
+        dvc_tools.retrieve_data_from_dvc(cfg, "era5_other")
+    with pytest.raises(KeyError, match="does not contain the path to the ERA5 slice"):
+        dvc_tools.retrieve_data_from_dvc({"variables": []}, "era5_slice")
+    with pytest.raises(ValueError, match="No matching version of the data found in DVC."):
+        dvc_tools.retrieve_data_from_dvc({**want, "n_components": 99, "era5_svd_path": str(data)}, "era5_svd")
+    # a version is logged but no commit carries its md5 (not a git repository here): the reference's ValueError
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(ValueError, match="could not retrieve it from DVC"):
+        dvc_tools.retrieve_data_from_dvc({**want, "era5_svd_path": str(data)}, "era5_svd")
