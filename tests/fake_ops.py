@@ -49,6 +49,46 @@ class FakeOps:
             Z.copy_(out)
         return Z
 
+    # -- tensor-core path stand-ins: exact float64 products of the float32 operands, rounded to float32 like the
+    #    kernels' outputs; tf32 rounding emulated on the bit pattern (round to nearest, ties away: cvt.rna) --------
+    @staticmethod
+    def _tf32(a: torch.Tensor) -> torch.Tensor:
+        bits = a.to(torch.float32).contiguous().view(torch.int32)
+        return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def tf32_ldy(self, l):
+        return (l + 15) // 16 * 16
+
+    def round_tf32_(self, A):
+        self._count("round_tf32")
+        A.copy_(self._tf32(A).double())
+        return A
+
+    def sketch_tf32x3(self, Xhi, Xlo, Om, Y, Yhi, Ylo, om_tf32=False):
+        self._count("sketch_tc")
+        X = Xhi.double() + (Xlo.double() if Xlo is not None else 0.0)
+        om = self._tf32(Om).double() if om_tf32 else Om
+        out = (X @ om).to(torch.float32)
+        if Y is not None:
+            Y.copy_(out)
+        if Yhi is not None:
+            hi = self._tf32(out)
+            Yhi.copy_(hi)
+            Ylo.copy_(out - hi)
+
+    def project_tf32x3(self, Xhi, Xlo, Yhi, Ylo, Z=None, accumulate=False):
+        self._count("project_tc")
+        X = Xhi.double() + (Xlo.double() if Xlo is not None else 0.0)
+        Yv = Yhi.double() + (Ylo.double() if Ylo is not None else 0.0)
+        out = X.t() @ Yv
+        if Z is None:
+            return out
+        if accumulate:
+            Z += out
+        else:
+            Z.copy_(out)
+        return Z
+
     def gemm(self, A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None):
         self._count("gemm")
         a = A.t() if transA else A

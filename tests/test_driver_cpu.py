@@ -39,6 +39,31 @@ def test_randomized_driver_matches_oracle(d):
     assert signs_agree(U.numpy(), U0)
 
 
+@pytest.mark.parametrize("d", [1, 2])
+def test_randomized_driver_tensor_core_schedule(d):
+    """The tensor-core schedule of the driver on CPU stand-ins (exact products of the float32 operands): Omega kept in
+    tf32-representable values after every orthonormalisation, ONE plain Y image through the power iterations, the
+    hi / lo pair only in the final pass.  Rounding Omega is a choice of basis, not an approximation: sigma agrees with
+    the float64 oracle on the same float32 data to 1e-6 (the float32 storage of Y), vectors to 1e-4 rad."""
+    from dmd_era5_b200._cabi import PREC_TF32X3
+
+    X = lowrank_field_np(3000, 160, r=60, rho=0.88, seed=3).astype(np.float32)
+    k = 12
+    Xd = delay_embed_np(X.astype(np.float64), d)
+    U0, s0, V0 = randomized_svd_ref(Xd, k, 7)
+    ops = FakeOps()
+    U, s, Vt = randomized_svd_device(ops, torch.from_numpy(X), k, draw_omega(Xd.shape[1], k, 7, torch.float32), delay=d,
+                                     precision=PREC_TF32X3)
+    assert U.dtype == torch.float32
+    assert sigma_rel_err(s, s0) < 1e-6
+    assert vector_angles(U.double().numpy(), U0).max() < 1e-4 and vector_angles(Vt.numpy().T, V0.T).max() < 1e-4
+    assert signs_agree(U.double().numpy(), U0)
+    q = n_iter_auto(Xd.shape[0], Xd.shape[1], k)
+    assert ops.calls["round_tf32"] == q + 1                       # the start matrix and every orthonormalised basis
+    assert ops.calls["sketch_tc"] == d * (q + 1) + 1              # q + 1 tall sketches per delay block + U = Y M
+    assert ops.calls["project_tc"] == d * (q + 1) + 1             # q + 1 projections per block + the Gram of Y
+
+
 def test_standard_driver_matches_oracle():
     X = lowrank_field_np(2000, 64, r=64, rho=0.9, seed=5)
     U0, s0, V0 = standard_svd_ref(delay_embed_np(X, 2), 10)
