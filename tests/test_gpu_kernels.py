@@ -315,3 +315,14 @@ def test_col_absmax_first_max_and_flip(ops, dtype):
     Ud = dev(U)
     ops.scale_cols(Ud, sg)
     assert np.array_equal(Ud.cpu().numpy(), U * sg.cpu().numpy().astype(dtype))
+
+
+@pytest.mark.parametrize("m,k,ld", [(70001, 100, 112), (33, 16, 16), (5, 128, 128), (1000, 100, 100)])
+def test_scale_cols_vectorised(ops, m, k, ld):
+    """float32 U with 16-byte aligned rows takes the float4 kernel: every entry scaled, the row padding untouched."""
+    rng = np.random.RandomState(m + k)
+    buf = torch.from_numpy(rng.standard_normal((m, ld)).astype(np.float32)).cuda()
+    ref = buf.clone()
+    sg = torch.from_numpy(rng.choice([-1.0, 1.0, 0.0], size=k)).cuda()
+    ops.scale_cols(buf[:, :k], sg)
+    assert torch.equal(buf[:, :k], ref[:, :k] * sg.float()) and torch.equal(buf[:, k:], ref[:, k:])
