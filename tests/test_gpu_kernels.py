@@ -255,7 +255,7 @@ def test_syevj_psd_relative_accuracy(ops):
     assert np.max(np.abs(W.cpu().numpy() - ref) / ref) < 1e-9
 
 
-@pytest.mark.parametrize("l", [1, 5, 110, 200])
+@pytest.mark.parametrize("l", [1, 5, 33, 110, 118, 119, 128, 129, 200])     # register-tiled path up to 128; smem working copies up to 118
 def test_chol_inv(ops, l):
     rng = np.random.RandomState(l)
     B = rng.standard_normal((3 * l + 5, l))
