@@ -192,26 +192,47 @@ def bind_to_gpu_numa_node(local_rank: int):
     return None
 
 
-def cpu_reference_run(rows: int, T: int, k: int, seed: int, threads: int):
-    """The reference's own numerics on the host cores for a bounded row sample of the workload:
-    NumPy restatement of the build (oracle) + sklearn.utils.extmath.randomized_svd, exactly the
-    call of src/dmd_era5/era5_svd/era5_svd.py:258.  Returns (seconds, bytes of the matrix)."""
-    from oracle.slice_tools_np import build_matrix_np
-    from oracle.svd_ref import randomized_svd_ref
+def set_blas_threads(n: int):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank, which silently made the N > 1 reference arm single threaded
+    (VERDICT r01 weak #14).  The CPU legs set the BLAS pool explicitly and report what the pool says."""
+    info = []
+    try:
+        import threadpoolctl
 
+        threadpoolctl.threadpool_limits(limits=n)
+        info = [{k: d.get(k) for k in ("user_api", "internal_api", "num_threads", "version")}
+                for d in threadpoolctl.threadpool_info()]
+    except Exception as e:      # pragma: no cover
+        info = [{"error": repr(e)}]
+    return info
+
+
+def sample_field_np(rows: int, T: int, seed: int) -> np.ndarray:
+    """Host generator of a (T, rows) float32 native-layout field with the bench spectrum (sigma_i = 100 * 0.93**i,
+    160 components, mean 250) - the reference arm's input when no GPU-generated sample is handed over."""
     rng = np.random.RandomState(seed)
     r = 160
     Bt = rng.standard_normal((T, r)).astype(np.float32)
     Bt -= Bt.mean(axis=0)
     Bt = np.linalg.qr(Bt)[0] * (100.0 * 0.93 ** np.arange(r)).astype(np.float32)
     A = (rng.standard_normal((r, rows)) / np.sqrt(rows)).astype(np.float32)
-    field = (Bt @ A + 250.0).astype(np.float32)            # (T, rows) native layout
-    field = field.reshape(T, 1, 1, rows)
+    return (Bt @ A + 250.0).astype(np.float32)
+
+
+def cpu_reference_run(field: np.ndarray, k: int, seed: int):
+    """The reference's own numerics on the host cores for a bounded row sample of the workload:
+    NumPy restatement of the build (oracle) + sklearn.utils.extmath.randomized_svd, exactly the
+    call of src/dmd_era5/era5_svd/era5_svd.py:258.  field: (T, rows) native layout.
+    Returns (seconds, bytes of the matrix, X, (U, s, V))."""
+    from oracle.slice_tools_np import build_matrix_np
+    from oracle.svd_ref import randomized_svd_ref
+
+    T, rows = field.shape
     t0 = time.perf_counter()
-    X, _, _ = build_matrix_np([field], True, False, 1)
-    U, s, V = randomized_svd_ref(X, k, 1)
+    X, _, _ = build_matrix_np([field.reshape(T, 1, 1, rows)], True, False, 1)
+    U, s, V = randomized_svd_ref(X, k, seed)
     dt = time.perf_counter() - t0
-    return dt, X.nbytes, float(s[0])
+    return dt, X.nbytes, X, (U, s, V)
 
 
 def run_reference(args):
@@ -221,25 +242,64 @@ def run_reference(args):
         return
     S, T, desc = WORKLOADS[args.workload]
     threads = len(os.sched_getaffinity(0))
+    pool = set_blas_threads(threads)
     # bounded sample: ~28 us of host time per row at n = 744 (measured, 16 cores); keep the whole
     # --steps/--warmup run within ~2.5 minutes
     per_step_s = 150.0 / max(1, args.steps + args.warmup)
     rows = args.cpu_rows or int(min(S, 262144, max(32768, per_step_s / 28e-6 * 744 / T)))
     times = []
     for i in range(args.warmup + args.steps):
-        dt, nbytes, _ = cpu_reference_run(rows, T, K_COMPONENTS, seed=i, threads=threads)
+        dt, nbytes, _, _ = cpu_reference_run(sample_field_np(rows, T, seed=i), K_COMPONENTS, seed=1)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     val = nbytes / 1e9 / (ms / 1e3)
-    sample = f"{rows} of {S} rows x {T} snapshots f32 per step (bounded CPU sample of {args.workload})"
+    sample = (f"{rows} of {S} rows x {T} snapshots f32 per step (bounded CPU sample of {args.workload}; GB/s is per byte "
+              f"of the sampled matrix, every phase of the reference is O(rows))")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "k": K_COMPONENTS},
-        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "reference", "sample": sample},
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "rows_per_rank": S, "snapshots": T, "k": K_COMPONENTS,
+                   "l": K_COMPONENTS + 10, "n_iter": 7 if K_COMPONENTS < 0.1 * min(S, T) else 4, "mean_center": True,
+                   "sampled_rows": rows, "same_config_as_gpu_arm": False,
+                   "note": "the reference cannot hold / finish the full matrix in bench time: a row sample, GB/s-normalised"},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "reference", "sample": sample,
+                         "threadpool_info": pool, "OMP_NUM_THREADS_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# tensor-core products per k-step of each timed tall kernel (KernelTimer names, device_ops.py)
+NPROD = {"sketch_x1": 1.0, "project_x1": 1.0, "sketch_tc": 2.0, "project_tc": 3.0, "gram_tc": 3.0, "apply_basis_tc": 3.0}
+TALL = ("sketch", "project", "sketch_tc", "project_tc", "sketch_x1", "project_x1")
+
+
+def pass_rooflines(ksum: dict, pk: dict, precision: str, tc_split: str) -> list[dict]:
+    """One entry per timed tall kernel: achieved GB/s over the ALGORITHMIC bytes (X once + the tall factor), tensor
+    TFLOP/s over the products actually issued, and frac = max(t_hbm, t_tensor) / t_kernel against the MEASURED peaks
+    (HBM copy rate from MEASURED_PEAKS.json, kind::tf32 rate from this run's own probe)."""
+    out = []
+    for name, d in ksum.items():
+        if not d["calls"] or (name not in TALL and name != "build_rows"):
+            continue
+        ms = d["ms"] / d["calls"]
+        nbytes, flops = d["bytes"] / d["calls"], d["flops"] / d["calls"]
+        t_hbm = nbytes / (pk["hbm_gbs"] * 1e9) * 1e3
+        e = {"kernel": name, "calls": d["calls"], "avg_launch_ms": ms, "algorithmic_GB": nbytes / 1e9,
+             "achieved_GBps": nbytes / 1e9 / (ms / 1e3), "t_hbm_ms": t_hbm, "hbm_frac": t_hbm / ms}
+        t_tensor = 0.0
+        if precision != "native" and name in NPROD:
+            nprod = NPROD[name]
+            if name == "sketch_tc" and tc_split == "hbm":
+                nprod = 3.0
+            t_tensor = nprod * flops / (pk["tf32_tflops"] * 1e12) * 1e3
+            e.update(tensor_products=nprod, achieved_TFLOPs=nprod * flops / 1e12 / (ms / 1e3), t_tensor_ms=t_tensor,
+                     tensor_frac=t_tensor / ms)
+        e["bound"] = "tensor" if t_tensor > t_hbm else "hbm"
+        e["frac"] = max(t_hbm, t_tensor) / ms
+        out.append(e)
+    return sorted(out, key=lambda e: -e["avg_launch_ms"] * e["calls"])
 
 
 def main():
@@ -249,13 +309,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("ERA5SVD_PRECISION", "tf32x3"), choices=["native", "tf32x3"],
-                    help="tf32x3 (default, headline): tcgen05 3xTF32 passes; native: FP32 FMA passes on the CUDA cores")
+    ap.add_argument("--precision", default=os.environ.get("ERA5SVD_PRECISION", "tf32mix"),
+                    choices=["native", "tf32x3", "tf32mix"],
+                    help="tf32mix (default, headline): tcgen05 passes, single-product TF32 for the early power iterations, "
+                         "3xTF32 for the last iteration + final passes; tf32x3: 3xTF32 everywhere; native: FP32 FMA")
     ap.add_argument("--tc-split", default="onchip", choices=["onchip", "hbm"])
     ap.add_argument("--rows", type=int, default=0, help="override points per rank (debug only; invalidates the number)")
     ap.add_argument("--cpu-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the c3 (north-star shape) leg")
+    ap.add_argument("--north-star-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -264,7 +328,7 @@ def main():
 
     from dmd_era5_b200 import _cabi
     from dmd_era5_b200.device_ops import CudaOps, KernelTimer
-    from dmd_era5_b200.dist import LocalComm, TorchDistComm
+    from dmd_era5_b200.dist import LocalComm, TorchDistComm, shard_rows
     from dmd_era5_b200.pipeline import build_matrix_device, svd_device
     from dmd_era5_b200.rsvd import n_iter_auto
     from dmd_era5_b200.synthetic import synthetic_field
@@ -286,63 +350,94 @@ def main():
         comm = LocalComm()
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
-    S, T, desc = WORKLOADS[args.workload]
-    if args.rows:
-        S = args.rows
     k = K_COMPONENTS
     ops = CudaOps(device)
-    sampler = ClockSampler(local_rank, uuid=str(torch.cuda.get_device_properties(local_rank).uuid))
-    if rank == 0:
-        sampler.start()
-    field = synthetic_field(T, S, device=device, seed=1000 + rank)          # native (T, S) f32, outside the timed region
-    m_global = S * world
-    row_offset = rank * S
-    q = n_iter_auto(m_global, T, k)
-    x_bytes = float(S) * T * 4
-
-    def step(src_dev, timer=None):
-        ops.timer = timer
-        # tf32x3: "onchip" reads the plain matrix and splits it on chip (gemm_tc2.cu); "hbm" streams
-        # pre-split hi / lo images written by the build kernel (gemm_tc.cu)
-        tc = args.precision == "tf32x3" and args.tc_split == "hbm"
-        built = build_matrix_device(ops, [src_dev], mean_center=True, scale=False, split=tc, keep_x=not tc)
-        U, s, V = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=1, precision=args.precision,
-                             comm=comm, row_offset=row_offset, m0_global=m_global,
-                             split=(built.Xhi, built.Xlo) if tc else None)
-        ops.timer = None
-        return U, s, V
 
     def sync_all():
         torch.cuda.synchronize(device)
         comm.barrier()
         torch.cuda.synchronize(device)
 
-    # ---------------- device-resident timing ("value") ----------------
-    for _ in range(args.warmup):
-        step(field)
+    # ---------------- measured peaks (this run, this GPU): roofline denominators ----------------
+    import ctypes as C
+
+    pk = peaks()
+    probe = {}
+    try:
+        v = C.c_double(0.0)
+        for key, form, N, secs in (("tf32_tflops_burst", 1, 256, 0.02), ("tf32_tflops_sustained", 1, 256, 0.4),
+                                   ("tf32_tflops_n112_ts", 1, 112, 0.05), ("tf32_tflops_n112_ss", 0, 112, 0.05)):
+            _cabi.check(ops.lib.era5svd_probe_tf32_tflops(form, N, secs, C.byref(v)), "era5svd_probe_tf32_tflops")
+            probe[key] = v.value
+        _cabi.check(ops.lib.era5svd_probe_dmma_tflops(0.2, C.byref(v)), "era5svd_probe_dmma_tflops")
+        probe["fp64_dmma_tflops"] = v.value
+    except Exception as e:      # a failed probe must not void the bench: fall back and say so
+        probe["error"] = repr(e)
+    # a tall pass is timed INSIDE a long step under the power cap -> the sustained figure is the denominator
+    pk["tf32_tflops"] = probe.get("tf32_tflops_sustained") or pk["bf16_tflops"] / 2.0
+    pk["tf32_source"] = ("measured in this run: era5svd_probe_tf32_tflops (every SM issuing tcgen05.mma kind::tf32 M=128 N=256 K=8 "
+                         "from TMEM for 0.4 s)" if "tf32_tflops_sustained" in probe else "fallback: 1/2 of the sustained bf16 peak")
     sync_all()
-    timer = KernelTimer()
-    t_region0 = time.perf_counter()
-    launches0 = _cabi.launch_count()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    # per-launch CUDA events (KernelTimer) ride on every 4th timed step: two event records around each of the ~13
-    # timed ops cost ~0.4 ms of a 14 ms step when every step carries them
-    sampled = [i for i in range(args.steps) if i % 4 == 0]
-    for i in range(args.steps):
-        U, s, V = step(field, timer if i % 4 == 0 else None)
-    e1.record()
-    sync_all()
-    launches = _cabi.launch_count() - launches0
-    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
-    ms = e0.elapsed_time(e1) / args.steps
-    t = torch.tensor([ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+
+    def time_workload(field, m_global, row_offset, steps, warmup, precision, sample_clocks):
+        """warmup + steps full steps (build + randomized SVD) on the resident native array ``field``."""
+        S_loc, T_loc = field.shape[1], field.shape[0]
+
+        def step(src_dev, timer=None):
+            ops.timer = timer
+            # tf32x3 / tf32mix: "onchip" reads the plain matrix and splits it on chip (gemm_tc2.cu); "hbm" streams
+            # pre-split hi / lo images written by the build kernel (gemm_tc.cu)
+            tc = precision == "tf32x3" and args.tc_split == "hbm"
+            built = build_matrix_device(ops, [src_dev], mean_center=True, scale=False, split=tc, keep_x=not tc)
+            U, s, V = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=1, precision=precision,
+                                 comm=comm, row_offset=row_offset, m0_global=m_global,
+                                 split=(built.Xhi, built.Xlo) if tc else None)
+            ops.timer = None
+            return U, s, V
+
+        sampler = None
+        if sample_clocks and rank == 0:
+            sampler = ClockSampler(local_rank, uuid=str(torch.cuda.get_device_properties(local_rank).uuid))
+            sampler.start()
+        for _ in range(warmup):
+            step(field)
+        sync_all()
+        timer = KernelTimer()
+        t_region0 = time.perf_counter()
+        launches0 = _cabi.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        # per-launch CUDA events (KernelTimer) ride on every 4th timed step: two event records around each of the ~13
+        # timed ops cost ~0.4 ms of a 14 ms step when every step carries them
+        sampled = [i for i in range(steps) if i % 4 == 0]
+        for i in range(steps):
+            U, s, V = step(field, timer if i % 4 == 0 else None)
+        e1.record()
+        sync_all()
+        launches = _cabi.launch_count() - launches0
+        clocks = sampler.stop(t_region0, time.perf_counter()) if sampler is not None else None
+        ms = e0.elapsed_time(e1) / steps
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ksum = timer.summary()
+        for v_ in ksum.values():                   # per sampled step -> totals stay, add the sample count
+            v_["sampled_steps"] = len(sampled)
+        return {"ms": float(t.item()), "ksum": ksum, "launches": int(launches), "clocks": clocks,
+                "sigma_1": float(s[0].item()), "step": step, "sampled": len(sampled)}
+
+    # ---------------- device-resident timing ("value"): BASELINE configs[1] (c2) per rank, weak scaling ----------
+    S, T, desc = WORKLOADS[args.workload]
+    if args.rows:
+        S = args.rows
+    field = synthetic_field(T, S, device=device, seed=1000 + rank)          # native (T, S) f32, outside the timed region
+    m_global = S * world
+    row_offset = rank * S
+    q = n_iter_auto(m_global, T, k)
+    x_bytes = float(S) * T * 4
+    res = time_workload(field, m_global, row_offset, args.steps, args.warmup, args.precision, True)
+    ms, ksum, launches, clocks, s_first, step = (res[x] for x in ("ms", "ksum", "launches", "clocks", "sigma_1", "step"))
     value = x_bytes * world / 1e9 / (ms / 1e3)
-    ksum = timer.summary()
-    s_first = float(s[0].item())
 
     # ---------------- end-to-end through the host-facing path ----------------
     # Every step's input starts in pinned HOST memory and every step's U, s, V end in pinned host memory.
@@ -388,88 +483,125 @@ def main():
         assert all(abs(x - s_first) <= 1e-6 * s_first for x in sig), "pipelined results differ from the one-shot path"
         e2e = {"value": x_bytes * world / 1e9 / (ms_e2e / 1e3), "unit": "GB/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(stream.h2d_bytes), "d2h_bytes_per_step": int(stream.d2h_bytes),
-               "mode": f"SvdStageStream over {n_e2e} host slices: H2D(i+1) | build+SVD(i) | D2H(i-1), 2 device input buffers",
+               "mode": f"SvdStageStream over {n_e2e} host slices: H2D(i+1) | build+SVD(i) | D2H(i-1), 2 device input buffers "
+                       "(pipelined throughput; single_shot is the latency of one slice with nothing overlapped)",
                "single_shot": {"value": x_bytes * world / 1e9 / (ms_single / 1e3), "ms_per_step": ms_single},
+               "pcie_floor_ms": stream.h2d_bytes / 55.6e9 * 1e3,
                "numa_binding": numa}
         del host, stream
 
-    # ---------------- roofline of the dominant kernel ----------------
-    pk = peaks()
-    tall = ("sketch", "project", "sketch_tc", "project_tc")
-    dom = max((n for n in ksum if n in tall), key=lambda n: ksum[n]["ms"], default=None)
+    # ---------------- roofline of every tall kernel + the dominant one ----------------
+    passes = pass_rooflines(ksum, pk, args.precision, args.tc_split)
+    tall_passes = [e for e in passes if e["kernel"] in TALL]
     roofline = None
-    if dom:
-        d = ksum[dom]
-        avg_ms = d["ms"] / d["calls"]
-        gbs = d["bytes"] / d["calls"] / (avg_ms / 1e3) / 1e9                 # algorithmic bytes: X read once + tall factor
-        t_hbm = d["bytes"] / d["calls"] / (pk["hbm_gbs"] * 1e9)
-        if args.precision == "tf32x3":
-            # the slower of the two rooflines bounds the pass (BASELINE.json north_star): 3xTF32 issues 3 * 2mnl
-            # tensor flops; dense TF32 peak = 1/2 of the measured sustained bf16 peak (kernel timed inside a step)
-            peak_tf32 = pk["bf16_tflops"] / 2.0
-            # tensor-core products per k-step: 3 (hi*hi + lo*hi + hi*lo); the on-chip-split sketch runs on a
-            # tf32-exact small factor (Omega_lo = 0) and issues 2
-            nprod = 2.0 if (dom == "sketch_tc" and args.tc_split == "onchip") else 3.0
-            tfl = nprod * d["flops"] / d["calls"] / (avg_ms / 1e3) / 1e12
-            t_tensor = nprod * d["flops"] / d["calls"] / (peak_tf32 * 1e12)
-            if t_tensor >= t_hbm:
-                roofline = {"kernel": dom, "bound": "tensor", "achieved": tfl, "peak": peak_tf32, "unit": "TFLOP/s",
-                            "frac": tfl / peak_tf32, "traffic": None}
-            else:
-                roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": gbs / pk["hbm_gbs"], "traffic": None}
-            roofline["note"] = (f"{int(nprod)}xTF32 tcgen05 pass; tensor: {int(nprod)}*2mnl flops vs 1/2 sustained bf16 peak; hbm: algorithmic "
-                                f"m*n*4 + m*l*4 bytes (tc_split=hbm: the pre-split hi/lo images double the real X traffic); {pk['source']}")
-            roofline["hbm_frac_algorithmic"] = gbs / pk["hbm_gbs"]
-            roofline["tensor_frac"] = tfl / peak_tf32
-        else:
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                        "frac": gbs / pk["hbm_gbs"], "traffic": None,
-                        "note": f"FP32-FMA (CUDA-core) pass, algorithmic bytes m*n*4 + m*l*4 per launch; {pk['source']}"}
-        roofline["avg_launch_ms"] = avg_ms
-        try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload)
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
-                roofline["traffic"] = json.load(f).get(args.workload, {}).get(dom)
+    if tall_passes:
+        dom = tall_passes[0]
+        unit_t = dom["bound"] == "tensor"
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"],
+                    "achieved": dom["achieved_TFLOPs"] if unit_t else dom["achieved_GBps"],
+                    "peak": pk["tf32_tflops"] if unit_t else pk["hbm_gbs"], "unit": "TFLOP/s" if unit_t else "GB/s",
+                    "frac": dom["frac"], "traffic": None, "avg_launch_ms": dom["avg_launch_ms"],
+                    "t_hbm_ms": dom["t_hbm_ms"], "t_tensor_ms": dom.get("t_tensor_ms"),
+                    "hbm_peak_GBps": pk["hbm_gbs"], "tf32_peak_TFLOPs": pk["tf32_tflops"],
+                    "note": ("frac = max(t_hbm, t_tensor) / t_kernel: the slower of the two MEASURED rooflines bounds the pass "
+                             f"(BASELINE.json north_star); hbm: {pk['source']}; tf32: {pk['tf32_source']}; algorithmic bytes = "
+                             "m*n*4 + m*l*4 (+ n*l*8), tensor flops = products per k-step x 2mnl"),
+                    "timed_launches": f"per-launch CUDA events on {res['sampled']} of the {args.steps} timed steps (every 4th)"}
+        try:   # DRAM bytes per launch of this kernel from a COMMITTED ncu --set full capture (same workload): a pointer,
+               # not a measurement of this run
+            for fn in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+                pth = os.path.join(ROOT, "profiles", fn)
+                if os.path.exists(pth):
+                    with open(pth) as f:
+                        tr = json.load(f)
+                    val = tr.get(args.workload, {}).get(dom["kernel"])
+                    if val is not None:
+                        roofline["traffic"] = val
+                        roofline["traffic_source"] = f"committed ncu capture ({tr.get('_source', fn)}), not measured in this run"
+                        break
         except Exception:
             pass
-    # the other tall pass, for the record: the two-product sketch is HBM bound (algorithmic bytes over the measured copy rate)
-    roofline_other = None
-    other = {"sketch_tc": "project_tc", "project_tc": "sketch_tc", "sketch": "project", "project": "sketch"}.get(dom)
-    if other in ksum and ksum[other]["calls"]:
-        o = ksum[other]
-        o_ms = o["ms"] / o["calls"]
-        o_gbs = o["bytes"] / o["calls"] / (o_ms / 1e3) / 1e9
-        roofline_other = {"kernel": other, "bound": "hbm", "achieved": o_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                          "frac": o_gbs / pk["hbm_gbs"], "avg_launch_ms": o_ms}
-        if args.precision == "tf32x3":
-            npo = 2.0 if (other == "sketch_tc" and args.tc_split == "onchip") else 3.0
-            roofline_other["tensor_frac"] = npo * o["flops"] / o["calls"] / (o_ms / 1e3) / 1e12 / (pk["bf16_tflops"] / 2.0)
-            if roofline_other["tensor_frac"] > roofline_other["frac"]:
-                roofline_other.update(bound="tensor", achieved=roofline_other["tensor_frac"] * pk["bf16_tflops"] / 2.0,
-                                      peak=pk["bf16_tflops"] / 2.0, unit="TFLOP/s", frac=roofline_other["tensor_frac"])
-    kernels = {n: {"calls_per_step": v["calls"] / len(sampled), "ms_per_step": v["ms"] / len(sampled)} for n, v in ksum.items()}
-    if roofline is not None:
-        roofline["timed_launches"] = f"per-launch CUDA events on {len(sampled)} of the {args.steps} timed steps (every 4th)"
+    kernels = {n: {"calls_per_step": v["calls"] / res["sampled"], "ms_per_step": v["ms"] / res["sampled"]}
+               for n, v in ksum.items()}
 
-    # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------
-    cpu = None
+    del field
+    torch.cuda.empty_cache()
+
+    # ---------------- north-star leg: BASELINE configs[2] (c3: 40 491 360 x 1460, k = 100, n_iter = 7) ----------------
+    # N >= 4: the WHOLE matrix, row-sharded (strong) over the N ranks - the north-star number.  N < 4: it does not fit
+    # (236.5 GB of X + the native arrays), so one rank's 1/8 share is timed instead (what each rank of the 8-GPU run
+    # executes, minus the all-reduces) and labelled as such.
+    north = None
+    if not args.no_north_star and args.workload == "c2" and not args.rows:
+        M3, T3 = 3 * 13 * 721 * 1440, 1460
+        if world >= 4:
+            r0, r1 = shard_rows(M3, world, rank)
+            label = f"c3 WHOLE: {M3} x {T3} f32 (236.5 GB) row-sharded over {world} GPUs (strong), randomized k=100, n_iter=7"
+            mg, ro = M3, r0
+        else:
+            r0, r1 = 0, M3 // 8
+            label = (f"c3 SHARD ONLY: 1/8 of the rows ({r1} x {T3} f32, 29.6 GB) on each of {world} GPU(s) - the whole matrix "
+                     "needs >= 4 GPUs; this is one rank's share of the 8-GPU run, not the north-star number")
+            mg, ro = r1 * world, rank * r1
+        f3 = synthetic_field(T3, r1 - r0, device=device, seed=2000 + rank)
+        r3 = time_workload(f3, mg, ro, args.north_star_steps, 3, args.precision, False)
+        tot_bytes = float(M3 if world >= 4 else (r1 - r0) * world) * T3 * 4
+        p3 = pass_rooflines(r3["ksum"], pk, args.precision, args.tc_split)
+        north = {"workload": label, "whole_matrix": world >= 4, "ms_per_step": r3["ms"],
+                 "GBps": tot_bytes / 1e9 / (r3["ms"] / 1e3), "steps": args.north_star_steps, "warmup": 3,
+                 "rows_this_rank": r1 - r0, "n_iter": n_iter_auto(mg, T3, k), "sigma_1": r3["sigma_1"],
+                 "passes": [{x: e[x] for x in ("kernel", "calls", "avg_launch_ms", "achieved_GBps", "hbm_frac", "bound", "frac")
+                             if x in e} | ({"tensor_frac": e["tensor_frac"], "achieved_TFLOPs": e["achieved_TFLOPs"]}
+                                           if "tensor_frac" in e else {}) for e in p3],
+                 "min_tall_pass_frac": min((e["frac"] for e in p3 if e["kernel"] in TALL), default=None),
+                 "target": ">= 0.60 of the slower of the HBM and tensor rooflines per pass (BASELINE.json north_star)"}
+        del f3, r3
+        torch.cuda.empty_cache()
+
+    # ---------------- CPU baseline + parity IN THE SAME RUN (rank 0, N = 1) ----------------
+    # The same <= 262 144-row sample of the workload goes through the reference's own calls on the host cores
+    # (cpu_baseline, timed) and through the CUDA path (parity: BASELINE.md section 5).
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.compare import recon_rel_err, sigma_rel_err, vector_angles
+
         threads = len(os.sched_getaffinity(0))
+        pool = set_blas_threads(threads)
         rows = args.cpu_rows or min(S, 262144)
-        dt, nbytes, _ = cpu_reference_run(rows, T, k, seed=0, threads=threads)
+        fs = synthetic_field(T, rows, device=device, seed=77)
+        fs_h = fs.cpu().numpy()
+        dt, nbytes, Xs, (U0, s0, V0) = cpu_reference_run(fs_h, k, seed=1)
         cpu = {"value": nbytes / 1e9 / dt, "unit": "GB/s", "cores": threads, "kind": "reference",
-               "sample": f"sklearn randomized_svd + NumPy build on {rows} of {S} rows x {T} f32 ({dt:.2f} s, single run)"}
+               "sample": f"sklearn randomized_svd + NumPy build on {rows} of {S} rows x {T} f32 ({dt:.2f} s, single cold run; "
+                         "the --impl reference arm reports a warm mean over its steps)",
+               "threadpool_info": pool}
+        built = build_matrix_device(ops, [fs], mean_center=True, scale=False)
+        Ug, sg, Vg = svd_device(ops, built.X, svd_type="randomized", n_components=k, seed=1, precision=args.precision)
+        Ug, sg, Vg = Ug.cpu().numpy(), sg.cpu().numpy(), Vg.cpu().numpy()
+        ang = vector_angles(Ug, U0)
+        ref_rec = recon_rel_err(Xs, U0, s0, V0)
+        parity = {"sample_rows": rows, "against": "the reference's own float32 call on the same sample (sklearn randomized_svd, "
+                                                 "np.random.seed(1)), era5_svd.py:258",
+                  "sigma_rel_err": sigma_rel_err(sg, s0), "max_angle_rad_first50": float(ang[:50].max()),
+                  "max_angle_rad": float(ang.max()), "recon_ratio": recon_rel_err(Xs, Ug, sg, Vg) / ref_rec,
+                  "matrix_max_abs_diff": float(np.max(np.abs(built.X.cpu().numpy() - Xs))),
+                  "tolerance": "sigma 1e-4 (FP32-split mode), recon within 1 %"}
+        del fs, built
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "native" else "tf32x3", "data": "synthetic",
+            "dtype": {"native": "f32", "tf32x3": "tf32x3", "tf32mix": "tf32x3+tf32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "rows_per_rank": S, "snapshots": T, "k": k, "l": k + 10,
                        "n_iter": q, "mean_center": True, "precision": args.precision, "tc_split": args.tc_split,
+                       "precision_note": ("tf32mix: 3xTF32 (fp32-level) products for the last power iteration and the final range / "
+                                          "projection passes, single-product TF32 for the earlier power iterations"
+                                          if args.precision == "tf32mix" else None),
                        "l2": "inputs larger than L2 (matrix shard >= 3 GB vs 126 MB)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "roofline_other_pass": roofline_other, "cpu_baseline": cpu,
+            "roofline_passes": passes, "peaks_measured": {"hbm_gbs": pk["hbm_gbs"], "hbm_source": pk["source"], **probe},
+            "north_star": north, "cpu_baseline": cpu, "parity": parity,
             "kernels": kernels, "sigma_1": s_first,
         }
         print(json.dumps(out))

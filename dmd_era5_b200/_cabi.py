@@ -23,8 +23,11 @@ PROTOTYPES = {
     "era5svd_version": (_int, []),
     "era5svd_last_error": (C.c_char_p, []),
     "era5svd_launch_count": (C.c_ulonglong, []),
+    "era5svd_probe_tf32_tflops": (_int, [_int, _int, _dbl, _vp]),
+    "era5svd_probe_dmma_tflops": (_int, [_dbl, _vp]),
     "era5svd_build_rows": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _vp, _vp, C.c_uint, _vp, _vp]),
     "era5svd_build_rows_split": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, C.c_uint, _vp, _vp]),
+    "era5svd_check_finite": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _vp]),
     "era5svd_sketch": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int, _vp]),
     "era5svd_project_workspace_bytes": (_sz, [_int, _i64, _i64, _i64, _int]),
     "era5svd_project": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int, _int, _vp, _sz, _vp]),
@@ -32,6 +35,8 @@ PROTOTYPES = {
     "era5svd_sketch_tf32x3_workspace_bytes": (_sz, [_i64, _i64]),
     "era5svd_sketch_tf32x3": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "era5svd_sketch_tf32x2": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "era5svd_sketch_tf32x1": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _sz, _vp]),
+    "era5svd_project_tf32x1": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int, _vp, _sz, _vp]),
     "era5svd_round_tf32_f64": (_int, [_vp, _i64, _i64, _i64, _vp]),
     "era5svd_project_tf32x3_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "era5svd_project_tf32x3": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _int, _vp, _sz, _vp]),

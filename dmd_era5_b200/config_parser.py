@@ -5,8 +5,10 @@ same literal types, same derived names and paths, same error texts the reference
 (tests/test_03_era5_svd.py:104-150).  Table-driven restatement, not a copy.
 
 Opt-in extension keys (absent = reference behaviour; the reference's parser ignores unknown keys):
-    precision ("native" | "tf32x3"), random_seed (int | None), area_weighting (bool), device (str),
-    matrix_dtype ("float32" | "float64": the build kernel casts while it stacks; north_star "float cast").
+    precision ("auto" | "native" | "tf32x3" | "tf32mix"), random_seed (int | None), area_weighting (bool), device (str),
+    matrix_dtype ("float32" | "float64": the build kernel casts while it stacks; north_star "float cast"),
+    n_gpus (int >= 1: row-shard the stage over that many GPUs of this node, stage.main).
+Their values are validated here with the same error style as the reference's own fields.
 """
 from __future__ import annotations
 
@@ -27,7 +29,22 @@ REQUIRED = {
 }
 _DELTA_UNITS = {"h": lambda x: timedelta(hours=x), "d": lambda x: timedelta(days=x), "w": lambda x: timedelta(weeks=x),
                 "m": lambda x: timedelta(days=x * 365 // 12), "y": lambda x: timedelta(days=x * 365)}
-EXTENSION_KEYS = ("precision", "random_seed", "area_weighting", "device", "matrix_dtype")
+EXTENSION_KEYS = ("precision", "random_seed", "area_weighting", "device", "matrix_dtype", "n_gpus")
+PRECISION_VALUES = ("auto", "native", "fp64", "fp32", "tf32x3", "tf32mix")
+
+
+def _check_extension(key: str, val, logger=None):
+    """Validate an opt-in key (a bad value used to surface as a bare KeyError deep inside the driver)."""
+    if key == "precision" and val not in PRECISION_VALUES:
+        _fail(f"precision {val} is not supported. Supported values are {', '.join(PRECISION_VALUES)}.", logger)
+    if key == "matrix_dtype" and val not in (None, "float32", "float64"):
+        _fail(f"matrix_dtype {val} is not supported. Supported values are float32, float64.", logger)
+    if key == "random_seed" and not (val is None or (isinstance(val, int) and not isinstance(val, bool) and val >= 0)):
+        _fail("random_seed must be None or a non-negative integer.", logger)
+    if key == "area_weighting" and not isinstance(val, bool):
+        _fail("area_weighting must be a boolean.", logger)
+    if key == "n_gpus" and not (isinstance(val, int) and not isinstance(val, bool) and val >= 1):
+        _fail("n_gpus must be an integer greater than 0.", logger)
 
 
 def project_root() -> str:
@@ -146,5 +163,6 @@ def config_parser(config: dict, section: str, logger=None) -> dict:
         _typed(config, parsed, "save_data_matrix", bool, "save_data_matrix", "save_data_matrix must be a boolean value.", logger)
         for key in EXTENSION_KEYS:
             if key in config:
+                _check_extension(key, config[key], logger)
                 parsed[key] = config[key]
     return parsed

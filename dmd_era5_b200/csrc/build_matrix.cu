@@ -93,7 +93,6 @@ transpose_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t 
     Ts v = Ts(0);
     if (t < T && p < P) {
       v = src[t * src_ld + p];
-      if (check_finite && !isfinite((double)v)) bad = 1;
     }
     tile[ty + 8 * i][tx] = v;
   }
@@ -106,6 +105,9 @@ transpose_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_t 
       Tx v = mean ? centre<Ts, Tx>(raw, mean[p]) : (Tx)raw;
       if (stdv) v = v / stdv[p];
       if (weights) v = v * weights[p];
+      // the flag reports what is WRITTEN: a NaN / Inf source value, but also 0 / 0 from a time-constant point under
+      // scale=True (std = 0; the reference then raises "Input contains NaN" in sklearn's check_array)
+      if (check_finite && !isfinite((double)v)) bad = 1;
       if (X) X[p * ldx + t] = v;
       if (Xhi) {   // tf32 hi / lo images for the tensor-core passes (float32 matrices only)
         const float h = tc::tf32_hi((float)v);
@@ -154,10 +156,7 @@ fused_build_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_
 #pragma unroll
     for (int i = 0; i < FB_UNROLL; ++i) {
       const int64_t t = tb + (int64_t)i * nwarps;
-      if (t < T) {
-        if (check_finite && !isfinite((double)v[i])) bad = 1;
-        tile[t * LD + lane] = v[i];
-      }
+      if (t < T) tile[t * LD + lane] = v[i];
     }
   }
   __syncthreads();
@@ -204,6 +203,7 @@ fused_build_kernel(const Ts* __restrict__ src, int64_t T, int64_t src_ld, int64_
       Tx v = center ? centre<Ts, Tx>(raw, mean_x) : (Tx)raw;
       if (do_scale) v = v / std_x;
       if (weights) v = v * w;
+      if (check_finite && !isfinite((double)v)) bad = 1;        // the value written (see transpose_kernel)
       if (X) X[gp * ldx + t] = v;
       if (Xhi) {
         const float h = tc::tf32_hi((float)v);
@@ -303,7 +303,6 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (v[e] == v[e]) { s[e] += (double)v[e]; ++cnt[e]; }
-        if (check_finite && valid[e] && !isfinite(v[e])) bad = 1;
       }
     }
 #pragma unroll
@@ -374,11 +373,11 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
     const float raw[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (!center && check_finite && valid[e] && !isfinite(raw[e])) bad = 1;
       if (valid[e]) {
         Tx v = center ? centre<float, Tx>(raw[e], mean_x[e]) : (Tx)raw[e];
         if (do_scale) v = v / std_x[e];
         if (weights) v = v * w4[e];
+        if (check_finite && !isfinite((double)v)) bad = 1;      // the value written (see transpose_kernel)
         const int64_t off = (gp0 + e) * ldx + t;
         if (X) X[off] = v;
         if (Xhi) {
@@ -485,7 +484,37 @@ int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void*
   return check_launch("transpose_kernel");
 }
 
+// finiteness pass over a matrix that did not come through the build kernel (svd_on_era5's array input): one CTA per
+// group of rows, lanes along the row (coalesced), 16-byte loads when the row pitch allows
+template <typename T>
+__global__ void __launch_bounds__(256)
+check_finite_kernel(const T* __restrict__ X, int64_t rows, int64_t cols, int64_t ld, int* __restrict__ flag) {
+  int bad = 0;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const T* row = X + r * ld;
+    for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+      const T v = row[c];
+      if (!(v - v == T(0))) bad = 1;           // NaN and +-Inf both fail
+    }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(flag, 1);
+}
+
 }  // namespace era5svd
+
+extern "C" int era5svd_check_finite(const void* X, int dtype, int64_t rows, int64_t cols, int64_t ld, int* flag,
+                                    void* stream) {
+  using namespace era5svd;
+  ERA5SVD_REQUIRE(X && flag, "check_finite: null pointer");
+  ERA5SVD_REQUIRE(valid_dtype(dtype), "check_finite: bad dtype");
+  ERA5SVD_REQUIRE(rows > 0 && cols > 0 && ld >= cols, "check_finite: bad shape");
+  int64_t blocks = rows < (int64_t)sm_count() * 16 ? rows : (int64_t)sm_count() * 16;
+  if (dtype == ERA5SVD_F32)
+    check_finite_kernel<float><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const float*)X, rows, cols, ld, flag);
+  else
+    check_finite_kernel<double><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>((const double*)X, rows, cols, ld, flag);
+  return check_launch("check_finite_kernel");
+}
 
 extern "C" int era5svd_build_rows(const void* src, int dtype_src, int64_t T, int64_t src_ld,
                                   int64_t P, void* X, int dtype_x, int64_t ldx, void* mean_out,

@@ -150,6 +150,8 @@ struct SketchParams {
   int num_k;          // ceil(n / 32)
   int npad;           // UMMA N (multiple of 16, <= 256)
   int stages;
+  int nprod;          // 3: hi/lo images of both operands (3xTF32); 1: ONE product on the raw float32 X tile (the tensor
+                      //    core truncates it to tf32) and the tf32-exact Om^T image - the low-precision power iterations
   float* Y;           // nullable
   float* Yhi;         // nullable
   float* Ylo;         // nullable
@@ -167,7 +169,9 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform
   const uint32_t a_bytes = BM * BK * 4;                 // 16 KB
   const uint32_t b_bytes = (uint32_t)p.npad * BK * 4;   // npad x 128 B
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const bool one = p.nprod == 1;                        // kernel parameter: uniform
+  const uint32_t stage_bytes = one ? a_bytes + b_bytes : 2 * a_bytes + 2 * b_bytes;
+  const uint32_t off_bhi = one ? a_bytes : 2 * a_bytes; // stage layout: A_hi [A_lo] B_hi [B_lo]
   // barriers + tmem pointer live after the stages
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -210,9 +214,11 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
           const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
           mbar_arrive_expect_tx(full_bar(s), stage_bytes);
           tma_load_2d(st, &tm_xhi, kc * BK, row0, full_bar(s));
-          tma_load_2d(st + a_bytes, &tm_xlo, kc * BK, row0, full_bar(s));
-          tma_load_2d(st + 2 * a_bytes, &tm_ohi, kc * BK, 0, full_bar(s));
-          tma_load_2d(st + 2 * a_bytes + b_bytes, &tm_olo, kc * BK, 0, full_bar(s));
+          tma_load_2d(st + off_bhi, &tm_ohi, kc * BK, 0, full_bar(s));
+          if (!one) {
+            tma_load_2d(st + a_bytes, &tm_xlo, kc * BK, row0, full_bar(s));
+            tma_load_2d(st + off_bhi + b_bytes, &tm_olo, kc * BK, 0, full_bar(s));
+          }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -235,12 +241,16 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
             const uint32_t koff = kk * UMMA_K * 4;   // 32 bytes per k-step inside the swizzle row
             const uint64_t a_hi = make_smem_desc(st + koff, 16, SWIZZLE_ATOM);
-            const uint64_t a_lo = make_smem_desc(st + a_bytes + koff, 16, SWIZZLE_ATOM);
-            const uint64_t b_hi = make_smem_desc(st + 2 * a_bytes + koff, 16, SWIZZLE_ATOM);
-            const uint64_t b_lo = make_smem_desc(st + 2 * a_bytes + b_bytes + koff, 16, SWIZZLE_ATOM);
-            umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | kk) != 0);   // small terms first
-            umma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1);
-            umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1);
+            const uint64_t b_hi = make_smem_desc(st + off_bhi + koff, 16, SWIZZLE_ATOM);
+            if (one) {
+              umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, (kc | kk) != 0);
+            } else {
+              const uint64_t a_lo = make_smem_desc(st + a_bytes + koff, 16, SWIZZLE_ATOM);
+              const uint64_t b_lo = make_smem_desc(st + off_bhi + b_bytes + koff, 16, SWIZZLE_ATOM);
+              umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | kk) != 0);   // small terms first
+              umma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1);
+              umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1);
+            }
           }
           umma_commit(empty_bar(s));               // smem stage free once these MMAs retire
           if (kc == p.num_k - 1) umma_commit(tfull_bar(buf));
@@ -300,6 +310,7 @@ struct ProjectParams {
   int ncc;            // 32-wide time chunks per CTA
   int nmma;           // UMMA pieces per k-step (N = ncc*32 / nmma each)
   int stages;
+  int nprod;          // 3: hi/lo images of X and Y; 1: one product on the raw float32 tiles (truncated by the tensor core)
   int xshift;         // the window starts xshift (0..3) columns right of the 16-byte aligned map origin
   int64_t rows_per_split;
   float* part;        // [splits][n][l]
@@ -317,7 +328,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   const uint32_t box_bytes = (uint32_t)p.ks * BK * 4;       // one [ks rows x 32] box (2 KB for ks = 16)
   const uint32_t y_bytes = 4 * box_bytes;                   // 128 sketch columns
   const uint32_t x_bytes = (uint32_t)p.ncc * box_bytes;
-  const uint32_t stage_bytes = 2 * y_bytes + 2 * x_bytes;
+  const bool one = p.nprod == 1;                            // kernel parameter: uniform
+  const uint32_t stage_bytes = one ? y_bytes + x_bytes : 2 * y_bytes + 2 * x_bytes;
+  const uint32_t off_xhi = one ? y_bytes : 2 * y_bytes;     // stage layout: Y_hi [Y_lo] X_hi [X_lo]
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -360,12 +373,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         mbar_arrive_expect_tx(full_bar(s), stage_bytes);
         for (int c = 0; c < 4; ++c) {
           tma_load_2d(st + c * box_bytes, &tm_yhi, c * BK, row0, full_bar(s));
-          tma_load_2d(st + y_bytes + c * box_bytes, &tm_ylo, c * BK, row0, full_bar(s));
+          if (!one) tma_load_2d(st + y_bytes + c * box_bytes, &tm_ylo, c * BK, row0, full_bar(s));
         }
         for (int c = 0; c < p.ncc; ++c) {
           const int32_t tc0 = (int32_t)(t0 + (int64_t)c * BK);
-          tma_load_2d(st + 2 * y_bytes + c * box_bytes, &tm_xhi, tc0, row0, full_bar(s));
-          tma_load_2d(st + 2 * y_bytes + x_bytes + c * box_bytes, &tm_xlo, tc0, row0, full_bar(s));
+          tma_load_2d(st + off_xhi + c * box_bytes, &tm_xhi, tc0, row0, full_bar(s));
+          if (!one) tma_load_2d(st + off_xhi + x_bytes + c * box_bytes, &tm_xlo, tc0, row0, full_bar(s));
         }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
@@ -385,12 +398,16 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
           const uint64_t a_lo = make_smem_desc(st + y_bytes + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
           for (int pc = 0; pc < p.nmma; ++pc) {
             const uint32_t xoff = (uint32_t)pc * (npiece / BK) * box_bytes + koff;
-            const uint64_t b_hi = make_smem_desc(st + 2 * y_bytes + xoff, box_bytes, 512, LAYOUT_SW128_BASE32B);
-            const uint64_t b_lo = make_smem_desc(st + 2 * y_bytes + x_bytes + xoff, box_bytes, 512, LAYOUT_SW128_BASE32B);
+            const uint64_t b_hi = make_smem_desc(st + off_xhi + xoff, box_bytes, 512, LAYOUT_SW128_BASE32B);
             const uint32_t d_tmem = tmem_base + (uint32_t)pc * npiece;
-            umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
-            umma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1);
-            umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1);
+            if (one) {
+              umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, (kc | ks) != 0);
+            } else {
+              const uint64_t b_lo = make_smem_desc(st + off_xhi + x_bytes + xoff, box_bytes, 512, LAYOUT_SW128_BASE32B);
+              umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
+              umma_tf32_ss(d_tmem, a_hi, b_lo, idesc, 1);
+              umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, 1);
+            }
           }
         }
         umma_commit(empty_bar(s));
@@ -445,7 +462,10 @@ struct PjPlan {
   size_t bytes;
 };
 
-static PjPlan pj_plan(int64_t m, int64_t n, int64_t l) {
+// max_rows: rows summed in one TMEM accumulator before the partial tile goes to float64.  The tensor core's fp32
+// accumulate truncates; for the 3xTF32 passes that bias must stay below the 1e-6 level (4096 rows), the single-product
+// power-iteration passes carry 2^-11 per operand anyway (16384 rows: a quarter of the partial-tile traffic).
+static PjPlan pj_plan(int64_t m, int64_t n, int64_t l, int64_t max_rows = 4096) {
   PjPlan pl;
   pl.nchunks = (int)ceil_div(n, 512);
   pl.ncc = (int)ceil_div(ceil_div(n, pl.nchunks), 32);          // 32-wide chunks per CTA (<= 16)
@@ -457,10 +477,11 @@ static PjPlan pj_plan(int64_t m, int64_t n, int64_t l) {
   }
   // rows per split <= 4096 (bounds the fp32 running sums), CTA count a multiple of the SM count
   const int sms = sm_count();
-  int64_t splits = ceil_div(m, 4096);
+  int64_t splits = ceil_div(m, max_rows);
   int64_t ctas = splits * pl.nchunks;
   ctas = ceil_div(ctas, sms) * sms;
-  splits = ceil_div(ctas, pl.nchunks);
+  splits = max_rows > 4096 ? ctas / pl.nchunks : ceil_div(ctas, pl.nchunks);   // x1: never more CTAs than whole waves
+  if (splits < 1) splits = 1;
   const int64_t cap = ((int64_t)512 << 20) / (n * l * 4 > 0 ? n * l * 4 : 1);
   if (splits > cap) splits = cap > 0 ? cap : 1;
   if (splits > 65535) splits = 65535;
@@ -496,7 +517,8 @@ size_t era5svd_sketch_tf32x3_workspace_bytes(int64_t n, int64_t l) {
 
 static int sketch_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
                            const double* Om, int64_t l, int64_t ldo, float* Y, float* Yhi, float* Ylo,
-                           int64_t ldy, void* workspace, size_t workspace_bytes, void* stream, int om_tf32) {
+                           int64_t ldy, void* workspace, size_t workspace_bytes, void* stream, int om_tf32,
+                           int nprod = 3) {
   using namespace era5svd;
   ERA5SVD_REQUIRE(Xhi && Om, "sketch_tf32x3: null pointer");
   ERA5SVD_REQUIRE(Y || Yhi, "sketch_tf32x3: no output requested");
@@ -518,9 +540,10 @@ static int sketch_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64
   }
   ERA5SVD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "sketch_tf32x3: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
-  if (!Xlo)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu), X read from HBM once
+  if (!Xlo && nprod != 1)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu), X read from HBM once
     return sketch_tf32x3_raw(Xhi, m, n, ldx, Om, l, ldo, Y, Yhi, Ylo, ldy, workspace, st, om_tf32);
   ERA5SVD_REQUIRE(!om_tf32, "sketch_tf32x2: needs the plain float32 matrix (Xlo == NULL, on-chip split)");
+  if (nprod == 1) Xlo = Xhi;   // single product: the raw tile is its own hi image (the tensor core truncates), no lo image
   CUtensorMap tm_xhi, tm_xlo, tm_ohi, tm_olo;
   int xs = 0, xs2 = 0, os = 0, os2 = 0, rc;
   if ((rc = tc::make_tmap(&tm_xhi, Xhi, n, m, ldx, tc::BK, tc::BM, &xs))) return rc;
@@ -541,12 +564,13 @@ static int sketch_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64
   p.num_tiles = ceil_div(m, tc::BM);
   p.num_k = (int)ceil_div(kspan, tc::BK);
   p.npad = npad;
+  p.nprod = nprod;
   p.Y = Y; p.Yhi = Yhi; p.Ylo = Ylo;
   p.ldy = ldy;
-  const size_t stage_bytes = 2 * (size_t)tc::BM * tc::BK * 4 + 2 * (size_t)npad * tc::BK * 4;
+  const size_t stage_bytes = (nprod == 1 ? 1 : 2) * ((size_t)tc::BM * tc::BK * 4 + (size_t)npad * tc::BK * 4);
   const size_t budget = 227 * 1024 - 1024 - 256;
   p.stages = (int)(budget / stage_bytes);
-  if (p.stages > 6) p.stages = 6;
+  if (p.stages > (nprod == 1 ? 7 : 6)) p.stages = nprod == 1 ? 7 : 6;
   ERA5SVD_REQUIRE(p.stages >= 2, "sketch_tf32x3: not enough shared memory for two stages");
   const size_t smem = p.stages * stage_bytes + 1024 + 256;
   ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -587,17 +611,25 @@ int era5svd_round_tf32_f64(double* A, int64_t rows, int64_t cols, int64_t lda, v
   return check_launch("round_tf32_f64_kernel");
 }
 
+int era5svd_sketch_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
+                          int64_t ldo, float* Y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream) {
+  return sketch_tf32_impl(X, nullptr, m, n, ldx, Om, l, ldo, Y, nullptr, nullptr, ldy, workspace, workspace_bytes,
+                          stream, 0, 1);
+}
+
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l) {
   using namespace era5svd;
   if (m <= 0 || n <= 0 || l <= 0) return 0;
-  const size_t a = pj_plan(m, n + 3, l).bytes, b = project_tf32x3_raw_workspace_bytes(m, n, l);
-  return a > b ? a : b;
+  size_t a = pj_plan(m, n + 3, l).bytes;
+  const size_t b = project_tf32x3_raw_workspace_bytes(m, n, l), c = pj_plan(m, n + 3, l, 16384).bytes;
+  if (b > a) a = b;
+  return c > a ? c : a;
 }
 
-int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
-                           const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,
-                           int64_t ldz, int accumulate, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+static int project_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                             const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,
+                             int64_t ldz, int accumulate, void* workspace, size_t workspace_bytes,
+                             void* stream, int nprod) {
   using namespace era5svd;
   ERA5SVD_REQUIRE(Xhi && Yhi && Z, "project_tf32x3: null pointer");
   ERA5SVD_REQUIRE(Ylo || !Xlo, "project_tf32x3: a plain Y (Ylo == NULL) needs the on-chip split path (Xlo == NULL too)");
@@ -607,11 +639,12 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
     return ERA5SVD_ERR_UNSUPPORTED;
   }
   ERA5SVD_REQUIRE(m < ((int64_t)1 << 31), "project_tf32x3: m too large for TMA coordinates");
-  if (!Xlo)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu)
+  if (!Xlo && nprod != 1)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu)
     return project_tf32x3_raw(Xhi, m, n, ldx, Yhi, Ylo, l, ldy, Z, ldz, accumulate, workspace, workspace_bytes,
                               as_stream(stream));
+  if (nprod == 1) { Xlo = Xhi; Ylo = Yhi; }   // single product on the raw tiles: no lo images are loaded
   // plan for the widest window (xshift <= 3) so that the workspace query needs no pointer
-  const PjPlan pl = pj_plan(m, n + 3, l);
+  const PjPlan pl = pj_plan(m, n + 3, l, nprod == 1 ? 16384 : 4096);
   if (!workspace || workspace_bytes < pl.bytes) {
     set_error("project_tf32x3: workspace too small (%zu < %zu)", workspace_bytes, pl.bytes);
     return ERA5SVD_ERR_WORKSPACE;
@@ -632,11 +665,12 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
   p.ks = KS;
   p.ncc = pl.ncc;
   p.nmma = pl.nmma;
+  p.nprod = nprod;
   p.xshift = xs;
   p.rows_per_split = pl.rows_per_split;
   p.part = (float*)workspace;
   const size_t box = (size_t)KS * tc::BK * 4;
-  const size_t stage_bytes = 2 * 4 * box + 2 * (size_t)pl.ncc * box;
+  const size_t stage_bytes = (nprod == 1 ? 1 : 2) * (4 * box + (size_t)pl.ncc * box);
   const size_t budget = 227 * 1024 - 1024 - 256;
   p.stages = (int)(budget / stage_bytes);
   if (p.stages > 8) p.stages = 8;
@@ -648,6 +682,21 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
   if ((rc = check_launch("project_tc_kernel"))) return rc;
   launch_reduce_partials_f32(p.part, pl.splits, n, l, l, Z, ldz, accumulate, st);
   return check_launch("reduce_partials_kernel");
+}
+
+int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
+                           const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,
+                           int64_t ldz, int accumulate, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  return project_tf32_impl(Xhi, Xlo, m, n, ldx, Yhi, Ylo, l, ldy, Z, ldz, accumulate, workspace, workspace_bytes,
+                           stream, 3);
+}
+
+int era5svd_project_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,
+                           int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return project_tf32_impl(X, nullptr, m, n, ldx, Y, nullptr, l, ldy, Z, ldz, accumulate, workspace, workspace_bytes,
+                           stream, 1);
 }
 
 }  // extern "C"

@@ -77,6 +77,8 @@ class CudaOps:
         if self.device.type != "cuda":
             raise RuntimeError("CudaOps needs a CUDA device")
         self.lib = _cabi.lib()
+        self._index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self._index)
         self._ws: dict[str, torch.Tensor] = {}
         self.timer: KernelTimer | None = None   # bench.py attaches one to time kernels with CUDA events
 
@@ -98,6 +100,10 @@ class CudaOps:
         return buf
 
     def _stream(self) -> int:
+        # the C ABI launches on the calling thread's CURRENT device: a foreign current device would pair this
+        # device's stream and pointers with another context - make it ours before handing the stream out
+        if torch.cuda.current_device() != self._index:
+            torch.cuda.set_device(self._index)
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # -- (a) matrix build --------------------------------------------------------------------
@@ -138,6 +144,14 @@ class CudaOps:
                                                 _vec(nonfinite_flag, "flag"), self._stream()), "era5svd_build_rows_split")
         if end is not None:
             end.record()
+
+    def check_finite(self, X: torch.Tensor) -> torch.Tensor:
+        """Device int32 flag (1,) = 1 if X holds a NaN / Inf (sklearn check_array, extmath.py:546); asynchronous."""
+        flag = self.zeros((1,), torch.int32)
+        xp, xld = _mat(X, "X")
+        check(self.lib.era5svd_check_finite(xp, _dt(X), X.shape[0], X.shape[1], xld, flag.data_ptr(), self._stream()),
+              "era5svd_check_finite")
+        return flag
 
     # -- (b) tall passes ---------------------------------------------------------------------
     def sketch(self, X: torch.Tensor, Om: torch.Tensor, Y: torch.Tensor | None = None,
@@ -245,6 +259,38 @@ class CudaOps:
                                                  self._stream()), "era5svd_sketch_tf32x3")
         if end is not None:
             end.record()
+
+    def sketch_tf32x1(self, X: torch.Tensor, Om: torch.Tensor, Y: torch.Tensor) -> None:
+        """Y (plain float32, pitch tf32_ldy(l)) = X @ tf32(Om): ONE tensor-core product per k-step on the raw float32
+        tiles (era5svd_sketch_tf32x1) - the early power iterations."""
+        m, n = X.shape
+        l = Om.shape[1]
+        if Om.dtype != torch.float64 or Om.shape[0] != n:
+            raise ValueError("sketch_tf32x1: Om must be float64 (n, l)")
+        xp, xld = _mat(X, "X"); op, old = _mat(Om, "Om"); yp, yld = _mat(Y, "Y")
+        ws = self._workspace("sketch_tc", int(self.lib.era5svd_sketch_tf32x3_workspace_bytes(n, l)))
+        end = self.timer.start("sketch_x1", bytes=4.0 * (m * n + m * l + n * l), flops=2.0 * m * n * l) if self.timer else None
+        check(self.lib.era5svd_sketch_tf32x1(xp, m, n, xld, op, l, old, yp, yld, ws.data_ptr(), ws.numel(), self._stream()),
+              "era5svd_sketch_tf32x1")
+        if end is not None:
+            end.record()
+
+    def project_tf32x1(self, X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor | None = None,
+                       accumulate: bool = False) -> torch.Tensor:
+        """Z (float64, n x l) (+)= X^T Y, one tensor-core product per k-step (era5svd_project_tf32x1)."""
+        m, n = X.shape
+        l = Y.shape[1]
+        if Z is None:
+            Z = self.empty((n, l), torch.float64)
+            accumulate = False
+        xp, xld = _mat(X, "X"); yp, yld = _mat(Y, "Y"); zp, zld = _mat(Z, "Z")
+        ws = self._workspace("project", int(self.lib.era5svd_project_tf32x3_workspace_bytes(m, n, l)))
+        end = self.timer.start("project_x1", bytes=4.0 * (m * n + m * l) + 8.0 * n * l, flops=2.0 * m * n * l) if self.timer else None
+        check(self.lib.era5svd_project_tf32x1(xp, m, n, xld, yp, l, yld, zp, zld, int(accumulate), ws.data_ptr(),
+                                              ws.numel(), self._stream()), "era5svd_project_tf32x1")
+        if end is not None:
+            end.record()
+        return Z
 
     def project_tf32x3(self, Xhi: torch.Tensor, Xlo: torch.Tensor, Yhi: torch.Tensor, Ylo: torch.Tensor,
                        Z: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:

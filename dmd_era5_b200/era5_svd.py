@@ -83,9 +83,14 @@ def svd_on_era5(da, parsed_config: dict) -> tuple[np.ndarray, np.ndarray, np.nda
     log_and_print(logger, f"Performing {label} SVD...")
     with torch.cuda.device(ops.device):
         Xd = host_to_device_matrix(ops, X)
+        nonfinite = ops.check_finite(Xd)        # asynchronous; read after the SVD has been queued
         U, s, V = svd_device(ops, Xd, svd_type=svd_type, n_components=n_components,
                              seed=parsed_config.get("random_seed"),
                              precision=parsed_config.get("precision", "auto"))
+        if int(nonfinite.item()):
+            # sklearn check_array (extmath.py:546) / LAPACK on the reference side; main() wraps it as
+            # "Error in the SVD on ERA5 process: ..." (era5_svd.py:426-429)
+            raise ValueError("Input contains NaN or infinity.")
         out_dtype = Xd.dtype
         U_h = U.to(out_dtype).cpu().numpy()
         s_h = s.to(out_dtype).cpu().numpy()

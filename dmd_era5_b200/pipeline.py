@@ -106,17 +106,21 @@ def _omega_on_device(ops: CudaOps, n: int, k: int, seed: int | None, dtype: torc
 def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_components: int, delay: int = 1,
                seed: int | None = None, precision: str = "auto", comm=None, row_offset: int = 0,
                m0_global: int | None = None, n_iter: int | None = None, stats: dict | None = None,
-               split: tuple[torch.Tensor, torch.Tensor] | None = None):
+               split: tuple[torch.Tensor, torch.Tensor] | None = None, full_iters: int | None = None):
     """SVD of the (virtual) delay-embedded matrix whose base rows are X (device, tall dtype).
     ``split`` = (Xhi, Xlo) passes pre-split tf32 images (precision "tf32x3"); X may then be None.
     Dispatch and error text follow svd_on_era5 (era5_svd.py:247-262)."""
     ref = X if X is not None else split[0]
     n = ref.shape[1] - delay + 1
+    if precision != "auto" and precision not in PRECISIONS:
+        raise ValueError(f"precision {precision} is not supported. Supported values are auto, {', '.join(PRECISIONS)}.")
+    if precision in ("tf32x3", "tf32mix") and ref.dtype != torch.float32:
+        raise ValueError(f"precision {precision} needs a float32 snapshot matrix (got {ref.dtype}); use 'native' or 'auto'.")
     if precision == "auto":
         # float32 data: tensor-core 3xTF32 passes whenever the sketch / component count fits one MMA tile (<= 128);
         # float64 data (and anything wider): the native path (FP64 DMMA / FP32 FMA)
         width = min(int(n_components) + 10, n) if svd_type == "randomized" else min(int(n_components), n)
-        precision = "tf32x3" if (ref.dtype == torch.float32 and width <= 128) else "native"
+        precision = "tf32mix" if (ref.dtype == torch.float32 and width <= 128) else "native"
     if svd_type == "standard":
         if X is None:
             X = split[0] + split[1]
@@ -125,6 +129,6 @@ def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_compone
         omega0 = _omega_on_device(ops, n, n_components, seed, ref.dtype)
         return randomized_svd_device(ops, X, n_components, omega0, n_iter=n_iter, delay=delay,
                                      precision=PRECISIONS[precision], comm=comm, row_offset=row_offset,
-                                     m0_global=m0_global, stats=stats, split=split)
+                                     m0_global=m0_global, stats=stats, split=split, full_iters=full_iters)
     msg = f"SVD type {svd_type} is not supported."
     raise ValueError(msg)

@@ -38,7 +38,13 @@ import torch
 from ._cabi import PREC_NATIVE, PREC_TF32X3
 from .dist import LocalComm
 
-PRECISIONS = {"native": PREC_NATIVE, "fp64": PREC_NATIVE, "fp32": PREC_NATIVE, "tf32x3": PREC_TF32X3}
+# driver-level precision: the tensor-core path with the EARLY power iterations in single-product TF32 (the C ABI only
+# knows PREC_NATIVE / PREC_TF32X3; this value never crosses it)
+PREC_TF32MIX = 2
+PRECISIONS = {"native": PREC_NATIVE, "fp64": PREC_NATIVE, "fp32": PREC_NATIVE, "tf32x3": PREC_TF32X3,
+              "tf32mix": PREC_TF32MIX}
+# power iterations (counted from the end) that keep fp32-level 3xTF32 products under "tf32mix"
+MIX_FULL_ITERS = 1
 
 
 def n_iter_auto(m: int, n: int, k: int) -> int:
@@ -100,18 +106,26 @@ def _orth(ops, P: torch.Tensor, rel_tol: float, shifted: bool = False, passes: i
 def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0, *, n_iter: int | None = None,
                           delay: int = 1, precision: int = PREC_NATIVE, comm=None, row_offset: int = 0,
                           m0_global: int | None = None, m_global: int | None = None, stats: dict | None = None,
-                          split: tuple[torch.Tensor, torch.Tensor] | None = None):
+                          split: tuple[torch.Tensor, torch.Tensor] | None = None, full_iters: int | None = None):
     """Randomized SVD of the (row-sharded, optionally delay-embedded) snapshot matrix.
 
     X          : this rank's rows of the BASE matrix, (m0_local, T) tall-dtype device tensor
     omega0     : (n, l) test matrix (host ndarray or tensor), n = T - delay + 1
     row_offset : global index of this rank's first base row; m0_global: total base rows
     split      : (Xhi, Xlo) pre-split tf32 images of X for precision tf32x3 (X may then be None)
+    precision  : PREC_NATIVE | PREC_TF32X3 | PREC_TF32MIX.  "tf32mix": subspace iteration is self-correcting - an error
+                 made in iteration i is contracted by (sigma_{l+1} / sigma_j)^2 in every later one - so only the last
+                 ``full_iters`` (default 1) power iterations and the final range / projection passes, which fix sigma and
+                 the vectors, run with fp32-level 3xTF32 products; the earlier ones use ONE tf32 product per k-step on the
+                 raw float32 tiles (era5svd_sketch_tf32x1 / era5svd_project_tf32x1: pure TMA -> tcgen05, HBM bound).
     Returns (U_local (m0_local * delay, k) tall dtype, s (k,) float64, Vt (k, n) float64).
     Rows of U_local are ordered block-major: block j holds rows [j * m0_local, (j + 1) * m0_local),
     i.e. global rows j * m0_global + row_offset + r.
     """
     comm = comm or LocalComm()
+    mixed = precision == PREC_TF32MIX and split is None
+    if precision == PREC_TF32MIX:
+        precision = PREC_TF32X3
     if X is None:
         if split is None or precision != PREC_TF32X3:
             raise ValueError("X may only be omitted when pre-split images are given with precision tf32x3")
@@ -166,7 +180,7 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     else:
         Y = ops.empty((m0 * d, l), tall)
 
-    def tall_pass(Omega64: torch.Tensor, keep_y: bool = False, final: bool = False) -> torch.Tensor:
+    def tall_pass(Omega64: torch.Tensor, keep_y: bool = False, final: bool = False, low: bool = False) -> torch.Tensor:
         """Y = X_d Omega (kept in the preallocated buffers), returns Z = X_d^T Y (all-reduced).
         On the on-chip-split path the power iterations keep Y as ONE plain float32 image (split again on chip by the
         projection); only the final pass writes the hi / lo pair that the Gram and U = Y M kernels consume."""
@@ -175,6 +189,10 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
             for j in range(d):
                 rows = slice(j * m0, (j + 1) * m0)
                 xh, xl = Xhi[:, j : j + n], (Xlo[:, j : j + n] if Xlo is not None else None)
+                if low:
+                    ops.sketch_tf32x1(xh, Omega64, Y[rows])
+                    Z = ops.project_tf32x1(xh, Y[rows], Z, accumulate=j > 0)
+                    continue
                 if xl is None and not final:
                     ops.sketch_tf32x3(xh, None, Omega64, Y[rows], None, None, om_tf32=om_tf32)
                     Z = ops.project_tf32x3(xh, None, Y[rows], None, Z, accumulate=j > 0)
@@ -192,8 +210,11 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
             stats["tall_passes"] = stats.get("tall_passes", 0) + 2
         return Z
 
+    n_low = max(0, n_iter - (MIX_FULL_ITERS if full_iters is None else int(full_iters))) if mixed else 0
+    if stats is not None:
+        stats["low_precision_iters"] = n_low
     for it in range(n_iter):
-        Z = tall_pass(Omega)
+        Z = tall_pass(Omega, low=it < n_low)
         if it == n_iter - 1:
             # Rayleigh-Ritz rotation before the final pass: T = Omega^T Z = Y^T Y (l x l) = W L W^T, so
             # the columns of X (Z W) come out nearly orthogonal and graded (~ sigma_j u_j) and the Gram

@@ -11,11 +11,20 @@ temporary U).  For the tall-skinny snapshot matrix:
                                     + one Rayleigh-Ritz step + back-transformation (eig_tridiag.cu)
     s = sqrt(L);  U_k = X V_k S_k^-1 (tall pass);  Vt_k = V_k^T
 
-Only k columns of U are ever formed.  Like the reference, no sign normalisation is applied
+Only k columns of U are ever formed.  Like the reference, no sign normalisation is promised
 (LAPACK's signs are arbitrary too); parity is up to a per-pair sign.  The Gram matrix squares the
 condition number: sigma_i is accurate to ~ eps * (sigma_1 / sigma_i)^2, i.e. 1e-6 down to
-sigma_i ~ 1e-5 sigma_1 in float64; with precision "tf32x3" (float32 data) eps is the
-~1e-6 of the tensor-core Gram, so only the leading components (sigma_i >~ 0.1 sigma_1) reach 1e-4.
+sigma_i ~ 1e-5 sigma_1 for float64 data.  Components whose eigenvalue comes out <= 0 (below that
+floor, e.g. the null direction of mean-centred data when n_components ~ n) get sigma = 0 and a ZERO column of U -
+the reference returns an arbitrary orthonormal completion there.
+
+float32 data (the real ERA5 dtype): the tensor-core Gram accumulates in fp32, eps ~ 1e-6, which alone would
+leave sigma_i at 1e-2 relative for sigma_i = 0.01 sigma_1 where LAPACK's sgesdd is backward stable.  The Gram route
+therefore only supplies the SUBSPACE: the k + 10 leading eigenvectors start REFINE_ITERS power iterations and the
+final Rayleigh-Ritz stage of the randomized driver (rsvd.py) on X itself - Y = X V, Q = orth(Y), B = Q^T X, small SVD -
+whose singular values carry the accuracy of the tall passes (3xTF32: 1e-7 relative to sigma_i, not to sigma_1^2) and
+whose error in the subspace enters only squared.  Cost: 2 * REFINE_ITERS + 2 tall passes of width k + 10 against the
+n / 2 column blocks of the Gram matrix (c4: +15 %).
 """
 from __future__ import annotations
 
@@ -24,6 +33,7 @@ import torch
 from ._cabi import PREC_NATIVE, PREC_TF32X3
 from .dist import LocalComm
 
+REFINE_ITERS = 2        # power iterations of the float32 refinement (each contracts the leak by (sigma_{k+11}/sigma_i)^2)
 JACOBI_MAX_N = 118      # largest n whose working copies fit one CTA's shared memory (syevj_kernel)
 TC_BLOCK = 112          # sketch-width block of the tensor-core project kernel
 
@@ -96,9 +106,18 @@ def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int =
     if n < 1:
         raise ValueError("delay embedding larger than the number of snapshots")
     k = min(int(n_components), n)
-    use_tc = precision == PREC_TF32X3 and X.dtype == torch.float32 and k <= 128
-    G = gram_device(ops, X, n, d, PREC_TF32X3 if use_tc else PREC_NATIVE)
+    tc_ok = precision in (PREC_TF32X3, 2) and X.dtype == torch.float32                   # 2 = rsvd.PREC_TF32MIX
+    use_tc = tc_ok and k <= 128
+    G = gram_device(ops, X, n, d, PREC_TF32X3 if tc_ok else PREC_NATIVE)
     comm.allreduce_sum_(G)
+    if X.dtype == torch.float32:
+        # float32 data: the Gram route supplies the subspace, the randomized driver's final stage the values
+        from .rsvd import randomized_svd_device
+
+        kk = min(n, k + 10)
+        _, V = sym_eig_topk(ops, G, kk)
+        prec = PREC_TF32X3 if (tc_ok and kk <= 128) else PREC_NATIVE
+        return randomized_svd_device(ops, X, k, V, n_iter=REFINE_ITERS, delay=d, precision=prec, comm=comm)
     lam, V = sym_eig_topk(ops, G, k)
     s, inv_s = ops.sigma_from_eig(lam)
     Vk = V.t().contiguous()                     # (k, n): rows = right singular vectors, descending

@@ -62,6 +62,13 @@ const char* era5svd_last_error(void);
 /* number of CUDA kernels launched by this library in the calling process (bench's gpu_launches) */
 unsigned long long era5svd_launch_count(void);
 
+/* Measured tensor peaks for the roofline denominators (bench.py; not part of the data path; synchronous).
+ * era5svd_probe_tf32_tflops : dense kind::tf32 TFLOP/s of the whole chip with every SM issuing tcgen05.mma M = 128,
+ *                             K = 8, width N back to back for ~`seconds` (form 0: A from shared memory, 1: A from TMEM).
+ * era5svd_probe_dmma_tflops : FP64 tensor TFLOP/s (mma.sync.m8n8k4.f64, the path of the float64 tall kernels). */
+int era5svd_probe_tf32_tflops(int form, int N, double seconds, double* tflops);
+int era5svd_probe_dmma_tflops(double seconds, double* tflops);
+
 /* ------------------------------------------------------------------------------------------
  * (a) matrix build.  Replaces standardize_data (slice_tools.py:171-177: xarray mean / subtract /
  * std(ddof=0) / divide), flatten_era5_variables' transpose+concat copy (slice_tools.py:323-336)
@@ -80,6 +87,11 @@ unsigned long long era5svd_launch_count(void);
 int era5svd_build_rows(const void* src, int dtype_src, int64_t T, int64_t src_ld, int64_t P,
                        void* X, int dtype_x, int64_t ldx, void* mean_out, void* std_out,
                        const void* weights, unsigned flags, int* nonfinite_flag, void* stream);
+
+/* The finiteness pass alone, for a matrix that did not come through the build (svd_on_era5's array input): sets *flag
+ * (device int, zeroed by the caller) to 1 if any element of X[rows x cols] (row pitch ld) is NaN or +-Inf.  Replaces
+ * sklearn's check_array inside randomized_svd (sklearn/utils/extmath.py:546), which raises "Input contains NaN". */
+int era5svd_check_finite(const void* X, int dtype, int64_t rows, int64_t cols, int64_t ld, int* flag, void* stream);
 
 /* Same build, float32 matrix, writing the tf32 hi / lo images the tensor-core passes consume
  * (Xhi + Xlo == X exactly) in the same pass; X itself is optional (nullable). */
@@ -145,6 +157,18 @@ int era5svd_round_tf32_f64(double* A, int64_t rows, int64_t cols, int64_t lda, v
 int era5svd_sketch_tf32x2(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
                           int64_t ldo, float* Y, float* Yhi, float* Ylo, int64_t ldy, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* Single-product TF32 passes for the EARLY power iterations (extmath.py:377-379): subspace iteration is self-correcting,
+ * so only the last iteration and the final range / projection passes (extmath.py:383, :606) need fp32-level products.
+ * The raw float32 tiles go TMA -> shared memory -> tcgen05.mma directly (the tensor core truncates fp32 operands to
+ * tf32), one product per k-step, no hi / lo images, no transform warps: the pass is HBM bound.
+ * era5svd_sketch_tf32x1  : Y (plain float32, pitch ldy as above) = X * tf32(Om); workspace as era5svd_sketch_tf32x3.
+ * era5svd_project_tf32x1 : Z (float64, n x l) (+)= X^T Y with both operands truncated to tf32; workspace as
+ *                          era5svd_project_tf32x3.  l <= 128. */
+int era5svd_sketch_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, const double* Om, int64_t l,
+                          int64_t ldo, float* Y, int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+int era5svd_project_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,
+                           int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
+                           size_t workspace_bytes, void* stream);
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l);
 int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
                            const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,

@@ -33,7 +33,7 @@ def main():
     X = lowrank_field_np(m0, T, r=80, rho=0.9, seed=11, dtype=np.float32)
     r0, r1 = shard_rows(m0, world, rank)
     out = {}
-    for precision, tol in (("native", 1e-4), ("tf32x3", 1e-4)):
+    for precision, tol in (("native", 1e-4), ("tf32x3", 1e-4), ("tf32mix", 1e-4)):
         Xd = torch.from_numpy(X[r0:r1].copy()).cuda()
         U, s, V = svd_device(ops, Xd, svd_type="randomized", n_components=k, delay=d, seed=5, precision=precision,
                              comm=comm, row_offset=r0, m0_global=m0)

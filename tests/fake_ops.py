@@ -76,6 +76,27 @@ class FakeOps:
             Yhi.copy_(hi)
             Ylo.copy_(out - hi)
 
+    @staticmethod
+    def _tf32_trunc(a: torch.Tensor) -> torch.Tensor:
+        """what the tensor core does to a raw fp32 operand: the low 13 mantissa bits are dropped"""
+        bits = a.to(torch.float32).contiguous().view(torch.int32)
+        return (bits & ~0x1FFF).view(torch.float32)
+
+    def sketch_tf32x1(self, X, Om, Y):
+        self._count("sketch_x1")
+        Y.copy_((self._tf32_trunc(X).double() @ self._tf32(Om).double()).to(torch.float32))
+
+    def project_tf32x1(self, X, Y, Z=None, accumulate=False):
+        self._count("project_x1")
+        out = self._tf32_trunc(X).double().t() @ self._tf32_trunc(Y).double()
+        if Z is None:
+            return out
+        if accumulate:
+            Z += out
+        else:
+            Z.copy_(out)
+        return Z
+
     def project_tf32x3(self, Xhi, Xlo, Yhi, Ylo, Z=None, accumulate=False):
         self._count("project_tc")
         X = Xhi.double() + (Xlo.double() if Xlo is not None else 0.0)

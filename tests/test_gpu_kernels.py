@@ -326,3 +326,38 @@ def test_scale_cols_vectorised(ops, m, k, ld):
     sg = torch.from_numpy(rng.choice([-1.0, 1.0, 0.0], size=k)).cuda()
     ops.scale_cols(buf[:, :k], sg)
     assert torch.equal(buf[:, :k], ref[:, :k] * sg.float()) and torch.equal(buf[:, k:], ref[:, k:])
+
+
+@pytest.mark.parametrize("T,P,dtype", [(25, 300, torch.float64), (744, 4096, torch.float32), (1460, 2048, torch.float32),
+                                       (2000, 512, torch.float32)])
+def test_nonfinite_flag_reports_the_written_value(ops, T, P, dtype):
+    """a time-constant point under scale=True has std 0, so 0 / 0 = NaN is WRITTEN to X although every
+    source value is finite; the reference raises "Input contains NaN" (sklearn check_array).  The flag must report it
+    in every build kernel (TMA tile kernel, register-staged tile kernel, two-kernel path for long series)."""
+    from dmd_era5_b200.pipeline import build_matrix_device
+
+    g = torch.Generator(device="cuda"); g.manual_seed(T)
+    src = torch.randn((T, P), generator=g, device="cuda", dtype=dtype) + 250.0
+    ok = build_matrix_device(ops, [src], mean_center=True, scale=True, check_finite=True)
+    assert int(ok.nonfinite.item()) == 0
+    src[:, P // 3] = 7.0                                       # constant in time: std = 0
+    bad = build_matrix_device(ops, [src], mean_center=True, scale=True, check_finite=True)
+    assert int(bad.nonfinite.item()) == 1
+    assert not bool(torch.isfinite(bad.X[P // 3]).all())
+    only_centred = build_matrix_device(ops, [src], mean_center=True, scale=False, check_finite=True)
+    assert int(only_centred.nonfinite.item()) == 0             # centring alone leaves zeros there
+    src[T // 2, 5] = float("inf")
+    assert int(build_matrix_device(ops, [src], mean_center=False, scale=False, check_finite=True).nonfinite.item()) == 1
+
+
+def test_svd_on_era5_rejects_nonfinite_input():
+    from dmd_era5_b200.era5_svd import svd_on_era5
+
+    X = np.random.RandomState(0).standard_normal((500, 40))
+    X[17, 3] = np.nan
+    for svd_type in ("randomized", "standard"):
+        with pytest.raises(ValueError, match="Input contains NaN or infinity"):
+            svd_on_era5(X, {"svd_type": svd_type, "n_components": 5, "random_seed": 0})
+    X[17, 3] = np.inf
+    with pytest.raises(ValueError, match="Input contains NaN or infinity"):
+        svd_on_era5(X.astype(np.float32), {"svd_type": "randomized", "n_components": 5, "random_seed": 0})

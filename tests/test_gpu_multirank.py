@@ -1,0 +1,27 @@
+"""GPU, >= 2 devices: the row-sharded paths over NCCL (randomized native / tf32x3 / tf32mix, standard FP64, sharded
+BOP-DMD trials) against the single-process oracles - scripts/check_multigpu.py run as a test (multi-rank
+NCCL parity was a hand-run script).  Skipped on a one-GPU box; the gloo CPU tests cover the host logic there."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_rank_nccl_parity():
+    port = 29600 + os.getpid() % 300
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "scripts", "check_multigpu.py")], capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = json.loads([ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")][-1])
+    assert line["world"] == 2
+    for key in ("native", "tf32x3", "tf32mix", "standard_fp64", "bopdmd_trials_sharded"):
+        assert line[key]["pass"], (key, line[key])

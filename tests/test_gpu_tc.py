@@ -232,3 +232,50 @@ def test_tc_kernels_write_only_their_outputs(ops, m, n, l):
     assert bool((Zbuf[:32] == CAN).all()) and bool((Zbuf[32 + n :] == CAN).all())
     ref = X.double().t() @ (Yhe.double() + Yle.double())
     assert float((Z - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+def _trunc_tf32(a: np.ndarray) -> np.ndarray:
+    """what the tensor core does to a raw fp32 operand (profiles/r01_microbench_mma_probe.txt): truncation to tf32"""
+    return (np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@pytest.mark.parametrize("m,n,l,off", [(128, 32, 16, 0), (1000, 744, 110, 0), (129, 40, 112, 0), (5000, 1460, 110, 0),
+                                       (2000, 742, 110, 2), (77, 25, 20, 1), (70000, 744, 100, 3), (300, 100, 128, 0)])
+def test_single_product_tf32_kernels(ops, m, n, l, off):
+    """era5svd_sketch_tf32x1 / era5svd_project_tf32x1 (the early power iterations under precision 'tf32mix'): ONE tensor
+    core product per k-step on the raw float32 tiles.  The kernels must equal the float64 product of the TRUNCATED
+    operands up to the fp32 accumulate - i.e. their only approximation is the documented tf32 truncation."""
+    rng = np.random.RandomState(m + n + 7)
+    Xfull = (rng.standard_normal((m, n + off)) * np.exp(rng.uniform(-3, 3, size=(m, 1)))).astype(np.float32)
+    Om = dev(rng.standard_normal((n, l)))
+    ops.round_tf32_(Om)
+    ld = (n + off + 7) // 8 * 8
+    Xb = torch.zeros((m, ld), device="cuda")
+    Xb[:, : n + off] = dev(Xfull)
+    ldy = ops.tf32_ldy(l)
+    CAN = 777.0
+    Ybuf = torch.full((m + 64, ldy), CAN, device="cuda")
+    Y = Ybuf[:m, :l]
+    ops.sketch_tf32x1(Xb[:, off:off + n], Om, Y)
+    assert bool((Ybuf[m:] == CAN).all()), "rows below the matrix were written"
+    Xt = _trunc_tf32(Xfull[:, off:]).astype(np.float64)
+    ref = Xt @ Om.cpu().numpy()
+    bound = TC_REL * np.linalg.norm(Xt, axis=1)[:, None] * np.linalg.norm(Om.cpu().numpy(), axis=0)[None, :]
+    Yh = Y.cpu().numpy()
+    assert np.all(np.abs(Yh - ref) <= bound + 1e-30)
+    # the truncation itself is what separates it from the exact product: ~2^-11 relative, never more than 2^-10
+    exact = Xfull[:, off:].astype(np.float64) @ Om.cpu().numpy()
+    scale = np.linalg.norm(Xfull[:, off:], axis=1)[:, None] * np.linalg.norm(Om.cpu().numpy(), axis=0)[None, :]
+    assert np.all(np.abs(Yh - exact) <= 2.0 ** -10 * scale)
+    Zbuf = torch.full((n + 64, l), CAN, dtype=torch.float64, device="cuda")
+    Z = Zbuf[32 : 32 + n]
+    ops.project_tf32x1(Xb[:, off:off + n], Y, Z, accumulate=False)
+    assert bool((Zbuf[:32] == CAN).all()) and bool((Zbuf[32 + n :] == CAN).all())
+    Yt = _trunc_tf32(Yh).astype(np.float64)
+    refz = Xt.T @ Yt
+    # fp32 running sums over up to 16384 rows per TMEM accumulator (the tensor core's accumulate truncates)
+    boundz = 6e-5 * np.linalg.norm(Xt, axis=0)[:, None] * np.linalg.norm(Yt, axis=0)[None, :]
+    assert np.all(np.abs(Z.cpu().numpy() - refz) <= boundz + 1e-30)
+    Z2 = ops.project_tf32x1(Xb[:, off:off + n], Y, Z.clone(), accumulate=True)
+    assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
+    assert torch.equal(ops.project_tf32x1(Xb[:, off:off + n], Y), Z)                 # reproducible
