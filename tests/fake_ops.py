@@ -126,16 +126,31 @@ class FakeOps:
         return torch.from_numpy(w[::-1].copy()), torch.from_numpy(np.ascontiguousarray(v[:, ::-1]))
 
     def chol_inv(self, G, rel_tol):
+        """Right-looking Cholesky with the kernel's pivot rule (small_f64.cu chol_inv_kernel): a pivot that falls below
+        rel_tol * G[j][j] (or is not positive) drops the direction - zero row of R, zero row / column of Rinv."""
         self._count("chol_inv")
         g = 0.5 * (G.numpy() + G.numpy().T)
-        R = np.linalg.cholesky(g).T
-        Rinv = np.linalg.inv(R)
-        return torch.from_numpy(R.copy()), torch.from_numpy(np.ascontiguousarray(Rinv))
+        l = g.shape[0]
+        A = g.copy()
+        R = np.zeros_like(g)
+        keep = []
+        for j in range(l):
+            d = A[j, j]
+            if d > rel_tol * g[j, j] and d > 0.0:
+                r = A[j, j:] / np.sqrt(d)
+                R[j, j:] = r
+                A[j:, j:] -= np.outer(r, r)
+                keep.append(j)
+        Rinv = np.zeros_like(g)
+        if keep:
+            ix = np.ix_(keep, keep)
+            Rinv[ix] = np.linalg.inv(R[ix])
+        return torch.from_numpy(R), torch.from_numpy(np.ascontiguousarray(Rinv))
 
     def col_normalize(self, P):
         self._count("col_normalize")
         nrm = torch.linalg.norm(P, dim=0)
-        P /= nrm
+        P /= torch.where(nrm > 0, nrm, torch.ones_like(nrm))       # a dropped (zero) column stays zero, like the kernel
         return nrm
 
     def sigma_from_eig(self, W):

@@ -139,3 +139,51 @@ def test_two_rank_gloo_row_sharding(tensor_core):
         assert sigma_rel_err(s, s0) < s_tol and vector_angles(Vt.T, V0.T).max() < a_tol
     assert np.array_equal(res[0][4], res[1][4])          # replicated small factors agree bitwise
     assert vector_angles(U, U0).max() < a_tol and signs_agree(U, U0)
+
+
+@pytest.mark.parametrize("d", [1, 2])
+def test_randomized_driver_mixed_precision_schedule(d):
+    """precision "tf32mix": the early power iterations run single-product TF32 passes on truncated operands (emulated on
+    the bit patterns here), only the last MIX_FULL_ITERS iteration(s) and the final range / projection passes keep
+    fp32-level products.  Subspace iteration contracts the early error, so sigma stays at the float32-storage level."""
+    from dmd_era5_b200.rsvd import MIX_FULL_ITERS, PREC_TF32MIX
+
+    X = lowrank_field_np(3000, 160, r=60, rho=0.88, seed=3).astype(np.float32)
+    k = 12
+    Xd = delay_embed_np(X.astype(np.float64), d)
+    U0, s0, V0 = randomized_svd_ref(Xd, k, 7)
+    ops, stats = FakeOps(), {}
+    U, s, Vt = randomized_svd_device(ops, torch.from_numpy(X), k, draw_omega(Xd.shape[1], k, 7, torch.float32), delay=d,
+                                     precision=PREC_TF32MIX, stats=stats)
+    q = n_iter_auto(Xd.shape[0], Xd.shape[1], k)
+    low = q - MIX_FULL_ITERS
+    assert stats["low_precision_iters"] == low and stats["tall_passes"] == 2 * q + 2
+    assert ops.calls["sketch_x1"] == d * low and ops.calls["project_x1"] == d * low
+    assert ops.calls["sketch_tc"] == d * (q + 1 - low) + 1 and ops.calls["project_tc"] == d * (q + 1 - low) + 1
+    assert sigma_rel_err(s, s0) < 1e-6
+    assert vector_angles(U.double().numpy(), U0).max() < 2e-4 and vector_angles(Vt.numpy().T, V0.T).max() < 2e-4
+    assert signs_agree(U.double().numpy(), U0)
+    # full_iters = q switches the low-precision passes off entirely
+    ops2 = FakeOps()
+    randomized_svd_device(ops2, torch.from_numpy(X), k, draw_omega(Xd.shape[1], k, 7, torch.float32), delay=d,
+                          precision=PREC_TF32MIX, full_iters=q)
+    assert "sketch_x1" not in ops2.calls
+
+
+def test_sketch_wider_than_the_rank_drops_noise_directions():
+    """rank(X) = 20 < l = 40, float32 mixed precision: the truncated X of the early iterations has full rank, so the
+    surplus directions survive until the Rayleigh-Ritz rotation of the last iteration, where the 1e-8 pivot threshold
+    removes them (rsvd.py): trailing singular values come out exactly zero, the true ones at float32 accuracy."""
+    from dmd_era5_b200.rsvd import PREC_TF32MIX
+
+    rng = np.random.RandomState(0)
+    rank, m, n, k = 20, 1500, 90, 30
+    A = np.linalg.qr(rng.standard_normal((m, rank)))[0]
+    B = np.linalg.qr(rng.standard_normal((n, rank)))[0]
+    X = ((A * (10.0 * 0.8 ** np.arange(rank))) @ B.T).astype(np.float32)
+    U0, s0, V0 = randomized_svd_ref(X.astype(np.float64), k, 2)
+    U, s, Vt = randomized_svd_device(FakeOps(), torch.from_numpy(X), k, draw_omega(n, k, 2, torch.float32),
+                                     precision=PREC_TF32MIX)
+    assert torch.isfinite(U).all() and torch.isfinite(s).all()
+    assert sigma_rel_err(s[:rank], s0[:rank]) < 1e-5
+    assert float(s[rank:].abs().max()) < 1e-6 * s0[0]

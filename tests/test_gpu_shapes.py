@@ -60,8 +60,9 @@ def test_c3_shape_float32_paths(precision, d):
     print(f"\nc3-shape {precision} d={d}: sigma {err:.2e}  angle U first50 {ang_u[:50].max():.2e} all {ang_u.max():.2e}  "
           f"V first50 {ang_v[:50].max():.2e} all {ang_v.max():.2e}  recon {rec:.6e} vs {ref:.6e}")
     assert err < 1e-4
-    assert ang_u[:50].max() < 2e-4 and ang_u.max() < 5e-3
-    assert ang_v[:50].max() < 2e-4 and ang_v.max() < 5e-3
+    # measured (profiles/r02_parity_shapes.txt): first 50 <= 3.0e-5, all <= 6.4e-5 rad on every float32 path
+    assert ang_u[:50].max() < 1e-4 and ang_u.max() < 3e-4
+    assert ang_v[:50].max() < 1e-4 and ang_v.max() < 3e-4
     assert signs_agree(U, U0)
     assert abs(rec - ref) <= 0.01 * ref
 
@@ -126,7 +127,7 @@ def test_exactly_rank_deficient_input(dtype, precision):
     assert np.all(np.isfinite(U)) and np.all(np.isfinite(s)) and np.all(np.isfinite(V))
     f64 = dtype == np.float64
     assert sigma_rel_err(s[:rank], s0[:rank]) < (1e-6 if f64 else 1e-4)
-    assert np.all(np.abs(s[rank:]) < (1e-9 if f64 else 2e-5) * s0[0])            # reference: ~1e-15 * sigma_1
+    assert np.all(np.abs(s[rank:]) < (1e-9 if f64 else 1e-6) * s0[0])            # reference: ~1e-15 * sigma_1
     ang = vector_angles(U[:, :rank], U0[:, :rank])
     print(f"\nrank-deficient {np.dtype(dtype).name} {precision}: sigma {sigma_rel_err(s[:rank], s0[:rank]):.2e} "
           f"trailing {np.abs(s[rank:]).max():.2e} angle {ang.max():.2e}")
@@ -153,5 +154,9 @@ def test_float32_input_against_the_references_own_float32_call(precision):
           f"angle ours-f64 {a_ours.max():.2e} ref32-f64 {a_ref.max():.2e}")
     assert ours_vs_ref32 < 1e-4 and ours_vs_64 < 1e-4
     assert ours_vs_64 <= max(10 * ref32_vs_64, 2e-6)
-    assert a_ours.max() <= max(10 * a_ref.max(), 5e-3)
-    assert signs_agree(U, U32)
+    assert a_ours.max() <= max(2 * a_ref.max(), 1e-3)
+    # signs follow the float64 truth; the reference's own float32 run may flip a column whose two largest |entries|
+    # tie within float32 noise (svd_flip picks the first maximum, extmath.py:964-972)
+    assert signs_agree(U, U64)
+    flips = int(np.sum(np.sum(U32.astype(np.float64) * U64, axis=0) < 0))
+    assert int(np.sum(np.sum(U.astype(np.float64) * U32, axis=0) < 0)) == flips

