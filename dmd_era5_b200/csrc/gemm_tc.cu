@@ -17,6 +17,8 @@
 // consumes them K-major (16 B swizzle granules), project MN-major (32-bit MN-major operands use the
 // 32 B-granule 128 B swizzle, TMA mode SWIZZLE_128B_ATOM_32B).
 // Replaces `A @ Q` / `A.T @ Q` / `Q.T @ M` (sklearn/utils/extmath.py:378-383, :606) for float32 data.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -301,6 +303,145 @@ sketch_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// single-product sketch, TWO row tiles per Om^T tile (persistent, warp specialised)
+//
+// sketch_tc_kernel re-streams the Om^T tile (npad x 32 floats, L2 resident) for every 128-row tile: per HBM byte of X
+// it moves 1.875 bytes through the L2 fabric and 3.75 bytes through the shared-memory port (TMA writes + SS-form
+// operand reads), and measured it is those two - not HBM - that bound it once the SM clock sits at the power cap
+// (c3: 7.27 ms in the step against 5.8 ms alone; profiles/r02_pitch_sensitivity.txt).  Here one stage holds a
+// [256 rows x 32] X box (one TMA call, two consecutive 128-row operand tiles) and ONE Om^T tile used by both:
+// 1.44 bytes of L2 traffic and 2.9 bytes of shared-memory traffic per HBM byte.  TMEM: 2 tiles x 2 buffers x 128
+// columns, so the epilogue of one 256-row group overlaps the MMAs of the next.
+// ---------------------------------------------------------------------------------------------
+struct SketchX1Params {
+  int64_t m;
+  int64_t num_groups;   // ceil(m / 256)
+  int num_k;            // ceil(kspan / 32)
+  int npad;             // UMMA N (multiple of 16, <= 128)
+  int stages;
+  float* Y;
+  int64_t ldy;
+};
+
+constexpr int SX1_THREADS = 192;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+__global__ void __launch_bounds__(SX1_THREADS, 1)
+sketch_x1_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_o,
+                 const SketchX1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform
+  const uint32_t a_bytes = BM * BK * 4;                 // one 128-row operand tile: 16 KB
+  const uint32_t b_bytes = (uint32_t)p.npad * BK * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + b_bytes;   // [A0 | A1 | B]
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_o); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // TMEM map: buffer b, tile t at column (2 b + t) * 128
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int s = 0; uint32_t ph = 0;
+      for (int64_t grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+        const int32_t row0 = (int32_t)(grp * 2 * BM);
+        for (int kc = 0; kc < p.num_k; ++kc) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+          tma_load_2d(st, &tm_x, kc * BK, row0, full_bar(s));                  // 256 rows: tiles A0, A1 back to back
+          tma_load_2d(st + 2 * a_bytes, &tm_o, kc * BK, 0, full_bar(s));
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected lane) =====
+    const uint32_t idesc = make_idesc_tf32(BM, p.npad, 0, 0);
+    int s = 0; uint32_t ph = 0;
+    int buf = 0; uint32_t aph = 0;
+    for (int64_t grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+      mbar_wait(tempty_bar(buf), aph ^ 1u);      // epilogue has drained this accumulator pair
+      tcgen05_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)buf * 256u, d1 = d0 + 128u;
+      for (int kc = 0; kc < p.num_k; ++kc) {
+        mbar_wait(full_bar(s), ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint32_t koff = kk * UMMA_K * 4;
+            const uint64_t b = make_smem_desc(st + 2 * a_bytes + koff, 16, SWIZZLE_ATOM);
+            umma_tf32_ss(d0, make_smem_desc(st + koff, 16, SWIZZLE_ATOM), b, idesc, (kc | kk) != 0);
+            umma_tf32_ss(d1, make_smem_desc(st + a_bytes + koff, 16, SWIZZLE_ATOM), b, idesc, (kc | kk) != 0);
+          }
+          umma_commit(empty_bar(s));
+          if (kc == p.num_k - 1) umma_commit(tfull_bar(buf));
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      if (++buf == 2) { buf = 0; aph ^= 1u; }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global Y =====
+    const int q = warp % 4;
+    int buf = 0; uint32_t aph = 0;
+    for (int64_t grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+      mbar_wait_hint(tfull_bar(buf), aph, 20000u);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int64_t row = grp * 2 * BM + t * BM + q * 32 + lane;
+        const uint32_t taddr = tmem_base + (uint32_t)(2 * buf + t) * 128u + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_wait_ld();
+          if (row < p.m) {
+            float4* dst = reinterpret_cast<float4*>(p.Y + row * p.ldy + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                   __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (++buf == 2) { buf = 0; aph ^= 1u; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // project kernel: one CTA = (time chunk, row split); accumulates Z^T chunk over its rows in TMEM
 // ---------------------------------------------------------------------------------------------
 struct ProjectParams {
@@ -559,6 +700,27 @@ static int sketch_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64
   if ((rc = tc::make_tmap(&tm_olo, olo, kspan, npad, ldt, tc::BK, (uint32_t)npad, &os2))) return rc;
   ERA5SVD_REQUIRE(os == 0 && os2 == 0, "sketch_tf32x3: workspace must be 16-byte aligned");
 
+  if (nprod == 1 && npad <= 128 && m > 2 * tc::BM && !getenv("ERA5SVD_SKETCH_X1_SINGLE")) {
+    // two 128-row tiles per Om^T tile (sketch_x1_kernel)
+    CUtensorMap tm_x2;
+    int xs3 = 0;
+    if ((rc = tc::make_tmap(&tm_x2, Xhi, n, m, ldx, tc::BK, 2 * tc::BM, &xs3))) return rc;
+    tc::SketchX1Params q;
+    q.m = m;
+    q.num_groups = ceil_div(m, 2 * tc::BM);
+    q.num_k = (int)ceil_div(kspan, tc::BK);
+    q.npad = npad;
+    q.Y = Y;
+    q.ldy = ldy;
+    const size_t stage = 2 * (size_t)tc::BM * tc::BK * 4 + (size_t)npad * tc::BK * 4;
+    q.stages = (int)((227 * 1024 - 1024 - 256) / stage);
+    if (q.stages > 6) q.stages = 6;
+    const size_t smem = q.stages * stage + 1024 + 256;
+    ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = q.num_groups < sm_count() ? q.num_groups : sm_count();
+    tc::sketch_x1_kernel<<<(unsigned)grid, tc::SX1_THREADS, smem, st>>>(tm_x2, tm_ohi, q);
+    return check_launch("sketch_x1_kernel");
+  }
   tc::SketchParams p;
   p.m = m;
   p.num_tiles = ceil_div(m, tc::BM);

@@ -225,12 +225,14 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         # cond(Z) ~ kappa(X)^2 after the random start (shifted CholeskyQR3), <~ kappa(X) afterwards.
         # Pivot threshold: 1e-13 while the columns are still coupled (a legitimate trailing direction of the random
         # start has a relative pivot ~ (sigma_l / sigma_1)^4).  After the Rayleigh-Ritz rotation the legitimate columns
-        # are decoupled (pivot ~ 1), so for float32 data 1e-8 separates them from directions that only exist as
+        # are decoupled (pivot ~ 1), so for float32 data 1e-6 separates them from directions that only exist as
         # rounding noise of the tall passes: a sketch wider than rank(X) leaves columns Z w = X^T (noise), which lie
-        # in the row space already spanned to ~5e-7 (pivot ~ 1e-13) and would otherwise survive as spurious singular
-        # values ~1e-5 sigma_1 (the single-product early iterations never drop them: truncated X has full rank).
+        # in the row space already spanned (measured pivots 1e-13 ... 1e-8: the fp32 accumulate of such a cancelling
+        # column is good to ~1e-4 of its own norm) and would otherwise survive as spurious singular values
+        # ~1e-5 sigma_1 (the single-product early iterations never drop them: truncated X has full rank).  A genuine
+        # direction only falls below 1e-6 when sigma_j <~ 1e-5 sigma_1, under the noise floor of float32 passes.
         last = it == n_iter - 1
-        Omega = _orth(ops, Z, 1e-8 if (last and tall == torch.float32) else 1e-13, shifted=(it == 0 and n_iter > 1))
+        Omega = _orth(ops, Z, 1e-6 if (last and tall == torch.float32) else 1e-13, shifted=(it == 0 and n_iter > 1))
         if om_tf32:
             ops.round_tf32_(Omega)
 

@@ -1,7 +1,7 @@
 """Does the row pitch of X matter for the tall passes?  Times sketch / project (x1 and 3x forms) on the same m x n data
 stored with different leading dimensions (CUDA events, L2-cold: the matrix is far larger than L2).
 
-    python scripts/time_pitch.py [n] [rows]
+    python scripts/time_pitch.py [n] [rows] [ld,ld,...]
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,7 +30,8 @@ def timeit(fn, reps=5):
 
 
 gb = m * n * 4 / 1e9
-for ld in sorted({(n + 7) // 8 * 8, (n + 31) // 32 * 32, (n + 63) // 64 * 64 + 8, (n + 63) // 64 * 64 + 32, (n + 127) // 128 * 128,
+lds = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
+for ld in lds or sorted({(n + 7) // 8 * 8, (n + 31) // 32 * 32, (n + 63) // 64 * 64 + 8, (n + 63) // 64 * 64 + 32, (n + 127) // 128 * 128,
                   (n + 127) // 128 * 128 + 32, (n + 511) // 512 * 512, (n + 511) // 512 * 512 + 32}):
     X = torch.randn((m, ld), device="cuda")[:, :n]
     t = {"sketch_x1": timeit(lambda: ops.sketch_tf32x1(X, Om, Y)),
