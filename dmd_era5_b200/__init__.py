@@ -13,6 +13,9 @@ stage), ``create_mock_era5`` / ``create_mock_era5_svd`` (test-data generators; t
 ``oracle/``), ``setup_logger`` (file logging set-up).
 """
 from ._cabi import Era5SvdError, LIB_PATH  # noqa: F401
+# like the reference (``from dmd_era5.core import config_parser`` after the submodule import), the FUNCTION shadows the
+# submodule of the same name on the package; the module stays reachable through sys.modules / ``from . import``
+from .config_parser import config_parser, config_reader  # noqa: F401
 
 __version__ = "0.2.0"
 
@@ -23,7 +26,7 @@ _EXPORTS = {
     "apply_delay_embedding": "slice_tools", "flatten_era5_variables": "slice_tools",
     "_apply_delay_embedding_np": "slice_tools", "space_coord_to_level_lat_lon": "slice_tools",
     # core (src/dmd_era5/core.py)
-    "config_parser": "config_parser", "config_reader": "config_parser", "log_and_print": "era5_svd",
+    "log_and_print": "era5_svd",
     # dvc_tools (src/dmd_era5/dvc_tools.py:50-63, :119-253)
     "add_data_to_dvc": "dvc_tools", "retrieve_data_from_dvc": "dvc_tools",
     # era5_svd (src/dmd_era5/era5_svd/__init__.py:10-17)
@@ -31,7 +34,7 @@ _EXPORTS = {
     "retrieve_svd_results": "stage", "add_config_attributes": "stage", "main": "stage",
 }
 
-__all__ = ["Era5SvdError", "LIB_PATH", "__version__", *sorted(_EXPORTS)]
+__all__ = ["Era5SvdError", "LIB_PATH", "__version__", "config_parser", "config_reader", *sorted(_EXPORTS)]
 
 
 def __getattr__(name):

@@ -189,58 +189,83 @@ def _netcdf3(path: str, mode: str, **kw):
     return _File(path, mode, **kw)
 
 
-def write_netcdf(ds: Dataset, path: str) -> str:
-    """Write ``ds``; returns the format used ("NETCDF4" through xarray, else "NETCDF3_64BIT")."""
+NETCDF3_VAR_LIMIT = 2 ** 31 - 4      # largest variable the NetCDF-3 (scipy) writer takes
+
+
+def _flatten_for_classic(ds: Dataset, allow_int64: bool):
+    """Dataset -> (dims, [(name, dims, array, attrs)], global attrs) in the classic data model: datetimes as seconds
+    since the epoch (CF units), strings as fixed-width char arrays, bool as int8; int64 kept only when the target
+    format has it (CDF-5), else int32 like the NetCDF-3 path."""
+    dims = {name: int(size) for name, size in ds.sizes.items()}
+    out = []
+
+    def put(name, vdims, arr, attrs=None):
+        arr = arr if isinstance(arr, np.memmap) else np.asarray(arr)
+        extra = {}
+        if np.issubdtype(arr.dtype, np.datetime64):
+            arr = (arr.astype("datetime64[s]") - _EPOCH).astype(np.float64)
+            extra = {"units": "seconds since 1970-01-01 00:00:00", "calendar": "proleptic_gregorian"}
+        if arr.dtype.kind in ("U", "O", "S"):
+            strs = np.asarray([str(x) for x in arr.ravel()], dtype="S")
+            n = strs.dtype.itemsize
+            dname = f"string{n}"
+            dims.setdefault(dname, n)
+            arr = strs.view("S1").reshape(arr.shape + (n,))
+            vdims = tuple(vdims) + (dname,)
+        elif arr.dtype == np.int64 and not allow_int64:
+            arr = arr.astype(np.int32)
+        elif arr.dtype == np.bool_:
+            arr = arr.astype(np.int8)
+        out.append((name, tuple(vdims), arr, {k: _encode_attr(v) for k, v in {**(attrs or {}), **extra}.items()}))
+
+    for name, (vdims, arr) in ds.coords.items():
+        put(name, vdims, arr)
+    for name, da in ds.data_vars.items():
+        put(name, da.dims, da.values, da.attrs)
+    gattrs = {k: _encode_attr(v) for k, v in ds.attrs.items()}
+    gattrs["coordinates_hint"] = " ".join(ds.coords)      # which variables are coordinates (for read_netcdf)
+    return dims, out, gattrs
+
+
+def write_netcdf(ds: Dataset, path: str, format: str | None = None) -> str:
+    """Write ``ds``; returns the format used:
+      "NETCDF4"            through xarray + netCDF4 when importable - the reference's call (era5_svd.py:434);
+      "NETCDF3_64BIT"      scipy's NetCDF-3 writer (CDF-2) while every variable fits its 2 GiB limit;
+      "NETCDF3_64BIT_DATA" the CDF-5 writer of cdf5.py otherwise (no size limit: c2's X, c3's U), readable by
+                           netCDF-C >= 4.4 / xarray's netcdf4 engine / ncdump.
+    ``format`` forces one of the three (tests)."""
     import os
 
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    if _have_xarray():
+    if format not in (None, "NETCDF4", "NETCDF3_64BIT", "NETCDF3_64BIT_DATA"):
+        raise ValueError(f"format {format} is not supported.")
+    if format == "NETCDF4" or (format is None and _have_xarray()):
         ds.to_xarray().to_netcdf(path, format="NETCDF4")     # the reference's call, era5_svd.py:434
         return "NETCDF4"
+    biggest = max([int(np.asarray(a).nbytes) if not isinstance(a, np.memmap) else int(a.nbytes)
+                   for _, a in ds.coords.values()] + [int(da.values.nbytes) for da in ds.data_vars.values()] + [0])
+    if format == "NETCDF3_64BIT_DATA" or (format is None and biggest > NETCDF3_VAR_LIMIT):
+        from .cdf5 import write_classic
+
+        dims, variables, gattrs = _flatten_for_classic(ds, allow_int64=True)
+        write_classic(path, dims, variables, gattrs, version=5)
+        return "NETCDF3_64BIT_DATA"
+    if biggest > NETCDF3_VAR_LIMIT:
+        raise ValueError(f"a variable of {biggest / 2 ** 30:.1f} GiB exceeds the 2 GiB per-variable limit of NetCDF-3; "
+                         "use format=None / 'NETCDF3_64BIT_DATA' (CDF-5) or install xarray + netCDF4")
+    dims, variables, gattrs = _flatten_for_classic(ds, allow_int64=False)
     with _netcdf3(path, "w", version=2) as f:
-        sizes = ds.sizes
-        strlen_dims = {}
-        for name, size in sizes.items():
+        for name, size in dims.items():
             f.createDimension(name, int(size))
-
-        def put(name, dims, arr, attrs=None):
-            arr = np.asarray(arr)
-            extra = {}
-            if np.issubdtype(arr.dtype, np.datetime64):
-                arr = (arr.astype("datetime64[s]") - _EPOCH).astype(np.float64)
-                extra = {"units": "seconds since 1970-01-01 00:00:00", "calendar": "proleptic_gregorian"}
-            if arr.dtype.kind in ("U", "O", "S"):
-                strs = np.asarray([str(x) for x in arr.ravel()], dtype="S")
-                n = strs.dtype.itemsize
-                dname = f"string{n}"
-                if dname not in strlen_dims:
-                    f.createDimension(dname, n)
-                    strlen_dims[dname] = n
-                var = f.createVariable(name, "c", tuple(dims) + (dname,))
-                var[:] = strs.view("S1").reshape(arr.shape + (n,))
-            else:
-                if arr.dtype == np.int64:
-                    arr = arr.astype(np.int32)
-                if arr.dtype == np.bool_:
-                    arr = arr.astype(np.int8)
-                if arr.nbytes >= 2 ** 31:
-                    raise ValueError(f"variable {name!r} ({arr.nbytes / 2 ** 30:.1f} GiB) exceeds the 2 GiB per-variable limit of "
-                                     "the NetCDF-3 fallback writer (scipy); install xarray + netCDF4 for the reference's "
-                                     "NETCDF4 output (era5_svd.py:434)")
-                var = f.createVariable(name, arr.dtype, tuple(dims))
-                var[:] = arr
-            for k, v in {**(attrs or {}), **extra}.items():
-                var._attributes[k] = _encode_attr(v)
-
-        for name, (dims, arr) in ds.coords.items():
-            put(name, dims, arr)
-        for name, da in ds.data_vars.items():
-            put(name, da.dims, da.values, da.attrs)
+        for name, vdims, arr, attrs in variables:
+            var = f.createVariable(name, "c" if arr.dtype.kind == "S" else arr.dtype, vdims)
+            var[:] = arr
+            for k, v in attrs.items():
+                var._attributes[k] = v
         # straight into the attribute table: an attribute called "variables" (the reference's schema has
         # one) must not shadow netcdf_file.variables
-        for k, v in ds.attrs.items():
-            f._attributes[k] = _encode_attr(v)
-        f._attributes["coordinates_hint"] = " ".join(ds.coords)   # which variables are coordinates (for read_netcdf)
+        for k, v in gattrs.items():
+            f._attributes[k] = v
     return "NETCDF3_64BIT"
 
 
@@ -263,6 +288,10 @@ def read_netcdf(path: str, lazy: bool = False) -> Dataset:
         dv = {k: DataArray(v.values, v.dims, attrs=dict(v.attrs)) for k, v in x.data_vars.items()}
         co = {k: (tuple(v.dims), v.values) for k, v in x.coords.items()}
         return Dataset(dv, co, dict(x.attrs))
+    with open(path, "rb") as fh:
+        magic = fh.read(4)
+    if magic == b"CDF\x05":
+        return _read_cdf5(path, lazy)
     # NetCDF-3 through scipy.  Large numeric variables (the slice itself: GBs) are NOT read here: they come back as
     # read-only np.memmap views of the file in its on-disk (big-endian) byte order, so that the only pass over the
     # data is the staging copy into pinned memory (stage.stage_blocks), which converts the byte order on the way.
@@ -317,4 +346,38 @@ def read_netcdf(path: str, lazy: bool = False) -> Dataset:
             co[name] = (dims, np.asarray(arr).astype(dt.newbyteorder("=")))
         else:
             dv[name] = DataArray(arr, dims, attrs=vattrs)
+    return Dataset(dv, co, attrs)
+
+
+def _read_cdf5(path: str, lazy: bool) -> Dataset:
+    """A CDF-5 file (cdf5.py): small variables decoded eagerly; with ``lazy`` numeric variables of at least
+    LAZY_READ_BYTES stay memory-mapped in their on-disk (big-endian) byte order, exactly like the NetCDF-3 path."""
+    from .cdf5 import read_classic
+
+    dims, variables, gattrs = read_classic(path)
+    attrs = dict(gattrs)
+    coord_names = set(str(attrs.pop("coordinates_hint", "")).split())
+    dv, co = {}, {}
+    for name, (vdims, data, vattrs) in variables.items():
+        vattrs = dict(vattrs)
+        units = str(vattrs.get("units", ""))
+        is_coord = name in coord_names or vdims == (name,)
+        if (lazy and not is_coord and data.dtype.kind in "fiu" and data.nbytes >= LAZY_READ_BYTES
+                and not units.startswith("seconds since")):
+            dv[name] = DataArray(data, vdims, attrs=vattrs)
+            continue
+        arr = np.array(data)
+        if arr.dtype.byteorder == ">":
+            arr = arr.astype(arr.dtype.newbyteorder("="))
+        if arr.dtype.kind == "S" and vdims and vdims[-1].startswith("string"):
+            arr = np.array([b"".join(row).decode().rstrip("\x00") for row in arr.reshape(-1, arr.shape[-1])],
+                           dtype=object).reshape(arr.shape[:-1]).astype(str)
+            vdims = vdims[:-1]
+        if units.startswith("seconds since 1970-01-01"):
+            arr = (_EPOCH + arr.astype(np.int64).astype("timedelta64[s]")).astype("datetime64[ns]")
+            vattrs = {k: v for k, v in vattrs.items() if k not in ("units", "calendar")}
+        if is_coord:
+            co[name] = (vdims, arr)
+        else:
+            dv[name] = DataArray(arr, vdims, attrs=vattrs)
     return Dataset(dv, co, attrs)
