@@ -202,7 +202,19 @@ def _gather_chunk_mt(base: np.ndarray, t_idx, l_idx, c0: int, c1: int, host: np.
         f.result()
 
 
-def stage_blocks(ds: Dataset, variables: list[str], ops, chunk_bytes: int | None = None) -> tuple[list[torch.Tensor], int]:
+def shard_pieces(S: int, n_vars: int, r0: int, r1: int) -> list[tuple[int, int, int]]:
+    """Base rows [r0, r1) of the stacked matrix (row r = v * S + p, slice_tools.py:323-336) as per-variable point
+    ranges [(v, p0, p1), ...] - what one rank of a row-sharded run has to stage."""
+    out = []
+    for v in range(n_vars):
+        a, b = max(r0, v * S), min(r1, (v + 1) * S)
+        if a < b:
+            out.append((v, a - v * S, b - v * S))
+    return out
+
+
+def stage_blocks(ds: Dataset, variables: list[str], ops, chunk_bytes: int | None = None,
+                 pieces: list[tuple[int, int, int]] | None = None) -> tuple[list[torch.Tensor], int]:
     """Host slice -> device blocks in the native (T, S = L*A*O) time-major layout, one per variable
     (what era5_svd.py:384-388 hands to the matrix build, era5_download.py:36-42 being the file layout).
 
@@ -220,7 +232,10 @@ def stage_blocks(ds: Dataset, variables: list[str], ops, chunk_bytes: int | None
     ring = None
     ring_events = [None, None]
     slot = 0
-    for v in variables:
+    S_full = None
+    todo = [(vi, None, None) for vi in range(len(variables))] if pieces is None else list(pieces)
+    for vi, p0, p1 in todo:
+        v = variables[vi]
         da = ds[v]
         lz = da.lazy()
         if da.dims != _NATIVE_DIMS:
@@ -229,16 +244,26 @@ def stage_blocks(ds: Dataset, variables: list[str], ops, chunk_bytes: int | None
             lz = type(lz)(np.ascontiguousarray(a))
         base = lz.base
         T, L, A, O = lz.shape
+        S_full = L * A * O
         t_idx, l_idx = lz.index.get(0), lz.index.get(1)
+        col0, ncols = 0, S_full
+        if p0 is not None:
+            # the levels that hold points [p0, p1): gather only those, keep the column window inside them
+            l_lo, l_hi = p0 // (A * O), (p1 - 1) // (A * O) + 1
+            l_idx = (np.arange(L) if l_idx is None else np.asarray(l_idx))[l_lo:l_hi]
+            col0, ncols, L = p0 - l_lo * A * O, p1 - p0, l_hi - l_lo
         if 2 in lz.index or 3 in lz.index:
             base = np.take(np.take(base, lz.index.get(2, np.arange(base.shape[2])), axis=2),
                            lz.index.get(3, np.arange(base.shape[3])), axis=3)
         tdt = torch.from_numpy(np.empty(0, dtype=base.dtype.newbyteorder("="))).dtype
         row_bytes = L * A * O * base.dtype.itemsize
-        block = torch.empty((T, L * A * O), dtype=tdt, device=dev)
+        block = torch.empty((T, ncols), dtype=tdt, device=dev)
         if T * row_bytes < (1 << 16):
             # tiny slice (the mock configuration): one pageable copy
-            block.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(lz), dtype=base.dtype.newbyteorder("=")).reshape(T, -1)))
+            full = np.ascontiguousarray(np.asarray(lz), dtype=base.dtype.newbyteorder("=")).reshape(T, -1)
+            if p0 is not None:
+                full = np.ascontiguousarray(full[:, p0:p1])
+            block.copy_(torch.from_numpy(full))
             blocks.append(block)
             continue
         rows = max(1, min(T, chunk_bytes // row_bytes))
@@ -254,7 +279,8 @@ def stage_blocks(ds: Dataset, variables: list[str], ops, chunk_bytes: int | None
             host = buf[: (c1 - c0) * row_bytes].view(tdt).view(c1 - c0, L, A, O).numpy()
             _gather_chunk_mt(base, t_idx, l_idx, c0, c1, host)
             with torch.cuda.stream(copy_stream):
-                block[c0:c1].copy_(buf[: (c1 - c0) * row_bytes].view(tdt).view(c1 - c0, L * A * O), non_blocking=True)
+                block[c0:c1].copy_(buf[: (c1 - c0) * row_bytes].view(tdt).view(c1 - c0, L * A * O)[:, col0 : col0 + ncols],
+                                   non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             ring_events[slot] = ev
@@ -263,7 +289,7 @@ def stage_blocks(ds: Dataset, variables: list[str], ops, chunk_bytes: int | None
     torch.cuda.current_stream(dev).wait_stream(copy_stream)
     for b in blocks:
         b.record_stream(copy_stream)
-    return blocks, blocks[0].shape[1]
+    return blocks, (S_full if pieces is not None else blocks[0].shape[1])
 
 
 def _to_blocks(ds: Dataset, variables: list[str], ops) -> tuple[list[torch.Tensor], int]:
@@ -329,24 +355,41 @@ def main(config: dict | None = None, write_to_netcdf: bool = False, use_dvc: boo
     return svd_results, added_to_dvc, retrieved_from_dvc
 
 
-def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
-    """The compute phase of main (era5_svd.py:384-425) on the device."""
-    variables, d = parsed_config["variables"], parsed_config["delay_embedding"]
-    ds = ds[variables]                                                   # config order (:384)
+def _prepare(ds: Dataset, parsed_config: dict) -> Dataset:
+    """Selections of the compute phase (era5_svd.py:384-388): host index work, lazy on file-backed data."""
+    ds = ds[parsed_config["variables"]]                                  # config order (:384)
     ds = slice_era5_dataset(ds, levels=parsed_config["levels"])          # (:385) no start/end: quirk Q7
-    ds = resample_era5_dataset(ds, parsed_config["delta_time"])          # (:388)
+    return resample_era5_dataset(ds, parsed_config["delta_time"])        # (:388)
+
+
+def _row_weights(ds: Dataset, n_vars: int) -> np.ndarray:
+    """sqrt(cos(latitude)) per base row - opt-in extension (absent in the reference)."""
+    lat = np.deg2rad(np.asarray(ds.coord("latitude"), dtype=np.float64))
+    w = np.sqrt(np.clip(np.cos(lat), 0.0, None))
+    L, O = len(ds.coord("level")), len(ds.coord("longitude"))
+    return np.tile(np.tile(np.repeat(w, O), L), n_vars)
+
+
+def _device_arrays(ds: Dataset, parsed_config: dict, ops, comm=None, rank: int = 0, world: int = 1) -> dict:
+    """Build + SVD of this rank's rows on ``ops.device`` (era5_svd.py:389-415).  Returns host arrays: U (rows of this
+    rank, block-major over the delay blocks), s, V, optional X / mean / std of this rank, and the row range."""
+    from .dist import shard_rows
+
+    variables, d = parsed_config["variables"], parsed_config["delay_embedding"]
     mean_center = bool(parsed_config["mean_center"])
     scale = bool(parsed_config["scale"]) and mean_center                 # quirk Q4 (:389-395)
-    ops = get_ops(parsed_config.get("device", "cuda:0"))
     precision = parsed_config.get("precision", "auto")
+    S = int(np.prod([len(ds.coord(c)) for c in ("level", "latitude", "longitude")]))
+    m0 = len(variables) * S
+    r0, r1 = shard_rows(m0, world, rank)
     with torch.cuda.device(ops.device):
-        blocks, S = _to_blocks(ds, variables, ops)
+        if world > 1:
+            blocks, _ = stage_blocks(ds, variables, ops, pieces=shard_pieces(S, len(variables), r0, r1))
+        else:
+            blocks, _ = _to_blocks(ds, variables, ops)
         weights = None
         if parsed_config.get("area_weighting"):                          # opt-in extension (absent in the reference)
-            lat = np.deg2rad(np.asarray(ds.coord("latitude"), dtype=np.float64))
-            w = np.sqrt(np.clip(np.cos(lat), 0.0, None))
-            L, O = len(ds.coord("level")), len(ds.coord("longitude"))
-            w_rows = np.tile(np.tile(np.repeat(w, O), L), len(variables))
+            w_rows = _row_weights(ds, len(variables))[r0:r1]
             weights = torch.from_numpy(w_rows.astype(np.float32 if blocks[0].dtype == torch.float32 else np.float64)).to(ops.device)
         # opt-in extension (north_star "float cast"; absent in the reference): matrix_dtype = "float32" stores the
         # snapshot matrix in float32 whatever the slice's dtype (the cast happens inside the build kernel, statistics
@@ -359,18 +402,42 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
             weights = weights.to(xdtype)
         built = build_matrix_device(ops, blocks, mean_center=mean_center, scale=scale, weights=weights,
                                     check_finite=True, dtype=xdtype)
+        del blocks
         label = "standard" if parsed_config["svd_type"] == "standard" else "randomized"
-        log_and_print(logger, f"Performing {label} SVD...")
+        if rank == 0:
+            log_and_print(logger, f"Performing {label} SVD...")
         U, s, V = svd_device(ops, built.X, svd_type=parsed_config["svd_type"], n_components=parsed_config["n_components"],
-                             delay=d, seed=parsed_config.get("random_seed"), precision=precision)
-        log_and_print(logger, f"{label.capitalize()} SVD complete.")
-        if int(built.nonfinite.item()):
+                             delay=d, seed=parsed_config.get("random_seed"), precision=precision, comm=comm,
+                             row_offset=r0, m0_global=m0)
+        if rank == 0:
+            log_and_print(logger, f"{label.capitalize()} SVD complete.")
+        bad = built.nonfinite.to(torch.float64)
+        if comm is not None:
+            comm.allreduce_sum_(bad)
+        if float(bad.item()) > 0:
             raise ValueError("Input contains NaN or infinity.")          # sklearn check_array (extmath.py:546)
         dt = built.X.dtype
-        U_h, s_h, V_h = U.to(dt).cpu().numpy(), s.to(dt).cpu().numpy(), V.to(dt).cpu().numpy()
-        X_h = built.X.cpu().numpy() if parsed_config["save_data_matrix"] else None
-        mean_h = built.mean.cpu().numpy() if built.mean is not None else None
-        std_h = built.std.cpu().numpy() if built.std is not None else None
+        out = {"U": U.to(dt).cpu().numpy(), "s": s.to(dt).cpu().numpy(), "V": V.to(dt).cpu().numpy(),
+               "X": built.X.cpu().numpy() if parsed_config["save_data_matrix"] else None,
+               "mean": built.mean.cpu().numpy() if built.mean is not None else None,
+               "std": built.std.cpu().numpy() if built.std is not None else None, "rows": (r0, r1), "m0": m0, "S": S}
+    return out
+
+
+def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
+    """The compute phase of main (era5_svd.py:384-425) on the device(s).  ``n_gpus`` > 1 (opt-in key)
+    row-shards the stage over that many GPUs of this node (stage_multi.py); the result is the same Dataset."""
+    variables, d = parsed_config["variables"], parsed_config["delay_embedding"]
+    n_gpus = int(parsed_config.get("n_gpus", 1) or 1)
+    dsp = _prepare(ds, parsed_config)
+    if n_gpus > 1:
+        from .stage_multi import compute_multi
+
+        arr = compute_multi(parsed_config, n_gpus)
+    else:
+        arr = _device_arrays(dsp, parsed_config, get_ops(parsed_config.get("device", "cuda:0")))
+    ds = dsp
+    U_h, s_h, V_h, X_h, mean_h, std_h, S = (arr[x] for x in ("U", "s", "V", "X", "mean", "std", "S"))
 
     m0 = len(variables) * S
     times = ds.coord("time")

@@ -214,3 +214,52 @@ def test_main_use_dvc_without_dvc(tmp_path, monkeypatch):
     assert added is False and retrieved is False and res["s"].shape == (6,)
     with pytest.raises(Exception, match="Error adding SVD results to DVC"):
         main(base_config(delay_embedding=1, n_components=5), write_to_netcdf=True, use_dvc=True)
+
+
+def test_stage_blocks_pieces_are_the_row_shards(tmp_path, monkeypatch, ops):
+    """Row-sharded staging (n_gpus > 1): the pieces a rank stages are exactly the columns [p0, p1) of the full per-variable
+    blocks, with level / time selections still pending on the lazy slice."""
+    import torch
+    from dmd_era5_b200.stage import _prepare, retrieve_era5_slice, shard_pieces, stage_blocks
+
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    cfg = base_config(delta_time="6h")
+    m, parsed = make_slice(tmp_path, cfg)
+    ds, _ = retrieve_era5_slice(parsed)
+    ds = _prepare(ds, parsed)
+    variables = parsed["variables"]
+    full, S = stage_blocks(ds, variables, ops)
+    assert S == 2 * 36 * 72 and len(full) == 2
+    m0 = 2 * S
+    for r0, r1 in ((0, 1000), (1000, S + 77), (S - 5, S + 5), (S + 77, m0), (0, m0), (2592 * 2 - 1, 2592 * 2 + 3)):
+        pieces = shard_pieces(S, 2, r0, r1)
+        blocks, S2 = stage_blocks(ds, variables, ops, pieces=pieces)
+        assert S2 == S and sum(b.shape[1] for b in blocks) == r1 - r0
+        for b, (v, p0, p1) in zip(blocks, pieces):
+            assert torch.equal(b, full[v][:, p0:p1])
+    torch.cuda.synchronize()
+
+
+def test_main_n_gpus_matches_single_device(tmp_path, monkeypatch):
+    """The opt-in ``n_gpus`` key: main() row-shards the stage over 2 worker processes / GPUs (stage_multi.py) and returns
+    the same Dataset as the single-device path (sigma, V to float64 round-off; U rows in the reference's order)."""
+    import torch
+    from dmd_era5_b200.era5_svd import main
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    for svd_type, d in (("randomized", 2), ("standard", 1)):
+        cfg = base_config(svd_type=svd_type, delay_embedding=d, mean_center=True, scale=True)
+        make_slice(tmp_path, cfg)
+        one, _, _ = main(cfg)
+        two, _, _ = main(dict(cfg, n_gpus=2))
+        assert sorted(one.data_vars) == sorted(two.data_vars)
+        assert sigma_rel_err(two["s"].values, one["s"].values) < 1e-10
+        assert np.max(np.abs(two["X"].values - one["X"].values)) == 0.0
+        assert vector_angles(two["U"].values, one["U"].values).max() < 1e-7
+        assert vector_angles(two["V"].values.T, one["V"].values.T).max() < 1e-7
+        if d > 1:
+            assert np.array_equal(two["X_mean"].values, one["X_mean"].values)
+        for c in one.coords:
+            assert np.array_equal(one.coord(c), two.coord(c)), c

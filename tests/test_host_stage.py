@@ -401,3 +401,36 @@ def test_write_netcdf_switches_to_cdf5_when_netcdf3_cannot_hold_the_result(tmp_p
         assert np.array_equal(a.coords[k][1], b.coords[k][1]), k
     assert a.attrs == b.attrs
     assert np.array_equal(b["U"].values, U) and b.coords["space"][1].dtype == np.int64     # CDF-5 keeps int64 coordinates
+
+
+def test_row_shard_bookkeeping_of_the_multi_gpu_stage(tmp_path):
+    """stage.shard_pieces (which points of which variable a rank stages) and stage_multi.assemble (per-rank files ->
+    the reference's row order, block-major over the delay blocks) - the host logic of ``n_gpus`` > 1, no GPU needed."""
+    from dmd_era5_b200.dist import shard_rows
+    from dmd_era5_b200.stage import shard_pieces
+    from dmd_era5_b200.stage_multi import assemble
+
+    S, V, d, k, world = 1000, 3, 2, 4, 3
+    m0 = S * V
+    assert shard_pieces(S, V, 0, m0) == [(0, 0, S), (1, 0, S), (2, 0, S)]
+    assert shard_pieces(S, V, 900, 2100) == [(0, 900, 1000), (1, 0, 1000), (2, 0, 100)]
+    assert shard_pieces(S, V, 1000, 1000) == []
+    rng = np.random.RandomState(0)
+    U = rng.standard_normal((m0 * d, k)).astype(np.float32)          # global, block-major over delays
+    mean = rng.standard_normal(m0).astype(np.float32)
+    X = rng.standard_normal((m0, 7)).astype(np.float32)
+    covered = 0
+    for r in range(world):
+        r0, r1 = shard_rows(m0, world, r)
+        covered += sum(p1 - p0 for _, p0, p1 in shard_pieces(S, V, r0, r1))
+        Ul = np.concatenate([U[j * m0 + r0 : j * m0 + r1] for j in range(d)])
+        np.save(tmp_path / f"U_{r}.npy", Ul)
+        np.save(tmp_path / f"mean_{r}.npy", mean[r0:r1])
+        np.save(tmp_path / f"X_{r}.npy", X[r0:r1])
+        np.save(tmp_path / f"rows_{r}.npy", np.array([r0, r1, m0, S], dtype=np.int64))
+    assert covered == m0
+    np.save(tmp_path / "s.npy", np.arange(k, dtype=np.float32))
+    np.save(tmp_path / "V.npy", rng.standard_normal((k, 6)).astype(np.float32))
+    out = assemble(str(tmp_path), world, d)
+    assert np.array_equal(out["U"], U) and np.array_equal(out["mean"], mean) and np.array_equal(out["X"], X)
+    assert out["std"] is None and out["m0"] == m0 and out["S"] == S
