@@ -249,7 +249,36 @@ __device__ __forceinline__ float4 tb_ld_chunk(uint32_t tile, int t, int c) {
 // longer series (T = 1460: 94 KB per tile), so that TWO CTAs stay resident and one CTA's loads overlap the other's
 // statistics / stores - with a single resident CTA the load and store phases alternate and HBM idles half the time.
 // Warp w: chunk w % (PB / 4), time part w / (PB / 4) (2 parts for PB = 32, 4 for PB = 16).
-template <typename Tx, int PB>
+// thread-block-cluster helpers (the CL > 1 instantiations: a long series is split over CL CTAs along time)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_peer_f64(const double* local, uint32_t rank) {
+  uint32_t a;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(tc::smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_peer_s32(const int* local, uint32_t rank) {
+  uint32_t a;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(tc::smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
+// CL = CTAs per point tile (thread-block cluster along TIME).  A series too long for two resident [T x 32] tiles
+// (T > ~850) used to fall back to 16-point tiles: 64-byte source segments, one DRAM activate per 64 bytes, 0.59 of
+// the copy rate at T = 1460.  With CL = 2 (4) each CTA holds [T / CL x 32 points] (128-byte segments, two resident
+// CTAs as at T = 744), the per-point sums cross the cluster through distributed shared memory (32 doubles per CTA)
+// and every CTA writes its own time range of the 32 rows (>= 2.9 KB contiguous per row at T = 1460).
+template <typename Tx, int PB, int CL>
 __global__ void __launch_bounds__(TB_THREADS)
 fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_t P, int col_shift,
                        Tx* __restrict__ X, int64_t ldx, Tx* __restrict__ mean_out, Tx* __restrict__ std_out,
@@ -262,23 +291,30 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
   __shared__ __align__(8) uint64_t bar_storage;
   const uint32_t tile = (tc::smem_u32(fb_smem) + 1023u) & ~1023u;
   const uint32_t bar = tc::smem_u32(&bar_storage);
+  __shared__ double cl_a[PB], cl_q[PB];     // this CTA's per-point sums, read by its cluster peers (CL > 1)
+  __shared__ int cl_n[PB];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int c = warp % NCH, h = warp / NCH;
-  const int64_t p0 = (int64_t)blockIdx.x * PB;
-  const int nbox = (T + TB_BOX_T - 1) / TB_BOX_T;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  const int64_t p0 = (int64_t)(blockIdx.x / CL) * PB;
+  // snapshots [tg0, tg0 + Tl) of the series belong to this CTA (whole 64-snapshot boxes per CTA); tile row = t - tg0
+  const int Tc = CL > 1 ? ((T + CL - 1) / CL + TB_BOX_T - 1) / TB_BOX_T * TB_BOX_T : T;
+  const int tg0 = (int)crank * Tc;
+  const int Tl = tg0 >= T ? 0 : (T - tg0 < Tc ? T - tg0 : Tc);
+  const int nbox = (Tl + TB_BOX_T - 1) / TB_BOX_T;
   if (threadIdx.x == 0) {
     tc::mbar_init(bar, 1);
     tc::fence_barrier_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc::mbar_arrive_expect_tx(bar, (uint32_t)nbox * (uint32_t)(TB_BOX_T * ROWB));
     for (int b = 0; b < nbox; ++b)
-      tc::tma_load_2d(tile + (uint32_t)b * (uint32_t)(TB_BOX_T * ROWB), &tm_src, (int32_t)p0, b * TB_BOX_T, bar);
+      tc::tma_load_2d(tile + (uint32_t)b * (uint32_t)(TB_BOX_T * ROWB), &tm_src, (int32_t)p0, tg0 + b * TB_BOX_T, bar);
   }
   __syncthreads();                 // barrier initialised before anyone polls it
-  // time range of this warp: NP parts split on multiples of 32 snapshots
-  const int t_part = ((T + 32 * NP - 1) / (32 * NP)) * 32;
-  const int t_begin = h * t_part < T ? h * t_part : T;
-  const int t_end = (h + 1) * t_part < T ? (h + 1) * t_part : T;
+  // time range of this warp: NP parts split on multiples of 32 snapshots (tile rows, i.e. relative to tg0)
+  const int t_part = ((Tl + 32 * NP - 1) / (32 * NP)) * 32;
+  const int t_begin = h * t_part < Tl ? h * t_part : Tl;
+  const int t_end = (h + 1) * t_part < Tl ? (h + 1) * t_part : Tl;
   // a source whose base is not 16-byte aligned is mapped from the aligned address below it (boxes under the 128-byte
   // swizzle must start on 16-byte boundaries): tile column x holds point p0 + x - col_shift
   const int64_t gp0 = p0 + 4 * c - col_shift;
@@ -314,13 +350,32 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
 #pragma unroll
       for (int e = 0; e < 4; ++e) { part_a[h][4 * c + e] = s[e]; part_n[h][4 * c + e] = cnt[e]; }
     __syncthreads();
+    if constexpr (CL > 1) {
+      // this CTA's totals -> cl_a / cl_n, visible to the peers after the cluster barrier
+      if (threadIdx.x < PB) {
+        double tot = 0.0;
+        int nv = 0;
+#pragma unroll
+        for (int hh = 0; hh < NP; ++hh) { nv += part_n[hh][threadIdx.x]; tot += part_a[hh][threadIdx.x]; }
+        cl_a[threadIdx.x] = tot;
+        cl_n[threadIdx.x] = nv;
+      }
+      cluster_sync_all();
+    }
     int n_valid[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       n_valid[e] = 0;
       double tot = 0.0;
+      if constexpr (CL > 1) {
+        for (uint32_t rk = 0; rk < (uint32_t)CL; ++rk) {       // fixed rank order: every CTA forms the same mean
+          tot += ld_peer_f64(&cl_a[4 * c + e], rk);
+          n_valid[e] += ld_peer_s32(&cl_n[4 * c + e], rk);
+        }
+      } else {
 #pragma unroll
-      for (int hh = 0; hh < NP; ++hh) { n_valid[e] += part_n[hh][4 * c + e]; tot += part_a[hh][4 * c + e]; }
+        for (int hh = 0; hh < NP; ++hh) { n_valid[e] += part_n[hh][4 * c + e]; tot += part_a[hh][4 * c + e]; }
+      }
       const double mean = n_valid[e] > 0 ? tot / (double)n_valid[e] : __longlong_as_double(0x7ff8000000000000LL);
       mean_x[e] = (Tx)mean;
     }
@@ -347,18 +402,36 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
 #pragma unroll
         for (int e = 0; e < 4; ++e) { part_a[h][4 * c + e] = a[e]; part_q[h][4 * c + e] = q[e]; }
       __syncthreads();
+      if constexpr (CL > 1) {
+        cluster_sync_all();        // every peer has finished reading cl_a of the mean pass
+        if (threadIdx.x < PB) {
+          double at = 0.0, qt = 0.0;
+#pragma unroll
+          for (int hh = 0; hh < NP; ++hh) { at += part_a[hh][threadIdx.x]; qt += part_q[hh][threadIdx.x]; }
+          cl_a[threadIdx.x] = at;
+          cl_q[threadIdx.x] = qt;
+        }
+        cluster_sync_all();
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         double at = 0.0, qt = 0.0;
+        if constexpr (CL > 1) {
+          for (uint32_t rk = 0; rk < (uint32_t)CL; ++rk) {
+            at += ld_peer_f64(&cl_a[4 * c + e], rk);
+            qt += ld_peer_f64(&cl_q[4 * c + e], rk);
+          }
+        } else {
 #pragma unroll
-        for (int hh = 0; hh < NP; ++hh) { at += part_a[hh][4 * c + e]; qt += part_q[hh][4 * c + e]; }
+          for (int hh = 0; hh < NP; ++hh) { at += part_a[hh][4 * c + e]; qt += part_q[hh][4 * c + e]; }
+        }
         const double m2 = n_valid[e] > 0 ? at / (double)n_valid[e] : 0.0;
         double var = n_valid[e] > 0 ? qt / (double)n_valid[e] - m2 * m2 : __longlong_as_double(0x7ff8000000000000LL);
         if (var < 0.0) var = 0.0;
         std_x[e] = (Tx)sqrt(var);
       }
     }
-    if (h == 0 && lane < 4 && gp0 + lane >= 0 && gp0 + lane < P) {
+    if (crank == 0 && h == 0 && lane < 4 && gp0 + lane >= 0 && gp0 + lane < P) {
       // lane e publishes point e (static register indexing kept by the unrolled select)
       Tx mv = mean_x[0], sv = std_x[0];
 #pragma unroll
@@ -378,7 +451,7 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
         if (do_scale) v = v / std_x[e];
         if (weights) v = v * w4[e];
         if (check_finite && !isfinite((double)v)) bad = 1;      // the value written (see transpose_kernel)
-        const int64_t off = (gp0 + e) * ldx + t;
+        const int64_t off = (gp0 + e) * ldx + tg0 + t;
         if (X) X[off] = v;
         if (Xhi) {
           const float hh = tc::tf32_hi((float)v);
@@ -391,6 +464,9 @@ fused_build_tma_kernel(const __grid_constant__ CUtensorMap tm_src, int T, int64_
   if (check_finite) {
     int any = __syncthreads_or(bad);
     if (any && threadIdx.x == 0) atomicExch(nonfinite_flag, 1);
+  }
+  if constexpr (CL > 1) {
+    if (center) cluster_sync_all();      // a CTA's shared memory must outlive its peers' reads of cl_a / cl_q
   }
 }
 
@@ -408,37 +484,68 @@ static unsigned build_debug_flags() {
   return ((e && e[0] == '1') ? 1u : 0u) | ((f && f[0] == '1') ? 2u : 0u);
 }
 
+template <typename Tx, int PB, int CL>
+static int launch_build_tma(const CUtensorMap& tm, unsigned tiles, size_t tile_bytes, int64_t T, int64_t P, int shift, Tx* X,
+                            int64_t ldx, Tx* mean_out, Tx* std_out, const Tx* weights, bool center, bool scale, bool check,
+                            int* nonfinite_flag, cudaStream_t st, float* Xhi, float* Xlo) {
+  auto kern = fused_build_tma_kernel<Tx, PB, CL>;
+  ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * CL);
+  cfg.blockDim = dim3(TB_THREADS);
+  cfg.dynamicSmemBytes = tile_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  ERA5SVD_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, (int)T, P, shift, X, ldx, mean_out, std_out, weights, center ? 1 : 0,
+                                  (center && scale) ? 1 : 0, check ? 1 : 0, nonfinite_flag, Xhi, Xlo));
+  return ERA5SVD_OK;
+}
+
 template <typename Tx>
 int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, Tx* X, int64_t ldx, Tx* mean_out,
                        Tx* std_out, const Tx* weights, bool center, bool scale, bool check, int* nonfinite_flag,
                        cudaStream_t st, float* Xhi, float* Xlo) {
-  const int64_t tpad = ceil_div(T, (int64_t)TB_BOX_T) * TB_BOX_T;
   if ((src_ld * 4) % 16 != 0 || P + 4 >= (int64_t)1 << 31) return 0;
-  // 32-point tiles while two of them fit one SM (T <= ~850), else 16-point tiles (two resident CTAs up to T ~ 1750)
-  const size_t tile32 = (size_t)tpad * 128 + 1024, tile16 = (size_t)tpad * 64 + 1024;
+  // 32-point tiles (128-byte source segments), two resident CTAs per SM: the whole series in one CTA while
+  // [T x 32] fits half an SM (T <= ~850), else split along time over a cluster of 2 (T <= ~1750) or 4 CTAs
+  // (T <= ~3500).  ERA5SVD_BUILD_PB16=1 / ERA5SVD_BUILD_PB32=1 select the earlier single-CTA variants (diagnostics).
   const size_t two_resident = 112 * 1024;
   const unsigned dbg = build_debug_flags();
-  const bool pb16 = ((tile32 > two_resident && tile16 <= two_resident) || (dbg & 2)) && !(dbg & 1);
-  const size_t tile_bytes = pb16 ? tile16 : tile32;
+  auto part_bytes = [&](int cl, int rowb) {
+    const int64_t tc_ = cl > 1 ? ceil_div(ceil_div(T, (int64_t)cl), (int64_t)TB_BOX_T) * TB_BOX_T
+                               : ceil_div(T, (int64_t)TB_BOX_T) * TB_BOX_T;
+    return (size_t)tc_ * rowb + 1024;
+  };
+  int cl = 1, pb = 32;
+  if (dbg & 2) {
+    pb = 16;
+  } else if (!(dbg & 1) && part_bytes(1, 128) > two_resident) {
+    if (part_bytes(2, 128) <= two_resident) cl = 2;
+    else if (part_bytes(4, 128) <= two_resident) cl = 4;
+    else if (part_bytes(1, 64) <= two_resident) pb = 16;
+  }
+  const size_t tile_bytes = part_bytes(cl, pb * 4);
   if (tile_bytes > 225 * 1024) return 0;
-  const int pb = pb16 ? 16 : 32;
   CUtensorMap tm;
   int shift = 0;
   int rc = tc::make_tmap(&tm, src, P, T, src_ld, (uint32_t)pb, TB_BOX_T, &shift,
-                         pb16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+                         pb == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  const unsigned grid = (unsigned)ceil_div(P + shift, (int64_t)pb);
-  if (pb16) {
-    auto kern = fused_build_tma_kernel<Tx, 16>;
-    ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
-    kern<<<grid, TB_THREADS, tile_bytes, st>>>(tm, (int)T, P, shift, X, ldx, mean_out, std_out, weights, center ? 1 : 0,
-                                               (center && scale) ? 1 : 0, check ? 1 : 0, nonfinite_flag, Xhi, Xlo);
-  } else {
-    auto kern = fused_build_tma_kernel<Tx, 32>;
-    ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
-    kern<<<grid, TB_THREADS, tile_bytes, st>>>(tm, (int)T, P, shift, X, ldx, mean_out, std_out, weights, center ? 1 : 0,
-                                               (center && scale) ? 1 : 0, check ? 1 : 0, nonfinite_flag, Xhi, Xlo);
-  }
+  const unsigned tiles = (unsigned)ceil_div(P + shift, (int64_t)pb);
+#define ERA5SVD_BUILD_ARGS tm, tiles, tile_bytes, T, P, shift, X, ldx, mean_out, std_out, weights, center, scale, check, \
+                           nonfinite_flag, st, Xhi, Xlo
+  if (pb == 16) rc = launch_build_tma<Tx, 16, 1>(ERA5SVD_BUILD_ARGS);
+  else if (cl == 1) rc = launch_build_tma<Tx, 32, 1>(ERA5SVD_BUILD_ARGS);
+  else if (cl == 2) rc = launch_build_tma<Tx, 32, 2>(ERA5SVD_BUILD_ARGS);
+  else rc = launch_build_tma<Tx, 32, 4>(ERA5SVD_BUILD_ARGS);
+#undef ERA5SVD_BUILD_ARGS
+  if (rc) return rc;
   rc = check_launch("fused_build_tma_kernel");
   return rc ? rc : 1;
 }

@@ -259,7 +259,9 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     cands = [ops.col_absmax(U[j * m0 : (j + 1) * m0], j * m0_global + row_offset) for j in range(d)]
     a = torch.stack([c[0] for c in cands]); r = torch.stack([c[1] for c in cands]); sg = torch.stack([c[2] for c in cands])
     if comm.world > 1:
-        a = comm.allgather(a).reshape(-1, kk); r = comm.allgather(r).reshape(-1, kk); sg = comm.allgather(sg).reshape(-1, kk)
+        # ONE all-gather for the three candidate arrays (value, global row, sign): row indices < 2^53 are exact in float64
+        packed = comm.allgather(torch.stack([a, r.to(torch.float64), sg])).permute(1, 0, 2, 3).reshape(3, -1, kk)
+        a, r, sg = packed[0].contiguous(), packed[1].to(torch.int64).contiguous(), packed[2].contiguous()
     sign = ops.maxloc_combine(a, r, sg)
     ops.scale_cols(U, sign)
     Vk = Vt[:kk]

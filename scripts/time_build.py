@@ -1,5 +1,7 @@
 """Time the build kernel alone (TMA tile loads vs the register-staged kernel, flag 8 = ERA5SVD_BUILD_NO_TMA) at the
-c2 shape and at a c3-shard-like shape (T = 1460, one resident CTA per SM).  Bytes = read m*n*4 + write m*n*4."""
+c2 shape and at a c3-shard-like shape (T = 1460).  Bytes = read m*n*4 + write m*n*4.
+ERA5SVD_BUILD_PB16=1 selects the round-1 variant for long series (16-point tiles, one CTA per tile) instead of the
+32-point tiles split along time over a thread-block cluster."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,7 +21,7 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
-for T, P in [(744, 1038240), (1460, 1265356)]:
+for T, P in [(744, 1038240), (1460, 1265356), (2920, 600000)]:
     src = torch.randn((T, P), device="cuda") * 10 + 250
     ld = T + (-T) % 8
     X = torch.empty((P, ld), device="cuda")[:, :T]
