@@ -481,7 +481,8 @@ int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer,
 static unsigned build_debug_flags() {
   const char* e = getenv("ERA5SVD_BUILD_PB32");
   const char* f = getenv("ERA5SVD_BUILD_PB16");       // bit 1: 16-point tiles for short series as well
-  return ((e && e[0] == '1') ? 1u : 0u) | ((f && f[0] == '1') ? 2u : 0u);
+  const char* g = getenv("ERA5SVD_BUILD_CLUSTER");    // bit 2: long series as 32-point tiles split over a cluster
+  return ((e && e[0] == '1') ? 1u : 0u) | ((f && f[0] == '1') ? 2u : 0u) | ((g && g[0] == '1') ? 4u : 0u);
 }
 
 template <typename Tx, int PB, int CL>
@@ -512,9 +513,12 @@ int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, T
                        Tx* std_out, const Tx* weights, bool center, bool scale, bool check, int* nonfinite_flag,
                        cudaStream_t st, float* Xhi, float* Xlo) {
   if ((src_ld * 4) % 16 != 0 || P + 4 >= (int64_t)1 << 31) return 0;
-  // 32-point tiles (128-byte source segments), two resident CTAs per SM: the whole series in one CTA while
-  // [T x 32] fits half an SM (T <= ~850), else split along time over a cluster of 2 (T <= ~1750) or 4 CTAs
-  // (T <= ~3500).  ERA5SVD_BUILD_PB16=1 / ERA5SVD_BUILD_PB32=1 select the earlier single-CTA variants (diagnostics).
+  // 32-point tiles (128-byte source segments) while two [T x 32] tiles fit one SM (T <= ~850); longer series take
+  // 16-point tiles (64-byte segments), still two resident CTAs (T <= ~1750).  The alternative for long series -
+  // 32-point tiles split along time over a cluster of 2 / 4 CTAs, statistics through distributed shared memory
+  // (ERA5SVD_BUILD_CLUSTER=1) - was measured and is NOT the default: with centring it is slower (T = 1460: 3.91 vs
+  // 3.00 ms, the cluster barriers couple the CTAs' load and store phases), without statistics slightly faster
+  // (2.83 vs 2.99 ms); profiles/r02_build_cluster.txt.  It remains the only TMA path for 1750 < T <= ~3500.
   const size_t two_resident = 112 * 1024;
   const unsigned dbg = build_debug_flags();
   auto part_bytes = [&](int cl, int rowb) {
@@ -526,7 +530,8 @@ int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, T
   if (dbg & 2) {
     pb = 16;
   } else if (!(dbg & 1) && part_bytes(1, 128) > two_resident) {
-    if (part_bytes(2, 128) <= two_resident) cl = 2;
+    if (!(dbg & 4) && part_bytes(1, 64) <= two_resident) pb = 16;
+    else if (part_bytes(2, 128) <= two_resident) cl = 2;
     else if (part_bytes(4, 128) <= two_resident) cl = 4;
     else if (part_bytes(1, 64) <= two_resident) pb = 16;
   }
