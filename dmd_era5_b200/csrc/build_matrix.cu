@@ -518,7 +518,9 @@ int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, T
   // 32-point tiles split along time over a cluster of 2 / 4 CTAs, statistics through distributed shared memory
   // (ERA5SVD_BUILD_CLUSTER=1) - was measured and is NOT the default: with centring it is slower (T = 1460: 3.91 vs
   // 3.00 ms, the cluster barriers couple the CTAs' load and store phases), without statistics slightly faster
-  // (2.83 vs 2.99 ms); profiles/r02_build_cluster.txt.  It remains the only TMA path for 1750 < T <= ~3500.
+  // (2.83 vs 2.99 ms); profiles/r02_build_cluster.txt.  Series too long for a 16-point tile (T > ~3500, e.g. c4's
+  // 8760 hourly snapshots) do take it, with 4 or 8 CTAs per tile: one read + one write instead of the 1.5x traffic of
+  // the two-kernel fallback.
   const size_t two_resident = 112 * 1024;
   const unsigned dbg = build_debug_flags();
   auto part_bytes = [&](int cl, int rowb) {
@@ -527,13 +529,17 @@ int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, T
     return (size_t)tc_ * rowb + 1024;
   };
   int cl = 1, pb = 32;
+  const size_t one_resident = 225 * 1024;
   if (dbg & 2) {
     pb = 16;
   } else if (!(dbg & 1) && part_bytes(1, 128) > two_resident) {
-    if (!(dbg & 4) && part_bytes(1, 64) <= two_resident) pb = 16;
-    else if (part_bytes(2, 128) <= two_resident) cl = 2;
-    else if (part_bytes(4, 128) <= two_resident) cl = 4;
-    else if (part_bytes(1, 64) <= two_resident) pb = 16;
+    if (dbg & 4) {                                               // diagnostics: cluster variant wherever it fits
+      cl = part_bytes(2, 128) <= two_resident ? 2 : (part_bytes(4, 128) <= one_resident ? 4 : 8);
+    } else if (part_bytes(1, 64) <= one_resident) {
+      pb = 16;                                                   // T <= ~3500 (two resident CTAs up to ~1750)
+    } else {
+      cl = part_bytes(4, 128) <= one_resident ? 4 : 8;           // T <= ~7000 / ~14000 (c4: 8760 hourly snapshots)
+    }
   }
   const size_t tile_bytes = part_bytes(cl, pb * 4);
   if (tile_bytes > 225 * 1024) return 0;
@@ -548,7 +554,8 @@ int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, T
   if (pb == 16) rc = launch_build_tma<Tx, 16, 1>(ERA5SVD_BUILD_ARGS);
   else if (cl == 1) rc = launch_build_tma<Tx, 32, 1>(ERA5SVD_BUILD_ARGS);
   else if (cl == 2) rc = launch_build_tma<Tx, 32, 2>(ERA5SVD_BUILD_ARGS);
-  else rc = launch_build_tma<Tx, 32, 4>(ERA5SVD_BUILD_ARGS);
+  else if (cl == 4) rc = launch_build_tma<Tx, 32, 4>(ERA5SVD_BUILD_ARGS);
+  else rc = launch_build_tma<Tx, 32, 8>(ERA5SVD_BUILD_ARGS);
 #undef ERA5SVD_BUILD_ARGS
   if (rc) return rc;
   rc = check_launch("fused_build_tma_kernel");

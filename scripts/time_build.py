@@ -21,7 +21,7 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
-for T, P in [(744, 1038240), (1460, 1265356), (2920, 600000)]:
+for T, P in [(744, 1038240), (1460, 1265356), (2920, 600000), (8760, 200000)]:
     src = torch.randn((T, P), device="cuda") * 10 + 250
     ld = T + (-T) % 8
     X = torch.empty((P, ld), device="cuda")[:, :T]

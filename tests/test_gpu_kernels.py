@@ -43,10 +43,12 @@ def test_build_rows(ops, dtype, tol, flags):
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 2e-6)])
-@pytest.mark.parametrize("T,P,ld_src", [(744, 1000, 1000), (1460, 333, 336), (2920, 200, 200), (5000, 64, 64), (744, 130, 131)])
+@pytest.mark.parametrize("T,P,ld_src", [(744, 1000, 1000), (1460, 333, 336), (2920, 200, 200), (5000, 64, 64), (744, 130, 131),
+                                        (8760, 96, 96), (3600, 40, 40)])
 def test_build_rows_long_series(ops, dtype, tol, T, P, ld_src):
-    """Long time axes: the single-read smem-tile kernel (T up to ~1700 for float32) and the two-kernel path beyond it,
-    aligned and misaligned source pitches, NaN skipping, scaling."""
+    """Long time axes: 16-point TMA tiles (float32, T up to ~3500), 32-point tiles split along time over a cluster of 4 / 8
+    CTAs with the statistics combined through distributed shared memory (T = 3600, 5000, 8760), the register-staged tile
+    kernel and the two-kernel path (float64), aligned and misaligned source pitches, NaN skipping, scaling."""
     rng = np.random.RandomState(T + P)
     src = (rng.rand(T, ld_src) * 30 + 250 + 5 * np.sin(np.arange(T))[:, None]).astype(dtype)
     src[T // 3, 7] = np.nan                      # skipped by mean / std like xarray does
