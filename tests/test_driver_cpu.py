@@ -187,3 +187,33 @@ def test_sketch_wider_than_the_rank_drops_noise_directions():
     assert torch.isfinite(U).all() and torch.isfinite(s).all()
     assert sigma_rel_err(s[:rank], s0[:rank]) < 1e-5
     assert float(s[rank:].abs().max()) < 1e-6 * s0[0]
+
+
+def test_subspace_eigensolver_topk_and_fallback(monkeypatch):
+    """standard.sym_eig_topk_subspace (the top-k route of the Gram-route standard SVD for time-sized matrices): block
+    subspace iteration with Rayleigh-Ritz on the CPU stand-ins.  A decaying spectrum converges to eigh's leading pairs to
+    the requested residual; a flat spectrum does not converge and the function says so (the caller then takes the
+    tridiagonal route)."""
+    from dmd_era5_b200 import standard
+
+    rng = np.random.RandomState(0)
+    n, k = 1100, 20
+    Qm = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    lam = 50.0 * 0.85 ** np.arange(n)
+    G = (Qm * lam) @ Qm.T
+    stats = {}
+    out = standard.sym_eig_topk_subspace(FakeOps(), torch.from_numpy(G), k, 1e-13, stats)
+    assert out is not None and "subspace iteration" in stats["eig_route"]
+    w, V = out
+    assert np.max(np.abs(w.numpy() - lam[:k]) / lam[:k]) < 1e-12
+    assert vector_angles(V.numpy(), Qm[:, :k]).max() < 1e-9
+    assert np.max(np.abs(V.numpy().T @ V.numpy() - np.eye(k))) < 1e-12
+    resid = np.linalg.norm(G @ V.numpy() - V.numpy() * w.numpy(), axis=0).max() / lam[0]
+    assert resid < 2e-13
+    # dispatch: sym_eig_topk takes this route for n >= SUBSPACE_MIN_N, 8 k <= n
+    w2, V2 = standard.sym_eig_topk(FakeOps(), torch.from_numpy(G), k)
+    assert np.array_equal(w2.numpy(), w.numpy())
+    # flat spectrum: no convergence within the iteration budget
+    monkeypatch.setattr(standard, "SUBSPACE_MAX_ITERS", 8)
+    Gf = (Qm * (1.0 + 1e-3 * rng.rand(n))) @ Qm.T
+    assert standard.sym_eig_topk_subspace(FakeOps(), torch.from_numpy(Gf), k, 1e-13) is None
