@@ -518,9 +518,9 @@ int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, T
   // 32-point tiles split along time over a cluster of 2 / 4 CTAs, statistics through distributed shared memory
   // (ERA5SVD_BUILD_CLUSTER=1) - was measured and is NOT the default: with centring it is slower (T = 1460: 3.91 vs
   // 3.00 ms, the cluster barriers couple the CTAs' load and store phases), without statistics slightly faster
-  // (2.83 vs 2.99 ms); profiles/r02_build_cluster.txt.  Series too long for a 16-point tile (T > ~3500, e.g. c4's
-  // 8760 hourly snapshots) do take it, with 4 or 8 CTAs per tile: one read + one write instead of the 1.5x traffic of
-  // the two-kernel fallback.
+  // (2.83 vs 2.99 ms); profiles/r02_build_cluster.txt.  Series too long for a 16-point tile (3500 < T <= ~7000) do take
+  // it with 4 CTAs per tile; with 8 (c4's 8760 hourly snapshots: 2.60 TB/s) it is no better than the register-staged
+  // fallback (2.51 TB/s, and faster with scaling), which therefore keeps those.
   const size_t two_resident = 112 * 1024;
   const unsigned dbg = build_debug_flags();
   auto part_bytes = [&](int cl, int rowb) {
@@ -537,8 +537,10 @@ int try_build_rows_tma(const float* src, int64_t T, int64_t src_ld, int64_t P, T
       cl = part_bytes(2, 128) <= two_resident ? 2 : (part_bytes(4, 128) <= one_resident ? 4 : 8);
     } else if (part_bytes(1, 64) <= one_resident) {
       pb = 16;                                                   // T <= ~3500 (two resident CTAs up to ~1750)
+    } else if (part_bytes(4, 128) <= one_resident) {
+      cl = 4;                                                    // T <= ~7000
     } else {
-      cl = part_bytes(4, 128) <= one_resident ? 4 : 8;           // T <= ~7000 / ~14000 (c4: 8760 hourly snapshots)
+      return 0;       // longer still (c4: 8760): 8 CTAs per tile measured no better than the staged fallback (r02_build_cluster.txt)
     }
   }
   const size_t tile_bytes = part_bytes(cl, pb * 4);

@@ -76,8 +76,8 @@ def sym_eig_topk_subspace(ops, G: torch.Tensor, k: int, tol: float, stats: dict 
     spectrum (white noise) does not converge and falls back.  Accepted only when EVERY returned pair satisfies
     ||G v - lam v|| <= tol * lam_1, so the result is an eigen-decomposition to that residual whichever route ran."""
     n = G.shape[0]
-    b = min(n, -(-(k + 24) // 16) * 16)
-    if b > 128:                      # the Rayleigh-Ritz problem must fit the one-CTA Jacobi solver
+    b = min(n, 128, -(-(k + 24) // 16) * 16)    # the Rayleigh-Ritz problem must fit the one-CTA Jacobi solver (<= 128)
+    if b < min(n, k + 8):                        # too few guard vectors to converge the k-th pair
         return None
     from .rsvd import _orth
 
