@@ -430,7 +430,9 @@ def main():
     S, T, desc = WORKLOADS[args.workload]
     if args.rows:
         S = args.rows
-    field = synthetic_field(T, S, device=device, seed=1000 + rank)          # native (T, S) f32, outside the timed region
+    # native (T, S) f32, outside the timed region; the ranks' shards form one field (shared temporal patterns)
+    field = synthetic_field(T, S, device=device, seed=1000 + rank, time_seed=1000 if world > 1 else None,
+                            total_points=S * world)
     m_global = S * world
     row_offset = rank * S
     q = n_iter_auto(m_global, T, k)
@@ -543,13 +545,14 @@ def main():
             label = (f"c3 SHARD ONLY: 1/8 of the rows ({r1} x {T3} f32, 29.6 GB) on each of {world} GPU(s) - the whole matrix "
                      "needs >= 4 GPUs; this is one rank's share of the 8-GPU run, not the north-star number")
             mg, ro = r1 * world, rank * r1
-        f3 = synthetic_field(T3, r1 - r0, device=device, seed=2000 + rank)
-        r3 = time_workload(f3, mg, ro, args.north_star_steps, 3, args.precision, False)
+        # ONE field over all ranks: shared temporal patterns, per-rank spatial patterns (synthetic.py)
+        f3 = synthetic_field(T3, r1 - r0, device=device, seed=2000 + rank, time_seed=77, total_points=mg)
+        r3 = time_workload(f3, mg, ro, args.north_star_steps, 3, args.precision, True)
         tot_bytes = float(M3 if world >= 4 else (r1 - r0) * world) * T3 * 4
         p3 = pass_rooflines(r3["ksum"], pk, args.precision, args.tc_split)
         north = {"workload": label, "whole_matrix": world >= 4, "ms_per_step": r3["ms"],
                  "GBps": tot_bytes / 1e9 / (r3["ms"] / 1e3), "steps": args.north_star_steps, "warmup": 3,
-                 "rows_this_rank": r1 - r0, "n_iter": n_iter_auto(mg, T3, k), "sigma_1": r3["sigma_1"],
+                 "rows_this_rank": r1 - r0, "n_iter": n_iter_auto(mg, T3, k), "sigma_1": r3["sigma_1"], "clocks": r3["clocks"],
                  "passes": [{x: e[x] for x in ("kernel", "calls", "avg_launch_ms", "achieved_GBps", "hbm_frac", "bound", "frac")
                              if x in e} | ({"tensor_frac": e["tensor_frac"], "achieved_TFLOPs": e["achieved_TFLOPs"]}
                                            if "tensor_frac" in e else {}) for e in p3],

@@ -245,7 +245,9 @@ class CudaOps:
         ldy = lds.pop()
         nbytes = int(self.lib.era5svd_sketch_tf32x3_workspace_bytes(n, l))
         ws = self._workspace("sketch_tc", nbytes)
-        end = self.timer.start("sketch_tc" if n > 2 * l else "apply_basis_tc", bytes=4.0 * (m * n + m * l + n * l),
+        n_out = sum(t is not None for t in (Y, Yhi, Ylo))
+        end = self.timer.start("sketch_tc" if n > 2 * l else "apply_basis_tc",
+                               bytes=4.0 * (m * n * (2 if Xlo is not None else 1) + m * l * n_out + n * l),
                                flops=2.0 * m * n * l) if self.timer else None
         outp = (Y.data_ptr() if Y is not None else None, Yhi.data_ptr() if Yhi is not None else None,
                 Ylo.data_ptr() if Ylo is not None else None)
@@ -310,7 +312,10 @@ class CudaOps:
             raise ValueError("project_tf32x3: hi/lo operands must share their row pitch")
         nbytes = int(self.lib.era5svd_project_tf32x3_workspace_bytes(m, n, l))
         ws = self._workspace("project", nbytes)
-        end = self.timer.start("project_tc" if n > 2 * l else "gram_tc", bytes=4.0 * (m * n + m * l) + 8.0 * n * l,
+        # algorithmic bytes: X once + the tall factor as it exists for this pass (ONE plain image in the power
+        # iterations, the hi / lo PAIR in the final pass, where the Gram and U = Y M kernels consume the pair too)
+        end = self.timer.start("project_tc" if n > 2 * l else "gram_tc",
+                               bytes=4.0 * (m * n + m * l * (2 if Ylo is not None else 1)) + 8.0 * n * l,
                                flops=2.0 * m * n * l) if self.timer else None
         check(self.lib.era5svd_project_tf32x3(hp, lp, m, n, hld, yhp, ylp, l, yhld, zp, zld, int(accumulate),
                                               ws.data_ptr(), ws.numel(), self._stream()), "era5svd_project_tf32x3")

@@ -124,7 +124,7 @@ def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_compone
     if svd_type == "standard":
         if X is None:
             X = split[0] + split[1]
-        return standard_svd_device(ops, X, n_components, delay=delay, comm=comm, precision=PRECISIONS[precision])
+        return standard_svd_device(ops, X, n_components, delay=delay, comm=comm, precision=PRECISIONS[precision], stats=stats)
     if svd_type == "randomized":
         omega0 = _omega_on_device(ops, n, n_components, seed, ref.dtype)
         return randomized_svd_device(ops, X, n_components, omega0, n_iter=n_iter, delay=delay,

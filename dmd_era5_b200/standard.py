@@ -28,6 +28,8 @@ n / 2 column blocks of the Gram matrix (c4: +15 %).
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from ._cabi import PREC_NATIVE, PREC_TF32X3
@@ -82,6 +84,7 @@ def sym_eig_topk_subspace(ops, G: torch.Tensor, k: int, tol: float, stats: dict 
     from .rsvd import _orth
 
     V = _orth(ops, _subspace_start(ops, n, b), 1e-14, passes=2)
+    hist: list[float] = []
     for it in range(SUBSPACE_MAX_ITERS):
         W = ops.sketch(G, V, None, PREC_NATIVE)                     # G V  (n x b, FP64 DMMA)
         # Rayleigh-Ritz in every iteration: the columns of W Q are then ~ lam_j v_j - nearly orthogonal, so that after
@@ -91,11 +94,20 @@ def sym_eig_topk_subspace(ops, G: torch.Tensor, k: int, tol: float, stats: dict 
         V = ops.gemm(V, Q)
         W = ops.gemm(W, Q)
         if it >= 2:
-            resid = torch.linalg.vector_norm(W[:, :k] - V[:, :k] * lam[:k], dim=0).max() / lam[0]
-            if float(resid) <= tol:                                 # one host read per check
+            resid = float(torch.linalg.vector_norm(W[:, :k] - V[:, :k] * lam[:k], dim=0).max() / lam[0])   # one host read
+            if resid <= tol:
                 if stats is not None:
-                    stats["eig_route"] = f"subspace iteration, {it + 1} iterations, residual {float(resid):.1e}"
+                    stats["eig_route"] = f"subspace iteration, {it + 1} iterations, residual {resid:.1e}"
                 return lam[:k].contiguous(), V[:, :k].contiguous()
+            hist.append(resid)
+            if len(hist) >= 6:
+                # measured contraction per iteration over the last four; give up as soon as it cannot reach tol within
+                # the budget (dense or flat spectrum): the direct route is then cheaper than iterating on
+                rate = (hist[-1] / hist[-5]) ** 0.25
+                if rate >= 1.0 or it + math.log(tol / resid) / math.log(rate) > SUBSPACE_MAX_ITERS:
+                    if stats is not None:
+                        stats["eig_route_note"] = f"subspace iteration abandoned after {it + 1} iterations (contraction {rate:.2f})"
+                    return None
         # shifted CholeskyQR3 while the Ritz vectors are still far from eigenvectors (columns of W strongly coupled)
         V = _orth(ops, W, 1e-14, shifted=it < 3, passes=1 if it >= 3 else 2)
     return None
@@ -158,7 +170,7 @@ def gram_device(ops, X: torch.Tensor, n: int, delay: int, precision: int) -> tor
 
 
 def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int = 1, comm=None,
-                        precision: int = PREC_NATIVE):
+                        precision: int = PREC_NATIVE, stats: dict | None = None):
     """X: this rank's base rows (m0_local, T).  Returns (U_local (m0_local*delay, k), s (k,), Vt (k, n))."""
     comm = comm or LocalComm()
     m0, T = X.shape
@@ -176,10 +188,10 @@ def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int =
         from .rsvd import randomized_svd_device
 
         kk = min(n, k + 10)
-        _, V = sym_eig_topk(ops, G, kk, tol=1e-9)       # the Gram matrix itself is only ~1e-6 accurate
+        _, V = sym_eig_topk(ops, G, kk, tol=1e-9, stats=stats)       # the Gram matrix itself is only ~1e-6 accurate
         prec = PREC_TF32X3 if (tc_ok and kk <= 128) else PREC_NATIVE
         return randomized_svd_device(ops, X, k, V, n_iter=REFINE_ITERS, delay=d, precision=prec, comm=comm)
-    lam, V = sym_eig_topk(ops, G, k)
+    lam, V = sym_eig_topk(ops, G, k, stats=stats)
     s, inv_s = ops.sigma_from_eig(lam)
     Vk = V.t().contiguous()                     # (k, n): rows = right singular vectors, descending
     M = Vk.clone()

@@ -15,18 +15,27 @@ import torch
 
 def synthetic_field(T: int, S: int, *, device, dtype=torch.float32, rank: int = 160, rho: float = 0.93,
                     sigma0: float = 100.0, noise: float = 1e-5, mean_level: float = 250.0, seed: int = 0,
-                    chunk: int = 1 << 20) -> torch.Tensor:
-    """(T, S) field whose time-centred version has singular values ~ sigma0 * rho**i."""
+                    chunk: int = 1 << 20, time_seed: int | None = None, total_points: int | None = None) -> torch.Tensor:
+    """(T, S) field whose time-centred version has singular values ~ sigma0 * rho**i.
+
+    Row-sharded runs: every rank passes the SAME ``time_seed`` (shared temporal patterns) and its own ``seed`` (its own
+    spatial patterns) plus ``total_points`` = the global number of points, so that the shards together form ONE field with
+    the designed spectrum; with per-rank temporal patterns the stacked matrix would instead carry world-size interleaved
+    copies of the spectrum (sigma_i clustered in groups)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
+    gt = g
+    if time_seed is not None:
+        gt = torch.Generator(device=device)
+        gt.manual_seed(time_seed)
     # temporal patterns: orthonormal columns (T x rank), exactly zero time mean
-    Bt = torch.randn((T, rank), generator=g, device=device, dtype=torch.float64)
+    Bt = torch.randn((T, rank), generator=gt, device=device, dtype=torch.float64)
     Bt -= Bt.mean(dim=0, keepdim=True)
     Bt, _ = torch.linalg.qr(Bt)
     s = sigma0 * rho ** torch.arange(rank, device=device, dtype=torch.float64)
     BtS = (Bt * s).to(torch.float32 if dtype == torch.float32 else torch.float64)      # (T, rank)
     out = torch.empty((T, S), device=device, dtype=dtype)
-    inv_sqrt_S = 1.0 / math.sqrt(S)
+    inv_sqrt_S = 1.0 / math.sqrt(total_points or S)
     for c0 in range(0, S, chunk):
         c1 = min(S, c0 + chunk)
         # spatial patterns: i.i.d. N(0, 1/S) columns are orthonormal up to O(sqrt(rank/S))

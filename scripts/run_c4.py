@@ -56,7 +56,8 @@ def main():
         comm = TimedComm(LocalComm())
     ops = CudaOps(dev)
     r0, r1 = shard_rows(M, world, rank)
-    field = synthetic_field(T, r1 - r0, device=dev, seed=40 + rank, rank=200, rho=0.96, chunk=1 << 17)
+    field = synthetic_field(T, r1 - r0, device=dev, seed=40 + rank, rank=200, rho=0.96, chunk=1 << 17, time_seed=40,
+                            total_points=M)
     built = build_matrix_device(ops, [field], mean_center=True, scale=False)
     del field
     torch.cuda.empty_cache()
@@ -69,7 +70,9 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        U, s, V = svd_device(ops, X, svd_type="standard", n_components=k, precision="auto", comm=comm, row_offset=r0, m0_global=M)
+        stats = {}
+        U, s, V = svd_device(ops, X, svd_type="standard", n_components=k, precision="auto", comm=comm, row_offset=r0,
+                             m0_global=M, stats=stats)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -84,7 +87,7 @@ def main():
                "allreduce_bytes": [b for b, _, _ in comm.events],
                "kernels_ms_rank0": {kk: round(v["ms"], 2) for kk, v in summ.items()},
                "kernel_calls_rank0": {kk: v["calls"] for kk, v in summ.items()},
-               "sigma_first3": s[:3].tolist(), "refine_iters": std_mod.REFINE_ITERS}
+               "sigma_first3": s[:3].tolist(), "refine_iters": std_mod.REFINE_ITERS, "eig_route": stats.get("eig_route")}
     # invariants on this rank's shard
     Ud = U.double()
     G = Ud.t() @ Ud
