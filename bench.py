@@ -271,8 +271,9 @@ def run_reference(args):
 
 
 # tensor-core products per k-step of each timed tall kernel (KernelTimer names, device_ops.py)
-NPROD = {"sketch_x1": 1.0, "project_x1": 1.0, "sketch_tc": 2.0, "project_tc": 3.0, "gram_tc": 3.0, "apply_basis_tc": 3.0}
-TALL = ("sketch", "project", "sketch_tc", "project_tc", "sketch_x1", "project_x1")
+NPROD = {"sketch_x1": 1.0, "project_x1": 1.0, "sketch_tc": 2.0, "project_x2": 2.0, "project_tc": 3.0, "gram_tc": 3.0,
+         "apply_basis_tc": 3.0}
+TALL = ("sketch", "project", "sketch_tc", "project_tc", "sketch_x1", "project_x1", "project_x2")
 
 
 def pass_rooflines(ksum: dict, pk: dict, precision: str, tc_split: str) -> list[dict]:

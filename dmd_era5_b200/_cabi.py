@@ -37,6 +37,7 @@ PROTOTYPES = {
     "era5svd_sketch_tf32x2": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "era5svd_sketch_tf32x1": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _sz, _vp]),
     "era5svd_project_tf32x1": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int, _vp, _sz, _vp]),
+    "era5svd_project_tf32x2": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _int, _vp, _sz, _vp]),
     "era5svd_round_tf32_f64": (_int, [_vp, _i64, _i64, _i64, _vp]),
     "era5svd_project_tf32x3_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "era5svd_project_tf32x3": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _int, _vp, _sz, _vp]),

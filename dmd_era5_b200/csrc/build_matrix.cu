@@ -490,7 +490,7 @@ static int launch_build_tma(const CUtensorMap& tm, unsigned tiles, size_t tile_b
                             int64_t ldx, Tx* mean_out, Tx* std_out, const Tx* weights, bool center, bool scale, bool check,
                             int* nonfinite_flag, cudaStream_t st, float* Xhi, float* Xlo) {
   auto kern = fused_build_tma_kernel<Tx, PB, CL>;
-  ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+  ERA5SVD_CUDA(ensure_dynamic_smem((const void*)kern, tile_bytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tiles * CL);
   cfg.blockDim = dim3(TB_THREADS);
@@ -582,7 +582,7 @@ int build_rows_impl(const void* src, int64_t T, int64_t src_ld, int64_t P, void*
   const size_t tile_bytes = (size_t)T * (FB_PB + 1) * sizeof(Ts);
   if (tile_bytes <= 220 * 1024) {
     auto kern = fused_build_kernel<Ts, Tx>;
-    ERA5SVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+    ERA5SVD_CUDA(ensure_dynamic_smem((const void*)kern, tile_bytes));
     kern<<<(unsigned)ceil_div(P, FB_PB), FB_THREADS, tile_bytes, st>>>(
         (const Ts*)src, T, src_ld, P, (Tx*)X, ldx, (Tx*)mean_out, (Tx*)std_out, (const Tx*)weights, center ? 1 : 0,
         (center && scale) ? 1 : 0, check ? 1 : 0, nonfinite_flag, Xhi, Xlo);

@@ -31,6 +31,24 @@ int sm_count() {
   return cached[dev];
 }
 
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+  struct Entry { const void* f; int dev; size_t bytes; };
+  static thread_local Entry cache[64];
+  static thread_local int used = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].f == func && cache[i].dev == dev) {
+      if (cache[i].bytes >= bytes) return cudaSuccess;
+      cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e == cudaSuccess) cache[i].bytes = bytes;
+      return e;
+    }
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && used < 64) cache[used++] = Entry{func, dev, bytes};
+  return e;
+}
+
 }  // namespace era5svd
 
 extern "C" {

@@ -50,6 +50,10 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // Number of SMs of the current device (cached per device).
 int sm_count();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size): the attribute is sticky, so repeating
+// the driver call on every launch is pure host overhead.  Returns a cudaError_t.
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

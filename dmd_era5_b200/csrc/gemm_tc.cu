@@ -31,7 +31,7 @@ int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const d
 
 int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Yhi, const float* Ylo,
                        int64_t l, int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
-                       size_t workspace_bytes, cudaStream_t st);
+                       size_t workspace_bytes, cudaStream_t st, int y_tf32);
 size_t project_tf32x3_raw_workspace_bytes(int64_t m, int64_t n, int64_t l);
 
 // from gemm_simt.cu
@@ -88,6 +88,20 @@ int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer,
     set_error("tf32x3: row pitch (%lld floats) must be a multiple of 4", (long long)ld);
     return ERA5SVD_ERR_ARG;
   }
+  // The encoding is a pure function of (address, shape, pitch, box, swizzle): a small per-thread cache saves the driver
+  // call for the descriptors that recur in every pass of a step (X, the workspace images of Om^T, Y).
+  struct Key { uintptr_t addr; int64_t inner, outer, ld; uint32_t bi, bo; int sw; };
+  struct Slot { Key k; CUtensorMap m; bool valid; };
+  static thread_local Slot cache[64];
+  const Key key{addr, inner + shift, outer, ld, box_inner, box_outer, (int)swizzle};
+  const size_t h = (size_t)((addr >> 4) * 0x9E3779B97F4A7C15ull + (uint64_t)outer * 31 + (uint64_t)inner * 7 + box_outer + (uint64_t)swizzle * 131) % 64;
+  Slot& sl = cache[h];
+  if (sl.valid && sl.k.addr == key.addr && sl.k.inner == key.inner && sl.k.outer == key.outer && sl.k.ld == key.ld &&
+      sl.k.bi == key.bi && sl.k.bo == key.bo && sl.k.sw == key.sw) {
+    *map = sl.m;
+    *col_shift = shift;
+    return ERA5SVD_OK;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)(inner + shift), (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -95,6 +109,7 @@ int make_tmap(CUtensorMap* map, const float* base, int64_t inner, int64_t outer,
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, reinterpret_cast<void*>(addr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) { sl.k = key; sl.m = *map; sl.valid = true; }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%ux%u", (int)r, (long long)inner,
               (long long)outer, (long long)ld, box_inner, box_outer);
@@ -716,7 +731,7 @@ static int sketch_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64
     q.stages = (int)((227 * 1024 - 1024 - 256) / stage);
     if (q.stages > 6) q.stages = 6;
     const size_t smem = q.stages * stage + 1024 + 256;
-    ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ERA5SVD_CUDA(ensure_dynamic_smem((const void*)tc::sketch_x1_kernel, smem));
     const int64_t grid = q.num_groups < sm_count() ? q.num_groups : sm_count();
     tc::sketch_x1_kernel<<<(unsigned)grid, tc::SX1_THREADS, smem, st>>>(tm_x2, tm_ohi, q);
     return check_launch("sketch_x1_kernel");
@@ -735,7 +750,7 @@ static int sketch_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int64
   if (p.stages > (nprod == 1 ? 7 : 6)) p.stages = nprod == 1 ? 7 : 6;
   ERA5SVD_REQUIRE(p.stages >= 2, "sketch_tf32x3: not enough shared memory for two stages");
   const size_t smem = p.stages * stage_bytes + 1024 + 256;
-  ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ERA5SVD_CUDA(ensure_dynamic_smem((const void*)tc::sketch_tc_kernel, smem));
   int64_t grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   tc::sketch_tc_kernel<<<(unsigned)grid, tc::SK_THREADS, smem, st>>>(tm_xhi, tm_xlo, tm_ohi, tm_olo, p);
   return check_launch("sketch_tc_kernel");
@@ -803,7 +818,7 @@ static int project_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int6
   ERA5SVD_REQUIRE(m < ((int64_t)1 << 31), "project_tf32x3: m too large for TMA coordinates");
   if (!Xlo && nprod != 1)   // Xhi is the plain float32 matrix: split on chip (gemm_tc2.cu)
     return project_tf32x3_raw(Xhi, m, n, ldx, Yhi, Ylo, l, ldy, Z, ldz, accumulate, workspace, workspace_bytes,
-                              as_stream(stream));
+                              as_stream(stream), nprod == 2);
   if (nprod == 1) { Xlo = Xhi; Ylo = Yhi; }   // single product on the raw tiles: no lo images are loaded
   // plan for the widest window (xshift <= 3) so that the workspace query needs no pointer
   const PjPlan pl = pj_plan(m, n + 3, l, nprod == 1 ? 16384 : 4096);
@@ -838,7 +853,7 @@ static int project_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int6
   if (p.stages > 8) p.stages = 8;
   ERA5SVD_REQUIRE(p.stages >= 2, "project_tf32x3: not enough shared memory for two stages");
   const size_t smem = p.stages * stage_bytes + 1024 + 256;
-  ERA5SVD_CUDA(cudaFuncSetAttribute(tc::project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ERA5SVD_CUDA(ensure_dynamic_smem((const void*)tc::project_tc_kernel, smem));
   dim3 grid((unsigned)pl.nchunks, (unsigned)pl.splits);
   tc::project_tc_kernel<<<grid, tc::PJ_THREADS, smem, st>>>(tm_xhi, tm_xlo, tm_yhi, tm_ylo, p);
   if ((rc = check_launch("project_tc_kernel"))) return rc;
@@ -852,6 +867,13 @@ int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_
                            void* stream) {
   return project_tf32_impl(Xhi, Xlo, m, n, ldx, Yhi, Ylo, l, ldy, Z, ldz, accumulate, workspace, workspace_bytes,
                            stream, 3);
+}
+
+int era5svd_project_tf32x2(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,
+                           int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return project_tf32_impl(X, nullptr, m, n, ldx, Y, nullptr, l, ldy, Z, ldz, accumulate, workspace, workspace_bytes,
+                           stream, 2);
 }
 
 int era5svd_project_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,

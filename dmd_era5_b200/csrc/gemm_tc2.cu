@@ -299,6 +299,7 @@ struct Project2Params {
   int ra, rb;
   int64_t rows_per_split;
   int split_y;        // 1: tm_yhi maps the PLAIN float32 Y; its lo image is formed on chip by the (otherwise idle) epilogue warps
+                      // 2: plain Y taken as tf32(Y) (the tensor core truncates it): NO lo image, two products per k-step
   int lp;             // column pitch of a partial tile: l rounded up to 16 (pad columns hold the zeros the MMA produced)
   float* part;        // [splits][n][lp]
 };
@@ -344,7 +345,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_init(araw_empty + 8u * i, 8);      // all eight transform warps read every slot
     }
     for (int i = 0; i < p.rb; ++i) {
-      mbar_init(b_full + 8u * i, p.split_y ? 4 : 1);   // split_y: the four warps that wrote the lo image arrive
+      mbar_init(b_full + 8u * i, p.split_y == 1 ? 4 : 1);   // split_y == 1: the four warps that wrote the lo image arrive
       mbar_init(b_empty + 8u * i, 1);
       mbar_init(b_raw + 8u * i, 1);
     }
@@ -386,9 +387,12 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         mbar_wait(b_empty + 8u * rb.i, rb.ph ^ 1u);
         const uint32_t dst = b_base + (uint32_t)rb.i * b_bytes;
         const int32_t row0 = (int32_t)(r_begin + (int64_t)kc * PJ2_KS);
-        if (p.split_y) {
+        if (p.split_y == 1) {
           mbar_arrive_expect_tx(b_raw + 8u * rb.i, y_half);
           for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * box_bytes, &tm_yhi, c * BK2, row0, b_raw + 8u * rb.i);
+        } else if (p.split_y == 2) {
+          mbar_arrive_expect_tx(b_full + 8u * rb.i, y_half);
+          for (int c = 0; c < 4; ++c) tma_load_2d(dst + c * box_bytes, &tm_yhi, c * BK2, row0, b_full + 8u * rb.i);
         } else {
           mbar_arrive_expect_tx(b_full + 8u * rb.i, b_bytes);
           for (int c = 0; c < 4; ++c) {
@@ -402,6 +406,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = make_idesc_tf32(128, (p.l + 15) / 16 * 16, 0, 1);   // A K-major (TMEM), B MN-major, N = l padded to 16
+    const bool with_ylo = p.split_y != 2;          // kernel parameter: uniform
     Ring rb(p.rb), at(AT_RING);
     for (int kc = 0; kc < num_k; ++kc) {
       mbar_wait(b_full + 8u * rb.i, rb.ph);
@@ -421,7 +426,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const uint64_t b_hi = make_smem_desc(bs + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
             const uint64_t b_lo = make_smem_desc(bs + y_half + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
             umma_tf32_ts(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
-            umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1);
+            if (with_ylo) umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1);
             umma_tf32_ts(d_tmem, a_hi, b_hi, idesc, 1);
           }
         }
@@ -477,7 +482,7 @@ project_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // ===== epilogue: accumulators -> float32 partial tile part[split][time][column] =====
     const int q = warp % 4;
     float* out = p.part + (int64_t)blockIdx.y * p.n * p.lp;
-    if (p.split_y) {
+    if (p.split_y == 1) {
       // Y arrives as ONE plain float32 image (the sketch then writes, and this pass reads, m*l*4 bytes instead of
       // twice that).  The tensor core truncates its operands to tf32, so the raw tile already serves as the hi
       // operand; these warps (idle until the accumulators are complete) form lo = y - trunc(y) next to it.  The
@@ -582,7 +587,7 @@ int sketch_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const d
   p.ra &= ~1;
   ERA5SVD_REQUIRE(p.ra >= 2, "sketch_tf32x3: not enough shared memory");
   const size_t smem = p.ra * a_bytes + p.rb * b_bytes + 1024 + 512;
-  ERA5SVD_CUDA(cudaFuncSetAttribute(tc::sketch_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ERA5SVD_CUDA(ensure_dynamic_smem((const void*)tc::sketch_tc2_kernel, smem));
   int64_t grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   tc::sketch_tc2_kernel<<<(unsigned)grid, tc::SK2_THREADS, smem, st>>>(tm_x, tm_ohi, tm_olo, p);
   return check_launch("sketch_tc2_kernel");
@@ -624,7 +629,7 @@ size_t project_tf32x3_raw_workspace_bytes(int64_t m, int64_t n, int64_t l) { ret
 // Z (+)= X^T Y with X a plain float32 matrix (split on chip), Y given as (Yhi, Ylo).
 int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Yhi, const float* Ylo,
                        int64_t l, int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
-                       size_t workspace_bytes, cudaStream_t st) {
+                       size_t workspace_bytes, cudaStream_t st, int y_tf32) {
   CUtensorMap tm_x, tm_yhi, tm_ylo;
   int xs = 0, ys = 0, ys2 = 0, rc;
   if ((rc = tc::make_tmap(&tm_x, X, n, m, ldx, tc::BK2, tc::PJ2_KS, &xs, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -639,7 +644,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
   }
   tc::Project2Params p;
   p.m = m; p.n = n; p.l = (int)l; p.lp = round_up2(l, 16);
-  p.split_y = Ylo ? 0 : 1;
+  p.split_y = Ylo ? 0 : (y_tf32 ? 2 : 1);
   p.xshift = xs;
   p.rows_per_split = pl.rows_per_split;
   p.part = (float*)workspace;
@@ -648,7 +653,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
   p.rb = 4;
   p.ra = 8;
   const size_t smem = p.ra * a_bytes + p.rb * b_bytes + 1024 + 512;     // 512 B hold the (2 ra + 3 rb + 2 AT_RING + 2) barriers
-  ERA5SVD_CUDA(cudaFuncSetAttribute(tc::project_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ERA5SVD_CUDA(ensure_dynamic_smem((const void*)tc::project_tc2_kernel, smem));
   dim3 grid((unsigned)ceil_div(n + xs, tc::PJ2_NC), (unsigned)pl.splits);
   tc::project_tc2_kernel<<<grid, tc::PJ2_THREADS, smem, st>>>(tm_x, tm_yhi, tm_ylo, p);
   if ((rc = check_launch("project_tc2_kernel"))) return rc;

@@ -277,6 +277,24 @@ class CudaOps:
         if end is not None:
             end.record()
 
+    def project_tf32x2(self, X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor | None = None,
+                       accumulate: bool = False) -> torch.Tensor:
+        """Z (float64, n x l) (+)= X^T tf32(Y): X split on chip, Y truncated - two products per k-step
+        (era5svd_project_tf32x2; the projection of the last power iteration)."""
+        m, n = X.shape
+        l = Y.shape[1]
+        if Z is None:
+            Z = self.empty((n, l), torch.float64)
+            accumulate = False
+        xp, xld = _mat(X, "X"); yp, yld = _mat(Y, "Y"); zp, zld = _mat(Z, "Z")
+        ws = self._workspace("project", int(self.lib.era5svd_project_tf32x3_workspace_bytes(m, n, l)))
+        end = self.timer.start("project_x2", bytes=4.0 * (m * n + m * l) + 8.0 * n * l, flops=2.0 * m * n * l) if self.timer else None
+        check(self.lib.era5svd_project_tf32x2(xp, m, n, xld, yp, l, yld, zp, zld, int(accumulate), ws.data_ptr(),
+                                              ws.numel(), self._stream()), "era5svd_project_tf32x2")
+        if end is not None:
+            end.record()
+        return Z
+
     def project_tf32x1(self, X: torch.Tensor, Y: torch.Tensor, Z: torch.Tensor | None = None,
                        accumulate: bool = False) -> torch.Tensor:
         """Z (float64, n x l) (+)= X^T Y, one tensor-core product per k-step (era5svd_project_tf32x1)."""

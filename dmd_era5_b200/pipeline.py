@@ -16,7 +16,7 @@ import torch
 from ._cabi import BUILD_CHECK_FINITE, BUILD_MEAN_CENTER, BUILD_SCALE, PREC_NATIVE
 from .device_ops import CudaOps
 from .dist import LocalComm, shard_rows
-from .rsvd import PRECISIONS, draw_omega, n_iter_auto, randomized_svd_device
+from .rsvd import PRECISIONS, draw_omega, n_iter_auto, nvtx_range, randomized_svd_device
 from .standard import standard_svd_device
 
 
@@ -69,17 +69,18 @@ def build_matrix_device(ops: CudaOps, var_blocks: list[torch.Tensor], *, mean_ce
     flag = ops.zeros((1,), torch.int32) if check_finite else None
     flags = (BUILD_MEAN_CENTER if do_center else 0) | (BUILD_SCALE if do_scale else 0) | (BUILD_CHECK_FINITE if check_finite else 0)
     r = 0
-    for b in var_blocks:
-        P = int(b.shape[1])
-        mu = mean[r : r + P] if do_center else None
-        sd = std[r : r + P] if do_scale else None
-        w = weights[r : r + P] if weights is not None else None
-        if split:
-            ops.build_rows_split(b, X[r : r + P] if X is not None else None, Xhi[r : r + P], Xlo[r : r + P], mu, sd, w,
-                                 flags, flag)
-        else:
-            ops.build_rows(b, X[r : r + P], mu, sd, w, flags, flag)
-        r += P
+    with nvtx_range("era5svd.build_matrix"):
+        for b in var_blocks:
+            P = int(b.shape[1])
+            mu = mean[r : r + P] if do_center else None
+            sd = std[r : r + P] if do_scale else None
+            w = weights[r : r + P] if weights is not None else None
+            if split:
+                ops.build_rows_split(b, X[r : r + P] if X is not None else None, Xhi[r : r + P], Xlo[r : r + P], mu, sd, w,
+                                     flags, flag)
+            else:
+                ops.build_rows(b, X[r : r + P], mu, sd, w, flags, flag)
+            r += P
     return BuiltMatrix(X=X, Xhi=Xhi, Xlo=Xlo, mean=mean, std=std, row_offset=0, m0_global=m0, nonfinite=flag)
 
 
@@ -124,10 +125,13 @@ def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_compone
     if svd_type == "standard":
         if X is None:
             X = split[0] + split[1]
-        return standard_svd_device(ops, X, n_components, delay=delay, comm=comm, precision=PRECISIONS[precision], stats=stats)
+        with nvtx_range("era5svd.standard_svd"):
+            return standard_svd_device(ops, X, n_components, delay=delay, comm=comm, precision=PRECISIONS[precision],
+                                       stats=stats)
     if svd_type == "randomized":
         omega0 = _omega_on_device(ops, n, n_components, seed, ref.dtype)
-        return randomized_svd_device(ops, X, n_components, omega0, n_iter=n_iter, delay=delay,
+        with nvtx_range("era5svd.randomized_svd"):
+            return randomized_svd_device(ops, X, n_components, omega0, n_iter=n_iter, delay=delay,
                                      precision=PRECISIONS[precision], comm=comm, row_offset=row_offset,
                                      m0_global=m0_global, stats=stats, split=split, full_iters=full_iters)
     msg = f"SVD type {svd_type} is not supported."

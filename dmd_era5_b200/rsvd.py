@@ -35,8 +35,23 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from contextlib import contextmanager
+
 from ._cabi import PREC_NATIVE, PREC_TF32X3
 from .dist import LocalComm
+
+
+@contextmanager
+def nvtx_range(name: str):
+    """NVTX range around a phase of the device schedule (visible in nsys / ncu timelines); no-op on CPU tensors."""
+    on = torch.cuda.is_available()
+    if on:
+        torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        if on:
+            torch.cuda.nvtx.range_pop()
 
 # driver-level precision: the tensor-core path with the EARLY power iterations in single-product TF32 (the C ABI only
 # knows PREC_NATIVE / PREC_TF32X3; this value never crosses it)
@@ -117,7 +132,8 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
                  made in iteration i is contracted by (sigma_{l+1} / sigma_j)^2 in every later one - so only the last
                  ``full_iters`` (default 1) power iterations and the final range / projection passes, which fix sigma and
                  the vectors, run with fp32-level 3xTF32 products; the earlier ones use ONE tf32 product per k-step on the
-                 raw float32 tiles (era5svd_sketch_tf32x1 / era5svd_project_tf32x1: pure TMA -> tcgen05, HBM bound).
+                 raw float32 tiles (era5svd_sketch_tf32x1 / era5svd_project_tf32x1: pure TMA -> tcgen05, HBM bound); the
+                 projection of the full-precision iteration(s) takes Y truncated (era5svd_project_tf32x2, two products).
     Returns (U_local (m0_local * delay, k) tall dtype, s (k,) float64, Vt (k, n) float64).
     Rows of U_local are ordered block-major: block j holds rows [j * m0_local, (j + 1) * m0_local),
     i.e. global rows j * m0_global + row_offset + r.
@@ -180,7 +196,8 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     else:
         Y = ops.empty((m0 * d, l), tall)
 
-    def tall_pass(Omega64: torch.Tensor, keep_y: bool = False, final: bool = False, low: bool = False) -> torch.Tensor:
+    def tall_pass(Omega64: torch.Tensor, keep_y: bool = False, final: bool = False, low: bool = False,
+                  ytrunc: bool = False) -> torch.Tensor:
         """Y = X_d Omega (kept in the preallocated buffers), returns Z = X_d^T Y (all-reduced).
         On the on-chip-split path the power iterations keep Y as ONE plain float32 image (split again on chip by the
         projection); only the final pass writes the hi / lo pair that the Gram and U = Y M kernels consume."""
@@ -195,7 +212,10 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
                     continue
                 if xl is None and not final:
                     ops.sketch_tf32x3(xh, None, Omega64, Y[rows], None, None, om_tf32=om_tf32)
-                    Z = ops.project_tf32x3(xh, None, Y[rows], None, Z, accumulate=j > 0)
+                    if ytrunc:      # X exact (split on chip), Y taken as tf32(Y): two products, error filtered by X^T
+                        Z = ops.project_tf32x2(xh, Y[rows], Z, accumulate=j > 0)
+                    else:
+                        Z = ops.project_tf32x3(xh, None, Y[rows], None, Z, accumulate=j > 0)
                     continue
                 ops.sketch_tf32x3(xh, xl, Omega64, Y[rows] if keep_y else None, Yhi[rows], Ylo[rows], om_tf32=om_tf32)
                 Z = ops.project_tf32x3(xh, xl, Yhi[rows], Ylo[rows], Z, accumulate=j > 0)
@@ -214,7 +234,11 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     if stats is not None:
         stats["low_precision_iters"] = n_low
     for it in range(n_iter):
-        Z = tall_pass(Omega, low=it < n_low)
+        # "tf32mix": the full-precision power iterations still take Y truncated to tf32 in their PROJECTION (two products):
+        # Z = X^T (Y + dY) = X^T Y + X^T dY - an error in Y is filtered by X^T exactly like the iteration filters the
+        # sketch; measured / emulated effect on sigma and the vectors: none (tests/test_driver_cpu.py)
+        with nvtx_range(f"era5svd.power_iteration[{it}]" + (".tf32x1" if it < n_low else "")):
+            Z = tall_pass(Omega, low=it < n_low, ytrunc=mixed)
         if it == n_iter - 1:
             # Rayleigh-Ritz rotation before the final pass: T = Omega^T Z = Y^T Y (l x l) = W L W^T, so
             # the columns of X (Z W) come out nearly orthogonal and graded (~ sigma_j u_j) and the Gram
@@ -236,7 +260,8 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         if om_tf32:
             ops.round_tf32_(Omega)
 
-    Zp = tall_pass(Omega, keep_y=not use_tc, final=True)           # n x l
+    with nvtx_range("era5svd.final_range_and_projection"):
+        Zp = tall_pass(Omega, keep_y=not use_tc, final=True)           # n x l
     # l x l Gram matrix of the STORED (rounded) Y, so that Q = Y R^-1 is orthonormal for the Y we keep
     G = ops.project_tf32x3(Yhi, Ylo, Yhi, Ylo) if use_tc else ops.project(Y, Y, precision=PREC_NATIVE)
     comm.allreduce_sum_(G)

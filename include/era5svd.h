@@ -169,6 +169,14 @@ int era5svd_sketch_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, con
 int era5svd_project_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,
                            int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* era5svd_project_tf32x2 : Z (+)= X^T tf32(Y): X split hi / lo on chip (exact), the plain float32 Y taken truncated to tf32 -
+ *                          two products per k-step instead of three, no lo image of Y.  For the projection of the LAST power
+ *                          iteration: Z = X^T (Y + dY) = X^T Y + X^T dY, and an error in Y is filtered by X^T like the
+ *                          iteration itself filters the sketch (it lands in the dominant subspace), whereas the final
+ *                          projection B = Q^T X (extmath.py:606) keeps all three products.  Workspace as project_tf32x3. */
+int era5svd_project_tf32x2(const float* X, int64_t m, int64_t n, int64_t ldx, const float* Y, int64_t l,
+                           int64_t ldy, double* Z, int64_t ldz, int accumulate, void* workspace,
+                           size_t workspace_bytes, void* stream);
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l);
 int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,
                            const float* Yhi, const float* Ylo, int64_t l, int64_t ldy, double* Z,

@@ -97,6 +97,17 @@ class FakeOps:
             Z.copy_(out)
         return Z
 
+    def project_tf32x2(self, X, Y, Z=None, accumulate=False):
+        self._count("project_x2")
+        out = X.double().t() @ self._tf32_trunc(Y).double()
+        if Z is None:
+            return out
+        if accumulate:
+            Z += out
+        else:
+            Z.copy_(out)
+        return Z
+
     def project_tf32x3(self, Xhi, Xlo, Yhi, Ylo, Z=None, accumulate=False):
         self._count("project_tc")
         X = Xhi.double() + (Xlo.double() if Xlo is not None else 0.0)

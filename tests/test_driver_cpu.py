@@ -159,7 +159,9 @@ def test_randomized_driver_mixed_precision_schedule(d):
     low = q - MIX_FULL_ITERS
     assert stats["low_precision_iters"] == low and stats["tall_passes"] == 2 * q + 2
     assert ops.calls["sketch_x1"] == d * low and ops.calls["project_x1"] == d * low
-    assert ops.calls["sketch_tc"] == d * (q + 1 - low) + 1 and ops.calls["project_tc"] == d * (q + 1 - low) + 1
+    # full-precision iteration(s): 2-product sketch + projection with Y truncated (project_x2); final passes: 3xTF32
+    assert ops.calls["sketch_tc"] == d * (q + 1 - low) + 1 and ops.calls["project_x2"] == d * (q - low)
+    assert ops.calls["project_tc"] == d + 1
     assert sigma_rel_err(s, s0) < 1e-6
     assert vector_angles(U.double().numpy(), U0).max() < 2e-4 and vector_angles(Vt.numpy().T, V0.T).max() < 2e-4
     assert signs_agree(U.double().numpy(), U0)

@@ -281,3 +281,30 @@ def test_single_product_tf32_kernels(ops, m, n, l, off):
     Z2 = ops.project_tf32x1(Xb[:, off:off + n], Y, Z.clone(), accumulate=True)
     assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
     assert torch.equal(ops.project_tf32x1(Xb[:, off:off + n], Y), Z)                 # reproducible
+
+
+@pytest.mark.parametrize("m,n,l,off", [(1000, 744, 110, 0), (50000, 1460, 110, 0), (4097, 25, 20, 1), (20000, 742, 112, 2)])
+def test_project_tf32x2_truncated_y(ops, m, n, l, off):
+    """era5svd_project_tf32x2 (projection of the last power iteration under 'tf32mix'): X exact (split on chip), Y taken
+    truncated to tf32 - must equal X^T trunc(Y) to the 3xTF32 bound, i.e. its only approximation is the documented
+    truncation of Y."""
+    rng = np.random.RandomState(m + l + 3)
+    Xfull = (rng.standard_normal((m, n + off)) * np.exp(rng.uniform(-3, 3, size=(m, 1)))).astype(np.float32)
+    Yh = rng.standard_normal((m, l)).astype(np.float32)
+    ld = (n + off + 7) // 8 * 8
+    Xb = torch.zeros((m, ld), device="cuda")
+    Xb[:, : n + off] = dev(Xfull)
+    ldy = ops.tf32_ldy(l)
+    Yb = torch.zeros((m, ldy), device="cuda")
+    Yb[:, :l] = dev(Yh)
+    Z = ops.project_tf32x2(Xb[:, off:off + n], Yb[:, :l])
+    Yt = _trunc_tf32(Yh).astype(np.float64)
+    ref = Xfull[:, off:].astype(np.float64).T @ Yt
+    bound = TC_REL * np.linalg.norm(Xfull[:, off:], axis=0)[:, None] * np.linalg.norm(Yt, axis=0)[None, :]
+    assert np.all(np.abs(Z.cpu().numpy() - ref) <= bound)
+    Z2 = ops.project_tf32x2(Xb[:, off:off + n], Yb[:, :l], Z.clone(), accumulate=True)
+    assert np.allclose(Z2.cpu().numpy(), 2 * Z.cpu().numpy(), rtol=1e-12)
+    # and it differs from the three-product result by no more than the truncation of Y allows
+    Z3 = ops.project_tf32x3(Xb[:, off:off + n], None, Yb[:, :l], None)
+    scale = np.linalg.norm(Xfull[:, off:], axis=0)[:, None] * np.linalg.norm(Yh, axis=0)[None, :]
+    assert np.all(np.abs(Z.cpu().numpy() - Z3.cpu().numpy()) <= 2.0 ** -10 * scale)
