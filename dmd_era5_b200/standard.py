@@ -38,6 +38,8 @@ from .dist import LocalComm
 REFINE_ITERS = 2        # power iterations of the float32 refinement (each contracts the leak by (sigma_{k+11}/sigma_i)^2)
 JACOBI_MAX_N = 118      # largest n whose working copies fit one CTA's shared memory (syevj_kernel)
 TC_BLOCK = 112          # sketch-width block of the tensor-core project kernel
+TC_BLOCK_X1 = 128       # column block of the single-product Gram (one full M = 128 operand tile)
+PREC_TF32MIX = 2        # = rsvd.PREC_TF32MIX (driver-level value, never crosses the C ABI)
 
 
 def _orth2(ops, Z: torch.Tensor) -> torch.Tensor:
@@ -146,8 +148,24 @@ def sym_eig_topk(ops, G: torch.Tensor, k: int, refine: bool = True, tol: float =
 
 
 def gram_device(ops, X: torch.Tensor, n: int, delay: int, precision: int) -> torch.Tensor:
-    """G = sum_j X_j^T X_j over the delay windows X_j = X[:, j : j + n] (float64, this rank's rows only)."""
+    """G = sum_j X_j^T X_j over the delay windows X_j = X[:, j : j + n] (float64, this rank's rows only).
+
+    precision PREC_TF32MIX: ONE tf32 product per k-step on the raw float32 tiles (era5svd_project_tf32x1, the HBM-bound
+    kernel of the early power iterations) - for float32 data the Gram matrix only supplies the SUBSPACE that the
+    full-precision refinement passes start from (standard_svd_device), exactly like the single-product power iterations
+    of the randomized driver; the column block itself (a view of X with X's pitch) is the Y operand: no split images."""
     G = None
+    if precision == PREC_TF32MIX:
+        if X.dtype != torch.float32:
+            raise TypeError("precision 'tf32mix' needs a float32 snapshot matrix")
+        G = ops.zeros((n, n), torch.float64)
+        for j in range(delay):
+            Xj = X[:, j : j + n]
+            for c0 in range(0, n, TC_BLOCK_X1):
+                c1 = min(n, c0 + TC_BLOCK_X1)
+                ops.project_tf32x1(Xj[:, c0:], Xj[:, c0:c1], G[c0:, c0:c1], accumulate=j > 0)   # G[c0:, c0:c1], t >= c0 only
+        low = torch.tril(G, -1)
+        return torch.tril(G) + low.t()
     if precision == PREC_TF32X3:
         if X.dtype != torch.float32:
             raise TypeError("precision 'tf32x3' needs a float32 snapshot matrix")
@@ -179,9 +197,10 @@ def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int =
     if n < 1:
         raise ValueError("delay embedding larger than the number of snapshots")
     k = min(int(n_components), n)
-    tc_ok = precision in (PREC_TF32X3, 2) and X.dtype == torch.float32                   # 2 = rsvd.PREC_TF32MIX
+    tc_ok = precision in (PREC_TF32X3, PREC_TF32MIX) and X.dtype == torch.float32
     use_tc = tc_ok and k <= 128
-    G = gram_device(ops, X, n, d, PREC_TF32X3 if tc_ok else PREC_NATIVE)
+    mixed = tc_ok and precision == PREC_TF32MIX and min(n, k + 10) <= 128
+    G = gram_device(ops, X, n, d, (PREC_TF32MIX if mixed else PREC_TF32X3) if tc_ok else PREC_NATIVE)
     comm.allreduce_sum_(G)
     if X.dtype == torch.float32:
         # float32 data: the Gram route supplies the subspace, the randomized driver's final stage the values
@@ -190,6 +209,11 @@ def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int =
         kk = min(n, k + 10)
         _, V = sym_eig_topk(ops, G, kk, tol=1e-9, stats=stats)       # the Gram matrix itself is only ~1e-6 accurate
         prec = PREC_TF32X3 if (tc_ok and kk <= 128) else PREC_NATIVE
+        if mixed:
+            # every refinement iteration is a full-precision one (the tf32 Gram matrix already holds what single-product
+            # iterations could deliver); their projections take Y truncated (two products, rsvd.py)
+            return randomized_svd_device(ops, X, k, V, n_iter=REFINE_ITERS, delay=d, precision=PREC_TF32MIX, comm=comm,
+                                         full_iters=REFINE_ITERS)
         return randomized_svd_device(ops, X, k, V, n_iter=REFINE_ITERS, delay=d, precision=prec, comm=comm)
     lam, V = sym_eig_topk(ops, G, k, stats=stats)
     s, inv_s = ops.sigma_from_eig(lam)
