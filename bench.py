@@ -329,7 +329,7 @@ def main():
 
     from dmd_era5_b200 import _cabi
     from dmd_era5_b200.device_ops import CudaOps, KernelTimer
-    from dmd_era5_b200.dist import LocalComm, TorchDistComm, shard_rows
+    from dmd_era5_b200.dist import LocalComm, PeerComm, make_comm, shard_rows
     from dmd_era5_b200.pipeline import build_matrix_device, svd_device
     from dmd_era5_b200.rsvd import n_iter_auto
     from dmd_era5_b200.synthetic import synthetic_field
@@ -346,13 +346,15 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=device)
-        comm = TorchDistComm()
-    else:
-        comm = LocalComm()
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
     k = K_COMPONENTS
     ops = CudaOps(device)
+    # collectives: our kernels over peer-mapped memory (csrc/comm.cu; the all-reduce of Z fused into the projection's
+    # reduction) when the GPUs of the node can map each other, else torch.distributed / NCCL; ERA5SVD_COMM=nccl forces NCCL
+    comm = make_comm(ops) if world > 1 else LocalComm()
+    comm_kind = "none (1 rank)" if world == 1 else ("peer memory (era5svd_comm_*, fused into reduce_partials)"
+                                                     if isinstance(comm, PeerComm) else "nccl (torch.distributed)")
 
     def sync_all():
         torch.cuda.synchronize(device)
@@ -613,7 +615,7 @@ def main():
                        "precision_note": ("tf32mix: 3xTF32 (fp32-level) products for the last power iteration and the final range / "
                                           "projection passes, single-product TF32 for the earlier power iterations"
                                           if args.precision == "tf32mix" else None),
-                       "l2": "inputs larger than L2 (matrix shard >= 3 GB vs 126 MB)"},
+                       "l2": "inputs larger than L2 (matrix shard >= 3 GB vs 126 MB)", "collectives": comm_kind},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "roofline_passes": passes, "peaks_measured": {"hbm_gbs": pk["hbm_gbs"], "hbm_source": pk["source"], **probe},
             "north_star": north, "cpu_baseline": cpu, "parity": parity,

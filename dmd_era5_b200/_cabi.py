@@ -57,6 +57,15 @@ PROTOTYPES = {
     "era5svd_col_normalize_f64": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "era5svd_sigma_from_eig_f64": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "era5svd_convert": (_int, [_vp, _int, _i64, _vp, _int, _i64, _i64, _i64, _vp]),
+    "era5svd_comm_handle_bytes": (_sz, []),
+    "era5svd_comm_create": (_int, [_int, _int, _i64, C.POINTER(_vp), _vp]),
+    "era5svd_comm_connect": (_int, [_vp, _vp]),
+    "era5svd_comm_destroy": (_int, [_vp]),
+    "era5svd_comm_capacity": (_i64, [_vp]),
+    "era5svd_comm_fused_count": (C.c_ulonglong, [_vp]),
+    "era5svd_comm_allreduce_f64": (_int, [_vp, _vp, _i64, _vp]),
+    "era5svd_comm_allgather_f64": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "era5svd_comm_fuse_next_project": (_int, [_vp, _i64, _i64]),
     "era5svd_col_absmax_workspace_bytes": (_sz, [_i64, _i64]),
     "era5svd_col_absmax": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "era5svd_maxloc_combine": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),

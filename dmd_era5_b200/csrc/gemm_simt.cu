@@ -12,6 +12,7 @@
 //   project: As[k][time] <- X[k=row][time] (straight copy)           Bs[k][col] <- Y[k=row][col]
 // project splits the row (k) range over blockIdx.z; partial tiles go to the workspace in the
 // accumulate type and reduce_partials_kernel sums them in float64 in a fixed order.
+#include "comm.cuh"
 #include "common.cuh"
 
 namespace era5svd {
@@ -370,6 +371,83 @@ reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, in
   }
 }
 
+// The same reduction fused with the all-reduce over the row shards (comm.cuh): phase 1 sums this rank's partial tiles into
+// its peer-mapped slot (compact n x l), one flag round per block, phase 2 adds the ranks' slots in rank order into Z.  The
+// grid is bounded (<= 2 CTAs per SM) and every block owns the same chunks on every rank, so block b only ever waits for
+// block b of its peers.
+template <typename T>
+__global__ void __launch_bounds__(RP_OUT * RP_GROUPS)
+reduce_partials_allreduce_kernel(const T* __restrict__ part, int64_t splits, int64_t n, int64_t l, int64_t lp,
+                                 double* __restrict__ Z, int64_t ldz, int accumulate, CommDev c) {
+  __shared__ double sm[RP_GROUPS][RP_OUT];
+  const int o = threadIdx.x % RP_OUT, g = threadIdx.x / RP_OUT;
+  const int64_t total = n * lp;
+  const int64_t nchunks = (total + RP_OUT - 1) / RP_OUT;
+  const int64_t per = (splits + RP_GROUPS - 1) / RP_GROUPS;
+  const int64_t k_end = (g + 1) * per < splits ? (g + 1) * per : splits;
+  double* mine = c.slot[c.rank];
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int64_t idx = chunk * RP_OUT + o;
+    double s = 0.0;
+    if (idx < total) {
+      int64_t k = g * per;
+      for (; k + 8 <= k_end; k += 8) {
+        T v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = part[(k + u) * total + idx];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+      }
+      for (; k < k_end; ++k) s += (double)part[k * total + idx];
+    }
+    sm[g][o] = s;
+    __syncthreads();
+    if (g == 0 && idx < total) {
+      double t = sm[0][o];
+#pragma unroll
+      for (int j = 1; j < RP_GROUPS; ++j) t += sm[j][o];
+      const int64_t r = idx / lp, cc = idx % lp;
+      if (cc < l) mine[r * l + cc] = accumulate ? (Z[r * ldz + cc] + t) : t;
+    }
+    __syncthreads();
+  }
+  comm_block_exchange(c);
+  const int64_t my_chunks = (int64_t)blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  for (int64_t e = threadIdx.x; e < my_chunks * RP_OUT; e += blockDim.x) {
+    const int64_t idx = ((int64_t)blockIdx.x + (e / RP_OUT) * gridDim.x) * RP_OUT + e % RP_OUT;
+    if (idx < total) {
+      const int64_t r = idx / lp, cc = idx % lp;
+      if (cc < l) Z[r * ldz + cc] = comm_sum_ranks(c, r * l + cc);
+    }
+  }
+}
+
+// Sum of the partial tiles -> Z; fused with the all-reduce over the ranks when a communicator was bound for this call
+// (era5svd_comm_fuse_next_project).
+template <typename T>
+static int launch_reduce_partials(const T* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z, int64_t ldz,
+                                  int accumulate, cudaStream_t st) {
+  int64_t bn = 0, bl = 0;
+  Comm* cm = take_bound_comm(&bn, &bl);
+  const int64_t nchunks = ceil_div(n * lp, (int64_t)RP_OUT);
+  if (cm) {
+    if (bn != n || bl != l) {
+      set_error("fused all-reduce was requested for a %lld x %lld projection, got %lld x %lld", (long long)bn,
+                (long long)bl, (long long)n, (long long)l);
+      return ERA5SVD_ERR_ARG;
+    }
+    CommDev d;
+    if (!comm_next(cm, n * l, &d)) return ERA5SVD_ERR_ARG;
+    const int64_t grid = nchunks < comm_max_grid() ? nchunks : comm_max_grid();
+    reduce_partials_allreduce_kernel<T><<<(unsigned)grid, RP_OUT * RP_GROUPS, 0, st>>>(part, splits, n, l, lp, Z, ldz,
+                                                                                      accumulate, d);
+    comm_note_fused(cm);
+    return check_launch("reduce_partials_allreduce_kernel");
+  }
+  reduce_partials_kernel<T><<<(unsigned)nchunks, RP_OUT * RP_GROUPS, 0, st>>>(part, splits, n, l, lp, Z, ldz, accumulate);
+  return check_launch("reduce_partials_kernel");
+}
+
 struct ProjectPlan {
   int64_t splits;
   int64_t rows_per_split;
@@ -436,8 +514,7 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
     }
     int rc = check_launch("project_dmma_kernel");
     if (rc) return rc;
-    reduce_partials_kernel<double><<<(unsigned)ceil_div(n * l, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const double*)ws, plan.splits, n, l, l, Z, ldz, accumulate);
-    return check_launch("reduce_partials_kernel");
+    return launch_reduce_partials<double>((const double*)ws, plan.splits, n, l, l, Z, ldz, accumulate, st);
   }
   if (use_tn7(l)) {
     dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 112), (unsigned)plan.splits);
@@ -448,15 +525,13 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
   }
   int rc = check_launch("project_kernel");
   if (rc) return rc;
-  int64_t total = n * l;
-  reduce_partials_kernel<T><<<(unsigned)ceil_div(total, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>((const T*)ws, plan.splits, n, l, l, Z, ldz, accumulate);
-  return check_launch("reduce_partials_kernel");
+  return launch_reduce_partials<T>((const T*)ws, plan.splits, n, l, l, Z, ldz, accumulate, st);
 }
 
 // shared with the tcgen05 path (gemm_tc.cu): float32 partial tiles -> float64 sum
-void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
-                                int64_t ldz, int accumulate, cudaStream_t st) {
-  reduce_partials_kernel<float><<<(unsigned)ceil_div(n * lp, (int64_t)RP_OUT), RP_OUT * RP_GROUPS, 0, st>>>(part, splits, n, l, lp, Z, ldz, accumulate);
+int launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
+                               int64_t ldz, int accumulate, cudaStream_t st) {
+  return launch_reduce_partials<float>(part, splits, n, l, lp, Z, ldz, accumulate, st);
 }
 
 }  // namespace era5svd

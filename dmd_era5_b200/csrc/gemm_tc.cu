@@ -35,8 +35,8 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
 size_t project_tf32x3_raw_workspace_bytes(int64_t m, int64_t n, int64_t l);
 
 // from gemm_simt.cu
-void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
-                                int64_t ldz, int accumulate, cudaStream_t st);
+int launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
+                               int64_t ldz, int accumulate, cudaStream_t st);
 
 namespace tc {
 
@@ -857,8 +857,7 @@ static int project_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int6
   dim3 grid((unsigned)pl.nchunks, (unsigned)pl.splits);
   tc::project_tc_kernel<<<grid, tc::PJ_THREADS, smem, st>>>(tm_xhi, tm_xlo, tm_yhi, tm_ylo, p);
   if ((rc = check_launch("project_tc_kernel"))) return rc;
-  launch_reduce_partials_f32(p.part, pl.splits, n, l, l, Z, ldz, accumulate, st);
-  return check_launch("reduce_partials_kernel");
+  return launch_reduce_partials_f32(p.part, pl.splits, n, l, l, Z, ldz, accumulate, st);
 }
 
 int era5svd_project_tf32x3(const float* Xhi, const float* Xlo, int64_t m, int64_t n, int64_t ldx,

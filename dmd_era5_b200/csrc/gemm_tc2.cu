@@ -24,8 +24,8 @@
 
 namespace era5svd {
 
-void launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
-                                int64_t ldz, int accumulate, cudaStream_t st);
+int launch_reduce_partials_f32(const float* part, int64_t splits, int64_t n, int64_t l, int64_t lp, double* Z,
+                               int64_t ldz, int accumulate, cudaStream_t st);
 
 namespace tc {
 
@@ -657,8 +657,7 @@ int project_tf32x3_raw(const float* X, int64_t m, int64_t n, int64_t ldx, const 
   dim3 grid((unsigned)ceil_div(n + xs, tc::PJ2_NC), (unsigned)pl.splits);
   tc::project_tc2_kernel<<<grid, tc::PJ2_THREADS, smem, st>>>(tm_x, tm_yhi, tm_ylo, p);
   if ((rc = check_launch("project_tc2_kernel"))) return rc;
-  launch_reduce_partials_f32(p.part, pl.splits, n, l, round_up2(l, 16), Z, ldz, accumulate, st);
-  return check_launch("reduce_partials_kernel");
+  return launch_reduce_partials_f32(p.part, pl.splits, n, l, round_up2(l, 16), Z, ldz, accumulate, st);
 }
 
 }  // namespace era5svd

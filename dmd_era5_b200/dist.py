@@ -6,6 +6,11 @@ The snapshot matrix shards by rows - grid points / levels / variables are indepe
   * all-reduce(sum) of G = Y^T Y        (l x l)     once
   * all-gather of the svd_flip candidates (k triples) once
 Nothing space-sized is ever communicated; U stays sharded.
+
+Two communicators over the same process group: ``TorchDistComm`` (NCCL / gloo through torch.distributed) and
+``PeerComm`` (one node, CUDA devices): the small float64 collectives as OUR kernels over peer-mapped memory
+(csrc/comm.cu) - the all-reduce of Z fused into the kernel that sums the projection's partial tiles - with
+torch.distributed used only to exchange the IPC handles and for anything that does not fit a slot.
 """
 from __future__ import annotations
 
@@ -26,6 +31,9 @@ class LocalComm:
 
     def barrier(self) -> None:
         pass
+
+    def fuse_next_project(self, n: int, l: int) -> bool:
+        return False
 
 
 class TorchDistComm:
@@ -59,6 +67,97 @@ class TorchDistComm:
 
     def barrier(self) -> None:
         self._dist.barrier(group=self.group)
+
+    def fuse_next_project(self, n: int, l: int) -> bool:
+        """True when the NEXT ops.project* call will leave the all-reduced result in Z (PeerComm only)."""
+        return False
+
+
+class PeerComm(TorchDistComm):
+    """Collectives as kernels of libera5svd.so over CUDA-IPC peer memory (NVLink / NVSwitch), one process per GPU of one
+    node (era5svd_comm_*, include/era5svd.h).  float64 tensors that fit a slot take the peer path - one kernel on the
+    compute stream, ranks summed in rank order (bit-identical replicas); everything else falls through to NCCL.
+    Raises when peer access is not available: callers that want a fallback catch that and keep TorchDistComm."""
+
+    def __init__(self, ops, group=None, slot_bytes: int = 4 << 20):
+        import ctypes as C
+
+        super().__init__(group)
+        from ._cabi import check
+
+        self.ops, self.lib = ops, ops.lib
+        self._check = check
+        hb = int(self.lib.era5svd_comm_handle_bytes())
+        handle = (C.c_ubyte * hb)()
+        comm = C.c_void_p()
+        with torch.cuda.device(ops.device):
+            check(self.lib.era5svd_comm_create(self.world, self.rank, int(slot_bytes), C.byref(comm), handle),
+                  "era5svd_comm_create")
+            self._comm = comm
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=ops.device)
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            self._dist.all_gather(parts, mine, group=self.group)          # plumbing: the handle exchange
+            allh = bytes(torch.cat(parts).cpu().tolist())
+            buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+            check(self.lib.era5svd_comm_connect(self._comm, buf), "era5svd_comm_connect")
+        self.capacity = int(self.lib.era5svd_comm_capacity(self._comm))
+        self._dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        if getattr(self, "_comm", None):
+            self._dist.barrier(group=self.group)
+            self.lib.era5svd_comm_destroy(self._comm)
+            self._comm = None
+
+    def _fits(self, t: torch.Tensor, count: int) -> bool:
+        return t.is_cuda and t.dtype == torch.float64 and 0 < count <= self.capacity
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if not (self._fits(t, t.numel()) and t.is_contiguous()):
+            return super().allreduce_sum_(t)
+        self._check(self.lib.era5svd_comm_allreduce_f64(self._comm, t.data_ptr(), t.numel(), self.ops._stream()),
+                    "era5svd_comm_allreduce_f64")
+        return t
+
+    def allgather(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.contiguous()
+        if not self._fits(t, t.numel()):
+            return super().allgather(t)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self._check(self.lib.era5svd_comm_allgather_f64(self._comm, t.data_ptr(), t.numel(), out.data_ptr(),
+                                                        self.ops._stream()), "era5svd_comm_allgather_f64")
+        return out
+
+    def fuse_next_project(self, n: int, l: int) -> bool:
+        if n * l > self.capacity:
+            return False
+        self._check(self.lib.era5svd_comm_fuse_next_project(self._comm, int(n), int(l)), "era5svd_comm_fuse_next_project")
+        return True
+
+    @property
+    def fused_count(self) -> int:
+        return int(self.lib.era5svd_comm_fused_count(self._comm))
+
+
+def make_comm(ops, group=None, prefer_peer: bool = True):
+    """Communicator for an initialised process group: PeerComm on CUDA devices of one node when peer memory can be mapped
+    (every rank must succeed), else TorchDistComm.  ERA5SVD_COMM=nccl forces the torch.distributed path."""
+    import os
+
+    import torch.distributed as dist
+
+    if not prefer_peer or os.environ.get("ERA5SVD_COMM", "peer") != "peer" or dist.get_backend(group) != "nccl":
+        return TorchDistComm(group)
+    ok = torch.ones(1, device=ops.device)
+    comm = None
+    try:
+        comm = PeerComm(ops, group)
+    except Exception:                     # noqa: BLE001 - no peer access / IPC refused: NCCL carries the collectives
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if float(ok) < 1:
+        return TorchDistComm(group)
+    return comm
 
 
 def shard_rows(m0: int, world: int, rank: int, align: int = 128) -> tuple[int, int]:

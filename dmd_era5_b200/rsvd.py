@@ -202,30 +202,44 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
         On the on-chip-split path the power iterations keep Y as ONE plain float32 image (split again on chip by the
         projection); only the final pass writes the hi / lo pair that the Gram and U = Y M kernels consume."""
         Z = None
+        fused = False
+
+        def last_block(j: int) -> None:
+            # the projection of the last delay block finishes with the all-reduce over the row shards inside the kernel
+            # that sums its partial tiles (PeerComm: era5svd_comm_fuse_next_project); other communicators return False
+            nonlocal fused
+            if j == d - 1:
+                fused = comm.fuse_next_project(n, l)
+
         if use_tc:
             for j in range(d):
                 rows = slice(j * m0, (j + 1) * m0)
                 xh, xl = Xhi[:, j : j + n], (Xlo[:, j : j + n] if Xlo is not None else None)
                 if low:
                     ops.sketch_tf32x1(xh, Omega64, Y[rows])
+                    last_block(j)
                     Z = ops.project_tf32x1(xh, Y[rows], Z, accumulate=j > 0)
                     continue
                 if xl is None and not final:
                     ops.sketch_tf32x3(xh, None, Omega64, Y[rows], None, None, om_tf32=om_tf32)
+                    last_block(j)
                     if ytrunc:      # X exact (split on chip), Y taken as tf32(Y): two products, error filtered by X^T
                         Z = ops.project_tf32x2(xh, Y[rows], Z, accumulate=j > 0)
                     else:
                         Z = ops.project_tf32x3(xh, None, Y[rows], None, Z, accumulate=j > 0)
                     continue
                 ops.sketch_tf32x3(xh, xl, Omega64, Y[rows] if keep_y else None, Yhi[rows], Ylo[rows], om_tf32=om_tf32)
+                last_block(j)
                 Z = ops.project_tf32x3(xh, xl, Yhi[rows], Ylo[rows], Z, accumulate=j > 0)
         else:
             Om_t = ops.convert(Omega64, tall)
             for j in range(d):
                 Yj = Y[j * m0 : (j + 1) * m0]
                 ops.sketch(blocks.view(j), Om_t, Yj, PREC_NATIVE)
+                last_block(j)
                 Z = ops.project(blocks.view(j), Yj, Z, accumulate=j > 0, precision=PREC_NATIVE)
-        comm.allreduce_sum_(Z)
+        if not fused:
+            comm.allreduce_sum_(Z)
         if stats is not None:
             stats["tall_passes"] = stats.get("tall_passes", 0) + 2
         return Z
@@ -263,8 +277,10 @@ def randomized_svd_device(ops, X: torch.Tensor | None, n_components: int, omega0
     with nvtx_range("era5svd.final_range_and_projection"):
         Zp = tall_pass(Omega, keep_y=not use_tc, final=True)           # n x l
     # l x l Gram matrix of the STORED (rounded) Y, so that Q = Y R^-1 is orthonormal for the Y we keep
+    fused_g = comm.fuse_next_project(l, l)
     G = ops.project_tf32x3(Yhi, Ylo, Yhi, Ylo) if use_tc else ops.project(Y, Y, precision=PREC_NATIVE)
-    comm.allreduce_sum_(G)
+    if not fused_g:
+        comm.allreduce_sum_(G)
     _, Rinv = ops.chol_inv(G, rel_tol)
     B = ops.gemm(Rinv, Zp, transA=True, transB=True)   # l x n  = R^-T Z'^T = Q^T X
     BBt = ops.gemm(B, B, transB=True)                  # l x l

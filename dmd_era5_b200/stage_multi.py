@@ -29,7 +29,7 @@ def _worker(rank: int, world: int, port: int, parsed_config: dict, outdir: str) 
     import torch.distributed as dist
 
     from .device_ops import CudaOps
-    from .dist import TorchDistComm
+    from .dist import make_comm
     from .stage import _device_arrays, _prepare, retrieve_era5_slice
 
     torch.cuda.set_device(rank)
@@ -39,8 +39,8 @@ def _worker(rank: int, world: int, port: int, parsed_config: dict, outdir: str) 
         ds, _ = retrieve_era5_slice(parsed_config, use_dvc=False)      # the parent has made sure the file is there
         if ds is None:
             raise FileNotFoundError(f"ERA5 slice {parsed_config['era5_slice_path']} not found by rank {rank}")
-        arr = _device_arrays(_prepare(ds, parsed_config), parsed_config, CudaOps(rank), comm=TorchDistComm(),
-                             rank=rank, world=world)
+        ops = CudaOps(rank)
+        arr = _device_arrays(_prepare(ds, parsed_config), parsed_config, ops, comm=make_comm(ops), rank=rank, world=world)
         np.save(os.path.join(outdir, f"U_{rank}.npy"), arr["U"])
         for key in ("X", "mean", "std"):
             if arr[key] is not None:

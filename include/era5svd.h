@@ -286,6 +286,30 @@ int era5svd_scale_cols(void* U, int dtype, int64_t m, int64_t k, int64_t ldu, co
 int era5svd_scale_rows_f64(double* V, int64_t k, int64_t n, int64_t ldv, const double* scale,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * era5svd_comm_* : the collectives of the row-sharded path as kernels over peer memory (NVLink / NVSwitch P2P through
+ * CUDA IPC), SURVEY.md 8b / 8e.  The reference has no counterpart (single process, era5_svd.py:246-259); what is
+ * reduced is what its GEMMs sum over ALL rows: Z = X^T Y (extmath.py:379, 606), the l x l Gram matrix, and the
+ * first-maximum rule of svd_flip (extmath.py:964-972).  One process per GPU of ONE node:
+ *   create   : allocates this rank's window (two data slots of slot_bytes + flags) and exports its IPC handle
+ *              (era5svd_comm_handle_bytes() bytes) - the caller exchanges the handles (torch.distributed all_gather);
+ *   connect  : maps every peer's window; `handles` = nranks consecutive handles in rank order;
+ *   allreduce_f64 / allgather_f64 : one kernel on `stream` each; sums are formed in rank order 0..R-1 on every rank,
+ *              so the replicated small factors stay bit-identical;  count <= era5svd_comm_capacity() doubles;
+ *   fuse_next_project(n, l) : the NEXT era5svd_project* call on this host thread (n x l result) finishes with ONE kernel
+ *              that sums the partial tiles of the projection AND the ranks (reduce_partials_allreduce_kernel): Z holds
+ *              the all-reduced result.  ERA5SVD_ERR_UNSUPPORTED when n * l does not fit a slot.
+ * Every rank must issue the same sequence of collectives.  Not thread safe per communicator. */
+size_t era5svd_comm_handle_bytes(void);
+int era5svd_comm_create(int nranks, int rank, int64_t slot_bytes, void** comm_out, void* handle_out);
+int era5svd_comm_connect(void* comm, const void* handles);
+int era5svd_comm_destroy(void* comm);
+int64_t era5svd_comm_capacity(void* comm);
+unsigned long long era5svd_comm_fused_count(void* comm);
+int era5svd_comm_allreduce_f64(void* comm, double* buf, int64_t count, void* stream);
+int era5svd_comm_allgather_f64(void* comm, const double* src, int64_t count, double* dst, void* stream);
+int era5svd_comm_fuse_next_project(void* comm, int64_t n, int64_t l);
+
 #ifdef __cplusplus
 }
 #endif

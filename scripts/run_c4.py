@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 from dmd_era5_b200 import standard as std_mod
 from dmd_era5_b200.device_ops import CudaOps, KernelTimer
-from dmd_era5_b200.dist import LocalComm, TorchDistComm, shard_rows
+from dmd_era5_b200.dist import LocalComm, make_comm, shard_rows
 from dmd_era5_b200.pipeline import build_matrix_device, svd_device
 from dmd_era5_b200.synthetic import synthetic_field
 
@@ -38,6 +38,9 @@ class TimedComm:
     def allgather(self, t):
         return self.inner.allgather(t)
 
+    def fuse_next_project(self, n, l):
+        return self.inner.fuse_next_project(n, l)
+
     def barrier(self):
         self.inner.barrier()
 
@@ -49,12 +52,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ops = CudaOps(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        comm = TimedComm(TorchDistComm())
+        comm = TimedComm(make_comm(ops))
     else:
         comm = TimedComm(LocalComm())
-    ops = CudaOps(dev)
     r0, r1 = shard_rows(M, world, rank)
     field = synthetic_field(T, r1 - r0, device=dev, seed=40 + rank, rank=200, rho=0.96, chunk=1 << 17, time_seed=40,
                             total_points=M)

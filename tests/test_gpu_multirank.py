@@ -1,5 +1,6 @@
-"""GPU, >= 2 devices: the row-sharded paths over NCCL (randomized native / tf32x3 / tf32mix, standard FP64, sharded
-BOP-DMD trials) against the single-process oracles - scripts/check_multigpu.py run as a test (multi-rank
+"""GPU, >= 2 devices: the row-sharded paths over NCCL and over the peer-memory communicator (era5svd_comm_*: collectives
+against NCCL on random data, the all-reduce fused into the projection's reduction, replicas bit-identical) - randomized
+native / tf32x3 / tf32mix, standard FP64, sharded BOP-DMD trials - against the single-process oracles - scripts/check_multigpu.py run as a test (multi-rank
 NCCL parity was a hand-run script).  Skipped on a one-GPU box; the gloo CPU tests cover the host logic there."""
 import json
 import os
@@ -23,5 +24,6 @@ def test_two_rank_nccl_parity():
     assert out.returncode == 0, out.stderr[-3000:]
     line = json.loads([ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")][-1])
     assert line["world"] == 2
-    for key in ("native", "tf32x3", "tf32mix", "standard_fp64", "bopdmd_trials_sharded"):
+    for key in ("peer_collectives", "native", "tf32x3", "tf32mix", "peer_native", "peer_tf32mix", "standard_fp64",
+                "bopdmd_trials_sharded"):
         assert line[key]["pass"], (key, line[key])
