@@ -320,6 +320,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-north-star", action="store_true", help="skip the c3 (north-star shape) leg")
+    ap.add_argument("--no-collectives", action="store_true",
+                    help="diagnosis only (the results are WRONG and the line says so): every rank factorises its shard "
+                         "alone, which isolates the rank skew from the cost of the collectives")
     ap.add_argument("--north-star-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -355,6 +358,11 @@ def main():
     comm = make_comm(ops) if world > 1 else LocalComm()
     comm_kind = "none (1 rank)" if world == 1 else ("peer memory (era5svd_comm_*, fused into reduce_partials)"
                                                      if isinstance(comm, PeerComm) else "nccl (torch.distributed)")
+    if args.no_collectives and world > 1:
+        class _NoCollectives(LocalComm):        # barrier only: each rank's SVD is that of its own shard (diagnosis)
+            barrier = staticmethod(comm.barrier)
+        comm = _NoCollectives()
+        comm_kind = "NONE - DIAGNOSIS RUN, results are per-shard SVDs, not the row-sharded SVD (invalid as a benchmark)"
 
     def sync_all():
         torch.cuda.synchronize(device)

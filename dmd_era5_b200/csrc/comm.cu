@@ -24,7 +24,8 @@ struct Comm {
   unsigned long long fused = 0, calls = 0;
 };
 
-static size_t flag_bytes() { return (size_t)COMM_MAX_BLOCKS * COMM_MAX_RANKS * sizeof(uint32_t); }
+// flag pad: [COMM_MAX_RANKS] arrival words (written by the peers) + the local words ctr[2], go
+static size_t flag_bytes() { return (size_t)(COMM_MAX_RANKS + 4) * sizeof(uint32_t); }
 
 static thread_local Comm* g_bound = nullptr;
 static thread_local int64_t g_bound_n = 0, g_bound_l = 0;
@@ -37,8 +38,7 @@ Comm* take_bound_comm(int64_t* n, int64_t* l) {
 }
 
 int comm_max_grid() {
-  const int g = 2 * sm_count();
-  return g < COMM_MAX_BLOCKS ? g : COMM_MAX_BLOCKS;
+  return 4 * sm_count();       // 256-thread kernels of <= 64 registers: four CTAs per SM are resident together
 }
 
 bool comm_next(Comm* c, int64_t count, CommDev* out) {
@@ -57,17 +57,20 @@ bool comm_next(Comm* c, int64_t count, CommDev* out) {
     out->slot[r] = r < c->nranks ? reinterpret_cast<double*>(c->peer[r] + off) : nullptr;
     out->flags[r] = r < c->nranks ? reinterpret_cast<uint32_t*>(c->peer[r] + 2 * c->slot_bytes) : nullptr;
   }
+  uint32_t* local = reinterpret_cast<uint32_t*>(c->base + 2 * c->slot_bytes) + COMM_MAX_RANKS;
+  out->ctr = local + (c->epoch & 1u);
+  out->go = local + 2;
   c->calls += 1;
   return true;
 }
 
-// In-place all-reduce (sum) of `count` doubles.  Block b copies, flags and then sums ITS contiguous range only.
+// In-place all-reduce (sum) of `count` doubles.
 __global__ void __launch_bounds__(256) comm_allreduce_f64_kernel(double* __restrict__ buf, int64_t count, CommDev c) {
   const int64_t per = (count + gridDim.x - 1) / gridDim.x;
   const int64_t a = (int64_t)blockIdx.x * per, b = a + per < count ? a + per : count;
   double* mine = c.slot[c.rank];
   for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) mine[i] = buf[i];
-  comm_block_exchange(c);
+  comm_grid_exchange(c);
   for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) buf[i] = comm_sum_ranks(c, i);
 }
 
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256) comm_allgather_f64_kernel(const double* _
   const int64_t a = (int64_t)blockIdx.x * per, b = a + per < count ? a + per : count;
   double* mine = c.slot[c.rank];
   for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) mine[i] = src[i];
-  comm_block_exchange(c);
+  comm_grid_exchange(c);
   for (int r = 0; r < c.nranks; ++r)
     for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) dst[(int64_t)r * count + i] = comm_load(c.slot[r] + i);
 }
@@ -86,7 +89,10 @@ __global__ void __launch_bounds__(256) comm_allgather_f64_kernel(const double* _
 void comm_note_fused(Comm* c) { if (c) c->fused += 1; }
 
 static unsigned grid_for(int64_t count) {
-  int64_t g = ceil_div(count, 1024);            // >= 4 values per thread before another block pays its flag round
+  // one value per thread while the grid allows: a thread's peer loads are one NVLink round trip however many ranks it
+  // reads, but consecutive values of the same thread would pay one round trip EACH (measured: 4 values per thread 20 us,
+  // against 9.4 us for a single block's exchange)
+  int64_t g = ceil_div(count, 256);
   const int mx = comm_max_grid();
   if (g > mx) g = mx;
   if (g < 1) g = 1;

@@ -2,8 +2,9 @@
 //
 // Every rank owns one window  [slot 0 | slot 1 | flag pad]  allocated with cudaMalloc and mapped into every peer through
 // cudaIpcOpenMemHandle.  A collective writes this rank's contribution into the slot of the current epoch's parity, raises
-// one flag per (block, peer) with a system-scope release store, waits for the peers' flags with system-scope acquire loads,
-// and then READS the peers' slots directly over NVLink - one kernel, no host round trip, no stream hop.
+// ONE flag per peer with a system-scope release store once all of its blocks have written, waits for the peers' flags with
+// system-scope acquire loads, and then READS the peers' slots directly over NVLink - one kernel, no host round trip, no
+// stream hop.
 //
 // Slot reuse is safe with two slots: a rank can only enter epoch e + 2 (which overwrites the slot of epoch e) after it left
 // epoch e + 1, i.e. after every peer raised its e + 1 flags - and a peer raises them from a kernel that runs, in stream
@@ -11,17 +12,20 @@
 #pragma once
 
 #include <stdint.h>
+#include <stdio.h>
 
 namespace era5svd {
 
 constexpr int COMM_MAX_RANKS = 16;
-constexpr int COMM_MAX_BLOCKS = 320;      // upper bound of the grids that take part (>= 2 x 148 SMs)
+constexpr long long COMM_TIMEOUT_CLOCKS = 40000000000ll;   // ~20 s at 2 GHz
 
 struct CommDev {                          // passed to kernels by value
   int nranks, rank;
   uint32_t epoch;                         // value the flags of this collective carry (monotonic, wraps)
   double* slot[COMM_MAX_RANKS];           // this epoch's data slot of every rank (own and peer-mapped)
-  uint32_t* flags[COMM_MAX_RANKS];        // flag pad of every rank: [COMM_MAX_BLOCKS][COMM_MAX_RANKS]
+  uint32_t* flags[COMM_MAX_RANKS];        // flag pad of every rank: [COMM_MAX_RANKS] arrival words, one per sender
+  uint32_t* ctr;                          // LOCAL: blocks of this grid that have written their part (this epoch's parity)
+  uint32_t* go;                           // LOCAL: epoch whose peer data may be read
 };
 
 struct Comm;
@@ -35,20 +39,56 @@ void comm_note_fused(Comm* c);
 int comm_max_grid();                      // largest grid a collective kernel may use
 
 #ifdef __CUDACC__
-// Block-level exchange: every thread of the block has written its part of the local slot; on return the same block's part
-// of EVERY rank's slot is visible.  Block b of one rank pairs with block b of the others (same grid on every rank).
-__device__ __forceinline__ void comm_block_exchange(const CommDev& c) {
-  __threadfence_system();
+__device__ __forceinline__ uint32_t comm_ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-level exchange.  Every block has written its part of the local slot; on return EVERY rank's whole slot is visible
+// to every block.  Two levels, so that what crosses NVLink for the synchronisation is one flag per peer and collective
+// (a flag round per block - the first version - cost 7 system-scope releases per block and made the large messages
+// slower than NCCL): blocks count in on a local word; block 0 waits for the count, raises this rank's flag at every
+// peer (release, system scope), waits for the peers' flags (acquire, system scope) and publishes a local go word that
+// the other blocks poll (gpu scope).  The grid must be co-resident (comm_max_grid()).
+__device__ __forceinline__ void comm_grid_exchange(const CommDev& c) {
   __syncthreads();
-  if ((int)threadIdx.x < c.nranks) {
-    const int t = threadIdx.x;
-    uint32_t* remote = c.flags[t] + (size_t)blockIdx.x * COMM_MAX_RANKS + c.rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(c.epoch) : "memory");
-    const uint32_t* mine = c.flags[c.rank] + (size_t)blockIdx.x * COMM_MAX_RANKS + t;
-    uint32_t v;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-    } while ((int32_t)(v - c.epoch) < 0);
+  if (threadIdx.x == 0) {
+    __threadfence();                            // this block's slot writes before its count
+    atomicAdd(c.ctr, 1u);
+  }
+  if (blockIdx.x == 0) {
+    const long long t0 = clock64();
+    if (threadIdx.x == 0) {
+      while (comm_ld_acquire_gpu(c.ctr) < gridDim.x) {
+        if (clock64() - t0 > COMM_TIMEOUT_CLOCKS) __trap();
+      }
+      *c.ctr = 0;                               // next used two epochs from now, after everybody has passed this point
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < c.nranks) {
+      const int t = threadIdx.x;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(c.flags[t] + c.rank), "r"(c.epoch) : "memory");
+      const uint32_t* mine = c.flags[c.rank] + t;
+      uint32_t v;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - c.epoch) >= 0) break;
+        // a peer that never arrives (it failed, or the ranks issued different collectives) must not hang the GPU: after
+        // ~20 s of polling the kernel aborts, the stream reports a launch failure and the process exits
+        if (clock64() - t0 > COMM_TIMEOUT_CLOCKS) {
+          printf("era5svd comm: rank %d waited too long for rank %d (epoch %u): aborting\n", c.rank, t, c.epoch);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c.go), "r"(c.epoch) : "memory");
+  } else if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while ((int32_t)(comm_ld_acquire_gpu(c.go) - c.epoch) < 0) {
+      if (clock64() - t0 > 2 * COMM_TIMEOUT_CLOCKS) __trap();
+    }
   }
   __syncthreads();
 }

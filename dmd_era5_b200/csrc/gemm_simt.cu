@@ -372,11 +372,10 @@ reduce_partials_kernel(const T* __restrict__ part, int64_t splits, int64_t n, in
 }
 
 // The same reduction fused with the all-reduce over the row shards (comm.cuh): phase 1 sums this rank's partial tiles into
-// its peer-mapped slot (compact n x l), one flag round per block, phase 2 adds the ranks' slots in rank order into Z.  The
-// grid is bounded (<= 2 CTAs per SM) and every block owns the same chunks on every rank, so block b only ever waits for
-// block b of its peers.
+// its peer-mapped slot (compact n x l), one grid-wide flag round (comm_grid_exchange), phase 2 adds the ranks' slots in
+// rank order into Z.  The grid is bounded (<= 4 CTAs per SM, all co-resident).
 template <typename T>
-__global__ void __launch_bounds__(RP_OUT * RP_GROUPS)
+__global__ void __launch_bounds__(RP_OUT * RP_GROUPS, 4)
 reduce_partials_allreduce_kernel(const T* __restrict__ part, int64_t splits, int64_t n, int64_t l, int64_t lp,
                                  double* __restrict__ Z, int64_t ldz, int accumulate, CommDev c) {
   __shared__ double sm[RP_GROUPS][RP_OUT];
@@ -411,7 +410,7 @@ reduce_partials_allreduce_kernel(const T* __restrict__ part, int64_t splits, int
     }
     __syncthreads();
   }
-  comm_block_exchange(c);
+  comm_grid_exchange(c);
   const int64_t my_chunks = (int64_t)blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   for (int64_t e = threadIdx.x; e < my_chunks * RP_OUT; e += blockDim.x) {
     const int64_t idx = ((int64_t)blockIdx.x + (e / RP_OUT) * gridDim.x) * RP_OUT + e % RP_OUT;

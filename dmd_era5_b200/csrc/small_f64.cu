@@ -82,6 +82,65 @@ gemm_f64_kernel(int transA, int transB, int64_t M, int64_t N, int64_t K, double 
 // column walks for doubles) when they fit, else in the global workspace (one CTA: block barriers
 // order the accesses; L1/L2 resident).  FP64-pipe bound: ~4 DFMA per updated element pair.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Register-tiled right-looking Cholesky of an l x l (l <= 128) symmetric matrix by one CTA of 32 x 32 threads, row
+// scaling deferred: thread (ty, tx) holds the entries rows ty + 32 a, columns tx + 32 b (a, b < 4) of the upper triangle in
+// r[a][b] for the whole factorisation; on return row i holds the UNSCALED final row (R = D^-1/2 r).  Two images of the
+// pivot row cross shared memory per step - prow_c = the row itself (column factors), prow_r = the row divided by its pivot
+// for the columns > j and ZERO elsewhere (row factors; rows <= j are final) - both formed by the warp that owns the row
+// (the pivot reaches its lanes by shuffle), so the other 31 warps execute no compare / select / multiply: 8 shared loads
+// and <= 10 DFMAs per step, one barrier.  (The first version, with the pivot test and the scaling in every thread, issued
+// 79 instructions per warp and step - ncu, profiles/r02_small_kernels.md.)  A dependent or non-positive pivot drops its
+// direction (zero row factors, *dropped = 1), never a NaN.  prow_c / prow_r: [2][128], zeroed here.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void chol_register_tiled(double (&r)[4][4], int l, const double* __restrict__ gdiag,
+                                                    double rel_tol, double (*prow_c)[128], double (*prow_r)[128],
+                                                    int* dropped, int tx, int ty) {
+  const int t = ty * 32 + tx;
+  if (t < 256) { (&prow_c[0][0])[t] = 0.0; (&prow_r[0][0])[t] = 0.0; }
+  if (t == 0) *dropped = 0;
+  __syncthreads();
+  auto publish = [&](int jn) {               // executed by the warp that owns row jn (ty == jn % 32): row jn is final
+    const int an = jn >> 5, ln = jn & 31;
+    double v[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v[b] = an == 0 ? r[0][b] : (an == 1 ? r[1][b] : (an == 2 ? r[2][b] : r[3][b]));
+    const double dsel = an == 0 ? v[0] : (an == 1 ? v[1] : (an == 2 ? v[2] : v[3]));
+    const double d = __shfl_sync(0xffffffffu, dsel, ln);
+    const double inv_d = (d > rel_tol * gdiag[jn] && d > 0.0) ? 1.0 / d : 0.0;
+    if (inv_d == 0.0 && tx == 0) *dropped = 1;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int c = tx + 32 * b;
+      if (c < l) {
+        prow_c[jn & 1][c] = v[b];
+        prow_r[jn & 1][c] = c > jn ? v[b] * inv_d : 0.0;
+      }
+    }
+  };
+  if (ty == 0) publish(0);
+  for (int j = 0; j < l; ++j) {
+    __syncthreads();
+    const double* pwc = prow_c[j & 1];
+    const double* pwr = prow_r[j & 1];
+    double pc[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) pc[b] = pwc[tx + 32 * b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (ty + 32 * a > j) {                                   // warp-uniform: rows of this slot still open
+        const double pra = pwr[ty + 32 * a];
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) r[a][b] = fma(-pra, pc[b], r[a][b]);
+        if (tx >= ty) r[a][a] = fma(-pra, pc[a], r[a][a]);     // diagonal block: upper part only
+      }
+    }
+    const int jn = j + 1;
+    if (jn < l && ty == (jn & 31)) publish(jn);                // the next pivot row is final now
+  }
+  __syncthreads();                                             // *dropped is complete
+}
+
 constexpr int JAC_THREADS = 1024;
 constexpr int JAC_GROUP = 16;
 constexpr int JAC_GROUPS = JAC_THREADS / JAC_GROUP;
@@ -234,14 +293,16 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
                         double* __restrict__ V, int64_t ldv, int max_sweeps, double tol_in, double pivot_tol,
                         int* __restrict__ status) {
   extern __shared__ double smem[];
-  __shared__ double prow[2][J1_MAXN];
-  __shared__ double s_inv[2];
+  __shared__ double prow_c[2][128];
+  __shared__ double prow_r[2][128];
+  __shared__ int s_dropped;
   __shared__ double gdiag[J1_MAXN];
   __shared__ double lam[J1_MAXN];
   __shared__ double nrm2[J1_MAXN];
   __shared__ int rank[J1_MAXN];
   const int t = threadIdx.x, tx = t % 32, ty = t / 32;
-  const int ldw = n + (n & 1);                  // even pitch: 16-byte aligned rows, contiguous row access
+  const int nper = (n + JAC_GROUP - 1) / JAC_GROUP;     // row elements per lane of a 16-lane group (uniform)
+  const int ldw = nper * JAC_GROUP;             // rows padded with zeros to whole groups: the sweeps load / store unguarded
   double* Rw = smem;                            // [n][ldw]
   for (int r = ty; r < n; r += 32)
     for (int c = tx; c < ldw; c += 32)
@@ -259,42 +320,8 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
         const int i = ty + 32 * a, c = tx + 32 * b;
         r[a][b] = (i < n && c < n && c >= i) ? Rw[i * ldw + c] : 0.0;
       }
-    if (ty == 0) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (tx + 32 * b < n) prow[0][tx + 32 * b] = r[0][b];
-      if (tx == 0) s_inv[0] = (r[0][0] > pivot_tol * gdiag[0] && r[0][0] > 0.0) ? 1.0 / r[0][0] : 0.0;
-    }
-    for (int j = 0; j < n; ++j) {
-      __syncthreads();
-      const double inv_d = s_inv[j & 1];
-      if (inv_d == 0.0) dropped = 1;           // uniform: every thread reads the same value
-      const double* pw = prow[j & 1];
-      double pc[4], pr[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) pc[b] = (tx + 32 * b < n) ? pw[tx + 32 * b] : 0.0;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = ty + 32 * a;
-        pr[a] = (i > j && i < n) ? pw[i] * inv_d : 0.0;
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (tx + 32 * b >= ty + 32 * a) r[a][b] = fma(-pr[a], pc[b], r[a][b]);
-      const int jn = j + 1;
-      if (jn < n && ty == (jn & 31)) {
-        const int an = jn >> 5;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c = tx + 32 * b;
-          const double v = an == 0 ? r[0][b] : (an == 1 ? r[1][b] : (an == 2 ? r[2][b] : r[3][b]));
-          if (c < n && c >= jn) prow[jn & 1][c] = v;
-          if (c == jn) s_inv[jn & 1] = (v > pivot_tol * gdiag[jn] && v > 0.0) ? 1.0 / v : 0.0;
-        }
-      }
-    }
+    chol_register_tiled(r, n, gdiag, pivot_tol, prow_c, prow_r, &s_dropped, tx, ty);
+    dropped = s_dropped;
     if (dropped) {                              // uniform over the CTA
       if (t == 0) *status = 1;
       return;
@@ -349,12 +376,15 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
           double x[J1_PER_LANE], y[J1_PER_LANE];
           const double app = nrm2[p], aqq = nrm2[q];
           double apq = 0.0;
+          double* px = Rw + p * ldw + gl;
+          double* py = Rw + q * ldw + gl;
 #pragma unroll
           for (int k = 0; k < J1_PER_LANE; ++k) {
-            const int c = gl + JAC_GROUP * k;
-            x[k] = c < n ? Rw[p * ldw + c] : 0.0;
-            y[k] = c < n ? Rw[q * ldw + c] : 0.0;
-            apq = fma(x[k], y[k], apq);
+            if (k < nper) {                    // uniform; the pad columns hold zeros and stay zero under rotations
+              x[k] = px[JAC_GROUP * k];
+              y[k] = py[JAC_GROUP * k];
+              apq = fma(x[k], y[k], apq);
+            }
           }
           apq = group16_sum(apq, gmask);
           if (early ? (apq * apq > tol_early * app * aqq) : (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300)) did = 1;
@@ -376,10 +406,9 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
             if (gl == 0) { nrm2[p] = app - t64 * apq; nrm2[q] = aqq + t64 * apq; }
 #pragma unroll
             for (int k = 0; k < J1_PER_LANE; ++k) {
-              const int c = gl + JAC_GROUP * k;
-              if (c < n) {
-                Rw[p * ldw + c] = cs * x[k] - sn * y[k];
-                Rw[q * ldw + c] = sn * x[k] + cs * y[k];
+              if (k < nper) {
+                px[JAC_GROUP * k] = cs * x[k] - sn * y[k];
+                py[JAC_GROUP * k] = sn * x[k] + cs * y[k];
               }
             }
           }
@@ -456,8 +485,9 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
     // double buffered, one barrier per step), and the reciprocal pivot is computed once, by the thread that owns
     // it.  ~45 instructions per thread and step; the smem read-modify-write version was issue bound
     // (ncu: 915 k warp instructions, 69 % issue utilisation for l = 110).
-    __shared__ double prow[2][128];
-    __shared__ double s_inv[2];
+    __shared__ double prow_c[2][128];
+    __shared__ double prow_r[2][128];
+    __shared__ int s_dropped;
     __syncthreads();                         // Rw (upper triangle, symmetrised) and gdiag are in place
     double r[4][4];
 #pragma unroll
@@ -467,42 +497,7 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
         const int i = ty + 32 * a, c = tx + 32 * b;
         r[a][b] = (i < l && c < l && c >= i) ? Rw[i * ld_r + c] : 0.0;
       }
-    if (ty == 0) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (tx + 32 * b < l) prow[0][tx + 32 * b] = r[0][b];
-      if (tx == 0) s_inv[0] = (r[0][0] > rel_tol * gdiag[0] && r[0][0] > 0.0) ? 1.0 / r[0][0] : 0.0;
-    }
-    for (int j = 0; j < l; ++j) {
-      __syncthreads();
-      const double inv_d = s_inv[j & 1];
-      const double* pw = prow[j & 1];
-      double pc[4], pr[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) pc[b] = (tx + 32 * b < l) ? pw[tx + 32 * b] : 0.0;
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = ty + 32 * a;
-        pr[a] = (i > j && i < l) ? pw[i] * inv_d : 0.0;       // rows <= j are final: factor 0
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (tx + 32 * b >= ty + 32 * a) r[a][b] = fma(-pr[a], pc[b], r[a][b]);
-      // publish the next pivot row (now final) and its reciprocal pivot
-      const int jn = j + 1;
-      if (jn < l && ty == (jn & 31)) {
-        const int an = jn >> 5;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c = tx + 32 * b;
-          const double v = an == 0 ? r[0][b] : (an == 1 ? r[1][b] : (an == 2 ? r[2][b] : r[3][b]));
-          if (c < l && c >= jn) prow[jn & 1][c] = v;
-          if (c == jn) s_inv[jn & 1] = (v > rel_tol * gdiag[jn] && v > 0.0) ? 1.0 / v : 0.0;
-        }
-      }
-    }
+    chol_register_tiled(r, l, gdiag, rel_tol, prow_c, prow_r, &s_dropped, tx, ty);
     // back to the working copy (the triangular inverse below reads columns of R)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -561,6 +556,13 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
 #pragma unroll
       for (int m = 0; m < 4; ++m) x[k][m] = (tx + 32 * m == ck && ck < l) ? 1.0 : 0.0;
     }
+    // The solved entry x_i stays UNSCALED in its owner lane (the factor 1 / r_ii is applied once at the end), and the
+    // strictly lower part of Rw is zero, so one step is: (slot + 1) column loads, the reciprocal diagonal, one shuffle
+    // broadcast + one multiply per solve and (slot + 1) DFMAs per solve - no per-row compare / select except for the owner
+    // lane's own diagonal entry.  Lanes whose row lies beyond l read a clamped (valid) row and hold values nobody uses.
+    const double* rowp[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) rowp[m] = Rw + (tx + 32 * m < l ? tx + 32 * m : l - 1) * ld_r;
     // rows are visited from the bottom; the 32-row slot of the current row is a compile-time constant inside each
     // of the four blocks below, so x[k][slot] needs no dynamic register indexing and rows of higher slots (> i,
     // already final) are not touched
@@ -572,18 +574,21 @@ chol_inv_kernel(const double* __restrict__ G, int l, int64_t ldg, double* __rest
         const double sc = scale[i];
         double rk[4];
 #pragma unroll
-        for (int m = 0; m <= slot; ++m) {
-          const int row = tx + 32 * m;
-          rk[m] = row < i ? Rw[row * ld_r + i] : 0.0;
-        }
+        for (int m = 0; m <= slot; ++m) rk[m] = rowp[m][i];
+        if (tx >= owner) rk[slot] = 0.0;       // own diagonal entry, and (rows beyond l only) the clamped row's values
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const double xi = __shfl_sync(0xffffffffu, x[k][slot], owner) * sc;
 #pragma unroll
-          for (int m = 0; m < slot; ++m) x[k][m] = fma(-rk[m], xi, x[k][m]);
-          x[k][slot] = (tx == owner) ? xi : fma(-rk[slot], xi, x[k][slot]);
+          for (int m = 0; m <= slot; ++m) x[k][m] = fma(-rk[m], xi, x[k][m]);
         }
       }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double sc = tx + 32 * m < l ? scale[tx + 32 * m] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k][m] *= sc;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -730,8 +735,8 @@ int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, i
   if (n <= J1_MAXN && n >= 2 && workspace && workspace_bytes >= era5svd_syevj_workspace_bytes(n) &&
       !(syevj_flags() & 1)) {
     status = reinterpret_cast<int*>(static_cast<char*>(workspace) + (size_t)(2 * n * (n | 1)) * sizeof(double));
-    const size_t sm1 = (size_t)n * (n + (n & 1)) * sizeof(double);
-    ERA5SVD_CUDA(cudaFuncSetAttribute(syev_chol_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    const size_t sm1 = (size_t)n * (size_t)((n + JAC_GROUP - 1) / JAC_GROUP * JAC_GROUP) * sizeof(double);   // rows padded to whole lane groups
+    ERA5SVD_CUDA(ensure_dynamic_smem((const void*)syev_chol_jacobi_kernel, sm1));
     syev_chol_jacobi_kernel<<<1, JAC_THREADS, sm1, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, 1e-13, status);
     int rc = check_launch("syev_chol_jacobi_kernel");
     if (rc) return rc;
@@ -747,8 +752,8 @@ int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, i
       return ERA5SVD_ERR_WORKSPACE;
     }
   }
-  ERA5SVD_CUDA(cudaFuncSetAttribute(syevj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-  ERA5SVD_CUDA(cudaFuncSetAttribute(syevj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+  ERA5SVD_CUDA(ensure_dynamic_smem((const void*)syevj_kernel<true>, limit));
+  ERA5SVD_CUDA(ensure_dynamic_smem((const void*)syevj_kernel<false>, limit));
   if (use_smem)
     syevj_kernel<true><<<1, JAC_THREADS, smem, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, (double*)workspace, status);
   else
@@ -766,7 +771,7 @@ int era5svd_chol_inv_f64(const double* G, int64_t l, int64_t ldg, double* R, int
   const int use_smem = full <= 220 * 1024;
   const size_t smem = use_smem ? full : small;
   if (use_smem) {
-    ERA5SVD_CUDA(cudaFuncSetAttribute(chol_inv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ERA5SVD_CUDA(ensure_dynamic_smem((const void*)chol_inv_kernel<true>, 220 * 1024));
     chol_inv_kernel<true><<<1, 1024, smem, as_stream(stream)>>>(G, (int)l, ldg, R, ldr, Rinv, ldri, rel_tol);
   } else {
     chol_inv_kernel<false><<<1, 1024, smem, as_stream(stream)>>>(G, (int)l, ldg, R, ldr, Rinv, ldri, rel_tol);
