@@ -61,6 +61,7 @@ class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    PERIOD = 0.005                           # seconds between NVML polls
 
     def __init__(self, index: int, uuid: str | None = None):
         self.index = index
@@ -108,7 +109,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), sm, mx, {nm for b, nm in bits if mask & b}))
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(self.PERIOD)
 
     # ---- nvidia-smi fallback ----
     def _poll_smi(self):
@@ -411,7 +412,7 @@ def main():
             sampler = ClockSampler(local_rank, uuid=str(torch.cuda.get_device_properties(local_rank).uuid))
             sampler.start()
         for _ in range(warmup):
-            step(field)
+            U, s, V = step(field)                 # results held like in the timed loop: the allocator's steady state
         sync_all()
         timer = KernelTimer()
         t_region0 = time.perf_counter()
@@ -421,10 +422,25 @@ def main():
         # per-launch CUDA events (KernelTimer) ride on every 4th timed step: two event records around each of the ~13
         # timed ops cost ~0.4 ms of a 14 ms step when every step carries them
         sampled = [i for i in range(steps) if i % 4 == 0]
+        step_ev = [] if os.environ.get("ERA5SVD_BENCH_STEP_EVENTS") else None   # diagnosis: one event per step
+        host_t, seg0 = [], None
+        if step_ev is not None:
+            import gc
+            seg0 = (torch.cuda.memory_stats(device).get("num_device_alloc", 0), gc.get_count(), [g["collections"] for g in gc.get_stats()])
         for i in range(steps):
+            h0 = time.perf_counter()
             U, s, V = step(field, timer if i % 4 == 0 else None)
+            if step_ev is not None:
+                step_ev.append(torch.cuda.Event(enable_timing=True)); step_ev[-1].record()
+                host_t.append(round((time.perf_counter() - h0) * 1e3, 2))
         e1.record()
         sync_all()
+        if step_ev:
+            per = [round(a.elapsed_time(b), 2) for a, b in zip([e0] + step_ev[:-1], step_ev)]
+            print(f"[bench] rank {rank} per-step device ms: {per}", file=sys.stderr)
+            print(f"[bench] rank {rank} per-step host enqueue ms: {host_t}; cudaMalloc calls in the region: "
+                  f"{torch.cuda.memory_stats(device).get('num_device_alloc', 0) - seg0[0]}; gc collections before / after: "
+                  f"{seg0[2]} / {[g['collections'] for g in gc.get_stats()]}", file=sys.stderr)
         launches = _cabi.launch_count() - launches0
         clocks = sampler.stop(t_region0, time.perf_counter()) if sampler is not None else None
         ms = e0.elapsed_time(e1) / steps
@@ -539,6 +555,7 @@ def main():
 
     del field
     torch.cuda.empty_cache()
+    ops.reserve_small_pool()
 
     # ---------------- north-star leg: BASELINE configs[2] (c3: 40 491 360 x 1460, k = 100, n_iter = 7) ----------------
     # N >= 4: the WHOLE matrix, row-sharded (strong) over the N ranks - the north-star number.  N < 4: it does not fit
@@ -571,6 +588,7 @@ def main():
                  "target": ">= 0.60 of the slower of the HBM and tensor rooflines per pass (BASELINE.json north_star)"}
         del f3, r3
         torch.cuda.empty_cache()
+        ops.reserve_small_pool()
 
     # ---------------- CPU baseline + parity IN THE SAME RUN (rank 0, N = 1) ----------------
     # The same <= 262 144-row sample of the workload goes through the reference's own calls on the host cores

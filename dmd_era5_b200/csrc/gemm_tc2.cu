@@ -602,14 +602,17 @@ struct Pj2Plan {
 
 // One plan for the workspace query and the launch: it depends on (m, n, l) only (the column shift of an
 // unaligned window adds at most one time chunk, which only matters for the wave rounding).
-static Pj2Plan pj2_plan(int64_t m, int64_t n, int64_t l) {
+static Pj2Plan pj2_plan(int64_t m, int64_t n, int64_t l, int64_t rows_cap = 4096) {
   Pj2Plan pl;
   pl.nchunks = (int)ceil_div(n + 3, tc::PJ2_NC);
   const int sms = sm_count();
   // <= ~4096 rows per TMEM accumulation: the tensor core's fp32 accumulate truncates, and the resulting bias on
   // sigma grows with the rows summed on chip (measured on the c2 bench: 2e-6 at 4096, 2e-5 at 8192, 4e-5 at 16384);
-  // the partial tiles are then added in float64
-  int64_t splits = ceil_div(m, 4096);
+  // the partial tiles are then added in float64.  This also holds for the two-product projection of the LAST power iteration
+  // (era5svd_project_tf32x2): its Z feeds the Rayleigh-Ritz matrix T = Omega^T Z, whose trailing eigenvalues sit at
+  // ~1e-7 of the leading one - with 16384 rows per accumulation (tried, round 2) the bias makes T numerically indefinite,
+  // the positive-definite eigensolver drops a pivot and the two-sided fallback costs 2 ms per step.
+  int64_t splits = ceil_div(m, rows_cap);
   int64_t ctas = ceil_div(splits * pl.nchunks, sms) * sms;      // whole waves
   splits = ctas / pl.nchunks;                                    // never more CTAs than whole waves
   if (splits < 1) splits = 1;

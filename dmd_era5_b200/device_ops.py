@@ -81,8 +81,19 @@ class CudaOps:
         self.device = torch.device("cuda", self._index)
         self._ws: dict[str, torch.Tensor] = {}
         self.timer: KernelTimer | None = None   # bench.py attaches one to time kernels with CUDA events
+        self.reserve_small_pool()
 
     # -- memory ------------------------------------------------------------------------------
+    def reserve_small_pool(self, nbytes: int = 32 << 20) -> None:
+        """Pre-grow the caching allocator's small-block pool (2 MiB segments serving tensors <= 1 MiB: every small factor
+        of the schedule).  Without it the pool grows lazily: with results of earlier calls still alive the 4th call of a
+        series needs one more segment, and that cudaMalloc - issued while the GPU is busy - was measured to block the
+        launching thread for 2 ... 88 ms, long enough to drain the launch queue (one 60 - 75 ms step in a run of 11 ms
+        steps, profiles/r02_bench_stall.txt).  Call after torch.cuda.empty_cache(), which returns the reservation."""
+        with torch.cuda.device(self.device):
+            hold = [torch.empty(1 << 20, dtype=torch.uint8, device=self.device) for _ in range(max(2, int(nbytes) >> 20))]
+            del hold
+
     def empty(self, shape, dtype) -> torch.Tensor:
         return torch.empty(shape, dtype=dtype, device=self.device)
 

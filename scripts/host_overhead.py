@@ -12,7 +12,7 @@ field = synthetic_field(T, S, device="cuda", seed=1000)
 
 def step():
     built = build_matrix_device(ops, [field], mean_center=True, scale=False)
-    return svd_device(ops, built.X, svd_type="randomized", n_components=100, seed=1, precision="tf32x3")
+    return svd_device(ops, built.X, svd_type="randomized", n_components=100, seed=1, precision="auto")
 
 for _ in range(3): step()
 torch.cuda.synchronize()
