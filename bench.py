@@ -187,7 +187,31 @@ def bind_to_gpu_numa_node(local_rank: int):
         allowed = os.sched_getaffinity(0) & cpus
         if len(allowed) >= 2:
             os.sched_setaffinity(0, allowed)
-            return {"node": node, "cpus": len(allowed)}
+            return {"node": node, "cpus": len(allowed), "source": "sysfs"}
+    except Exception:
+        pass
+    try:                                  # containers often hide the PCI sysfs tree: ask NVML for the GPU's ideal CPUs
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = None
+        for u in (uuid, "GPU-" + uuid):
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(u.encode())
+                break
+            except Exception:
+                pass
+        if h is None:
+            return None
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0) & cpus
+        if len(allowed) >= 2:
+            os.sched_setaffinity(0, allowed)
+            return {"cpus": len(allowed), "of_ideal": len(cpus), "source": "nvml"}
+        return {"cpus": 0, "of_ideal": len(cpus), "source": "nvml", "note": "none of the GPU's ideal CPUs is in this process's cpuset"}
     except Exception:
         pass
     return None
