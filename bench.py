@@ -349,6 +349,9 @@ def main():
                     help="diagnosis only (the results are WRONG and the line says so): every rank factorises its shard "
                          "alone, which isolates the rank skew from the cost of the collectives")
     ap.add_argument("--north-star-steps", type=int, default=5)
+    ap.add_argument("--balance", action="store_true",
+                    help="north-star leg: second run with row shards proportional to each rank's measured speed (measured at 8 "
+                         "GPUs: speeds within +-3.5 %%, 119.5 against 117.8 ms with equal shards - not faster, hence opt-in)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -357,7 +360,7 @@ def main():
 
     from dmd_era5_b200 import _cabi
     from dmd_era5_b200.device_ops import CudaOps, KernelTimer
-    from dmd_era5_b200.dist import LocalComm, PeerComm, make_comm, shard_rows
+    from dmd_era5_b200.dist import LocalComm, PeerComm, make_comm, shard_rows, shard_rows_weighted
     from dmd_era5_b200.pipeline import build_matrix_device, svd_device
     from dmd_era5_b200.rsvd import n_iter_auto
     from dmd_era5_b200.synthetic import synthetic_field
@@ -601,6 +604,43 @@ def main():
         f3 = synthetic_field(T3, r1 - r0, device=device, seed=2000 + rank, time_seed=77, total_points=mg)
         r3 = time_workload(f3, mg, ro, args.north_star_steps, 3, args.precision, True)
         tot_bytes = float(M3 if world >= 4 else (r1 - r0) * world) * T3 * 4
+        balance = None
+        if world >= 4:
+            # Strong scaling of ONE matrix: every collective waits for the slowest rank.  The line reports the speed each rank
+            # showed (device time of its own tall kernels per row, per-launch events, the waits excluded); with --balance a
+            # second run uses row shards proportional to it and both runs are reported.
+            try:
+                busy = sum(v["ms"] for nm, v in r3["ksum"].items() if nm in TALL or nm == "build_rows")
+                mine = torch.tensor([float(r1 - r0), float(busy)], device=device, dtype=torch.float64)
+                every = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(every, mine)
+                speed = [float(e[0] / e[1]) for e in every]
+                mean_speed = sum(speed) / world
+                weights = [min(1.15, max(0.85, sp / mean_speed)) for sp in speed]
+                equal = {"ms_per_step": r3["ms"], "GBps": tot_bytes / 1e9 / (r3["ms"] / 1e3), "rows_this_rank": r1 - r0}
+                if args.balance and max(speed) / min(speed) > 1.02:
+                    del f3
+                    torch.cuda.empty_cache()
+                    ops.reserve_small_pool()
+                    r0, r1 = shard_rows_weighted(M3, weights, rank)
+                    ro = r0
+                    f3 = synthetic_field(T3, r1 - r0, device=device, seed=2000 + rank, time_seed=77, total_points=mg)
+                    r3b = time_workload(f3, mg, ro, args.north_star_steps, 3, args.precision, True)
+                    balance = {"sharding": "rows proportional to each rank's measured speed (tall-kernel device time per row in "
+                                           "the equal-shard run of this same process)",
+                               "relative_speed_per_rank": [round(sp / mean_speed, 4) for sp in speed],
+                               "equal_shards": equal, "balanced_ms_per_step": r3b["ms"]}
+                    if r3b["ms"] < r3["ms"]:
+                        r3 = r3b
+                        label += "; row shards proportional to the measured per-rank speed"
+                    else:
+                        balance["note"] = "the balanced run was not faster: the equal-shard numbers are reported"
+                else:
+                    balance = {"sharding": "equal", "relative_speed_per_rank": [round(sp / mean_speed, 4) for sp in speed],
+                               "note": "speed = rows per ms of each rank's own tall kernels (per-launch events, waits for other "
+                                       "ranks excluded); --balance re-runs with shards proportional to it"}
+            except Exception as e:                      # noqa: BLE001 - the equal-shard result stands
+                balance = {"sharding": "equal", "error": repr(e)[:200]}
         p3 = pass_rooflines(r3["ksum"], pk, args.precision, args.tc_split)
         north = {"workload": label, "whole_matrix": world >= 4, "ms_per_step": r3["ms"],
                  "GBps": tot_bytes / 1e9 / (r3["ms"] / 1e3), "steps": args.north_star_steps, "warmup": 3,
@@ -608,6 +648,7 @@ def main():
                  "passes": [{x: e[x] for x in ("kernel", "calls", "avg_launch_ms", "achieved_GBps", "hbm_frac", "bound", "frac")
                              if x in e} | ({"tensor_frac": e["tensor_frac"], "achieved_TFLOPs": e["achieved_TFLOPs"]}
                                            if "tensor_frac" in e else {}) for e in p3],
+                 "load_balance": balance,
                  "min_tall_pass_frac": min((e["frac"] for e in p3 if e["kernel"] in TALL), default=None),
                  "target": ">= 0.60 of the slower of the HBM and tensor rooflines per pass (BASELINE.json north_star)"}
         del f3, r3

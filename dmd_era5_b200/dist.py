@@ -174,3 +174,21 @@ def shard_rows(m0: int, world: int, rank: int, align: int = 128) -> tuple[int, i
     r0 = min(m0, rank * per * align)
     r1 = min(m0, (rank + 1) * per * align)
     return r0, r1
+
+
+def shard_rows_weighted(m0: int, weights, rank: int, align: int = 128) -> tuple[int, int]:
+    """Contiguous block of base rows owned by ``rank`` when the ranks' shares are proportional to ``weights`` (one
+    positive number per rank, e.g. the rows per millisecond each GPU sustained in a calibration step: GPUs of one node
+    differ by ~10 % under their power caps, and every collective waits for the slowest rank).  Shard edges are aligned to
+    ``align`` rows except the last one; equal weights reproduce ``shard_rows`` up to rounding."""
+    w = [max(float(x), 0.0) for x in weights]
+    tot = sum(w)
+    if tot <= 0 or len(w) <= 1:
+        return shard_rows(m0, len(w), rank, align)
+    tiles = -(-m0 // align)
+    edges, acc = [0], 0.0
+    for x in w:
+        acc += x
+        edges.append(max(edges[-1], min(tiles, int(round(acc / tot * tiles)))))
+    edges[-1] = tiles
+    return min(m0, edges[rank] * align), min(m0, edges[rank + 1] * align)

@@ -219,3 +219,22 @@ def test_subspace_eigensolver_topk_and_fallback(monkeypatch):
     monkeypatch.setattr(standard, "SUBSPACE_MAX_ITERS", 8)
     Gf = (Qm * (1.0 + 1e-3 * rng.rand(n))) @ Qm.T
     assert standard.sym_eig_topk_subspace(FakeOps(), torch.from_numpy(Gf), k, 1e-13) is None
+
+
+def test_shard_rows_weighted_partitions_all_rows():
+    """Row shards proportional to per-rank speed (bench.py north-star leg): contiguous, aligned, complete; equal weights
+    reproduce the equal split up to one tile."""
+    from dmd_era5_b200.dist import shard_rows_weighted
+
+    m0 = 40491360
+    for w in ([1.0] * 8, [1.05, 1, 0.95, 1, 1.1, 0.9, 1, 1], [1, 2], [3.0]):
+        sh = [shard_rows_weighted(m0, w, r) for r in range(len(w))]
+        assert sh[0][0] == 0 and sh[-1][1] == m0
+        assert all(sh[i][1] == sh[i + 1][0] for i in range(len(w) - 1))
+        assert all(a % 128 == 0 for a, _ in sh)
+        sizes = [b - a for a, b in sh]
+        tot = sum(w)
+        assert all(abs(sz - m0 * wi / tot) <= 256 for sz, wi in zip(sizes, w))
+    eq = [shard_rows_weighted(m0, [1.0] * 8, r) for r in range(8)]
+    ref = [shard_rows(m0, 8, r) for r in range(8)]
+    assert all(abs((b - a) - (d - c)) <= 1024 for (a, b), (c, d) in zip(eq, ref))
