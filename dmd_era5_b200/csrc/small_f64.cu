@@ -282,12 +282,20 @@ syevj_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restric
 constexpr int J1_MAXN = 128;
 constexpr int J1_PER_LANE = J1_MAXN / JAC_GROUP;     // 8 row elements per lane
 
-__device__ __forceinline__ double group16_sum(double v, unsigned mask) {
+template <typename TS>
+__device__ __forceinline__ TS group16_sum(TS v, unsigned mask) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 16);
   return v;
 }
 
+// TS = the type the SWEEPS run in.  double: the eigen-decomposition to working precision.  float (callers that ask for a
+// relative decoupling >= 1e-5, i.e. the Rayleigh-Ritz rotation of the randomized driver, which is a choice of basis and not
+// a result): the Cholesky factor is still formed in float64 (cond(G) ~ 1e7 is beyond float32) and then rotated as float32
+// rows (cond(R) ~ 3e3) - FFMA instead of the 2-cycle DFMA, single instead of paired shuffles, half the shared-memory
+// bytes; the dependent chain of a step, which bounds the sweeps, is about half as long.  Eigenvalues / vectors then carry
+// float32 accuracy (~1e-6).
+template <typename TS>
 __global__ void __launch_bounds__(JAC_THREADS, 1)
 syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double* __restrict__ W,
                         double* __restrict__ V, int64_t ldv, int max_sweeps, double tol_in, double pivot_tol,
@@ -298,19 +306,14 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
   __shared__ int s_dropped;
   __shared__ double gdiag[J1_MAXN];
   __shared__ double lam[J1_MAXN];
-  __shared__ double nrm2[J1_MAXN];
+  __shared__ TS nrm2[J1_MAXN];
   __shared__ int rank[J1_MAXN];
   const int t = threadIdx.x, tx = t % 32, ty = t / 32;
   const int nper = (n + JAC_GROUP - 1) / JAC_GROUP;     // row elements per lane of a 16-lane group (uniform)
   const int ldw = nper * JAC_GROUP;             // rows padded with zeros to whole groups: the sweeps load / store unguarded
-  double* Rw = smem;                            // [n][ldw]
-  for (int r = ty; r < n; r += 32)
-    for (int c = tx; c < ldw; c += 32)
-      Rw[r * ldw + c] = (c >= r && c < n) ? 0.5 * (A[(int64_t)r * lda + c] + A[(int64_t)c * lda + r]) : 0.0;
+  TS* Rw = reinterpret_cast<TS*>(smem);         // [n][ldw]
   for (int j = t; j < n; j += JAC_THREADS) gdiag[j] = A[(int64_t)j * lda + j];
-  __syncthreads();
-  // ---- register-tiled right-looking Cholesky (see chol_inv_kernel) ----
-  int dropped = 0;
+  // ---- register-tiled right-looking Cholesky (chol_register_tiled), straight from global memory ----
   {
     double r[4][4];
 #pragma unroll
@@ -318,16 +321,15 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int i = ty + 32 * a, c = tx + 32 * b;
-        r[a][b] = (i < n && c < n && c >= i) ? Rw[i * ldw + c] : 0.0;
+        r[a][b] = (i < n && c < n && c >= i) ? 0.5 * (A[(int64_t)i * lda + c] + A[(int64_t)c * lda + i]) : 0.0;
       }
+    __syncthreads();
     chol_register_tiled(r, n, gdiag, pivot_tol, prow_c, prow_r, &s_dropped, tx, ty);
-    dropped = s_dropped;
-    if (dropped) {                              // uniform over the CTA
+    if (s_dropped) {                            // uniform over the CTA
       if (t == 0) *status = 1;
       return;
     }
     // R = D^(-1/2) * (unscaled rows); the diagonal owner of row i publishes the scale
-    __syncthreads();
 #pragma unroll
     for (int a = 0; a < 4; ++a)
       if (ty == tx && ty + 32 * a < n) lam[ty + 32 * a] = rsqrt(r[a][a]);
@@ -337,7 +339,7 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int i = ty + 32 * a, c = tx + 32 * b;
-        if (i < n && c < n && c >= i) Rw[i * ldw + c] = r[a][b] * lam[i];
+        if (i < n && c < ldw) Rw[i * ldw + c] = (c < n && c >= i) ? (TS)(r[a][b] * lam[i]) : (TS)0;
       }
   }
   if (t == 0) *status = 0;
@@ -348,21 +350,22 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
   const unsigned gmask = 0xFFFFu << (16 * (g & 1));
   const int n_pad = n + (n & 1);
   const int npairs = n_pad / 2;
+  const TS tiny = sizeof(TS) == 8 ? (TS)1e-300 : (TS)1e-37;
   const double tol = tol_in > 0.0 ? tol_in : 2.220446049250313e-16 * sqrt((double)n);
-  const double tol2 = tol * tol;
+  const TS tol2 = (TS)(tol * tol);
   // Early stop for a caller-given tolerance (float32 data paths): the iteration converges quadratically, so a sweep
   // that met no pair above sqrt(tol / 100) leaves every pair below tol (the factor 100 covers relative gaps down
   // to ~1 %); the usual extra sweep that only verifies convergence is then skipped.  With tol_in <= 0 (float64
   // parity) the sweep-without-rotation rule stays.
   const bool early = tol_in > 0.0;
-  const double tol_early = tol * 0.01;
+  const TS tol_early = (TS)(tol * 0.01);
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     int did = 0;
     // squared row norms, recomputed once per sweep and then carried through the rotations (a'_pp = a_pp - t a_pq,
     // a'_qq = a_qq + t a_pq): they only steer the angle and the convergence test, so a step needs ONE dot product
-    // (a_pq) instead of three - the kernel is bound by the float64 pipe.  The eigenvalues come from fresh norms below.
+    // (a_pq) instead of three.  The eigenvalues come from fresh norms below.
     for (int i = g; i < n; i += JAC_GROUPS) {
-      double sq = 0.0;
+      TS sq = 0;
       for (int c = gl; c < n; c += JAC_GROUP) sq = fma(Rw[i * ldw + c], Rw[i * ldw + c], sq);
       sq = group16_sum(sq, gmask);
       if (gl == 0) nrm2[i] = sq;
@@ -373,11 +376,11 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
         int p, q;
         jacobi_pair(step, g, n_pad, p, q);
         if (q < n) {
-          double x[J1_PER_LANE], y[J1_PER_LANE];
-          const double app = nrm2[p], aqq = nrm2[q];
-          double apq = 0.0;
-          double* px = Rw + p * ldw + gl;
-          double* py = Rw + q * ldw + gl;
+          TS x[J1_PER_LANE], y[J1_PER_LANE];
+          const TS app = nrm2[p], aqq = nrm2[q];
+          TS apq = 0;
+          TS* px = Rw + p * ldw + gl;
+          TS* py = Rw + q * ldw + gl;
 #pragma unroll
           for (int k = 0; k < J1_PER_LANE; ++k) {
             if (k < nper) {                    // uniform; the pad columns hold zeros and stay zero under rotations
@@ -387,23 +390,24 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
             }
           }
           apq = group16_sum(apq, gmask);
-          if (early ? (apq * apq > tol_early * app * aqq) : (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300)) did = 1;
-          if (apq * apq > tol2 * app * aqq && fabs(apq) > 1e-300) {
+          const bool big = apq * apq > tol2 * app * aqq && fabs(apq) > tiny;
+          if (early ? (apq * apq > tol_early * app * aqq) : big) did = 1;
+          if (big) {
             // rotation that orthogonalises rows p, q (same angle as the two-sided rotation of the 2 x 2 Gram block);
-            // tan(theta) from fast float32 ops, c and s completed in float64 (exactly orthogonal rotation)
+            // tan(theta) from fast float32 ops, c and s completed in the sweep type (exactly orthogonal rotation)
             const float dq = (float)(aqq - app), ap2 = 2.0f * (float)apq;
-            double t64;
+            TS tt;
             if (fabsf(ap2) > 1e-30f && fabsf(dq) < 1e30f) {
               const float tau = __fdividef(dq, ap2);
               const float tf = __fdividef(copysignf(1.0f, tau), fabsf(tau) + sqrtf(fmaf(tau, tau, 1.0f)));
-              t64 = (double)tf;
+              tt = (TS)tf;
             } else {
-              const double tau = (aqq - app) / (2.0 * apq);
-              t64 = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+              const double tau = ((double)aqq - (double)app) / (2.0 * (double)apq);
+              tt = (TS)((tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau)));
             }
-            const double cs = rsqrt(fma(t64, t64, 1.0));
-            const double sn = t64 * cs;
-            if (gl == 0) { nrm2[p] = app - t64 * apq; nrm2[q] = aqq + t64 * apq; }
+            const TS cs = rsqrt(fma(tt, tt, (TS)1));
+            const TS sn = tt * cs;
+            if (gl == 0) { nrm2[p] = app - tt * apq; nrm2[q] = aqq + tt * apq; }
 #pragma unroll
             for (int k = 0; k < J1_PER_LANE; ++k) {
               if (k < nper) {
@@ -421,7 +425,7 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
   // ---- eigenvalues = squared row norms, eigenvectors = normalised rows; descending order ----
   for (int i = g; i < n; i += JAC_GROUPS) {
     double s = 0.0;
-    for (int c = gl; c < n; c += JAC_GROUP) s = fma(Rw[i * ldw + c], Rw[i * ldw + c], s);
+    for (int c = gl; c < n; c += JAC_GROUP) s = fma((double)Rw[i * ldw + c], (double)Rw[i * ldw + c], s);
     s = group16_sum(s, gmask);
     if (gl == 0) lam[i] = s;
   }
@@ -438,7 +442,7 @@ syev_chol_jacobi_kernel(const double* __restrict__ A, int n, int64_t lda, double
   }
   __syncthreads();
   for (int r = ty; r < n; r += 32) {           // r = component, c = eigenvector (row of R)
-    for (int c = tx; c < n; c += 32) V[(int64_t)r * ldv + rank[c]] = Rw[c * ldw + r] * rsqrt(lam[c]);
+    for (int c = tx; c < n; c += 32) V[(int64_t)r * ldv + rank[c]] = (double)Rw[c * ldw + r] * rsqrt(lam[c]);
   }
 }
 
@@ -735,10 +739,17 @@ int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, i
   if (n <= J1_MAXN && n >= 2 && workspace && workspace_bytes >= era5svd_syevj_workspace_bytes(n) &&
       !(syevj_flags() & 1)) {
     status = reinterpret_cast<int*>(static_cast<char*>(workspace) + (size_t)(2 * n * (n | 1)) * sizeof(double));
-    const size_t sm1 = (size_t)n * (size_t)((n + JAC_GROUP - 1) / JAC_GROUP * JAC_GROUP) * sizeof(double);   // rows padded to whole lane groups
-    ERA5SVD_CUDA(ensure_dynamic_smem((const void*)syev_chol_jacobi_kernel, sm1));
-    syev_chol_jacobi_kernel<<<1, JAC_THREADS, sm1, as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, 1e-13, status);
-    int rc = check_launch("syev_chol_jacobi_kernel");
+    const size_t elems = (size_t)n * (size_t)((n + JAC_GROUP - 1) / JAC_GROUP * JAC_GROUP);   // rows padded to whole lane groups
+    int rc;
+    if (tol >= 1e-5) {        // a basis rotation, not a result (the randomized driver's Rayleigh-Ritz step): float32 sweeps
+      ERA5SVD_CUDA(ensure_dynamic_smem((const void*)syev_chol_jacobi_kernel<float>, elems * sizeof(float)));
+      syev_chol_jacobi_kernel<float><<<1, JAC_THREADS, elems * sizeof(float), as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, 1e-13, status);
+      rc = check_launch("syev_chol_jacobi_kernel<float>");
+    } else {
+      ERA5SVD_CUDA(ensure_dynamic_smem((const void*)syev_chol_jacobi_kernel<double>, elems * sizeof(double)));
+      syev_chol_jacobi_kernel<double><<<1, JAC_THREADS, elems * sizeof(double), as_stream(stream)>>>(A, (int)n, lda, W, V, ldv, max_sweeps, tol, 1e-13, status);
+      rc = check_launch("syev_chol_jacobi_kernel<double>");
+    }
     if (rc) return rc;
   }
   const size_t full = syevj_smem_bytes(n);

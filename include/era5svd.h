@@ -202,7 +202,10 @@ int era5svd_gemm_f64(int transA, int transB, int64_t M, int64_t N, int64_t K, do
  * (eigenvalue = squared row norm, eigenvector = normalised row; a third of the shared-memory traffic of the
  * two-sided iteration).  A dropped pivot (A numerically singular or indefinite) falls back to the two-sided
  * iteration inside the same call, so the contract above holds for any symmetric A.  The workspace
- * (era5svd_syevj_workspace_bytes, required for n <= 128) also carries the 4-byte status word of that hand-over. */
+ * (era5svd_syevj_workspace_bytes, required for n <= 128) also carries the 4-byte status word of that hand-over.
+ * tol >= 1e-5 on that path means the caller wants a basis ROTATION, not a result (the Rayleigh-Ritz step of the randomized
+ * driver: any well-conditioned W serves, as long as the same W is used afterwards): the Cholesky factor is formed in
+ * float64 and then rotated as FLOAT32 rows; W / V come back with float32 accuracy (~1e-6). */
 size_t era5svd_syevj_workspace_bytes(int64_t n);
 int era5svd_syevj_f64(double* A, int64_t n, int64_t lda, double* W, double* V, int64_t ldv,
                       int max_sweeps, double tol, void* workspace, size_t workspace_bytes, void* stream);
