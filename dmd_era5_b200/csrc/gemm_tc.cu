@@ -467,6 +467,8 @@ struct ProjectParams {
   int nmma;           // UMMA pieces per k-step (N = ncc*32 / nmma each)
   int stages;
   int nprod;          // 3: hi/lo images of X and Y; 1: one product on the raw float32 tiles (truncated by the tensor core)
+  int nya;            // 128-column tiles of Y (M tiles of the MMA): 1, or 2 for 128 < l <= 256 (single product only: the
+                      // Gram blocks of the standard route - twice the columns per read of X)
   int xshift;         // the window starts xshift (0..3) columns right of the 16-byte aligned map origin
   int64_t rows_per_split;
   float* part;        // [splits][n][l]
@@ -482,7 +484,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x / 32, 0), lane = threadIdx.x % 32;   // warp-uniform
   const uint32_t box_bytes = (uint32_t)p.ks * BK * 4;       // one [ks rows x 32] box (2 KB for ks = 16)
-  const uint32_t y_bytes = 4 * box_bytes;                   // 128 sketch columns
+  const uint32_t y_bytes = 4u * (uint32_t)p.nya * box_bytes;   // 128 sketch columns per Y tile
   const uint32_t x_bytes = (uint32_t)p.ncc * box_bytes;
   const bool one = p.nprod == 1;                            // kernel parameter: uniform
   const uint32_t stage_bytes = one ? y_bytes + x_bytes : 2 * y_bytes + 2 * x_bytes;
@@ -493,7 +495,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
   const uint32_t tfull_bar = bar_base + 8u * (2 * p.stages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 1);
   const uint32_t nc = (uint32_t)p.ncc * BK;                 // time columns of this CTA
-  const uint32_t tmem_cols = nc <= 32 ? 32u : nc <= 64 ? 64u : nc <= 128 ? 128u : nc <= 256 ? 256u : 512u;
+  const uint32_t acc_cols = nc * (uint32_t)p.nya;           // accumulator of Y tile a: columns [a * nc, (a + 1) * nc)
+  const uint32_t tmem_cols = acc_cols <= 32 ? 32u : acc_cols <= 64 ? 64u : acc_cols <= 128 ? 128u : acc_cols <= 256 ? 256u : 512u;
 
   const int64_t t0 = (int64_t)blockIdx.x * nc;              // first time column
   const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
@@ -527,7 +530,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
         const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
         const int32_t row0 = (int32_t)(r_begin + (int64_t)kc * p.ks);
         mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4 * p.nya; ++c) {
           tma_load_2d(st + c * box_bytes, &tm_yhi, c * BK, row0, full_bar(s));
           if (!one) tma_load_2d(st + y_bytes + c * box_bytes, &tm_ylo, c * BK, row0, full_bar(s));
         }
@@ -558,6 +561,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
             const uint32_t d_tmem = tmem_base + (uint32_t)pc * npiece;
             if (one) {
               umma_tf32_ss(d_tmem, a_hi, b_hi, idesc, (kc | ks) != 0);
+              if (p.nya == 2) {               // second 128-column tile of Y against the same X boxes
+                const uint64_t a2 = make_smem_desc(st + 4 * box_bytes + koff, box_bytes, 512, LAYOUT_SW128_BASE32B);
+                umma_tf32_ss(d_tmem + nc, a2, b_hi, idesc, (kc | ks) != 0);
+              }
             } else {
               const uint64_t b_lo = make_smem_desc(st + off_xhi + x_bytes + xoff, box_bytes, 512, LAYOUT_SW128_BASE32B);
               umma_tf32_ss(d_tmem, a_lo, b_hi, idesc, (kc | ks) != 0);
@@ -581,21 +588,24 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_const
       mbar_wait(tfull_bar, 0);
       tcgen05_fence_after();
     }
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (uint32_t c0 = 0; c0 < nc; c0 += 16) {
-      uint32_t v[16];
-      if (num_k > 0) {
-        tmem_ld16(taddr + c0, v);
-        tmem_wait_ld();
-      } else {
+    for (int a = 0; a < p.nya; ++a) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * nc;
+      const int col = i + 128 * a;                       // sketch column held by this lane in Y tile a
+      for (uint32_t c0 = 0; c0 < nc; c0 += 16) {
+        uint32_t v[16];
+        if (num_k > 0) {
+          tmem_ld16(taddr + c0, v);
+          tmem_wait_ld();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
-      }
-      if (i < p.l) {
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (col < p.l) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int64_t t = t0 + c0 + j - p.xshift;     // window-relative time index
-          if (t >= 0 && t < p.n) out[t * p.l + i] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) {
+            const int64_t t = t0 + c0 + j - p.xshift;     // window-relative time index
+            if (t >= 0 && t < p.n) out[t * p.l + col] = __uint_as_float(v[j]);
+          }
         }
       }
     }
@@ -623,7 +633,8 @@ struct PjPlan {
 // power-iteration passes carry 2^-11 per operand anyway (16384 rows: a quarter of the partial-tile traffic).
 static PjPlan pj_plan(int64_t m, int64_t n, int64_t l, int64_t max_rows = 4096) {
   PjPlan pl;
-  pl.nchunks = (int)ceil_div(n, 512);
+  // l > 128: two Y tiles share the 512 TMEM columns, so a CTA takes at most 256 time columns
+  pl.nchunks = (int)ceil_div(n, l > 128 ? 256 : 512);
   pl.ncc = (int)ceil_div(ceil_div(n, pl.nchunks), 32);          // 32-wide chunks per CTA (<= 16)
   // UMMA N = ncc * 32 / nmma must be <= 256 and a multiple of 32 (whole boxes per piece)
   pl.nmma = 1;
@@ -797,6 +808,7 @@ int era5svd_sketch_tf32x1(const float* X, int64_t m, int64_t n, int64_t ldx, con
 size_t era5svd_project_tf32x3_workspace_bytes(int64_t m, int64_t n, int64_t l) {
   using namespace era5svd;
   if (m <= 0 || n <= 0 || l <= 0) return 0;
+  if (l > 128) return pj_plan(m, n + 3, l, 16384).bytes;      // single-product projection with two Y tiles (l <= 256)
   size_t a = pj_plan(m, n + 3, l).bytes;
   const size_t b = project_tf32x3_raw_workspace_bytes(m, n, l), c = pj_plan(m, n + 3, l, 16384).bytes;
   if (b > a) a = b;
@@ -811,8 +823,9 @@ static int project_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int6
   ERA5SVD_REQUIRE(Xhi && Yhi && Z, "project_tf32x3: null pointer");
   ERA5SVD_REQUIRE(Ylo || !Xlo, "project_tf32x3: a plain Y (Ylo == NULL) needs the on-chip split path (Xlo == NULL too)");
   ERA5SVD_REQUIRE(m > 0 && n > 0 && l > 0 && ldx >= n && ldy >= l && ldz >= l, "project_tf32x3: bad shape");
-  if (l > 128) {
-    set_error("project_tf32x3: l = %lld > 128 is not supported by the tensor-core path", (long long)l);
+  if (l > 128 && !(nprod == 1 && l <= 256)) {
+    set_error("project_tf32x3: l = %lld is not supported by the tensor-core path (<= 128; <= 256 single product)",
+              (long long)l);
     return ERA5SVD_ERR_UNSUPPORTED;
   }
   ERA5SVD_REQUIRE(m < ((int64_t)1 << 31), "project_tf32x3: m too large for TMA coordinates");
@@ -843,11 +856,12 @@ static int project_tf32_impl(const float* Xhi, const float* Xlo, int64_t m, int6
   p.ncc = pl.ncc;
   p.nmma = pl.nmma;
   p.nprod = nprod;
+  p.nya = l > 128 ? 2 : 1;
   p.xshift = xs;
   p.rows_per_split = pl.rows_per_split;
   p.part = (float*)workspace;
   const size_t box = (size_t)KS * tc::BK * 4;
-  const size_t stage_bytes = (nprod == 1 ? 1 : 2) * (4 * box + (size_t)pl.ncc * box);
+  const size_t stage_bytes = (nprod == 1 ? 1 : 2) * (4 * (size_t)p.nya * box + (size_t)pl.ncc * box);
   const size_t budget = 227 * 1024 - 1024 - 256;
   p.stages = (int)(budget / stage_bytes);
   if (p.stages > 8) p.stages = 8;

@@ -38,7 +38,7 @@ from .dist import LocalComm
 REFINE_ITERS = 2        # power iterations of the float32 refinement (each contracts the leak by (sigma_{k+11}/sigma_i)^2)
 JACOBI_MAX_N = 118      # largest n whose working copies fit one CTA's shared memory (syevj_kernel)
 TC_BLOCK = 112          # sketch-width block of the tensor-core project kernel
-TC_BLOCK_X1 = 128       # column block of the single-product Gram (one full M = 128 operand tile)
+TC_BLOCK_X1 = 256       # column block of the single-product Gram (two M = 128 operand tiles per CTA: half the reads of X)
 PREC_TF32MIX = 2        # = rsvd.PREC_TF32MIX (driver-level value, never crosses the C ABI)
 
 

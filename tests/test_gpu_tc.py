@@ -308,3 +308,28 @@ def test_project_tf32x2_truncated_y(ops, m, n, l, off):
     Z3 = ops.project_tf32x3(Xb[:, off:off + n], None, Yb[:, :l], None)
     scale = np.linalg.norm(Xfull[:, off:], axis=0)[:, None] * np.linalg.norm(Yh, axis=0)[None, :]
     assert np.all(np.abs(Z.cpu().numpy() - Z3.cpu().numpy()) <= 2.0 ** -10 * scale)
+
+
+@pytest.mark.parametrize("m,n,c0,w", [(3000, 1000, 0, 256), (20000, 1460, 512, 256), (4097, 700, 256, 200), (2500, 300, 0, 129)])
+def test_project_tf32x1_two_y_tiles_gram_block(ops, m, n, c0, w):
+    """Single-product projection with 128 < l <= 256 (two M = 128 tiles of Y per CTA): the Gram blocks of the standard route,
+    G[c0:, c0:c0+w] = X[:, c0:]^T X[:, c0:c0+w] with the column block itself (a view with X's pitch) as the Y operand.  Must
+    equal the float64 product of the truncated operands up to the fp32 accumulate, and leave the rest of G untouched."""
+    rng = np.random.RandomState(m + n + w)
+    Xh = (rng.standard_normal((m, n)) * np.exp(rng.uniform(-2, 2, size=(m, 1)))).astype(np.float32)
+    ld = (n + 7) // 8 * 8
+    Xb = torch.zeros((m, ld), device="cuda")
+    Xb[:, :n] = dev(Xh)
+    X = Xb[:, :n]
+    CAN = 777.0
+    G = torch.full((n, n), CAN, dtype=torch.float64, device="cuda")
+    c1 = min(n, c0 + w)
+    ops.project_tf32x1(X[:, c0:], X[:, c0:c1], G[c0:, c0:c1])
+    Xt = _trunc_tf32(Xh).astype(np.float64)
+    ref = Xt[:, c0:].T @ Xt[:, c0:c1]
+    nrm = np.linalg.norm(Xt, axis=0)
+    bound = 6e-5 * nrm[c0:, None] * nrm[None, c0:c1]              # fp32 running sums over up to 16384 rows per TMEM accumulator
+    got = G[c0:, c0:c1].cpu().numpy()
+    assert np.all(np.abs(got - ref) <= bound + 1e-30), float(np.max(np.abs(got - ref) / (bound + 1e-30)))
+    Gh = G.cpu().numpy()
+    assert np.all(Gh[:c0] == CAN) and np.all(Gh[:, :c0] == CAN) and np.all(Gh[:, c1:] == CAN)
