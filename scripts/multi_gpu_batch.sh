@@ -2,7 +2,7 @@
 N=$1; TAG=$2
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 set -x
-timeout 300 $TR --master-port 29721 scripts/check_multigpu.py > gpurun_out/${TAG}_check.json 2> gpurun_out/${TAG}_check.err; echo check rc=$?
+timeout 300 $TR --master-port 29721 tests/multigpu_check.py > gpurun_out/${TAG}_check.json 2> gpurun_out/${TAG}_check.err; echo check rc=$?
 timeout 200 $TR --master-port 29722 scripts/time_comm.py > gpurun_out/${TAG}_time_comm.json 2> /dev/null; echo comm rc=$?
 for c in peer nccl; do
   ERA5SVD_COMM=$c timeout 300 $TR --master-port 29723 bench.py --gpus $N --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --no-north-star 2> /dev/null | grep "^{" > gpurun_out/${TAG}_bench_c2_$c.json; echo bench $c rc=$?

@@ -2,7 +2,7 @@
 N=$1; TAG=$2
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 set -x
-timeout 200 $TR --master-port 29721 scripts/check_multigpu.py 2> gpurun_out/${TAG}_check.err | grep "^{" > gpurun_out/${TAG}_check.json; echo check rc=$?
+timeout 200 $TR --master-port 29721 tests/multigpu_check.py 2> gpurun_out/${TAG}_check.err | grep "^{" > gpurun_out/${TAG}_check.json; echo check rc=$?
 timeout 400 $TR --master-port 29722 bench.py --gpus $N --steps 10 --warmup 3 2> gpurun_out/${TAG}_bench.err | grep "^{" > gpurun_out/${TAG}_bench.json; echo bench rc=$?
 timeout 300 $TR --master-port 29723 scripts/run_c4.py 2> gpurun_out/${TAG}_c4.err | grep "^{" > gpurun_out/${TAG}_c4.json; echo c4 rc=$?
 timeout 120 $TR --master-port 29724 scripts/time_comm.py 2> /dev/null > gpurun_out/${TAG}_time_comm.json; echo comm rc=$?

@@ -1,6 +1,6 @@
 """Row-sharded randomized SVD over NCCL vs the single-process oracle.
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/check_multigpu.py
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/multigpu_check.py
 
 Every rank builds the same host matrix, keeps its row shard (delay-embedded, d = 2), runs the device
 driver with the NCCL communicator, and rank 0 compares the gathered U / s / V with sklearn's

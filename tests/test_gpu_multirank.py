@@ -1,6 +1,6 @@
 """GPU, >= 2 devices: the row-sharded paths over NCCL and over the peer-memory communicator (era5svd_comm_*: collectives
 against NCCL on random data, the all-reduce fused into the projection's reduction, replicas bit-identical) - randomized
-native / tf32x3 / tf32mix, standard FP64, sharded BOP-DMD trials - against the single-process oracles - scripts/check_multigpu.py run as a test (multi-rank
+native / tf32x3 / tf32mix, standard FP64, sharded BOP-DMD trials - against the single-process oracles - tests/multigpu_check.py run as a test (multi-rank
 NCCL parity was a hand-run script).  Skipped on a one-GPU box; the gloo CPU tests cover the host logic there."""
 import json
 import os
@@ -19,7 +19,7 @@ def test_two_rank_nccl_parity():
     port = 29600 + os.getpid() % 300
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
-                          os.path.join(ROOT, "scripts", "check_multigpu.py")], capture_output=True, text=True,
+                          os.path.join(ROOT, "tests", "multigpu_check.py")], capture_output=True, text=True,
                          timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-3000:]
     line = json.loads([ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")][-1])
