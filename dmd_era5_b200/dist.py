@@ -87,21 +87,36 @@ class PeerComm(TorchDistComm):
 
         self.ops, self.lib = ops, ops.lib
         self._check = check
+        self._comm = None
         hb = int(self.lib.era5svd_comm_handle_bytes())
         handle = (C.c_ubyte * hb)()
         comm = C.c_void_p()
+        # Every rank walks through the SAME collectives whatever happens locally: a rank whose window cannot be created or
+        # mapped reports that in an agreed all-reduce, and then all ranks raise together (no rank is left waiting inside
+        # a collective the others never enter).
         with torch.cuda.device(ops.device):
-            check(self.lib.era5svd_comm_create(self.world, self.rank, int(slot_bytes), C.byref(comm), handle),
-                  "era5svd_comm_create")
-            self._comm = comm
+            rc = self.lib.era5svd_comm_create(self.world, self.rank, int(slot_bytes), C.byref(comm), handle)
+            err = "" if rc == 0 else self.lib.era5svd_last_error().decode(errors="replace")
+            self._agree(rc == 0, "era5svd_comm_create", err, comm if rc == 0 else None)
             mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=ops.device)
             parts = [torch.empty_like(mine) for _ in range(self.world)]
             self._dist.all_gather(parts, mine, group=self.group)          # plumbing: the handle exchange
             allh = bytes(torch.cat(parts).cpu().tolist())
             buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
-            check(self.lib.era5svd_comm_connect(self._comm, buf), "era5svd_comm_connect")
+            rc = self.lib.era5svd_comm_connect(comm, buf)
+            err = "" if rc == 0 else self.lib.era5svd_last_error().decode(errors="replace")
+            self._agree(rc == 0, "era5svd_comm_connect", err, comm)
+        self._comm = comm
         self.capacity = int(self.lib.era5svd_comm_capacity(self._comm))
         self._dist.barrier(group=self.group)
+
+    def _agree(self, ok_here: bool, what: str, err: str, comm) -> None:
+        flag = torch.tensor([1.0 if ok_here else 0.0], device=self.ops.device)
+        self._dist.all_reduce(flag, op=self._dist.ReduceOp.MIN, group=self.group)
+        if float(flag) < 1.0:
+            if comm is not None:
+                self.lib.era5svd_comm_destroy(comm)
+            raise RuntimeError(f"PeerComm: {what} failed on " + (f"this rank: {err}" if not ok_here else "another rank"))
 
     def close(self) -> None:
         if getattr(self, "_comm", None):
@@ -152,16 +167,10 @@ def make_comm(ops, group=None, prefer_peer: bool = True):
 
     if not prefer_peer or os.environ.get("ERA5SVD_COMM", "peer") != "peer" or dist.get_backend(group) != "nccl":
         return TorchDistComm(group)
-    ok = torch.ones(1, device=ops.device)
-    comm = None
     try:
-        comm = PeerComm(ops, group)
-    except Exception:                     # noqa: BLE001 - no peer access / IPC refused: NCCL carries the collectives
-        ok.zero_()
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-    if float(ok) < 1:
+        return PeerComm(ops, group)       # raises on EVERY rank when any rank could not create / map its window
+    except RuntimeError:                  # no peer access / IPC refused: NCCL carries the collectives
         return TorchDistComm(group)
-    return comm
 
 
 def shard_rows(m0: int, world: int, rank: int, align: int = 128) -> tuple[int, int]:
