@@ -95,8 +95,13 @@ class PeerComm(TorchDistComm):
         # mapped reports that in an agreed all-reduce, and then all ranks raise together (no rank is left waiting inside
         # a collective the others never enter).
         with torch.cuda.device(ops.device):
-            rc = self.lib.era5svd_comm_create(self.world, self.rank, int(slot_bytes), C.byref(comm), handle)
-            err = "" if rc == 0 else self.lib.era5svd_last_error().decode(errors="replace")
+            import os
+
+            if os.environ.get("ERA5SVD_COMM_TEST_FAIL_RANK") == str(self.rank):      # test hook: this rank has no peer access
+                rc, err = -2, "simulated failure (ERA5SVD_COMM_TEST_FAIL_RANK)"
+            else:
+                rc = self.lib.era5svd_comm_create(self.world, self.rank, int(slot_bytes), C.byref(comm), handle)
+                err = "" if rc == 0 else self.lib.era5svd_last_error().decode(errors="replace")
             self._agree(rc == 0, "era5svd_comm_create", err, comm if rc == 0 else None)
             mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=ops.device)
             parts = [torch.empty_like(mine) for _ in range(self.world)]

@@ -27,3 +27,17 @@ def test_two_rank_nccl_parity():
     for key in ("peer_collectives", "native", "tf32x3", "tf32mix", "peer_native", "peer_tf32mix", "standard_fp64",
                 "bopdmd_trials_sharded"):
         assert line[key]["pass"], (key, line[key])
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_peer_comm_falls_back_together_when_one_rank_fails():
+    """One rank without peer access (simulated): make_comm must hand NCCL to EVERY rank - no rank may be left inside a
+    collective the others never enter - and the peer path must come up again without the failure."""
+    port = 29900 + os.getpid() % 90
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(ROOT, "tests", "multigpu_fallback_check.py")], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = json.loads([ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")][-1])
+    assert all(line[k] for k in ("fell_back_on_every_rank", "nccl_allreduce_ok", "peer_path_comes_up", "peer_allreduce_ok")), line
