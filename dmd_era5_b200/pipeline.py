@@ -111,6 +111,13 @@ def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_compone
     """SVD of the (virtual) delay-embedded matrix whose base rows are X (device, tall dtype).
     ``split`` = (Xhi, Xlo) passes pre-split tf32 images (precision "tf32x3"); X may then be None.
     Dispatch and error text follow svd_on_era5 (era5_svd.py:247-262)."""
+    if X is not None and X.dim() == 2 and (X.stride(1) != 1 or X.stride(0) % (4 if X.dtype == torch.float32 else 2) != 0
+                                          or X.data_ptr() % 16 != 0):
+        # the TMA-fed kernels need rows that start on 16-byte boundaries: a caller's tightly packed (or transposed) device
+        # matrix is repacked once into the padded layout the build kernel produces (one extra copy of X)
+        buf = ops.empty((X.shape[0], padded_ld(X.shape[1], X.dtype)), X.dtype)
+        buf[:, : X.shape[1]].copy_(X)
+        X = buf[:, : X.shape[1]]
     ref = X if X is not None else split[0]
     n = ref.shape[1] - delay + 1
     if precision != "auto" and precision not in PRECISIONS:

@@ -160,3 +160,20 @@ def test_float32_input_against_the_references_own_float32_call(precision):
     assert signs_agree(U, U64)
     flips = int(np.sum(np.sum(U32.astype(np.float64) * U64, axis=0) < 0))
     assert int(np.sum(np.sum(U.astype(np.float64) * U32, axis=0) < 0)) == flips
+
+
+@pytest.mark.parametrize("layout", ["packed_odd_pitch", "transposed_view"])
+def test_svd_device_accepts_unaligned_device_matrices(layout):
+    """A caller's own device matrix - tightly packed with an odd row pitch (T = 97: the reference's default 4-day hourly
+    slice), or a transposed view - is repacked into the padded layout instead of failing in the TMA set-up; the
+    reference's default configuration otherwise (randomized, delay_embedding = 2, n_components = 10, config.ini)."""
+    ops = get_ops()
+    m, n, k, d = 20000, 97, 10, 2
+    X = lowrank_field_np(m, n, r=40, rho=0.85, seed=21, dtype=np.float32)
+    Xd = torch.from_numpy(X).cuda() if layout == "packed_odd_pitch" else torch.from_numpy(np.ascontiguousarray(X.T)).cuda().t()
+    assert Xd.shape == (m, n) and (Xd.stride(0) % 4 != 0 or Xd.stride(1) != 1)
+    U, s, V = svd_device(ops, Xd, svd_type="randomized", n_components=k, delay=d, seed=1, precision="auto")
+    U0, s0, V0 = randomized_svd_ref(delay_embed_np(X.astype(np.float64), d), k, 1)
+    assert sigma_rel_err(s.cpu().numpy(), s0) < 1e-4
+    assert vector_angles(U.cpu().numpy(), U0).max() < 1e-3 and vector_angles(V.cpu().numpy().T, V0.T).max() < 1e-3
+    assert signs_agree(U.cpu().numpy(), U0)
