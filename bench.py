@@ -714,6 +714,7 @@ def main():
         }
         print(json.dumps(out))
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 

@@ -35,6 +35,9 @@ class LocalComm:
     def fuse_next_project(self, n: int, l: int) -> bool:
         return False
 
+    def close(self) -> None:
+        pass
+
 
 class TorchDistComm:
     """Communicator over an initialised ``torch.distributed`` process group (NCCL on GPUs,
@@ -71,6 +74,10 @@ class TorchDistComm:
     def fuse_next_project(self, n: int, l: int) -> bool:
         """True when the NEXT ops.project* call will leave the all-reduced result in Z (PeerComm only)."""
         return False
+
+    def close(self) -> None:
+        """Release communicator resources (PeerComm: barrier, then unmap the peers' windows and free this rank's - a rank
+        must not free its window while a peer's last collective kernel may still be reading it)."""
 
 
 class PeerComm(TorchDistComm):

@@ -40,7 +40,11 @@ def _worker(rank: int, world: int, port: int, parsed_config: dict, outdir: str) 
         if ds is None:
             raise FileNotFoundError(f"ERA5 slice {parsed_config['era5_slice_path']} not found by rank {rank}")
         ops = CudaOps(rank)
-        arr = _device_arrays(_prepare(ds, parsed_config), parsed_config, ops, comm=make_comm(ops), rank=rank, world=world)
+        comm = make_comm(ops)
+        try:
+            arr = _device_arrays(_prepare(ds, parsed_config), parsed_config, ops, comm=comm, rank=rank, world=world)
+        finally:
+            comm.close()              # barrier first: no rank frees its peer window while another may still read it
         np.save(os.path.join(outdir, f"U_{rank}.npy"), arr["U"])
         for key in ("X", "mean", "std"):
             if arr[key] is not None:

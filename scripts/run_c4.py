@@ -41,6 +41,9 @@ class TimedComm:
     def fuse_next_project(self, n, l):
         return self.inner.fuse_next_project(n, l)
 
+    def close(self):
+        self.inner.close()
+
     def barrier(self):
         self.inner.barrier()
 
@@ -109,6 +112,7 @@ def main():
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
+        comm.close()
         dist.destroy_process_group()
 
 
