@@ -112,14 +112,12 @@ def build_matrix_np(var_arrays: list[np.ndarray], mean_center: bool, scale: bool
 def resample_nearest_index(times_ns: np.ndarray, delta_ns: int) -> tuple[np.ndarray, np.ndarray]:
     """slice_tools.py:126-141: ds.resample(time=delta).nearest().
 
-    pandas/xarray semantics: bins of width delta anchored at midnight of the first
-    day ("start_day" origin); the label grid runs from floor(first) to floor(last);
-    every label takes the nearest original sample (ties -> the later one is never hit
-    for regular hourly data; np.argmin picks the first/earlier on exact ties, matching
-    pandas 'nearest' reindex which prefers the earlier on ties? -> pandas prefers the
-    *later*; for ERA5's regular grids no tie occurs when delta is a multiple of the
-    sampling step, the only case the reference's test covers (25 hourly -> 5 six-hourly,
-    tests/test_02_slice_tools.py:85-101)).
+    pandas/xarray semantics (xarray Resample.nearest = reindex(full_index, method="nearest"); pandas
+    Index.get_indexer(method="nearest")): bins of width delta anchored at midnight of the first day ("start_day"
+    origin); the label grid runs from floor(first) to floor(last); every label takes the nearest original sample and
+    a label exactly half way between two samples takes the LATER one (pandas breaks ties towards the larger index
+    value).  Pinned against pandas itself in tests/test_oracle.py (regular, tied, irregular, up- and down-sampling
+    cases), beyond the reference's own 25 hourly -> 5 six-hourly case (tests/test_02_slice_tools.py:85-101).
     Returns (label_times_ns, source_index).
     """
     times_ns = np.asarray(times_ns, dtype=np.int64)
@@ -128,5 +126,7 @@ def resample_nearest_index(times_ns: np.ndarray, delta_ns: int) -> tuple[np.ndar
     first = origin + ((times_ns[0] - origin) // delta_ns) * delta_ns
     last = origin + ((times_ns[-1] - origin) // delta_ns) * delta_ns
     labels = np.arange(first, last + 1, delta_ns, dtype=np.int64)
-    idx = np.array([int(np.argmin(np.abs(times_ns - t))) for t in labels])
+    # argmin over the reversed distances: the LAST minimum, i.e. the later sample on an exact tie
+    n = len(times_ns)
+    idx = np.array([n - 1 - int(np.argmin(np.abs(times_ns - t)[::-1])) for t in labels])
     return labels, idx

@@ -125,3 +125,35 @@ def test_golden_svd_vectors(golden_dir):
     X = lowrank_field_np(m, n, r=r, rho=0.8, seed=seed)
     U, s, V = randomized_svd_ref(X, k, rs)
     assert sigma_rel_err(s, g["s"]) < 1e-12 and vector_angles(V.T, g["V"].T).max() < 1e-9
+
+
+H_NS = 3600 * 10**9
+RESAMPLE_CASES = {
+    "25 hourly -> 6h": (np.datetime64("2019-01-01T00", "ns").astype(np.int64) + H_NS * np.arange(25), 6 * H_NS),
+    "hourly -> 90 min (ties)": (np.datetime64("2019-01-01T00", "ns").astype(np.int64) + H_NS * np.arange(13), 90 * 60 * 10**9),
+    "start 05:00, 6h": (np.datetime64("2019-01-01T05", "ns").astype(np.int64) + H_NS * np.arange(30), 6 * H_NS),
+    "3-hourly -> 2h (ties)": (np.datetime64("2019-03-01T00", "ns").astype(np.int64) + 3 * H_NS * np.arange(17), 2 * H_NS),
+    "irregular": (np.datetime64("2019-01-01T00", "ns").astype(np.int64) + np.array([0, 1, 2, 5, 6, 7, 11, 12, 20, 21, 30]) * H_NS, 4 * H_NS),
+    "identity": (np.datetime64("2019-01-02T03", "ns").astype(np.int64) + H_NS * np.arange(10), H_NS),
+    "6-hourly -> 1h (upsampling, ties)": (np.datetime64("2019-01-01T00", "ns").astype(np.int64) + 6 * H_NS * np.arange(5), H_NS),
+}
+
+
+@pytest.mark.parametrize("name", list(RESAMPLE_CASES))
+def test_resample_nearest_pinned_against_pandas(name):
+    """``ds.resample(time=delta).nearest()`` (slice_tools.py:139) is xarray's reindex onto the resample bins' labels with
+    pandas' method='nearest' - both the oracle restatement and the product's index form must reproduce pandas itself,
+    including its tie rule (a label half way between two samples takes the later one)."""
+    pd = pytest.importorskip("pandas")
+    from dmd_era5_b200.slice_tools import resample_nearest_index as product_index
+    from oracle.slice_tools_np import resample_nearest_index as oracle_index
+
+    t, delta = RESAMPLE_CASES[name]
+    idx = pd.DatetimeIndex(t)
+    labels = pd.Series(np.arange(len(idx)), index=idx).resample(pd.Timedelta(delta, "ns")).first().index
+    src = idx.get_indexer(labels, method="nearest")
+    want_labels = labels.values.astype("datetime64[ns]").astype(np.int64)
+    for fn in (oracle_index, product_index):
+        got_labels, got_src = fn(t, delta)
+        assert np.array_equal(got_labels, want_labels), fn.__module__
+        assert np.array_equal(got_src, src), fn.__module__
