@@ -434,3 +434,56 @@ def test_row_shard_bookkeeping_of_the_multi_gpu_stage(tmp_path):
     out = assemble(str(tmp_path), world, d)
     assert np.array_equal(out["U"], U) and np.array_equal(out["mean"], mean) and np.array_equal(out["X"], X)
     assert out["std"] is None and out["m0"] == m0 and out["S"] == S
+
+
+def _golden_config_cases():
+    import json
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "config_parser_era5_svd.json")
+    with open(path) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(_golden_config_cases()["cases"]))
+def test_config_parser_matches_the_references_own_parser(name, monkeypatch):
+    """Golden vectors produced by the reference's OWN config_parser (tests/golden/make_golden_config.py loads
+    src/dmd_era5/config_parser.py from source, with pyprojroot.here stubbed): every reference key must come out with the
+    same value (datetimes, timedeltas, lists, derived file names and paths) and every rejected config must be rejected
+    with the same exception type and message."""
+    from datetime import datetime, timedelta
+
+    monkeypatch.setenv("DMD_ERA5_ROOT", "/ROOT")
+    rec = _golden_config_cases()["cases"][name]
+
+    def decode(v):
+        if isinstance(v, dict) and "__datetime__" in v:
+            return datetime.fromisoformat(v["__datetime__"])
+        if isinstance(v, dict) and "__timedelta_s__" in v:
+            return timedelta(seconds=v["__timedelta_s__"])
+        if isinstance(v, str):
+            return v.replace("<ROOT>", "/ROOT")
+        if isinstance(v, list):
+            return [decode(x) for x in v]
+        return v
+
+    if "error" in rec:
+        with pytest.raises(Exception) as ei:
+            config_parser(dict(rec["config"]), section="era5-svd")
+        assert type(ei.value).__name__ == rec["error"]["type"]
+        assert " ".join(str(ei.value).split()) == rec["error"]["message"]
+        return
+    parsed = config_parser(dict(rec["config"]), section="era5-svd")
+    for key, want in rec["parsed"].items():
+        want = decode(want)
+        got = parsed[key]
+        if key == "variables" and rec["config"]["variables"] == "all_pressure_level_vars":
+            assert sorted(got) == sorted(want)           # reference quirk Q2: list(set) order is hash-seed dependent
+        else:
+            assert got == want, (key, got, want)
+
+
+def test_config_parser_bad_section_matches_reference():
+    rec = _golden_config_cases()["bad_section"]
+    with pytest.raises(Exception) as ei:
+        config_parser({}, section="nope")
+    assert type(ei.value).__name__ == rec["type"] and str(ei.value) == rec["message"]
