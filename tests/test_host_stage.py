@@ -487,3 +487,74 @@ def test_config_parser_bad_section_matches_reference():
     with pytest.raises(Exception) as ei:
         config_parser({}, section="nope")
     assert type(ei.value).__name__ == rec["type"] and str(ei.value) == rec["message"]
+
+
+def _golden_dvc():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "dvc_tools.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("kind", ["era5_slice", "era5_svd"])
+def test_dvc_side_log_is_byte_identical_to_the_references(kind, tmp_path):
+    """The YAML side-log written by the reference's OWN add_config_to_dvc_log (tests/golden/make_golden_dvc.py loads
+    src/dmd_era5/dvc_tools.py from source with dvc / git / pyprojroot stubbed): same entries -> same bytes."""
+    from dmd_era5_b200 import dvc_tools
+
+    g = _golden_dvc()["logs"][kind]
+    data_path = str(tmp_path / f"{kind}.nc")
+    for i, attrs in enumerate(g["attrs"]):
+        with open(data_path + ".dvc", "w") as f:
+            f.write(f"outs:\n- md5: {('abcdef0123456789' * 2)[:-1]}{i}\n  size: 1\n  path: {kind}.nc\n")
+        dvc_tools.add_config_to_dvc_log(data_path + ".dvc", data_path, attrs, git_add=False)
+    with open(data_path + ".yaml") as f:
+        assert f.read() == g["text"]
+
+
+def _dvc_matching_cases():
+    g = _golden_dvc()["matching"]
+    return [(kind, name) for kind in sorted(g) for name in sorted(g[kind])]
+
+
+@pytest.mark.parametrize("kind,name", _dvc_matching_cases())
+def test_dvc_version_matching_follows_the_references_loop(kind, name, tmp_path, monkeypatch):
+    """Which logged version the reference's OWN retrieve_data_from_dvc selects (its matching loop, dvc_tools.py:181-207,
+    recorded through a stand-in for find_first_commit_with_md5_hash) and how it ends when nothing matches / nothing can
+    be retrieved: select_logged_version and retrieve_data_from_dvc must agree on every case, including the quirks
+    (superset match for slices; order-sensitive lists and no svd_type comparison for results)."""
+    import yaml
+
+    from dmd_era5_b200 import dvc_tools
+
+    g = _golden_dvc()
+    rec = g["matching"][kind][name]
+    data_path = str(tmp_path / f"{kind}.nc")
+    with open(data_path + ".yaml", "w") as f:
+        f.write(g["logs"][kind]["text"])
+    with open(data_path + ".dvc", "w") as f:
+        f.write("outs:\n- md5: 0\n")
+    cfg = dict(rec["request"])
+    cfg["era5_slice_path" if kind == "era5_slice" else "era5_svd_path"] = data_path
+    with open(data_path + ".yaml") as f:
+        log = yaml.safe_load(f)
+    assert dvc_tools.select_logged_version(log, cfg, kind) == rec["selected"]
+    picked = []
+    monkeypatch.setattr(dvc_tools, "find_first_commit_with_md5_hash", lambda md5, path: picked.append(md5) or None)
+    with pytest.raises(Exception) as ei:
+        dvc_tools.retrieve_data_from_dvc(cfg, kind)
+    assert (picked[-1] if picked else None) == rec["selected"]
+    assert type(ei.value).__name__ == rec["error"]["type"]
+    assert " ".join(str(ei.value).split()) == rec["error"]["message"]
+
+
+def test_dvc_error_contract_matches_the_reference(tmp_path):
+    from dmd_era5_b200 import dvc_tools
+
+    errs = _golden_dvc()["errors"]
+    for label, cfg, kind in (("missing files", {"era5_slice_path": str(tmp_path / "absent.nc")}, "era5_slice"),
+                             ("missing key", {}, "era5_svd"), ("bad type", {}, "era5_other")):
+        with pytest.raises(Exception) as ei:
+            dvc_tools.retrieve_data_from_dvc(cfg, kind)
+        assert type(ei.value).__name__ == errs[label]["type"], label
+        assert " ".join(str(ei.value).replace("'", "").split()) == errs[label]["message"], label
