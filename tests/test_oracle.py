@@ -157,3 +157,35 @@ def test_resample_nearest_pinned_against_pandas(name):
         got_labels, got_src = fn(t, delta)
         assert np.array_equal(got_labels, want_labels), fn.__module__
         assert np.array_equal(got_src, src), fn.__module__
+
+
+def _svd_on_era5_cases():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "svd_on_era5_reference.npz"), allow_pickle=True)
+    return g, [tuple(row) for row in g["meta"]]
+
+
+@pytest.mark.parametrize("row", _svd_on_era5_cases()[1], ids=[r[0] for r in _svd_on_era5_cases()[1]])
+def test_oracle_reproduces_the_references_own_svd_on_era5_bit_for_bit(row):
+    """tests/golden/svd_on_era5_reference.npz holds what the reference's OWN svd_on_era5 (extracted from
+    src/dmd_era5/era5_svd/era5_svd.py:230-263 with ast and executed unchanged, tests/golden/make_golden_svd_on_era5.py)
+    returned for seeded inputs.  The oracle's calls must give exactly those arrays (same libraries in this image: NumPy /
+    OpenBLAS gesdd, scikit-learn 1.9 randomized_svd), for float64 and float32 input, tall and wide, k > n - bit for bit on
+    the CPU type that generated them, to rounding on any other (OpenBLAS dispatches per CPU)."""
+    g, _ = _svd_on_era5_cases()
+    name, m, n, k, kind, dt, seed, data_seed = row
+    X = lowrank_field_np(int(m), int(n), r=min(30, int(m), int(n)), rho=0.85, seed=int(data_seed), dtype=np.dtype(dt))
+    if kind == "standard":
+        U, s, V = standard_svd_ref(X, int(k))
+    else:
+        U, s, V = randomized_svd_ref(X, int(k), int(seed))
+    f64 = np.dtype(dt) == np.float64
+    kk = min(int(k), int(m), int(n))
+    lead = min(kk, 8)                              # well-separated leading part (the generator's spectrum is 0.85^i)
+    for got, key in ((U, "U"), (s, "s"), (V, "V")):
+        want = g[f"{name}_{key}"]
+        assert got.shape == want.shape and got.dtype == want.dtype
+        if np.array_equal(got, want):
+            continue
+        # another CPU type dispatches other BLAS kernels: then the last bits may differ - but nothing more than that
+        a, b = (got[:, :lead], want[:, :lead]) if key == "U" else ((got[:lead], want[:lead]) if key == "V" else (got[:lead], want[:lead]))
+        assert np.allclose(a, b, rtol=1e-9 if f64 else 2e-4, atol=(1e-11 if f64 else 2e-5) * float(np.max(np.abs(b)))), (name, key)
