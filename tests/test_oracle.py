@@ -189,3 +189,21 @@ def test_oracle_reproduces_the_references_own_svd_on_era5_bit_for_bit(row):
         # another CPU type dispatches other BLAS kernels: then the last bits may differ - but nothing more than that
         a, b = (got[:, :lead], want[:, :lead]) if key == "U" else ((got[:lead], want[:lead]) if key == "V" else (got[:lead], want[:lead]))
         assert np.allclose(a, b, rtol=1e-9 if f64 else 2e-4, atol=(1e-11 if f64 else 2e-5) * float(np.max(np.abs(b)))), (name, key)
+
+
+def test_mock_data_generator_reproduces_the_references_own_bit_for_bit():
+    """BASELINE config 1's input: the reference's OWN _generate_variable_data (create_mock_data.py:112-155, executed from
+    source by tests/golden/make_golden_mock.py with NumPy's global RNG seeded) against oracle.synthetic_np.mock_era5_np -
+    same draws in the same order, so the arrays agree bit for bit (sha256 of the bytes)."""
+    import hashlib
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "mock_era5.json")) as f:
+        g = json.load(f)
+    for rec in g["cases"]:
+        ds = mock_era5_np(rec["n_times"], rec["variables"], rec["levels"], seed=rec["seed"])
+        for var, want in rec["arrays"].items():
+            a = ds["vars"][var]
+            assert list(a.shape) == want["shape"] and str(a.dtype) == want["dtype"]
+            assert np.allclose(a.ravel()[:5], want["first"], rtol=0, atol=0)
+            assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == want["sha256"], var
