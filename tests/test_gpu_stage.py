@@ -263,3 +263,39 @@ def test_main_n_gpus_matches_single_device(tmp_path, monkeypatch):
             assert np.array_equal(two["X_mean"].values, one["X_mean"].values)
         for c in one.coords:
             assert np.array_equal(one.coord(c), two.coord(c)), c
+
+
+def _golden_compute():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "main_flow.json")) as f:
+        return json.load(f)["compute"]
+
+
+@pytest.mark.parametrize("name", list(_golden_compute()))
+def test_compute_phase_follows_the_references_own_main(name, tmp_path, monkeypatch):
+    """Which pre-processing a configuration switches on and which variables the result carries, as recorded from the
+    reference's OWN ``main`` (era5_svd.py:383-425, executed unchanged with recording stand-ins,
+    tests/golden/make_golden_main.py): X iff save_data_matrix; X_mean / X_std only when they exist AND delay_embedding > 1
+    (quirk Q3); `scale` without `mean_center` does nothing (quirk Q4) - for all 16 combinations."""
+    from dmd_era5_b200.era5_svd import main
+
+    rec = _golden_compute()[name]
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    cfg = base_config(**rec["config"])
+    m, parsed = make_slice(tmp_path, cfg)
+    res, added, retrieved = main(cfg, write_to_netcdf=False)
+    assert ("X" in res) == rec["has_X"]
+    assert ("X_mean" in res) == rec["has_X_mean"]
+    assert ("X_std" in res) == rec["has_X_std"]
+    d = rec["config"]["delay_embedding"]
+    if rec["has_X"]:
+        X = np.asarray(res["X"].values, dtype=np.float64)
+        rows = X[: X.shape[0] // d]                                  # first delay block = the base rows, n columns each
+        if rec["standardize"] is None:
+            vs = [v.strip() for v in cfg["variables"].split(",")]
+            lv = [LEVELS.index(int(x)) for x in cfg["levels"].split(",")]
+            raw = np.concatenate([m["vars"][v][:, lv].reshape(25, -1).T for v in vs], axis=0)
+            assert np.allclose(rows, raw[:, : rows.shape[1]], rtol=1e-12, atol=0)       # untouched data
+    if rec["has_X_mean"]:
+        assert res["X_mean"].values.shape[0] == res["U"].values.shape[0]                 # replicated d times along space

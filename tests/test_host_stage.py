@@ -611,3 +611,71 @@ def test_cache_retrieval_follows_the_references_own_functions(kind, name, tmp_pa
     assert (found is not None) == rec["found"]
     assert bool(from_dvc) == rec["retrieved_from_dvc"]
     assert log == rec["log"]
+
+
+def _golden_main():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "main_flow.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", list(_golden_main()["flow"]))
+def test_main_control_flow_follows_the_references_own_main(name, monkeypatch):
+    """Return flags, exception types / messages / causes and log lines of the reference's OWN ``main``
+    (era5_svd.py:336-453, extracted with ast and executed unchanged with every collaborator replaced by a scenario-driven
+    stand-in: tests/golden/make_golden_main.py) against stage.main with ITS collaborators replaced the same way: cache hit,
+    cache from DVC, failing cache lookup, missing slice with and without DVC, computed / failing compute, written / failing
+    write, added to DVC / failing add, DVC without writing."""
+    from dmd_era5_b200 import dvc_tools, stage
+
+    rec = _golden_main()["flow"][name]
+    sc = rec["scenario"]
+    monkeypatch.setenv("DMD_ERA5_ROOT", "/ROOT")
+    log = []
+    monkeypatch.setattr(stage, "log_and_print", lambda lg, msg, level="info": log.append([level, " ".join(str(msg).split()).replace("/ROOT", "<ROOT>")]))
+
+    class Res:
+        def __init__(self, what):
+            self.what, self.attrs = what, {"attr": 1}
+
+    def raiser(text):
+        kind, _, msg = text.partition("(")
+        return {"OSError": OSError, "ValueError": ValueError, "PermissionError": PermissionError,
+                "RuntimeError": RuntimeError}[kind](msg.rstrip(")").strip("'\""))
+
+    def retrieve_svd_results(parsed, use_dvc):
+        if "cache_raises" in sc:
+            raise raiser(sc["cache_raises"])
+        return (Res("cached") if sc.get("cached") else None), bool(sc.get("cached_from_dvc", False))
+
+    def compute(ds, parsed):
+        if "compute_raises" in sc:
+            raise raiser(sc["compute_raises"])
+        return Res("svd_results")
+
+    def write(ds, path, *a, **k):
+        if "write_raises" in sc:
+            raise raiser(sc["write_raises"])
+        return "NETCDF4"
+
+    def add(path, attrs):
+        if "dvc_raises" in sc:
+            raise raiser(sc["dvc_raises"])
+
+    monkeypatch.setattr(stage, "retrieve_svd_results", retrieve_svd_results)
+    monkeypatch.setattr(stage, "retrieve_era5_slice", lambda parsed, use_dvc: ((object() if sc.get("slice_found", True) else None), False))
+    monkeypatch.setattr(stage, "_compute", compute)
+    monkeypatch.setattr(stage, "write_netcdf", write)
+    monkeypatch.setattr(dvc_tools, "add_data_to_dvc", add)
+    if "raised" in rec:
+        with pytest.raises(Exception) as ei:
+            stage.main(dict(rec["config"]), write_to_netcdf=rec["write_to_netcdf"], use_dvc=rec["use_dvc"])
+        assert type(ei.value).__name__ == rec["raised"]["type"]
+        assert " ".join(str(ei.value).split()) == rec["raised"]["message"]
+        assert type(ei.value.__cause__).__name__ == rec["raised"]["cause"]
+    else:
+        res, added, retrieved = stage.main(dict(rec["config"]), write_to_netcdf=rec["write_to_netcdf"], use_dvc=rec["use_dvc"])
+        assert res.what == rec["returned"]["results"]
+        assert bool(added) == rec["returned"]["added_to_dvc"] and bool(retrieved) == rec["returned"]["retrieved_from_dvc"]
+    assert log == rec["log"]
