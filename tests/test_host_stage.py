@@ -679,3 +679,21 @@ def test_main_control_flow_follows_the_references_own_main(name, monkeypatch):
         assert res.what == rec["returned"]["results"]
         assert bool(added) == rec["returned"]["added_to_dvc"] and bool(retrieved) == rec["returned"]["retrieved_from_dvc"]
     assert log == rec["log"]
+
+
+def test_space_coords_match_the_references_own_conversion():
+    """level / latitude / longitude per row as the reference's OWN space_coord_to_level_lat_lon (slice_tools.py:368-414,
+    executed unchanged on the tuple labels of stack + tile, tests/golden/make_golden_coords.py) writes them, against the
+    closed form used here (slice_tools.space_coords) - values, order and dtypes, several variables and delay blocks."""
+    import json
+
+    from dmd_era5_b200.slice_tools import space_coords
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "space_coords.json")) as f:
+        g = json.load(f)
+    for c in g["cases"]:
+        lev, lat, lon = space_coords(np.asarray(c["levels"]), np.asarray(c["latitudes"]), np.asarray(c["longitudes"]),
+                                     c["n_vars"], c["d"])
+        assert lev.tolist() == c["level"] and lat.tolist() == c["latitude"] and lon.tolist() == c["longitude"]
+        assert str(lev.dtype) == c["level_dtype"] and str(lat.dtype) == c["latitude_dtype"] and str(lon.dtype) == c["longitude_dtype"]
+        assert c["space"] == list(range(len(c["level"]))) and c["level_dim"] == "space"
