@@ -89,7 +89,7 @@ class _Blocks:
         self.m0 = X.shape[0]
         self.n = X.shape[1] - d + 1
         if self.n < 1:
-            raise ValueError("delay embedding larger than the number of snapshots")
+            raise ValueError("window shape cannot be larger than input array shape")   # numpy's text in the reference (sliding_window_view, slice_tools.py:207)
 
     def view(self, j: int) -> torch.Tensor:
         return self.X[:, j : j + self.n]

@@ -131,6 +131,8 @@ def _apply_delay_embedding_np(X: np.ndarray, d: int) -> np.ndarray:
     if not isinstance(d, int) or isinstance(d, bool) or d <= 0:
         raise ValueError("Delay must be an integer greater than 0.")
     n = X.shape[1] - d + 1
+    if n < 1:       # the reference's sliding_window_view raises here (numpy's text), slice_tools.py:207
+        raise ValueError("window shape cannot be larger than input array shape")
     return np.concatenate([X[:, j : j + n] for j in range(d)], axis=0)
 
 

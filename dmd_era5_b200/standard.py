@@ -195,7 +195,7 @@ def standard_svd_device(ops, X: torch.Tensor, n_components: int, *, delay: int =
     d = delay
     n = T - d + 1
     if n < 1:
-        raise ValueError("delay embedding larger than the number of snapshots")
+        raise ValueError("window shape cannot be larger than input array shape")   # numpy's text in the reference (sliding_window_view, slice_tools.py:207)
     k = min(int(n_components), n)
     tc_ok = precision in (PREC_TF32X3, PREC_TF32MIX) and X.dtype == torch.float32
     use_tc = tc_ok and k <= 128

@@ -697,3 +697,39 @@ def test_space_coords_match_the_references_own_conversion():
         assert lev.tolist() == c["level"] and lat.tolist() == c["latitude"] and lon.tolist() == c["longitude"]
         assert str(lev.dtype) == c["level_dtype"] and str(lat.dtype) == c["latitude_dtype"] and str(lon.dtype) == c["longitude_dtype"]
         assert c["space"] == list(range(len(c["level"]))) and c["level_dim"] == "space"
+
+
+def test_apply_delay_embedding_matches_the_references_own_wrapper():
+    """The DataArray-level wrapper: data, time / original_variable / delay coordinates, the delay_embedding attribute and
+    the error messages of the reference's OWN apply_delay_embedding (slice_tools.py:214-274, executed unchanged,
+    tests/golden/make_golden_delay_da.py).  ``space`` differs by design: arange here, tiled labels there (both end as
+    arange in the output file, slice_tools.py:406-407)."""
+    from dmd_era5_b200.dataset import DataArray
+    from dmd_era5_b200.slice_tools import apply_delay_embedding
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "delay_embedding_dataarray.npz"))
+    t0 = np.datetime64("2019-01-01T00", "ns")
+    for i in range(int(g["n_cases"])):
+        X, d, variables = g[f"c{i}_X"], int(g[f"c{i}_d"]), [str(v) for v in g[f"c{i}_variables"]]
+        m0, T = X.shape
+        da = DataArray(X, ("space", "time"), {"space": np.arange(m0), "time": t0 + np.arange(T) * np.timedelta64(1, "h"),
+                                              "original_variable": (("space",), np.repeat(variables, m0 // len(variables)))},
+                       {"source": "mock"})
+        r = apply_delay_embedding(da, d)
+        assert np.array_equal(np.asarray(r.values), g[f"c{i}_values"]) and tuple(r.dims) == tuple(str(x) for x in g[f"c{i}_dims"])
+        assert np.array_equal(r.coord("time").astype("datetime64[ns]").astype(np.int64), g[f"c{i}_time"])
+        assert [str(x) for x in r.coord("original_variable")] == [str(x) for x in g[f"c{i}_original_variable"]]
+        assert np.array_equal(r.coord("delay"), g[f"c{i}_delay"])
+        assert r.coord("space").shape == g[f"c{i}_space"].shape
+        assert r.attrs["delay_embedding"] == int(g[f"c{i}_delay_attr"]) and r.attrs["source"] == "mock"
+    want = dict(e.split(" -> ", 1) for e in g["errors"])
+    good = DataArray(np.zeros((2, 3)), ("space", "time"), {"space": np.arange(2), "time": np.arange(3),
+                                                          "original_variable": (("space",), np.array(["a", "a"]))})
+    cases = {"not a DataArray": (np.zeros((2, 3)), 1),
+             "bad dims": (DataArray(np.zeros((2, 3)), ("x", "time"), {"time": np.arange(3)}), 1),
+             "bad coords": (DataArray(np.zeros((2, 3)), ("space", "time"), {"space": np.arange(2), "time": np.arange(3)}), 1),
+             "d = 0": (good, 0), "d float": (good, 1.5), "d too large": (good, 4)}
+    for label, (arg, d) in cases.items():
+        with pytest.raises(Exception) as ei:
+            apply_delay_embedding(arg, d)
+        assert f"{type(ei.value).__name__}: {ei.value}" == want[label], label
