@@ -733,3 +733,46 @@ def test_apply_delay_embedding_matches_the_references_own_wrapper():
         with pytest.raises(Exception) as ei:
             apply_delay_embedding(arg, d)
         assert f"{type(ei.value).__name__}: {ei.value}" == want[label], label
+
+
+def _golden_slice():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "slice_era5_dataset.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", list(_golden_slice()["cases"]))
+def test_slice_era5_dataset_matches_the_references_own(name, monkeypatch):
+    """Which time labels and which levels - in which ORDER - the reference's OWN slice_era5_dataset selects
+    (slice_tools.py:20-103, executed unchanged on a stand-in with xarray's label-based ``sel`` contract,
+    tests/golden/make_golden_slice.py), and its error types / messages / causes, against slice_tools.slice_era5_dataset on
+    a real Dataset.  TZ = UTC (quirk Q1 is reproduced: the bounds go through datetime.fromtimestamp)."""
+    import time as _time
+    from datetime import datetime
+
+    from dmd_era5_b200.dataset import DataArray, Dataset
+    from dmd_era5_b200.slice_tools import slice_era5_dataset
+
+    monkeypatch.setenv("TZ", "UTC")
+    _time.tzset()
+    g = _golden_slice()
+    rec = g["cases"][name]
+    T, levels = g["n_times"], g["levels"]
+    times = np.datetime64("2019-01-01T00", "ns") + np.arange(T) * np.timedelta64(1, "h")
+    data = np.arange(T * len(levels) * 4, dtype=np.float64).reshape(T, len(levels), 2, 2)
+    ds = Dataset({"temperature": DataArray(data, ("time", "level", "latitude", "longitude"))},
+                 {"time": times, "level": np.asarray(levels), "latitude": np.array([1.0, 0.0]), "longitude": np.array([0.0, 1.0])})
+    kw = {k: (datetime.fromisoformat(v) if k in rec["datetime_args"] else v) for k, v in rec["kwargs"].items()}
+    if "error" in rec:
+        with pytest.raises(Exception) as ei:
+            slice_era5_dataset(ds, **kw)
+        assert type(ei.value).__name__ == rec["error"]["type"] and str(ei.value) == rec["error"]["message"]
+        if rec["error"]["cause"]:
+            assert ei.value.__cause__ is not None          # KeyError from xarray's sel there, ValueError from list.index here
+        return
+    out = slice_era5_dataset(ds, **kw)
+    ti, li = rec["selected"]["time_index"], rec["selected"]["level_index"]
+    assert np.array_equal(out.coord("time"), times[ti])
+    assert list(out.coord("level")) == [levels[i] for i in li]
+    assert np.array_equal(np.asarray(out["temperature"].values), data[ti][:, li])
