@@ -776,3 +776,28 @@ def test_slice_era5_dataset_matches_the_references_own(name, monkeypatch):
     assert np.array_equal(out.coord("time"), times[ti])
     assert list(out.coord("level")) == [levels[i] for i in li]
     assert np.array_equal(np.asarray(out["temperature"].values), data[ti][:, li])
+
+
+def test_add_config_attributes_matches_the_references_own(monkeypatch):
+    """Names, ORDER, values and Python types of the result attributes, as the reference's OWN add_config_attributes
+    (era5_svd.py:42-66, executed unchanged on its own parser's output: tests/golden/make_golden_attrs.py) sets them."""
+    import json
+    from datetime import datetime
+
+    from dmd_era5_b200.dataset import Dataset
+    from dmd_era5_b200.stage import add_config_attributes
+
+    monkeypatch.setenv("DMD_ERA5_ROOT", "/ROOT")
+    with open(os.path.join(os.path.dirname(__file__), "golden", "config_attributes.json")) as f:
+        g = json.load(f)
+    for case in g["cases"]:
+        parsed = config_parser(dict(case["config"]), section="era5-svd")
+        ds = add_config_attributes(Dataset(attrs={"pre_existing": "kept"}), parsed)
+        assert list(ds.attrs) == list(case["attrs"])                       # same names in the same order
+        for k, want in case["attrs"].items():
+            got = ds.attrs[k]
+            assert type(got).__name__ == case["types"][k], k
+            if k == "date_processed":
+                datetime.fromisoformat(got)
+            else:
+                assert (got.replace("/ROOT", "<ROOT>") if isinstance(got, str) else got) == want, k
