@@ -61,7 +61,7 @@ class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    PERIOD = 0.02                            # seconds between NVML polls (every 5 ms an occasional poll delayed a step by ~2 ms, profiles/r02_step_jitter.txt)
+    PERIOD = 0.01                            # seconds between NVML polls (every 5 ms an occasional poll delayed a step by ~2 ms, profiles/r02_step_jitter.txt)
 
     def __init__(self, index: int, uuid: str | None = None):
         self.index = index
