@@ -452,11 +452,18 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
     extra = {}
     if X_h is not None:
         n = X_h.shape[1] - d + 1
-        extra["X"] = np.concatenate([X_h[:, j : j + n] for j in range(d)], axis=0)
+        # the reference hands its DataArray to the Dataset (era5_svd.py:416-418), so X carries the attributes that
+        # flatten_era5_variables / apply_delay_embedding set on it (slice_tools.py:362-363, :271), after the slice's own
+        # attributes when nothing was centred (xarray's arithmetic in standardize_data drops them otherwise)
+        x_attrs = {} if parsed_config["mean_center"] else dict(ds.attrs)
+        x_attrs.update(original_variables=list(variables), space_coords=["level", "latitude", "longitude"], delay_embedding=d)
+        extra["X"] = DataArray(np.concatenate([X_h[:, j : j + n] for j in range(d)], axis=0), ("space", "time"), attrs=x_attrs)
     if mean_h is not None and d > 1:                                     # quirk Q3 (:400-414): dropped when d == 1
-        extra["X_mean"] = np.concatenate([mean_h] * d)
+        # flattened by the same function as X (:401, :406), hence with its two attributes; xr.concat keeps them
+        stat_attrs = {"original_variables": list(variables), "space_coords": ["level", "latitude", "longitude"]}
+        extra["X_mean"] = DataArray(np.concatenate([mean_h] * d), ("space",), attrs=stat_attrs)
         if std_h is not None:
-            extra["X_std"] = np.concatenate([std_h] * d)
+            extra["X_std"] = DataArray(np.concatenate([std_h] * d), ("space",), attrs=stat_attrs)
     out = combine_svd_results(U_h, s_h, V_h, coords, **extra)
     out = add_config_attributes(out, parsed_config)
     return space_coord_to_level_lat_lon(out)

@@ -1,0 +1,220 @@
+"""CPU: the compute phase of the reference's OWN ``main`` with all of its own collaborators (slice_era5_dataset,
+resample_era5_dataset, standardize_data, flatten_era5_variables, apply_delay_embedding, svd_on_era5, combine_svd_results,
+add_config_attributes, space_coord_to_level_lat_lon - executed unchanged on the xarray stand-in of
+tests/golden/xr_contract.py, see tests/golden/make_golden_compute_phase.py) against
+
+* the ORACLE's build (oracle/slice_tools_np.build_matrix_np - what every GPU parity test compares the kernels with):
+  X, X_mean, X_std bit for bit, so reference -> oracle -> device is a closed chain;
+* the product's host functions flatten_era5_variables / apply_delay_embedding on the stage's own containers;
+* the product's ``stage._compute`` packaging - complete result Dataset: variables, dims, dtypes, values, coordinates and
+  their values, the attributes of X, the global attributes - with the device arrays supplied by a NumPy stand-in (no GPU
+  here; the device arrays themselves are compared with the oracle in tests/test_gpu_stage.py).
+"""
+import json
+import os
+import time as _time
+
+import numpy as np
+import pytest
+
+from dmd_era5_b200.config_parser import config_parser
+from dmd_era5_b200.dataset import DataArray, Dataset
+from oracle.slice_tools_np import build_matrix_np, delay_embed_np, flatten_np, resample_nearest_index, standardize_np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "compute_phase.json")) as f:
+    GOLD = json.load(f)
+CASES = list(GOLD["cases"])
+
+
+def golden_array(rec):
+    if rec["dtype"] == "datetime64[ns]":
+        return np.asarray(rec["values"], dtype=np.int64).astype("datetime64[ns]")
+    if rec["dtype"] == "str":
+        return np.asarray(rec["values"])
+    return np.asarray(rec["values"], dtype=rec["dtype"])
+
+
+def make_slice(dtype):
+    """The generator's mock slice (tests/golden/make_golden_compute_phase.py::make_slice), same seed."""
+    s = GOLD["slice"]
+    rng = np.random.RandomState(s["seed"])
+    shape = (s["n_times"], len(s["levels"]), len(s["latitude"]), len(s["longitude"]))
+    dv = {}
+    for i, v in enumerate(s["variables"]):
+        a = rng.standard_normal(shape) * (3.0 + i) + (250.0 if i == 0 else 0.0)
+        dv[v] = np.asarray(a, dtype=dtype)
+    times = np.datetime64("2019-01-01T00", "ns") + np.arange(s["n_times"]) * np.timedelta64(1, "h")
+    return dv, times
+
+
+def selected_arrays(case):
+    """Variable / level / time selection of the case in plain NumPy (request order, nearest resampling)."""
+    cfg, s = case["config"], GOLD["slice"]
+    dv, times = make_slice(case["slice_dtype"])
+    variables = cfg["variables"].split(",")
+    levels = [int(x) for x in cfg["levels"].split(",")]
+    li = [s["levels"].index(lv) for lv in levels]
+    hours = int(cfg["delta_time"][:-1])
+    labels, ti = resample_nearest_index(times.astype(np.int64), hours * 3600 * 10**9)
+    return variables, levels, labels.astype("datetime64[ns]"), [dv[v][ti][:, li] for v in variables]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_build_reproduces_the_references_own_chain_bit_for_bit(name):
+    case = GOLD["cases"][name]
+    cfg, res = case["config"], case["result"]
+    _, _, _, arrays = selected_arrays(case)
+    X, X_mean, X_std = build_matrix_np(arrays, cfg["mean_center"], cfg["scale"], cfg["delay_embedding"])
+    if "X" in res["data_vars"]:
+        want = golden_array(res["data_vars"]["X"])
+        assert X.dtype == want.dtype and np.array_equal(X, want)
+    for key, got in (("X_mean", X_mean), ("X_std", X_std)):
+        if key in res["data_vars"]:
+            want = golden_array(res["data_vars"][key])
+            assert got is not None and got.dtype == want.dtype and np.array_equal(got, want), key
+        else:
+            assert got is None, key                      # Q3 (d == 1) / Q4 (scale without centring)
+    # the reference's U, s, V are its own LAPACK call on that X
+    U, sv, Vt = np.linalg.svd(X, full_matrices=False)
+    k = cfg["n_components"]
+    assert np.array_equal(sv[:k], golden_array(res["data_vars"]["s"]))
+    assert np.array_equal(U[:, :k], golden_array(res["data_vars"]["U"]))
+    assert np.array_equal(Vt[:k], golden_array(res["data_vars"]["V"]))
+
+
+def product_slice(case):
+    s = GOLD["slice"]
+    dv, times = make_slice(case["slice_dtype"])
+    dims = ("time", "level", "latitude", "longitude")
+    return Dataset({k: DataArray(v, dims) for k, v in dv.items()},
+                   {"time": times, "level": np.asarray(s["levels"]), "latitude": np.asarray(s["latitude"]),
+                    "longitude": np.asarray(s["longitude"])}, dict(s["attrs"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_flatten_and_delay_embedding_follow_the_references_own(name, monkeypatch):
+    """flatten_era5_variables + apply_delay_embedding of the product (host index work on the stage's containers) on the
+    selected / standardised variables: data, dims, time / original_variable / delay coordinates, the three attributes the
+    reference sets on the matrix, and level / latitude / longitude = the components of the reference's space tuples."""
+    from dmd_era5_b200.slice_tools import apply_delay_embedding, flatten_era5_variables, resample_era5_dataset, slice_era5_dataset
+
+    monkeypatch.setenv("TZ", "UTC")
+    _time.tzset()
+    case = GOLD["cases"][name]
+    cfg, res = case["config"], case["result"]
+    if "X" not in res["data_vars"]:
+        pytest.skip("no data matrix recorded for this case")
+    parsed = config_parser(dict(cfg), section="era5-svd")
+    ds = product_slice(case)[parsed["variables"]]
+    ds = resample_era5_dataset(slice_era5_dataset(ds, levels=parsed["levels"]), parsed["delta_time"])
+    dv = {}
+    for v in parsed["variables"]:
+        a = np.asarray(ds[v].values)
+        if parsed["mean_center"]:
+            a = standardize_np(a, scale=bool(parsed["scale"]))[0]
+        dv[v] = DataArray(a, ds[v].dims)
+    flat = flatten_era5_variables(Dataset(dv, ds.coords, ds.attrs if not parsed["mean_center"] else {}))
+    da = apply_delay_embedding(flat, parsed["delay_embedding"])
+    want = res["data_vars"]["X"]
+    assert list(da.dims) == want["dims"] and np.array_equal(np.asarray(da.values), golden_array(want))
+    for key in ("time", "original_variable", "delay", "level", "latitude", "longitude"):
+        g = golden_array(res["coords"][key])
+        got = np.asarray(da.coord(key))
+        assert np.array_equal(got.astype(g.dtype) if g.dtype.kind == "M" else got, g), key
+    for key in ("original_variables", "space_coords", "delay_embedding"):
+        assert da.attrs[key] == want["attrs"][key], key
+    assert list(da.attrs) == list(want["attrs"])          # incl. the slice's own attributes when nothing was centred
+
+
+def fake_device_arrays(ds, parsed_config, ops, comm=None, rank=0, world=1):
+    """NumPy stand-in for stage._device_arrays (the device build + SVD): same contract, reference numerics."""
+    variables, d = parsed_config["variables"], parsed_config["delay_embedding"]
+    mc = bool(parsed_config["mean_center"])
+    sc = bool(parsed_config["scale"]) and mc
+    arrays = [np.asarray(ds[v].values) for v in variables]
+    X0, _, _ = build_matrix_np(arrays, mc, sc, 1)
+    stats = [standardize_np(a, scale=sc) for a in arrays] if mc else None
+    mean = flatten_np([st[1] for st in stats]) if mc else None
+    std = flatten_np([st[2] for st in stats]) if sc else None
+    U, s, Vt = np.linalg.svd(delay_embed_np(X0, d), full_matrices=False)
+    k = parsed_config["n_components"]
+    S = X0.shape[0] // len(variables)
+    return {"U": U[:, :k], "s": s[:k], "V": Vt[:k], "X": X0 if parsed_config["save_data_matrix"] else None, "mean": mean,
+            "std": std, "rows": (0, X0.shape[0]), "m0": X0.shape[0], "S": S}
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_compute_phase_packaging_matches_the_references_own_result(name, monkeypatch):
+    from dmd_era5_b200 import stage
+
+    monkeypatch.setenv("TZ", "UTC")
+    _time.tzset()
+    monkeypatch.setenv("DMD_ERA5_ROOT", "/ROOT")
+    monkeypatch.setattr(stage, "_device_arrays", fake_device_arrays)
+    monkeypatch.setattr(stage, "get_ops", lambda *a, **k: None)
+    case = GOLD["cases"][name]
+    res = case["result"]
+    parsed = config_parser(dict(case["config"]), section="era5-svd")
+    out = stage._compute(product_slice(case), parsed)
+    # variables: names in the reference's order, dims, dtype, values
+    assert list(out.data_vars) == res["var_order"]
+    for k, rec in res["data_vars"].items():
+        got = out[k]
+        want = golden_array(rec)
+        assert list(got.dims) == rec["dims"], k
+        assert np.asarray(got.values).dtype == want.dtype, k
+        assert np.array_equal(np.asarray(got.values), want), k
+    # coordinates: the reference's set (ORDER is not part of a NetCDF file's contract), dims, values, dtype kind
+    assert sorted(out.coords) == sorted(res["coord_order"])
+    for k, rec in res["coords"].items():
+        want = golden_array(rec)
+        dims, got = out.coords[k]
+        got = np.asarray(got)
+        assert list(dims) == rec["dims"], k
+        assert got.dtype.kind == want.dtype.kind and np.array_equal(got.astype(want.dtype), want), k
+    # attributes of the data matrix (original_variables / space_coords / delay_embedding, + the slice's own attributes
+    # when nothing was centred: xarray arithmetic drops them otherwise)
+    if "X" in res["data_vars"]:
+        assert out["X"].attrs == res["data_vars"]["X"]["attrs"]
+        assert list(out["X"].attrs) == list(res["data_vars"]["X"]["attrs"])
+    for k in ("U", "s", "V", "X_mean", "X_std"):
+        if k in res["data_vars"]:
+            want_attrs = res["data_vars"][k]["attrs"]
+            assert dict(out[k].attrs) == want_attrs, k
+    # global attributes: names in order, values
+    assert list(out.attrs) == list(res["attrs"])
+    for k, v in res["attrs"].items():
+        if k == "date_processed":
+            continue
+        got = out.attrs[k]
+        assert (got.replace("/ROOT", "<ROOT>") if isinstance(got, str) else got) == v, k
+
+
+@pytest.mark.parametrize("version", ["netcdf3", "cdf5"])
+def test_result_with_the_references_variable_attributes_survives_the_file_round_trip(version, tmp_path, monkeypatch):
+    """X / X_mean / X_std carry list-valued attributes (original_variables, space_coords): both classic writers hold them
+    (comma-joined strings, like the global ``variables`` attribute) and every value comes back."""
+    from dmd_era5_b200 import dataset, stage
+
+    monkeypatch.setenv("TZ", "UTC")
+    _time.tzset()
+    monkeypatch.setenv("DMD_ERA5_ROOT", "/ROOT")
+    monkeypatch.setattr(stage, "_device_arrays", fake_device_arrays)
+    monkeypatch.setattr(stage, "get_ops", lambda *a, **k: None)
+    if version == "cdf5":
+        monkeypatch.setattr(dataset, "NETCDF3_VAR_LIMIT", 64)          # force the CDF-5 writer
+    case = GOLD["cases"][CASES[1]]                                      # X, X_mean and X_std present
+    out = stage._compute(product_slice(case), config_parser(dict(case["config"]), section="era5-svd"))
+    path = str(tmp_path / "svd.nc")
+    fmt = dataset.write_netcdf(out, path)
+    if not dataset._have_xarray():
+        assert fmt == ("NETCDF3_64BIT_DATA" if version == "cdf5" else "NETCDF3_64BIT")
+    back = dataset.read_netcdf(path)
+    assert sorted(back.data_vars) == sorted(out.data_vars)
+    for k in out.data_vars:
+        assert np.array_equal(np.asarray(back[k].values), np.asarray(out[k].values)), k
+    for k in ("X", "X_mean", "X_std"):
+        assert back[k].attrs["original_variables"] == ",".join(out[k].attrs["original_variables"])
+        assert back[k].attrs["space_coords"] == "level,latitude,longitude"
+    assert int(back["X"].attrs["delay_embedding"]) == case["config"]["delay_embedding"]
