@@ -15,6 +15,7 @@ Here ``space`` is ``arange(m)`` from the start and the three per-row coordinates
 """
 from __future__ import annotations
 
+import logging
 from datetime import datetime, timedelta
 
 import numpy as np
@@ -22,6 +23,13 @@ import numpy as np
 from .dataset import DataArray, Dataset
 
 SPATIAL_ORDER = ("level", "latitude", "longitude")
+logger = logging.getLogger("ERA5Processing")            # the reference's logger name (slice_tools.py:12)
+
+
+def log_and_print(lg: logging.Logger, msg: str, level: str = "info") -> None:
+    """src/dmd_era5/logger.py:42-46 (kept local: importing era5_svd here would load torch for pure index work)."""
+    getattr(lg, level)(msg)
+    print(msg)
 
 
 def _get_dataset_time_bounds(ds: Dataset) -> dict:
@@ -51,9 +59,12 @@ def slice_era5_dataset(ds: Dataset, start_datetime=None, end_datetime=None, leve
     if start_dt < bounds["first"] or end_dt > bounds["last"]:
         msg = f"Time range ({start_dt} to {end_dt}) is outside dataset"
         msg += f"bounds ({bounds['first']} to {bounds['last']})."
+        log_and_print(logger, msg, "error")
         raise ValueError(msg)
     if start_dt >= end_dt:
-        raise ValueError("Start datetime must be before end datetime.")
+        msg = "Start datetime must be before end datetime."
+        log_and_print(logger, msg, "error")
+        raise ValueError(msg)
     all_levels = list(ds.coord("level"))
     levels = levels or all_levels
     times = ds.coord("time").astype("datetime64[ns]")
@@ -64,7 +75,9 @@ def slice_era5_dataset(ds: Dataset, start_datetime=None, end_datetime=None, leve
     except ValueError as e:
         msg = "Requested level is not available in the dataset."
         msg += f"Available levels: {all_levels}"
+        log_and_print(logger, msg, "error")
         raise ValueError(msg) from e
+    log_and_print(logger, f"Dataset slicing completed successfully using {start_dt}to {end_dt} and levels {levels}")
     return _subset(out, "level", idx)
 
 
@@ -88,7 +101,18 @@ def resample_era5_dataset(ds: Dataset, delta_time: timedelta) -> Dataset:
     """slice_tools.py:126-141."""
     t = ds.coord("time").astype("datetime64[ns]").astype(np.int64)
     labels, idx = resample_nearest_index(t, int(delta_time.total_seconds()) * 10**9)
-    return _subset(ds, "time", idx, labels.astype("datetime64[ns]"))
+    out = _subset(ds, "time", idx, labels.astype("datetime64[ns]"))
+    log_and_print(logger, f"Resampled the dataset with time delta: {delta_time}")
+    return out
+
+
+def log_standardize(dim: str, scale: bool) -> None:
+    """The reference's progress lines of standardize_data (slice_tools.py:164-176); also emitted by the fused device
+    build of the stage, which replaces that call (stage._compute)."""
+    log_and_print(logger, f"Standardizing data along {dim} dimension...")
+    log_and_print(logger, f"Removing mean along {dim} dimension...")
+    if scale:
+        log_and_print(logger, f"Scaling to unit variance along {dim} dimension...")
 
 
 def standardize_data(data: Dataset, dim: str = "time", scale: bool = True):
@@ -100,6 +124,7 @@ def standardize_data(data: Dataset, dim: str = "time", scale: bool = True):
     from .era5_svd import get_ops
 
     ops = get_ops()
+    log_standardize(dim, scale)
     flags = BUILD_MEAN_CENTER | (BUILD_SCALE if scale else 0)
     out, means, stds = {}, {}, {}
     with torch.cuda.device(ops.device):

@@ -21,7 +21,8 @@ from .config_parser import config_parser
 from .dataset import DataArray, Dataset, read_netcdf, write_netcdf
 from .era5_svd import get_ops, log_and_print, logger
 from .pipeline import build_matrix_device, svd_device
-from .slice_tools import resample_era5_dataset, slice_era5_dataset, space_coord_to_level_lat_lon, space_coords
+from .slice_tools import (log_standardize, resample_era5_dataset, slice_era5_dataset, space_coord_to_level_lat_lon,
+                          space_coords)
 
 
 def add_config_attributes(ds: Dataset, parsed_config: dict) -> Dataset:
@@ -430,6 +431,8 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
     variables, d = parsed_config["variables"], parsed_config["delay_embedding"]
     n_gpus = int(parsed_config.get("n_gpus", 1) or 1)
     dsp = _prepare(ds, parsed_config)
+    if parsed_config["mean_center"]:                 # standardize_data's progress lines (:389-392); Q4: scale needs centring
+        log_standardize("time", bool(parsed_config["scale"]))
     if n_gpus > 1:
         from .stage_multi import compute_multi
 

@@ -153,10 +153,19 @@ def test_compute_phase_packaging_matches_the_references_own_result(name, monkeyp
     monkeypatch.setenv("DMD_ERA5_ROOT", "/ROOT")
     monkeypatch.setattr(stage, "_device_arrays", fake_device_arrays)
     monkeypatch.setattr(stage, "get_ops", lambda *a, **k: None)
+    from dmd_era5_b200 import slice_tools
+
+    log = []
+    for mod in (stage, slice_tools):
+        monkeypatch.setattr(mod, "log_and_print", lambda lg, msg, level="info": log.append([level, " ".join(str(msg).split())]))
     case = GOLD["cases"][name]
     res = case["result"]
     parsed = config_parser(dict(case["config"]), section="era5-svd")
     out = stage._compute(product_slice(case), parsed)
+    # progress lines of the phase, in order: slicing, resampling, standardisation (the fused device build replaces the
+    # call but keeps its lines); the last two of the reference's are the SVD pair, emitted by the device leg
+    assert case["log"][-2:] == [["info", "Performing standard SVD..."], ["info", "Standard SVD complete."]]
+    assert log == case["log"][:-2]
     # variables: names in the reference's order, dims, dtype, values
     assert list(out.data_vars) == res["var_order"]
     for k, rec in res["data_vars"].items():

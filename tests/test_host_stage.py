@@ -764,14 +764,20 @@ def test_slice_era5_dataset_matches_the_references_own(name, monkeypatch):
     ds = Dataset({"temperature": DataArray(data, ("time", "level", "latitude", "longitude"))},
                  {"time": times, "level": np.asarray(levels), "latitude": np.array([1.0, 0.0]), "longitude": np.array([0.0, 1.0])})
     kw = {k: (datetime.fromisoformat(v) if k in rec["datetime_args"] else v) for k, v in rec["kwargs"].items()}
+    from dmd_era5_b200 import slice_tools
+
+    log = []
+    monkeypatch.setattr(slice_tools, "log_and_print", lambda lg, msg, level="info": log.append([level, str(msg)]))
     if "error" in rec:
         with pytest.raises(Exception) as ei:
             slice_era5_dataset(ds, **kw)
         assert type(ei.value).__name__ == rec["error"]["type"] and str(ei.value) == rec["error"]["message"]
+        assert log == rec["log"]                               # the error is logged before it is raised
         if rec["error"]["cause"]:
             assert ei.value.__cause__ is not None          # KeyError from xarray's sel there, ValueError from list.index here
         return
     out = slice_era5_dataset(ds, **kw)
+    assert log == rec["log"]                                   # "Dataset slicing completed successfully using ..."
     ti, li = rec["selected"]["time_index"], rec["selected"]["level_index"]
     assert np.array_equal(out.coord("time"), times[ti])
     assert list(out.coord("level")) == [levels[i] for i in li]
