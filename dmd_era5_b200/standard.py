@@ -150,40 +150,41 @@ def sym_eig_topk(ops, G: torch.Tensor, k: int, refine: bool = True, tol: float =
 def gram_device(ops, X: torch.Tensor, n: int, delay: int, precision: int) -> torch.Tensor:
     """G = sum_j X_j^T X_j over the delay windows X_j = X[:, j : j + n] (float64, this rank's rows only).
 
+    The windows overlap: (X_j^T X_j)[a, b] = F[j + a, j + b] with F = X^T X the Gram matrix of the BASE matrix (T x T,
+    T = n + delay - 1), so F is formed ONCE - on aligned column blocks whatever the delay - and G is the sum of its
+    ``delay`` shifted diagonal blocks: one pass set over X instead of ``delay``, and no operand ever starts at an
+    unaligned column (the Y operand of the tensor-core kernels needs 16-byte alignment).
+
     precision PREC_TF32MIX: ONE tf32 product per k-step on the raw float32 tiles (era5svd_project_tf32x1, the HBM-bound
     kernel of the early power iterations) - for float32 data the Gram matrix only supplies the SUBSPACE that the
     full-precision refinement passes start from (standard_svd_device), exactly like the single-product power iterations
     of the randomized driver; the column block itself (a view of X with X's pitch) is the Y operand: no split images."""
-    G = None
-    if precision == PREC_TF32MIX:
+    T = n + delay - 1
+    X = X[:, :T]
+    if precision in (PREC_TF32MIX, PREC_TF32X3):
         if X.dtype != torch.float32:
-            raise TypeError("precision 'tf32mix' needs a float32 snapshot matrix")
-        G = ops.zeros((n, n), torch.float64)
-        for j in range(delay):
-            Xj = X[:, j : j + n]
-            for c0 in range(0, n, TC_BLOCK_X1):
-                c1 = min(n, c0 + TC_BLOCK_X1)
-                ops.project_tf32x1(Xj[:, c0:], Xj[:, c0:c1], G[c0:, c0:c1], accumulate=j > 0)   # G[c0:, c0:c1], t >= c0 only
-        low = torch.tril(G, -1)
-        return torch.tril(G) + low.t()
-    if precision == PREC_TF32X3:
-        if X.dtype != torch.float32:
-            raise TypeError("precision 'tf32x3' needs a float32 snapshot matrix")
+            raise TypeError("precision 'tf32mix' / 'tf32x3' needs a float32 snapshot matrix")
         # symmetric: block column [c0, c1) is computed for the time rows t >= c0 only (the column window X[:, c0:]
         # is the X operand) and mirrored, which halves the passes over X
-        G = ops.zeros((n, n), torch.float64)
-        for j in range(delay):
-            Xj = X[:, j : j + n]
-            for c0 in range(0, n, TC_BLOCK):
-                c1 = min(n, c0 + TC_BLOCK)
-                hi, lo = ops.split_tf32(Xj[:, c0:c1])             # the (Y_hi, Y_lo) operand of the project kernel
-                Z = ops.project_tf32x3(Xj[:, c0:], None, hi, lo)  # (n - c0, c1 - c0) float64 = G[c0:, c0:c1]
-                G[c0:, c0:c1] += Z
-        low = torch.tril(G, -1)
-        return torch.tril(G) + low.t()                             # the diagonal blocks' upper parts come from the mirror
-    for j in range(delay):
-        Xj = X[:, j : j + n]
-        G = ops.project(Xj, Xj, G, accumulate=j > 0, precision=PREC_NATIVE)
+        F = ops.zeros((T, T), torch.float64)
+        if precision == PREC_TF32MIX:
+            for c0 in range(0, T, TC_BLOCK_X1):
+                c1 = min(T, c0 + TC_BLOCK_X1)
+                ops.project_tf32x1(X[:, c0:], X[:, c0:c1], F[c0:, c0:c1])     # F[c0:, c0:c1], t >= c0 only
+        else:
+            for c0 in range(0, T, TC_BLOCK):
+                c1 = min(T, c0 + TC_BLOCK)
+                hi, lo = ops.split_tf32(X[:, c0:c1])              # the (Y_hi, Y_lo) operand of the project kernel
+                F[c0:, c0:c1] = ops.project_tf32x3(X[:, c0:], None, hi, lo)   # (T - c0, c1 - c0) float64
+        low = torch.tril(F, -1)
+        F = torch.tril(F) + low.t()                               # the diagonal blocks' upper parts come from the mirror
+    else:
+        F = ops.project(X, X, None, precision=PREC_NATIVE)
+    if delay == 1:
+        return F
+    G = F[:n, :n].clone()
+    for j in range(1, delay):
+        G += F[j : j + n, j : j + n]
     return G
 
 

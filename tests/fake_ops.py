@@ -82,12 +82,25 @@ class FakeOps:
         bits = a.to(torch.float32).contiguous().view(torch.int32)
         return (bits & ~0x1FFF).view(torch.float32)
 
+    @staticmethod
+    def _check_y(*ys):
+        """the tensor-core projection kernels take their Y operand by TMA: 16-byte aligned base (include/era5svd.h)"""
+        for y in ys:
+            if y is not None and y.data_ptr() % 16:
+                raise ValueError("project_tf32x3: Yhi / Ylo must be 16-byte aligned")
+
+    def split_tf32(self, X):
+        self._count("split_tf32")
+        hi = self._tf32_trunc(X)
+        return hi, (X - hi)
+
     def sketch_tf32x1(self, X, Om, Y):
         self._count("sketch_x1")
         Y.copy_((self._tf32_trunc(X).double() @ self._tf32(Om).double()).to(torch.float32))
 
     def project_tf32x1(self, X, Y, Z=None, accumulate=False):
         self._count("project_x1")
+        self._check_y(Y)
         out = self._tf32_trunc(X).double().t() @ self._tf32_trunc(Y).double()
         if Z is None:
             return out
@@ -99,6 +112,7 @@ class FakeOps:
 
     def project_tf32x2(self, X, Y, Z=None, accumulate=False):
         self._count("project_x2")
+        self._check_y(Y)
         out = X.double().t() @ self._tf32_trunc(Y).double()
         if Z is None:
             return out
@@ -110,6 +124,7 @@ class FakeOps:
 
     def project_tf32x3(self, Xhi, Xlo, Yhi, Ylo, Z=None, accumulate=False):
         self._count("project_tc")
+        self._check_y(Yhi, Ylo)
         X = Xhi.double() + (Xlo.double() if Xlo is not None else 0.0)
         Yv = Yhi.double() + (Ylo.double() if Ylo is not None else 0.0)
         out = X.t() @ Yv

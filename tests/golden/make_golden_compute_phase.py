@@ -32,19 +32,27 @@ FILE_VARIABLES = ["temperature", "u_component_of_wind", "v_component_of_wind"]
 FILE_LEVELS = [1000, 925, 850]
 LAT = [10.0, 7.5, 5.0]
 LON = [0.0, 2.5, 5.0, 7.5]
-N_TIMES = 13                       # hourly, 2019-01-01T00 ... T12
 SLICE_ATTRS = {"source_path": BASE["source_path"], "variables": FILE_VARIABLES, "levels": FILE_LEVELS, "note": "mock slice"}
+NP_RANDOM_SEED = 123               # np.random.seed(...) right before main: the randomized route draws from the global RNG (Q6)
 
 
-def make_slice(dtype):
-    """Deterministic mock slice, dims (time, level, latitude, longitude) like the file era5_download writes."""
+def make_slice(dtype, n_times, kind):
+    """Deterministic mock slice, dims (time, level, latitude, longitude) like the file era5_download writes; hourly from
+    2019-01-01T00.  kind "noise": independent normal values (+ 250 on the first variable); kind "modes": ten space x time
+    modes with amplitudes 10 * 0.6^i plus 1e-3 noise, i.e. a decaying spectrum (a well-posed randomized SVD)."""
     rng = np.random.RandomState(11)
-    shape = (N_TIMES, len(FILE_LEVELS), len(LAT), len(LON))
+    shape = (n_times, len(FILE_LEVELS), len(LAT), len(LON))
     dv = {}
     for i, v in enumerate(FILE_VARIABLES):
-        a = rng.standard_normal(shape) * (3.0 + i) + (250.0 if i == 0 else 0.0)
+        if kind == "noise":
+            a = rng.standard_normal(shape) * (3.0 + i) + (250.0 if i == 0 else 0.0)
+        else:
+            sp = rng.standard_normal((10,) + shape[1:])
+            tm = rng.standard_normal((10, n_times))
+            a = np.einsum("i,it,ilao->tlao", 10.0 * 0.6 ** np.arange(10), tm, sp) + 1e-3 * rng.standard_normal(shape)
+            a = a + (250.0 if i == 0 else 0.0)
         dv[v] = np.asarray(a, dtype=dtype)
-    times = np.datetime64("2019-01-01T00", "ns") + np.arange(N_TIMES) * np.timedelta64(1, "h")
+    times = np.datetime64("2019-01-01T00", "ns") + np.arange(n_times) * np.timedelta64(1, "h")
     return dv, times
 
 
@@ -54,8 +62,8 @@ def functions(path, names=None):
             if isinstance(n, ast.FunctionDef) and (names is None or n.name in names)}
 
 
-def run(config_delta, dtype):
-    dv, times = make_slice(dtype)
+def run(config_delta, dtype, n_times, kind):
+    dv, times = make_slice(dtype, n_times, kind)
     dims = ("time", "level", "latitude", "longitude")
     ds = xr.Dataset({k: xr.DataArray(v, dims) for k, v in dv.items()},
                     {"time": times, "level": np.asarray(FILE_LEVELS), "latitude": np.asarray(LAT), "longitude": np.asarray(LON)},
@@ -72,6 +80,7 @@ def run(config_delta, dtype):
         for name, code in functions(path, names).items():
             exec(compile(code, path, "exec"), ns)
     cfg = dict(BASE, **config_delta)
+    np.random.seed(NP_RANDOM_SEED)
     res, added, retrieved = ns["main"](cfg, write_to_netcdf=False, use_dvc=False)
     assert not added and not retrieved
     return cfg, res, log
@@ -112,36 +121,43 @@ def record(res):
 CASES = {
     "centre, d=2, two variables, levels in request order, 2h resampling": (
         {"variables": "temperature,u_component_of_wind", "levels": "850,1000", "delta_time": "2h", "svd_type": "standard",
-         "n_components": 3, "delay_embedding": 2, "mean_center": True, "scale": False, "save_data_matrix": True}, np.float64),
+         "n_components": 3, "delay_embedding": 2, "mean_center": True, "scale": False, "save_data_matrix": True}, np.float64, 13, "noise"),
     "centre + scale, d=3, one variable, all file levels": (
         {"variables": "v_component_of_wind", "levels": "1000,925,850", "delta_time": "1h", "svd_type": "standard",
-         "n_components": 4, "delay_embedding": 3, "mean_center": True, "scale": True, "save_data_matrix": True}, np.float64),
+         "n_components": 4, "delay_embedding": 3, "mean_center": True, "scale": True, "save_data_matrix": True}, np.float64, 13, "noise"),
     "centre + scale, d=1 (Q3: no X_mean / X_std)": (
         {"variables": "u_component_of_wind,temperature", "levels": "925", "delta_time": "1h", "svd_type": "standard",
-         "n_components": 2, "delay_embedding": 1, "mean_center": True, "scale": True, "save_data_matrix": True}, np.float64),
+         "n_components": 2, "delay_embedding": 1, "mean_center": True, "scale": True, "save_data_matrix": True}, np.float64, 13, "noise"),
     "scale without centring (Q4), d=2, no data matrix": (
         {"variables": "temperature", "levels": "1000,850", "delta_time": "3h", "svd_type": "standard",
-         "n_components": 2, "delay_embedding": 2, "mean_center": False, "scale": True, "save_data_matrix": False}, np.float64),
+         "n_components": 2, "delay_embedding": 2, "mean_center": False, "scale": True, "save_data_matrix": False}, np.float64, 13, "noise"),
     "no centring, d=1, data matrix kept (slice attributes reach X)": (
         {"variables": "temperature,v_component_of_wind", "levels": "850", "delta_time": "1h", "svd_type": "standard",
-         "n_components": 3, "delay_embedding": 1, "mean_center": False, "scale": False, "save_data_matrix": True}, np.float64),
+         "n_components": 3, "delay_embedding": 1, "mean_center": False, "scale": False, "save_data_matrix": True}, np.float64, 13, "noise"),
     "float32 slice, centre, d=2": (
         {"variables": "temperature,u_component_of_wind,v_component_of_wind", "levels": "1000", "delta_time": "1h",
          "svd_type": "standard", "n_components": 3, "delay_embedding": 2, "mean_center": True, "scale": False,
-         "save_data_matrix": True}, np.float32),
+         "save_data_matrix": True}, np.float32, 13, "noise"),
+    "randomized, float64, centre, d=2, two variables, 49 hourly snapshots": (
+        {"variables": "u_component_of_wind,temperature", "levels": "1000,850", "delta_time": "1h", "svd_type": "randomized",
+         "n_components": 5, "delay_embedding": 2, "mean_center": True, "scale": False, "save_data_matrix": True}, np.float64, 49, "modes"),
+    "randomized, float32, centre, d=1, three variables, 2h resampling of 97 hourly snapshots": (
+        {"variables": "temperature,u_component_of_wind,v_component_of_wind", "levels": "925,1000,850", "delta_time": "2h",
+         "svd_type": "randomized", "n_components": 4, "delay_embedding": 1, "mean_center": True, "scale": False,
+         "save_data_matrix": False}, np.float32, 97, "modes"),
 }
 
 
 def main():
     assert datetime.fromtimestamp(0) == datetime(1970, 1, 1), "run with TZ=UTC"
     out = {"_generated_by": "tests/golden/make_golden_compute_phase.py from " + REF_SVD + " and " + REF_SLICE,
-           "slice": {"variables": FILE_VARIABLES, "levels": FILE_LEVELS, "latitude": LAT, "longitude": LON, "n_times": N_TIMES,
-                     "seed": 11, "attrs": SLICE_ATTRS},
+           "slice": {"variables": FILE_VARIABLES, "levels": FILE_LEVELS, "latitude": LAT, "longitude": LON, "seed": 11, "attrs": SLICE_ATTRS},
+           "np_random_seed": NP_RANDOM_SEED,
            "cases": {}}
-    for name, (delta, dtype) in CASES.items():
-        cfg, res, log = run(delta, dtype)
+    for name, (delta, dtype, n_times, kind) in CASES.items():
+        cfg, res, log = run(delta, dtype, n_times, kind)
         rec = record(res)
-        out["cases"][name] = {"config": cfg, "slice_dtype": np.dtype(dtype).name, "result": rec,
+        out["cases"][name] = {"config": cfg, "slice_dtype": np.dtype(dtype).name, "n_times": n_times, "kind": kind, "result": rec,
                               "log": [[lv, m.replace("/ROOT", "<ROOT>")] for lv, m in log]}
         print(f"{name}\n    vars {rec['var_order']}  coords {rec['coord_order']}\n    X attrs {list(rec['data_vars'].get('X', {}).get('attrs', {}))}"
               f"  U {res.data_vars['U'].shape} {res.data_vars['U'].dtype}")

@@ -35,23 +35,42 @@ def golden_array(rec):
     return np.asarray(rec["values"], dtype=rec["dtype"])
 
 
-def make_slice(dtype):
+def make_slice(case):
     """The generator's mock slice (tests/golden/make_golden_compute_phase.py::make_slice), same seed."""
     s = GOLD["slice"]
+    dtype, n_times, kind = case["slice_dtype"], case["n_times"], case["kind"]
     rng = np.random.RandomState(s["seed"])
-    shape = (s["n_times"], len(s["levels"]), len(s["latitude"]), len(s["longitude"]))
+    shape = (n_times, len(s["levels"]), len(s["latitude"]), len(s["longitude"]))
     dv = {}
     for i, v in enumerate(s["variables"]):
-        a = rng.standard_normal(shape) * (3.0 + i) + (250.0 if i == 0 else 0.0)
+        if kind == "noise":
+            a = rng.standard_normal(shape) * (3.0 + i) + (250.0 if i == 0 else 0.0)
+        else:
+            sp = rng.standard_normal((10,) + shape[1:])
+            tm = rng.standard_normal((10, n_times))
+            a = np.einsum("i,it,ilao->tlao", 10.0 * 0.6 ** np.arange(10), tm, sp) + 1e-3 * rng.standard_normal(shape)
+            a = a + (250.0 if i == 0 else 0.0)
         dv[v] = np.asarray(a, dtype=dtype)
-    times = np.datetime64("2019-01-01T00", "ns") + np.arange(s["n_times"]) * np.timedelta64(1, "h")
+    times = np.datetime64("2019-01-01T00", "ns") + np.arange(n_times) * np.timedelta64(1, "h")
     return dv, times
+
+
+def reference_svd(X, cfg):
+    """The reference's own two calls (era5_svd.py:251, :258; the randomized one draws from NumPy's global RNG, Q6)."""
+    k = cfg["n_components"]
+    if cfg["svd_type"] == "standard":
+        U, s, Vt = np.linalg.svd(X, full_matrices=False)
+        return U[:, :k], s[:k], Vt[:k]
+    from sklearn.utils.extmath import randomized_svd
+
+    np.random.seed(GOLD["np_random_seed"])
+    return randomized_svd(X, n_components=k)
 
 
 def selected_arrays(case):
     """Variable / level / time selection of the case in plain NumPy (request order, nearest resampling)."""
     cfg, s = case["config"], GOLD["slice"]
-    dv, times = make_slice(case["slice_dtype"])
+    dv, times = make_slice(case)
     variables = cfg["variables"].split(",")
     levels = [int(x) for x in cfg["levels"].split(",")]
     li = [s["levels"].index(lv) for lv in levels]
@@ -75,17 +94,16 @@ def test_oracle_build_reproduces_the_references_own_chain_bit_for_bit(name):
             assert got is not None and got.dtype == want.dtype and np.array_equal(got, want), key
         else:
             assert got is None, key                      # Q3 (d == 1) / Q4 (scale without centring)
-    # the reference's U, s, V are its own LAPACK call on that X
-    U, sv, Vt = np.linalg.svd(X, full_matrices=False)
-    k = cfg["n_components"]
-    assert np.array_equal(sv[:k], golden_array(res["data_vars"]["s"]))
-    assert np.array_equal(U[:, :k], golden_array(res["data_vars"]["U"]))
-    assert np.array_equal(Vt[:k], golden_array(res["data_vars"]["V"]))
+    # the reference's U, s, V are its own library call on that X
+    U, sv, Vt = reference_svd(X, cfg)
+    assert np.array_equal(sv, golden_array(res["data_vars"]["s"]))
+    assert np.array_equal(U, golden_array(res["data_vars"]["U"]))
+    assert np.array_equal(Vt, golden_array(res["data_vars"]["V"]))
 
 
 def product_slice(case):
     s = GOLD["slice"]
-    dv, times = make_slice(case["slice_dtype"])
+    dv, times = make_slice(case)
     dims = ("time", "level", "latitude", "longitude")
     return Dataset({k: DataArray(v, dims) for k, v in dv.items()},
                    {"time": times, "level": np.asarray(s["levels"]), "latitude": np.asarray(s["latitude"]),
@@ -137,10 +155,9 @@ def fake_device_arrays(ds, parsed_config, ops, comm=None, rank=0, world=1):
     stats = [standardize_np(a, scale=sc) for a in arrays] if mc else None
     mean = flatten_np([st[1] for st in stats]) if mc else None
     std = flatten_np([st[2] for st in stats]) if sc else None
-    U, s, Vt = np.linalg.svd(delay_embed_np(X0, d), full_matrices=False)
-    k = parsed_config["n_components"]
+    U, s, Vt = reference_svd(delay_embed_np(X0, d), parsed_config)
     S = X0.shape[0] // len(variables)
-    return {"U": U[:, :k], "s": s[:k], "V": Vt[:k], "X": X0 if parsed_config["save_data_matrix"] else None, "mean": mean,
+    return {"U": U, "s": s, "V": Vt, "X": X0 if parsed_config["save_data_matrix"] else None, "mean": mean,
             "std": std, "rows": (0, X0.shape[0]), "m0": X0.shape[0], "S": S}
 
 
@@ -164,7 +181,8 @@ def test_compute_phase_packaging_matches_the_references_own_result(name, monkeyp
     out = stage._compute(product_slice(case), parsed)
     # progress lines of the phase, in order: slicing, resampling, standardisation (the fused device build replaces the
     # call but keeps its lines); the last two of the reference's are the SVD pair, emitted by the device leg
-    assert case["log"][-2:] == [["info", "Performing standard SVD..."], ["info", "Standard SVD complete."]]
+    kind = case["config"]["svd_type"]
+    assert case["log"][-2:] == [["info", f"Performing {kind} SVD..."], ["info", f"{kind.capitalize()} SVD complete."]]
     assert log == case["log"][:-2]
     # variables: names in the reference's order, dims, dtype, values
     assert list(out.data_vars) == res["var_order"]
@@ -227,3 +245,57 @@ def test_result_with_the_references_variable_attributes_survives_the_file_round_
         assert back[k].attrs["original_variables"] == ",".join(out[k].attrs["original_variables"])
         assert back[k].attrs["space_coords"] == "level,latitude,longitude"
     assert int(back["X"].attrs["delay_embedding"]) == case["config"]["delay_embedding"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_main_on_the_device_reproduces_the_references_own_main(name, tmp_path, monkeypatch):
+    """The drop-in ``main`` (slice file -> device build -> SVD -> Dataset) against the result of the reference's OWN main on
+    the same slice and configuration: X / X_mean / X_std, singular values, singular vectors up to sign (LAPACK's signs
+    are not part of the contract: no svd_flip on the standard route, era5_svd.py:251), coordinates, attributes.
+    Tolerances: float64 slices sigma 1e-9 relative, vectors 1e-6 rad; the float32 slice 1e-4 / 1e-3."""
+    from dmd_era5_b200.dataset import write_netcdf
+    from dmd_era5_b200.era5_svd import main
+    from oracle.compare import sigma_rel_err, vector_angles
+
+    monkeypatch.setenv("TZ", "UTC")
+    _time.tzset()
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    case = GOLD["cases"][name]
+    res, cfg = case["result"], dict(case["config"])
+    parsed = config_parser(dict(cfg), section="era5-svd")
+    os.makedirs(os.path.dirname(parsed["era5_slice_path"]), exist_ok=True)
+    write_netcdf(product_slice(case), parsed["era5_slice_path"])
+    np.random.seed(GOLD["np_random_seed"])          # the randomized route draws Omega from NumPy's global RNG, like the reference
+    out, added, retrieved = main(cfg, write_to_netcdf=False)
+    assert not added and not retrieved
+    f32 = case["slice_dtype"] == "float32"
+    assert list(out.data_vars) == res["var_order"]
+    for k in ("X", "X_mean", "X_std"):
+        if k in res["data_vars"]:
+            want, got = golden_array(res["data_vars"][k]), np.asarray(out[k].values)
+            assert got.dtype == want.dtype and list(out[k].dims) == res["data_vars"][k]["dims"], k
+            assert np.max(np.abs(got.astype(np.float64) - want)) <= (1e-4 if f32 else 1e-10), k
+    U0, s0, V0 = (golden_array(res["data_vars"][k]).astype(np.float64) for k in ("U", "s", "V"))
+    U, s, V = (np.asarray(out[k].values) for k in ("U", "s", "V"))
+    assert U.dtype == golden_array(res["data_vars"]["U"]).dtype and U.shape == U0.shape and V.shape == V0.shape
+    assert sigma_rel_err(s.astype(np.float64), s0) < (1e-4 if f32 else 1e-9)
+    tol = 1e-3 if f32 else 1e-6
+    assert vector_angles(U.astype(np.float64), U0).max() < tol and vector_angles(V.astype(np.float64).T, V0.T).max() < tol
+    sign = np.sign(np.sum(U.astype(np.float64) * U0, axis=0))             # the same sign on U_j and V_j
+    assert np.allclose(V.astype(np.float64) * sign[:, None], V0, atol=10 * tol)
+    if cfg["svd_type"] == "randomized":
+        assert np.all(sign == 1.0)                                       # svd_flip (extmath.py:964-972): the SAME signs
+    for k, rec in res["coords"].items():
+        want = golden_array(rec)
+        dims, got = out.coords[k]
+        got = np.asarray(got)
+        assert list(dims) == rec["dims"] and got.dtype.kind == want.dtype.kind, k
+        assert np.array_equal(got.astype(want.dtype), want), k
+    if "X" in res["data_vars"]:
+        for k in ("original_variables", "space_coords", "delay_embedding"):
+            assert out["X"].attrs[k] == res["data_vars"]["X"]["attrs"][k], k
+        assert list(out["X"].attrs) == list(res["data_vars"]["X"]["attrs"])
+    assert list(out.attrs) == list(res["attrs"])
+    for k in ("n_components", "variables", "levels", "mean_center", "scale", "delay_embedding", "svd_type", "save_data_matrix"):
+        assert out.attrs[k] == res["attrs"][k], k

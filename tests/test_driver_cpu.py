@@ -71,6 +71,42 @@ def test_standard_driver_matches_oracle():
     assert sigma_rel_err(s, s0) < 1e-9 and vector_angles(U.numpy(), U0).max() < 1e-6
 
 
+@pytest.mark.parametrize("precision", ["native", "tf32x3", "tf32mix"])
+@pytest.mark.parametrize("d", [1, 2, 3])
+def test_gram_of_the_delay_embedded_matrix_from_the_base_gram(precision, d):
+    """standard.gram_device: G = sum_j X_j^T X_j over the overlapping delay windows is the sum of d shifted diagonal
+    blocks of ONE Gram matrix of the base matrix - same values, one pass set over X instead of d, and no tensor-core
+    operand starts at an unaligned column (float32 + standard + delay > 1 failed in the kernel's alignment check on the
+    device before; the stand-in enforces the same rule)."""
+    from dmd_era5_b200.rsvd import PRECISIONS
+    from dmd_era5_b200.standard import gram_device
+
+    dtype = np.float64 if precision == "native" else np.float32
+    X = lowrank_field_np(700, 301, r=40, rho=0.9, seed=8).astype(dtype)        # 301 columns: two 256-column blocks
+    n = X.shape[1] - d + 1
+    ops = FakeOps()
+    G = gram_device(ops, torch.from_numpy(X), n, d, PRECISIONS[precision]).numpy()
+    Xe = X.astype(np.float64)
+    if precision == "tf32mix":                                                  # what the single-product kernel computes
+        Xe = FakeOps._tf32_trunc(torch.from_numpy(X)).double().numpy()
+    want = sum(Xe[:, j : j + n].T @ Xe[:, j : j + n] for j in range(d))
+    assert G.shape == (n, n) and np.allclose(G, G.T, rtol=0, atol=0)
+    assert np.max(np.abs(G - want)) <= 1e-12 * np.abs(want).max()
+    if precision != "native":
+        # column blocks of the BASE matrix (256 / 112 columns), whatever d is
+        assert (ops.calls["project_x1"] == 2) if precision == "tf32mix" else (ops.calls["project_tc"] == 3)
+
+
+def test_standard_driver_float32_with_delay():
+    """float32 data, standard SVD, delay 2 (the configuration that failed on the device): Gram route + refinement."""
+    from dmd_era5_b200.rsvd import PREC_TF32MIX
+
+    X = lowrank_field_np(1500, 40, r=40, rho=0.8, seed=6).astype(np.float32)
+    U0, s0, V0 = standard_svd_ref(delay_embed_np(X.astype(np.float64), 2), 6)
+    U, s, Vt = standard_svd_device(FakeOps(), torch.from_numpy(X), 6, delay=2, precision=PREC_TF32MIX)
+    assert sigma_rel_err(s, s0) < 1e-6 and vector_angles(U.double().numpy(), U0).max() < 1e-4
+
+
 def test_sketch_wider_than_time_axis():
     X = lowrank_field_np(500, 12, r=12, rho=0.7, seed=1)
     U0, s0, V0 = randomized_svd_ref(X, 8, 2)           # l = 18 > n = 12

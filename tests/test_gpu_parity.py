@@ -116,6 +116,36 @@ def test_device_build_plus_svd_vs_oracle(ops, svd_type, mean_center, scale, d):
     assert abs(recon_rel_err(Xref, U.cpu().numpy(), s.cpu().numpy(), V.cpu().numpy()) - ref) <= 0.01 * ref
 
 
+@pytest.mark.parametrize("svd_type", ["standard", "randomized"])
+@pytest.mark.parametrize("mean_center,scale,d", [(True, False, 2), (True, True, 1), (False, False, 3), (True, True, 3)])
+def test_device_build_plus_svd_float32_slices(ops, svd_type, mean_center, scale, d):
+    """The same chain on FLOAT32 slices (the real ERA5 dtype) for every route x delay combination, default precision
+    ("auto": tensor-core passes; the standard route = Gram of the base matrix + refinement).  float32 + standard +
+    delay > 1 once failed in the projection kernel's alignment check (a delay window as its Y operand) - found by
+    tests/test_compute_phase_golden.py, fixed in standard.gram_device.  Oracle: float64 arithmetic on the same float32 data."""
+    ds = mock_era5_np(25, ["temperature", "u_component_of_wind"], [1000, 500], seed=3)
+    arrs = [a.astype(np.float32) for a in ds["vars"].values()]
+    Xref, _, _ = build_matrix_np([a.astype(np.float64) for a in arrs], mean_center, scale, d)
+    blocks = [torch.from_numpy(a.reshape(a.shape[0], -1).copy()).cuda() for a in arrs]
+    built = build_matrix_device(ops, blocks, mean_center=mean_center, scale=scale)
+    assert built.X.dtype == torch.float32
+    Xdev = built.X.cpu().numpy().astype(np.float64)
+    assert np.max(np.abs(delay_embed_np(Xdev, d) - Xref)) < (1e-4 if mean_center else 1e-30)   # float32 storage of x - mean
+    k = 8
+    U, s, V = svd_device(ops, built.X, svd_type=svd_type, n_components=k, delay=d, seed=2)
+    U, s, V = U.cpu().numpy().astype(np.float64), s.cpu().numpy().astype(np.float64), V.cpu().numpy().astype(np.float64)
+    Xd = delay_embed_np(Xdev, d)                                       # the matrix the device factorised, exactly
+    U0, s0, V0 = standard_svd_ref(Xd, k) if svd_type == "standard" else randomized_svd_ref(Xd, k, 2)
+    assert U.shape == (Xref.shape[0], k) and V.shape == (k, Xref.shape[1])
+    err = sigma_rel_err(s, s0)
+    ref = recon_rel_err(Xd, U0, s0, V0)
+    rec = recon_rel_err(Xd, U, s, V)
+    print(f"float32 {svd_type} mc={mean_center} sc={scale} d={d}: sigma {err:.2e} recon {rec:.6e} (reference {ref:.6e})")
+    assert err < SIGMA_TOL_FP32
+    assert abs(rec - ref) <= 0.01 * ref
+    assert np.max(np.abs(U.T @ U - np.eye(k))) < 1e-4
+
+
 def test_invariants_at_bench_shape_reduced_rows(ops):
     """Size-independent properties on a float32 device-generated field (no CPU oracle):
     orthonormal U and V, X^T U = V^T S, descending sigma."""
