@@ -6,7 +6,9 @@ from dmd_era5_b200.device_ops import CudaOps
 from dmd_era5_b200._cabi import PREC_NATIVE
 ops = CudaOps("cuda:0")
 m, n, l = 1038240, 744, 110
-for dt in (torch.float64, torch.float32):
+only64 = "--f64" in sys.argv
+print("DMMA tiles per CTA:", 1 if os.environ.get("ERA5SVD_DMMA_SINGLE_BUFFER") == "1" else 2)
+for dt in ((torch.float64,) if only64 else (torch.float64, torch.float32)):
     X = torch.randn((m, n), device="cuda", dtype=dt)
     Om = torch.randn((n, l), device="cuda", dtype=dt)
     Y = torch.empty((m, l), device="cuda", dtype=dt)
