@@ -12,6 +12,8 @@
 //   project: As[k][time] <- X[k=row][time] (straight copy)           Bs[k][col] <- Y[k=row][col]
 // project splits the row (k) range over blockIdx.z; partial tiles go to the workspace in the
 // accumulate type and reduce_partials_kernel sums them in float64 in a fixed order.
+#include <stdlib.h>
+
 #include "comm.cuh"
 #include "common.cuh"
 
@@ -206,7 +208,11 @@ project_kernel(const T* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const
 // ---------------------------------------------------------------------------------------------
 // FP64 on the tensor cores (DMMA): same staging as sketch_kernel / project_kernel<double>, product by dmma_tile.
 // ---------------------------------------------------------------------------------------------
-template <int TN>
+// COAL (the staging of the X tile, third session of round 2): false = every thread loads 8 consecutive k of ITS row
+// (64 bytes per lane, 32 sectors per warp-level LDG.64); true = lane-contiguous - 16 lanes read the 128 contiguous bytes
+// of one row's k-tile, two rows per warp instruction (8 sectors) - and the transposing shared-memory store takes the
+// bank conflicts instead (4-way on a 64-bit store).
+template <int TN, bool COAL>
 __global__ void __launch_bounds__(NTHREADS)
 sketch_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const double* __restrict__ Om,
                    int64_t l, int64_t ldo, double* __restrict__ Y, int64_t ldy) {
@@ -216,7 +222,8 @@ sketch_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t l
   const int tx = t % 16;
   const int64_t row0 = (int64_t)blockIdx.x * BM;
   const int64_t col0 = (int64_t)blockIdx.y * BN;
-  const int a_row = t % BM, a_k0 = (t / BM) * 8;
+  const int a_row = t % BM, a_k0 = (t / BM) * 8;      // strided staging: row a_row, k in [a_k0, a_k0 + 8)
+  const int c_k = t % 16, c_r0 = t / 16;              // coalesced staging: k = c_k, rows c_r0 + 16 i
   const int64_t g_row = row0 + a_row;
   const double* a_ptr = X + (g_row < m ? g_row : 0) * ldx;
   const int b_k = t / 16;
@@ -227,10 +234,19 @@ sketch_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t l
 #pragma unroll
     for (int j = 0; j < 2 * TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   auto load = [&](int64_t k0) {
+    if constexpr (COAL) {
+      const int64_t k = k0 + c_k;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int64_t k = k0 + a_k0 + i;
-      a_reg[i] = (g_row < m && k < n) ? a_ptr[k] : 0.0;
+      for (int i = 0; i < 8; ++i) {
+        const int64_t r = row0 + c_r0 + 16 * i;
+        a_reg[i] = (r < m && k < n) ? X[r * ldx + k] : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int64_t k = k0 + a_k0 + i;
+        a_reg[i] = (g_row < m && k < n) ? a_ptr[k] : 0.0;
+      }
     }
     int64_t kb = k0 + b_k;
 #pragma unroll
@@ -241,8 +257,13 @@ sketch_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t l
   };
   load(0);
   for (int64_t k0 = 0; k0 < n; k0 += BK) {
+    if constexpr (COAL) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s.As[a_k0 + i][a_row] = a_reg[i];
+      for (int i = 0; i < 8; ++i) s.As[c_k][c_r0 + 16 * i] = a_reg[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s.As[a_k0 + i][a_row] = a_reg[i];
+    }
 #pragma unroll
     for (int j = 0; j < TN; ++j) s.Bs[b_k][tx + 16 * j] = b_reg[j];
     __syncthreads();
@@ -265,7 +286,7 @@ sketch_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t l
   }
 }
 
-template <int TN>
+template <int TN, bool COAL>
 __global__ void __launch_bounds__(NTHREADS)
 project_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t ldx, const double* __restrict__ Y,
                     int64_t l, int64_t ldy, double* __restrict__ part, int64_t rows_per_split) {
@@ -277,7 +298,8 @@ project_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t 
   const int64_t col0 = (int64_t)blockIdx.y * BN;   // sketch-column tile
   const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
   const int64_t r_end = min(m, r_begin + rows_per_split);
-  const int a_k = t / 16, a_i0 = (t % 16) * 8;
+  const int a_k = t / 16, a_i0 = (t % 16) * 8;        // strided staging: row a_k, time columns [a_i0, a_i0 + 8)
+  const int c_c = t % BM, c_k0 = t / BM;              // coalesced staging: time column c_c, rows c_k0 + 2 i
   double a_reg[8], b_reg[TN];
   double acc[2][2 * TN][2];
 #pragma unroll
@@ -286,11 +308,20 @@ project_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t 
     for (int j = 0; j < 2 * TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   auto load = [&](int64_t r0) {
     int64_t r = r0 + a_k;
-    const double* xr = X + (r < r_end ? r : r_begin) * ldx;
+    if constexpr (COAL) {
+      const int64_t tt = t0 + c_c;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int64_t tt = t0 + a_i0 + i;
-      a_reg[i] = (r < r_end && tt < n) ? xr[tt] : 0.0;
+      for (int i = 0; i < 8; ++i) {
+        const int64_t rr = r0 + c_k0 + 2 * i;
+        a_reg[i] = (rr < r_end && tt < n) ? X[rr * ldx + tt] : 0.0;
+      }
+    } else {
+      const double* xr = X + (r < r_end ? r : r_begin) * ldx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int64_t tt = t0 + a_i0 + i;
+        a_reg[i] = (r < r_end && tt < n) ? xr[tt] : 0.0;
+      }
     }
     const double* yr = Y + (r < r_end ? r : r_begin) * ldy;
 #pragma unroll
@@ -302,8 +333,13 @@ project_dmma_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t 
   if (r_begin < r_end) {
     load(r_begin);
     for (int64_t r0 = r_begin; r0 < r_end; r0 += BK) {
+      if constexpr (COAL) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s.As[a_k][a_i0 + i] = a_reg[i];
+        for (int i = 0; i < 8; ++i) s.As[c_k0 + 2 * i][c_c] = a_reg[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s.As[a_k][a_i0 + i] = a_reg[i];
+      }
 #pragma unroll
       for (int j = 0; j < TN; ++j) s.Bs[a_k][tx + 16 * j] = b_reg[j];
       __syncthreads();
@@ -473,6 +509,13 @@ static ProjectPlan project_plan(int dtype, int64_t m, int64_t n, int64_t l) {
   return p;
 }
 
+// Staging of the X tile in the DMMA kernels: lane-contiguous loads unless ERA5SVD_DMMA_STAGING=strided asks for the first
+// version (kept for A/B timing).
+static bool dmma_coalesced() {
+  static const bool on = [] { const char* e = getenv("ERA5SVD_DMMA_STAGING"); return !(e && e[0] == 's'); }();
+  return on;
+}
+
 // Column tile width: 112 (TN = 7) or 128 (TN = 8), whichever pads l = k + 10 less.
 static bool use_tn7(int64_t l) { return ceil_div(l, 112) * 112 <= ceil_div(l, 128) * 128; }
 
@@ -480,13 +523,11 @@ template <typename T>
 int sketch_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void* Om, int64_t l,
                   int64_t ldo, void* Y, int64_t ldy, cudaStream_t st) {
   if constexpr (sizeof(T) == 8) {      // float64: FP64 tensor cores (mma.sync m8n8k4)
-    if (use_tn7(l)) {
-      dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, 112));
-      sketch_dmma_kernel<7><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Om, l, ldo, (double*)Y, ldy);
-    } else {
-      dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, 128));
-      sketch_dmma_kernel<8><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Om, l, ldo, (double*)Y, ldy);
-    }
+    const bool tn7 = use_tn7(l);
+    dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(l, tn7 ? 112 : 128));
+    auto kern = tn7 ? (dmma_coalesced() ? sketch_dmma_kernel<7, true> : sketch_dmma_kernel<7, false>)
+                    : (dmma_coalesced() ? sketch_dmma_kernel<8, true> : sketch_dmma_kernel<8, false>);
+    kern<<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Om, l, ldo, (double*)Y, ldy);
     return check_launch("sketch_dmma_kernel");
   }
   if (use_tn7(l)) {
@@ -504,13 +545,11 @@ int project_native(const void* X, int64_t m, int64_t n, int64_t ldx, const void*
                    int64_t ldy, double* Z, int64_t ldz, int accumulate, void* ws,
                    const ProjectPlan& plan, cudaStream_t st) {
   if constexpr (sizeof(T) == 8) {      // float64: FP64 tensor cores (mma.sync m8n8k4)
-    if (use_tn7(l)) {
-      dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 112), (unsigned)plan.splits);
-      project_dmma_kernel<7><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Y, l, ldy, (double*)ws, plan.rows_per_split);
-    } else {
-      dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, 128), (unsigned)plan.splits);
-      project_dmma_kernel<8><<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Y, l, ldy, (double*)ws, plan.rows_per_split);
-    }
+    const bool tn7 = use_tn7(l);
+    dim3 grid((unsigned)ceil_div(n, BM), (unsigned)ceil_div(l, tn7 ? 112 : 128), (unsigned)plan.splits);
+    auto kern = tn7 ? (dmma_coalesced() ? project_dmma_kernel<7, true> : project_dmma_kernel<7, false>)
+                    : (dmma_coalesced() ? project_dmma_kernel<8, true> : project_dmma_kernel<8, false>);
+    kern<<<grid, NTHREADS, 0, st>>>((const double*)X, m, n, ldx, (const double*)Y, l, ldy, (double*)ws, plan.rows_per_split);
     int rc = check_launch("project_dmma_kernel");
     if (rc) return rc;
     return launch_reduce_partials<double>((const double*)ws, plan.splits, n, l, l, Z, ldz, accumulate, st);

@@ -7,7 +7,7 @@ from dmd_era5_b200._cabi import PREC_NATIVE
 ops = CudaOps("cuda:0")
 m, n, l = 1038240, 744, 110
 only64 = "--f64" in sys.argv
-print("DMMA tiles per CTA:", 1 if os.environ.get("ERA5SVD_DMMA_SINGLE_BUFFER") == "1" else 2)
+print("DMMA staging of the X tile:", "strided (first version)" if os.environ.get("ERA5SVD_DMMA_STAGING", "").startswith("s") else "lane-contiguous")
 for dt in ((torch.float64,) if only64 else (torch.float64, torch.float32)):
     X = torch.randn((m, n), device="cuda", dtype=dt)
     Om = torch.randn((n, l), device="cuda", dtype=dt)
