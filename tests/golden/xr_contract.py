@@ -51,6 +51,8 @@ class Coords(dict):
 class DataArray:
     def __init__(self, data, dims=None, coords=None, attrs=None, name=None):
         self._data = data.values if isinstance(data, DataArray) else np.asarray(data)
+        if self._data.dtype.kind == "M":                 # xarray holds times as datetime64[ns] (the reference relies on it:
+            self._data = self._data.astype("datetime64[ns]")     # ``time.values[0].astype(int) * 1e-9``, slice_tools.py:121)
         if dims is None:
             raise TypeError("the stand-in needs explicit dims")
         self.dims = _as_dims(dims)
@@ -76,6 +78,83 @@ class DataArray:
         """positional indexing of a 1-D coordinate (``X.coords["time"][d - 1:]``, slice_tools.py:260)"""
         assert len(self.dims) == 1 and isinstance(key, slice)
         return DataArray(self._data[key], self.dims, None, self.attrs)
+
+    # -- what the reference's own TESTS additionally use (run_reference_tests_on_standin.py) --------------------
+    ndim = property(lambda self: self._data.ndim)
+    sizes = property(lambda self: dict(zip(self.dims, self._data.shape)))
+
+    def __len__(self):
+        return self._data.shape[0]
+
+    def __getattr__(self, name):
+        coords = self.__dict__.get("coords", {})
+        if name in coords:
+            c = coords[name]
+            return DataArray(c.values, c.dims, {k: v for k, v in coords.items() if set(v.dims) <= set(c.dims)})
+        raise AttributeError(name)
+
+    def __eq__(self, other):
+        return DataArray(self._data == (other.values if isinstance(other, DataArray) else other), self.dims)
+
+    __hash__ = None
+
+    def all(self):
+        return bool(np.all(self._data))
+
+    def astype(self, dtype):
+        return DataArray(self._data.astype(dtype), self.dims, None, self.attrs)
+
+    def _reduce(self, fn, dim=None):
+        if dim is None:
+            return DataArray(fn(self._data), ())
+        ax = self.dims.index(dim)
+        return DataArray(fn(self._data, axis=ax), tuple(d for d in self.dims if d != dim),
+                         {k: c for k, c in self.coords.items() if dim not in c.dims})
+
+    def mean(self, dim=None):
+        return self._reduce(np.nanmean if self._data.dtype.kind == "f" else np.mean, dim)
+
+    def std(self, dim=None):
+        return self._reduce(np.nanstd if self._data.dtype.kind == "f" else np.std, dim)
+
+    def min(self, dim=None):
+        return self._reduce(np.min, dim)
+
+    def max(self, dim=None):
+        return self._reduce(np.max, dim)
+
+    def diff(self, dim):
+        return DataArray(np.diff(self._data, axis=self.dims.index(dim)), self.dims)
+
+    def to_dataset(self, name):
+        return Dataset({name: self})
+
+    def sel(self, **indexers):
+        """Label selection: a tuple is ONE label (xarray keeps tuples whole); a label that occurs several times keeps the
+        dimension (pandas ``get_loc`` on a non-unique index gives a mask), a unique scalar label drops it; a boolean
+        array is a mask."""
+        out = self
+        for dim, lab in indexers.items():
+            ax = out.dims.index(dim)
+            labels = out.coords[dim].values
+            mask = None
+            if isinstance(lab, (DataArray, np.ndarray)) and np.asarray(lab).dtype.kind == "b":
+                mask = np.asarray(lab)
+            else:
+                hits = np.array([x == lab for x in labels.tolist()], dtype=bool)
+                if not hits.any():
+                    raise KeyError(lab)
+                if hits.sum() > 1:
+                    mask = hits
+                else:                                                # unique scalar label: the dimension goes
+                    i = int(np.argmax(hits))
+                    co = {k: c for k, c in out.coords.items() if dim not in c.dims}
+                    out = DataArray(np.take(out._data, i, axis=ax), tuple(d for d in out.dims if d != dim), co, out.attrs)
+                    continue
+            co = {k: (DataArray(np.compress(mask, c.values, axis=c.dims.index(dim)), c.dims) if dim in c.dims else c)
+                  for k, c in out.coords.items()}
+            out = DataArray(np.compress(mask, out._data, axis=ax), out.dims, co, out.attrs)
+        return out
 
     def transpose(self, *dims):
         assert sorted(dims) == sorted(self.dims)
@@ -120,8 +199,20 @@ class Dataset:
     def __getattr__(self, name):
         coords = self.__dict__.get("coords", {})
         if name in coords:
-            return coords[name]
+            c = coords[name]
+            return DataArray(c.values, c.dims, {name: c} if c.dims == (name,) else None)
+        if name in self.__dict__.get("data_vars", {}):
+            return self[name]
         raise AttributeError(name)
+
+    @property
+    def sizes(self):
+        out = {}
+        for v in list(self.data_vars.values()) + list(self.coords.values()):
+            out.update(zip(v.dims, v.shape))
+        return out
+
+    dims = sizes
 
     def _coords_for(self, dims):
         return {k: c for k, c in self.coords.items() if all(d in dims for d in c.dims)}

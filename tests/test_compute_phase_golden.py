@@ -299,3 +299,18 @@ def test_main_on_the_device_reproduces_the_references_own_main(name, tmp_path, m
     assert list(out.attrs) == list(res["attrs"])
     for k in ("n_components", "variables", "levels", "mean_center", "scale", "delay_embedding", "svd_type", "save_data_matrix"):
         assert out.attrs[k] == res["attrs"][k], k
+
+
+def test_the_xarray_stand_in_passed_the_references_own_tests():
+    """The stand-in the golden vectors were generated on is itself checked by the reference's OWN tests (collected
+    unchanged, ``xarray`` -> stand-in, ``dmd_era5`` -> the reference's functions from source):
+    tests/golden/run_reference_tests_on_standin.py writes the outcome next to the vectors."""
+    with open(os.path.join(HERE, "golden", "reference_tests_on_standin.log")) as f:
+        lines = [ln.split() for ln in f if ln.strip() and not ln.startswith("#")]
+    assert len(lines) == 33 and all(ln[0] == "PASSED" for ln in lines)
+    names = {ln[1].split("[")[0] for ln in lines}
+    for must in ("test_02_slice_tools.py::test_flatten_era5_variables_array_dims",
+                 "test_02_slice_tools.py::test_apply_delay_embedding_dataarray_values",
+                 "test_02_slice_tools.py::test_standardize_data", "test_02_slice_tools.py::test_resample_era5_dataset",
+                 "test_03_era5_svd.py::test_svd_on_era5", "test_03_era5_svd.py::test_combine_svd_results"):
+        assert must in names, must
