@@ -122,7 +122,7 @@ def test_shard_rows():
     assert all(p[0] % 128 == 0 for p in parts)
 
 
-def _gloo_worker(rank, world, port, q, tensor_core=False):
+def _gloo_worker(rank, world, port, q, tensor_core=False, route="randomized"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
 
@@ -138,6 +138,13 @@ def _gloo_worker(rank, world, port, q, tensor_core=False):
         k, d = 9, 2
         r0, r1 = shard_rows(X.shape[0], world, rank, align=128)
         n = X.shape[1] - d + 1
+        if route == "standard":
+            from dmd_era5_b200.rsvd import PREC_TF32MIX
+
+            U, s, Vt = standard_svd_device(FakeOps(), torch.from_numpy(X[r0:r1].copy()), k, delay=d, comm=comm,
+                                           precision=PREC_TF32MIX if tensor_core else PREC_NATIVE)
+            q.put((rank, r0, r1, U.double().numpy(), s.numpy(), Vt.numpy()))
+            return
         U, s, Vt = randomized_svd_device(FakeOps(), torch.from_numpy(X[r0:r1].copy()), k,
                                          draw_omega(n, k, 4, torch.float32 if tensor_core else torch.float64), delay=d,
                                          comm=comm, row_offset=r0, m0_global=X.shape[0],
@@ -175,6 +182,39 @@ def test_two_rank_gloo_row_sharding(tensor_core):
         assert sigma_rel_err(s, s0) < s_tol and vector_angles(Vt.T, V0.T).max() < a_tol
     assert np.array_equal(res[0][4], res[1][4])          # replicated small factors agree bitwise
     assert vector_angles(U, U0).max() < a_tol and signs_agree(U, U0)
+
+
+@pytest.mark.parametrize("tensor_core", [False, True])
+def test_two_rank_gloo_standard_route_with_delay(tensor_core):
+    """The standard route row-sharded over 2 ranks (gloo), delay 2: each rank forms the Gram matrix of ITS rows of the base
+    matrix once, the shifted diagonal blocks are summed, the n x n result is all-reduced; float32 data additionally runs
+    the sharded refinement passes.  Against np.linalg.svd of the embedded matrix (signs are not part of the contract)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + (1 if tensor_core else 0)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q, tensor_core, "standard")) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    X = lowrank_field_np(1030, 90, r=40, rho=0.85, seed=9)
+    if tensor_core:
+        X = X.astype(np.float32).astype(np.float64)
+    k, d, m0 = 9, 2, 1030
+    U0, s0, V0 = standard_svd_ref(delay_embed_np(X, d), k)
+    s_tol, a_tol = (1e-6, 1e-4) if tensor_core else (1e-9, 1e-6)
+    U = np.zeros((m0 * d, k))
+    for rank, r0, r1, Ul, s, Vt in res:
+        ml = r1 - r0
+        for j in range(d):
+            U[j * m0 + r0 : j * m0 + r1] = Ul[j * ml : (j + 1) * ml]
+        assert sigma_rel_err(s, s0) < s_tol and vector_angles(Vt.T, V0.T).max() < a_tol
+    assert np.array_equal(res[0][4], res[1][4]) and np.array_equal(res[0][5], res[1][5])      # replicas agree bitwise
+    assert vector_angles(U, U0).max() < a_tol
 
 
 @pytest.mark.parametrize("d", [1, 2])
