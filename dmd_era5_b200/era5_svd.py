@@ -111,3 +111,33 @@ def __getattr__(name):
 
         return getattr(stage, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
+def check_if_dvc_repo() -> bool:
+    """era5_svd.py:457-464: is the project root a DVC repository?  (``dvc`` imported lazily; absent = no repository.)"""
+    try:
+        from dvc.repo import Repo as DvcRepo
+
+        from .config_parser import project_root
+
+        with DvcRepo(project_root()) as _:
+            return True
+    except Exception:
+        return False
+
+
+def run_module() -> None:
+    """``python -m dmd_era5_b200.era5_svd`` = the reference's ``python -m dmd_era5.era5_svd.era5_svd`` (era5_svd.py:455-478):
+    the ``[era5-svd]`` section of config.ini, results written to NetCDF, DVC used when the project is a DVC repository."""
+    from .stage import main
+
+    if not check_if_dvc_repo():
+        log_and_print(logger, "Not a Data Version Control (DVC) repository. Will not use DVC.", level="warning")
+        log_and_print(logger, "To initialize a DVC repository, run `dvc init`.", level="warning")
+        main(write_to_netcdf=True)
+    else:
+        main(write_to_netcdf=True, use_dvc=True)
+
+
+if __name__ == "__main__":
+    run_module()

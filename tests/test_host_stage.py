@@ -807,3 +807,52 @@ def test_add_config_attributes_matches_the_references_own(monkeypatch):
                 datetime.fromisoformat(got)
             else:
                 assert (got.replace("/ROOT", "<ROOT>") if isinstance(got, str) else got) == want, k
+
+
+@pytest.mark.parametrize("scenario", ["not a DVC repository", "DVC repository"])
+def test_module_entry_follows_the_references_own_main_block(scenario, monkeypatch):
+    """``python -m dmd_era5_b200.era5_svd`` against the ``if __name__ == "__main__"`` block of the reference's era5_svd.py
+    (:455-478, executed unchanged with recorders: tests/golden/make_golden_module_entry.py): the two warnings and
+    ``main(write_to_netcdf=True)`` outside a DVC repository, ``main(write_to_netcdf=True, use_dvc=True)`` inside one."""
+    import json
+    import sys
+    import types
+
+    from dmd_era5_b200 import era5_svd, stage
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "module_entry.json")) as f:
+        want = json.load(f)[scenario]
+    is_repo = scenario == "DVC repository"
+
+    class Repo:
+        def __init__(self, root):
+            if not is_repo:
+                raise RuntimeError("not a dvc repository")
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    dvc, repo = types.ModuleType("dvc"), types.ModuleType("dvc.repo")
+    repo.Repo = Repo
+    dvc.repo = repo
+    monkeypatch.setitem(sys.modules, "dvc", dvc)
+    monkeypatch.setitem(sys.modules, "dvc.repo", repo)
+    log, calls = [], []
+    monkeypatch.setattr(era5_svd, "log_and_print", lambda lg, msg, level="info": log.append([level, str(msg)]))
+    monkeypatch.setattr(stage, "main", lambda *a, **k: calls.append({"args": list(a), "kwargs": k}))
+    era5_svd.run_module()
+    assert log == want["log"] and calls == want["main_calls"]
+
+
+def test_module_entry_without_dvc_installed(monkeypatch):
+    """dvc is an optional import: without it the project is "not a DVC repository" (this image)."""
+    from dmd_era5_b200 import era5_svd
+
+    try:
+        import dvc  # noqa: F401
+        pytest.skip("dvc is installed here")
+    except ImportError:
+        assert era5_svd.check_if_dvc_repo() is False
