@@ -53,19 +53,33 @@ def project_root() -> str:
 
 
 def config_reader(section: str, config_path: str | None = None) -> dict:
-    """INI section -> dict, every value through ast.literal_eval (config_reader.py:16-62)."""
+    """INI section -> dict, every value through ast.literal_eval (config_reader.py:16-62), with the reference's error
+    contract: a missing file reads as "no such section" (ConfigParser.read skips it), a missing section raises
+    ``Exception("Section ... not found in the ... file")``, an unparsable value is logged / printed and the ORIGINAL
+    exception of ast.literal_eval propagates."""
+    import logging
+
     path = config_path or os.path.join(project_root(), "config.ini")
-    cp = configparser.ConfigParser()
-    if not cp.read(path):
-        raise FileNotFoundError(f"Configuration file not found: {path}")
-    if section not in cp:
-        raise KeyError(f"Section {section} not found in {path}")
+    log = logging.getLogger("ConfigReader")
+    parser = configparser.ConfigParser()
+    parser.read(path, encoding="utf-8-sig")
     out = {}
-    for key, val in cp[section].items():
-        try:
-            out[key] = ast.literal_eval(val)
-        except (ValueError, SyntaxError) as e:
-            raise ValueError(f"Error parsing {key} in section {section}: {e}") from e
+    if parser.has_section(section):
+        for param_name, param_value in parser.items(section):
+            try:
+                out[param_name] = ast.literal_eval(param_value)
+            except Exception as e:
+                msg = f"""
+                    Error while parsing {param_name} from {section} section
+                    in the config file: {e}
+                    """
+                log.error(msg)
+                print(msg)
+                raise
+    else:
+        msg = f"Section {section} not found in the {path} file"
+        log.error(msg)
+        raise Exception(msg)
     return out
 
 

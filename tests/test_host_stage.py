@@ -856,3 +856,47 @@ def test_module_entry_without_dvc_installed(monkeypatch):
         pytest.skip("dvc is installed here")
     except ImportError:
         assert era5_svd.check_if_dvc_repo() is False
+
+
+def _golden_config_reader():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "config_reader.json")) as f:
+        return json.load(f)
+
+
+def test_config_reader_matches_the_references_own(tmp_path, capsys):
+    """config_reader against the reference's OWN function (config_reader.py:16-62, loaded from source:
+    tests/golden/make_golden_config_reader.py): values and Python types for its own config.ini / tests/config.ini and a
+    set of INI texts (literals, lower-cased keys, byte order mark, continuation lines), and the exception type and text of a
+    missing file, a missing section and unparsable values (the ORIGINAL ast.literal_eval exception propagates)."""
+    g = _golden_config_reader()
+
+    def check(rec, got_fn, path):
+        if "values" in rec:
+            got = got_fn()
+            assert got == rec["values"] and list(got) == list(rec["values"])
+            assert [type(v).__name__ for v in got.values()] == [type(v).__name__ for v in rec["values"].values()]
+            return
+        with pytest.raises(Exception) as ei:
+            got_fn()
+        assert type(ei.value).__name__ == rec["error"]["type"]
+        want = rec["error"]["message"].replace("<PATH>", path)
+        got = str(ei.value)
+        if " object at 0x" in want:                          # an object address inside Python's own message
+            want, got = want.split(" object at 0x")[0], got.split(" object at 0x")[0]
+        assert got == want
+
+    for r in g["requests"]:
+        p = str(tmp_path / ("config.ini" if r["text"] is not None else "does-not-exist.ini"))
+        if r["text"] is not None:
+            with open(p, "w", encoding="utf-8") as f:
+                f.write(g["texts"][r["text"]])
+        check(r, lambda: config_reader(r["section"], p), p)
+    for label, rec in g["files"].items():
+        p = str(tmp_path / "ref.ini")
+        with open(p, "w", encoding="utf-8") as f:
+            f.write(rec["text"])
+        for section, want in rec["sections"].items():
+            check(want, lambda: config_reader(section, p), p)
+    assert "Error while parsing a from s section" in capsys.readouterr().out      # printed like the reference does
