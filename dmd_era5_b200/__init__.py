@@ -10,7 +10,7 @@ slice_era5_dataset, config_parser, add_data_to_dvc`` and ``from dmd_era5_b200.er
 read like the reference's own imports.  Names are resolved lazily (PEP 562) so that importing the package neither
 loads torch nor needs the CUDA library.  Out of scope and therefore absent: ``download_era5_data`` (the network
 stage), ``create_mock_era5`` / ``create_mock_era5_svd`` (test-data generators; their seeded restatement lives in
-``oracle/``), ``setup_logger`` (file logging set-up).
+``oracle/``).
 """
 from ._cabi import Era5SvdError, LIB_PATH  # noqa: F401
 # like the reference (``from dmd_era5.core import config_parser`` after the submodule import), the FUNCTION shadows the
@@ -26,7 +26,7 @@ _EXPORTS = {
     "apply_delay_embedding": "slice_tools", "flatten_era5_variables": "slice_tools",
     "_apply_delay_embedding_np": "slice_tools", "space_coord_to_level_lat_lon": "slice_tools",
     # core (src/dmd_era5/core.py)
-    "log_and_print": "era5_svd",
+    "log_and_print": "era5_svd", "setup_logger": "era5_svd",
     # dvc_tools (src/dmd_era5/dvc_tools.py:50-63, :119-253)
     "add_data_to_dvc": "dvc_tools", "retrieve_data_from_dvc": "dvc_tools",
     # era5_svd (src/dmd_era5/era5_svd/__init__.py:10-17)

@@ -28,8 +28,31 @@ logger = logging.getLogger("ERA5-SVD")
 
 def log_and_print(lg: logging.Logger, msg: str, level: str = "info") -> None:
     """src/dmd_era5/logger.py:42-46: log and print."""
-    getattr(lg, level)(msg)
+    getattr(lg, level.lower())(msg)
     print(msg)
+
+
+def setup_logger(name: str, log_file: str, level=logging.INFO) -> logging.Logger:
+    """src/dmd_era5/logger.py:7-39: logger ``name`` writing ``<project root>/logs/<log_file>`` in the reference's format;
+    existing handlers are replaced.  The reference does this when its modules are IMPORTED (quirk Q8: importing
+    era5_svd.py creates ``logs/``); here importing has no side effects and the module entry (``run_module``) sets the two
+    loggers of the path up."""
+    import os
+
+    from .config_parser import project_root
+
+    formatter = logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s")
+    log_path = os.path.join(project_root(), "logs")
+    if not os.path.exists(log_path):
+        os.makedirs(log_path)
+    file_handler = logging.FileHandler(os.path.join(log_path, log_file))
+    file_handler.setFormatter(formatter)
+    lg = logging.getLogger(name)
+    lg.setLevel(level)
+    for handler in lg.handlers[:]:
+        lg.removeHandler(handler)
+    lg.addHandler(file_handler)
+    return lg
 
 
 _OPS: dict[str, CudaOps] = {}
@@ -131,6 +154,8 @@ def run_module() -> None:
     the ``[era5-svd]`` section of config.ini, results written to NetCDF, DVC used when the project is a DVC repository."""
     from .stage import main
 
+    setup_logger("ERA5-SVD", "era5_svd.log")                    # era5_svd.py:33
+    setup_logger("ERA5Processing", "era5_processing.log")        # slice_tools.py:12
     if not check_if_dvc_repo():
         log_and_print(logger, "Not a Data Version Control (DVC) repository. Will not use DVC.", level="warning")
         log_and_print(logger, "To initialize a DVC repository, run `dvc init`.", level="warning")

@@ -28,7 +28,7 @@ logger = logging.getLogger("ERA5Processing")            # the reference's logger
 
 def log_and_print(lg: logging.Logger, msg: str, level: str = "info") -> None:
     """src/dmd_era5/logger.py:42-46 (kept local: importing era5_svd here would load torch for pure index work)."""
-    getattr(lg, level)(msg)
+    getattr(lg, level.lower())(msg)
     print(msg)
 
 

@@ -264,7 +264,7 @@ def test_package_keeps_the_reference_import_surface():
     import dmd_era5_b200 as pkg
     from dmd_era5_b200 import era5_svd
 
-    for name in ("apply_delay_embedding", "flatten_era5_variables", "config_reader", "log_and_print", "resample_era5_dataset",
+    for name in ("apply_delay_embedding", "flatten_era5_variables", "config_reader", "log_and_print", "setup_logger", "resample_era5_dataset",
                  "slice_era5_dataset", "standardize_data", "config_parser", "add_data_to_dvc", "retrieve_data_from_dvc",
                  "space_coord_to_level_lat_lon", "_apply_delay_embedding_np"):
         assert callable(getattr(pkg, name)), name
@@ -810,7 +810,7 @@ def test_add_config_attributes_matches_the_references_own(monkeypatch):
 
 
 @pytest.mark.parametrize("scenario", ["not a DVC repository", "DVC repository"])
-def test_module_entry_follows_the_references_own_main_block(scenario, monkeypatch):
+def test_module_entry_follows_the_references_own_main_block(scenario, monkeypatch, tmp_path):
     """``python -m dmd_era5_b200.era5_svd`` against the ``if __name__ == "__main__"`` block of the reference's era5_svd.py
     (:455-478, executed unchanged with recorders: tests/golden/make_golden_module_entry.py): the two warnings and
     ``main(write_to_netcdf=True)`` outside a DVC repository, ``main(write_to_netcdf=True, use_dvc=True)`` inside one."""
@@ -843,8 +843,18 @@ def test_module_entry_follows_the_references_own_main_block(scenario, monkeypatc
     log, calls = [], []
     monkeypatch.setattr(era5_svd, "log_and_print", lambda lg, msg, level="info": log.append([level, str(msg)]))
     monkeypatch.setattr(stage, "main", lambda *a, **k: calls.append({"args": list(a), "kwargs": k}))
-    era5_svd.run_module()
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))          # the entry sets the path's two file loggers up under <root>/logs
+    try:
+        era5_svd.run_module()
+    finally:
+        import logging
+
+        for name in ("ERA5-SVD", "ERA5Processing"):
+            for h in logging.getLogger(name).handlers[:]:
+                h.close()
+                logging.getLogger(name).removeHandler(h)
     assert log == want["log"] and calls == want["main_calls"]
+    assert sorted(os.listdir(tmp_path / "logs")) == ["era5_processing.log", "era5_svd.log"]
 
 
 def test_module_entry_without_dvc_installed(monkeypatch):
@@ -900,3 +910,29 @@ def test_config_reader_matches_the_references_own(tmp_path, capsys):
         for section, want in rec["sections"].items():
             check(want, lambda: config_reader(section, p), p)
     assert "Error while parsing a from s section" in capsys.readouterr().out      # printed like the reference does
+
+
+def test_setup_logger_writes_the_references_log_file(tmp_path, monkeypatch):
+    """setup_logger (logger.py:7-39): ``<root>/logs/<file>``, the reference's line format, previous handlers replaced;
+    log_and_print takes the level in any case (``level.lower()``, :44)."""
+    import logging
+    import re
+
+    from dmd_era5_b200 import log_and_print, setup_logger
+
+    monkeypatch.setenv("DMD_ERA5_ROOT", str(tmp_path))
+    lg = setup_logger("ERA5-SVD-test", "era5_svd.log")
+    lg2 = setup_logger("ERA5-SVD-test", "era5_svd.log")
+    try:
+        assert lg is lg2 and len(lg.handlers) == 1 and lg.level == logging.INFO
+        log_and_print(lg, "Performing randomized SVD...")
+        log_and_print(lg, "SVD results not found in working directory.", "WARNING")
+        lg.handlers[0].flush()
+        lines = open(tmp_path / "logs" / "era5_svd.log").read().splitlines()
+        assert len(lines) == 2
+        assert re.fullmatch(r"\d{4}-\d\d-\d\d \d\d:\d\d:\d\d,\d{3} - ERA5-SVD-test - INFO - Performing randomized SVD\.\.\.", lines[0])
+        assert lines[1].endswith(" - ERA5-SVD-test - WARNING - SVD results not found in working directory.")
+    finally:
+        for h in lg.handlers[:]:
+            h.close()
+            lg.removeHandler(h)
