@@ -191,10 +191,10 @@ def shard_rows(m0: int, world: int, rank: int, align: int = 128) -> tuple[int, i
     if world <= 1:
         return 0, m0
     tiles = -(-m0 // align)
-    per = -(-tiles // world)
-    r0 = min(m0, rank * per * align)
-    r1 = min(m0, (rank + 1) * per * align)
-    return r0, r1
+    base, extra = divmod(tiles, world)          # balanced: the first ``extra`` ranks own one tile more, so no rank is
+    t0 = rank * base + min(rank, extra)         # left empty while tiles >= world (ceil(tiles / world) per rank left the
+    t1 = t0 + base + (1 if rank < extra else 0)  # last ranks of a small matrix without rows: 21 tiles on 8 ranks)
+    return min(m0, t0 * align), min(m0, t1 * align)
 
 
 def shard_rows_weighted(m0: int, weights, rank: int, align: int = 128) -> tuple[int, int]:

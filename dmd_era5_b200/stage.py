@@ -434,6 +434,14 @@ def _compute(ds: Dataset, parsed_config: dict) -> Dataset:
     if parsed_config["mean_center"]:                 # standardize_data's progress lines (:389-392); Q4: scale needs centring
         log_standardize("time", bool(parsed_config["scale"]))
     if n_gpus > 1:
+        # a rank needs at least one 128-row tile of the base matrix (dist.shard_rows): small inputs use fewer GPUs
+        S_ = int(np.prod([len(dsp.coord(c)) for c in ("level", "latitude", "longitude")]))
+        tiles = -(-(len(variables) * S_) // 128)
+        if tiles < n_gpus:
+            log_and_print(logger, f"n_gpus = {n_gpus}, but the matrix has only {tiles} row tile(s) of 128: using {tiles} GPU(s).",
+                          "warning")
+            n_gpus = tiles
+    if n_gpus > 1:
         from .stage_multi import compute_multi
 
         arr = compute_multi(parsed_config, n_gpus)

@@ -314,3 +314,24 @@ def test_the_xarray_stand_in_passed_the_references_own_tests():
                  "test_02_slice_tools.py::test_standardize_data", "test_02_slice_tools.py::test_resample_era5_dataset",
                  "test_03_era5_svd.py::test_svd_on_era5", "test_03_era5_svd.py::test_combine_svd_results"):
         assert must in names, must
+
+
+def test_n_gpus_is_capped_by_the_number_of_row_tiles(monkeypatch):
+    """``n_gpus`` larger than the number of 128-row tiles of the base matrix (a small slice): the stage uses as many GPUs
+    as there are tiles - here one, i.e. the single-device path - instead of handing a rank an empty shard."""
+    from dmd_era5_b200 import slice_tools, stage, stage_multi
+
+    monkeypatch.setenv("TZ", "UTC")
+    _time.tzset()
+    monkeypatch.setenv("DMD_ERA5_ROOT", "/ROOT")
+    monkeypatch.setattr(stage, "_device_arrays", fake_device_arrays)
+    monkeypatch.setattr(stage, "get_ops", lambda *a, **k: None)
+    monkeypatch.setattr(stage_multi, "compute_multi", lambda *a, **k: pytest.fail("no multi-GPU run for a one-tile matrix"))
+    log = []
+    for mod in (stage, slice_tools):
+        monkeypatch.setattr(mod, "log_and_print", lambda lg, msg, level="info": log.append([level, str(msg)]))
+    case = GOLD["cases"][CASES[0]]                                  # 48 base rows: one tile
+    parsed = config_parser(dict(case["config"], n_gpus=4), section="era5-svd")
+    out = stage._compute(product_slice(case), parsed)
+    assert ["warning", "n_gpus = 4, but the matrix has only 1 row tile(s) of 128: using 1 GPU(s)."] in log
+    assert np.array_equal(np.asarray(out["U"].values), golden_array(case["result"]["data_vars"]["U"]))

@@ -120,6 +120,17 @@ def test_shard_rows():
     assert parts[0][0] == 0 and parts[-1][1] == 1038240
     assert all(parts[i][1] == parts[i + 1][0] for i in range(7))
     assert all(p[0] % 128 == 0 for p in parts)
+    # balanced: no rank is left without rows while there are at least as many 128-row tiles as ranks (2592 rows = the
+    # reference's mock grid with one level: 21 tiles on 8 ranks), and shard sizes differ by at most one tile
+    for m0, world in ((2592, 8), (1024, 8), (129, 2), (40491360, 8), (7232760, 8), (1000, 3)):
+        parts = [shard_rows(m0, world, r) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == m0
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        assert all(a % 128 == 0 for a, _ in parts)
+        sizes = [b - a for a, b in parts]
+        assert min(sizes) > 0 and max(sizes) - min(sizes) <= 128 + 127
+    # fewer tiles than ranks: the surplus ranks are empty, at the END (callers cap the rank count: stage._compute)
+    assert [shard_rows(200, 4, r) for r in range(4)] == [(0, 128), (128, 200), (200, 200), (200, 200)]
 
 
 def _gloo_worker(rank, world, port, q, tensor_core=False, route="randomized"):
