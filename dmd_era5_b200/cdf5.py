@@ -148,10 +148,25 @@ def write_classic(path: str, dims: dict, variables: list, gattrs: dict, version:
             be = arr.dtype.newbyteorder(">") if arr.dtype.kind != "S" else arr.dtype
             if arr.ndim == 0 or nbytes <= chunk_bytes:
                 fp.write(np.ascontiguousarray(arr, dtype=be).tobytes())
-            else:                                            # row chunks: one big-endian copy of a chunk at a time
+            else:
+                # row chunks: ONE big-endian copy of a chunk at a time (the byte swap), written from that buffer directly
+                # (no second ``tobytes`` copy); the swap of chunk i + 1 runs on a helper thread while chunk i is written
+                # (NumPy releases the GIL in the conversion, the file write releases it too)
+                from concurrent.futures import ThreadPoolExecutor
+
                 rows = max(1, chunk_bytes // max(1, nbytes // arr.shape[0]))
-                for r0 in range(0, arr.shape[0], rows):
-                    fp.write(np.ascontiguousarray(arr[r0 : r0 + rows], dtype=be).tobytes())
+                starts = list(range(0, arr.shape[0], rows))
+
+                def swapped(r0: int) -> np.ndarray:
+                    return np.ascontiguousarray(arr[r0 : r0 + rows], dtype=be).reshape(-1).view(np.uint8)
+
+                with ThreadPoolExecutor(max_workers=1) as pool:
+                    nxt = pool.submit(swapped, starts[0])
+                    for i in range(len(starts)):
+                        cur = nxt.result()
+                        if i + 1 < len(starts):
+                            nxt = pool.submit(swapped, starts[i + 1])
+                        fp.write(cur.data)
             fp.write(b"\x00" * (vsize - nbytes))
 
 
