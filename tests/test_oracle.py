@@ -159,6 +159,32 @@ def test_resample_nearest_pinned_against_pandas(name):
         assert np.array_equal(got_src, src), fn.__module__
 
 
+def test_resample_nearest_against_pandas_on_random_time_axes():
+    """300 seeded random cases - irregular, sorted, minute-resolution time axes (gaps, exact half-way ties, starts off
+    midnight) and bin widths from 30 minutes to 2 days: the oracle and the product index form give pandas' labels and
+    pandas' nearest sample for every label."""
+    pd = pytest.importorskip("pandas")
+    from dmd_era5_b200.slice_tools import resample_nearest_index as product_index
+    from oracle.slice_tools_np import resample_nearest_index as oracle_index
+
+    rng = np.random.RandomState(12)
+    minute = 60 * 10**9
+    t0 = np.datetime64("2019-01-01T00", "ns").astype(np.int64)
+    for case in range(300):
+        n = int(rng.randint(2, 60))
+        steps = rng.choice([15, 30, 60, 60, 60, 120, 180, 360], size=n)          # minutes between samples
+        t = t0 + int(rng.randint(0, 3 * 24 * 60)) * minute + np.concatenate([[0], np.cumsum(steps[:-1])]) * minute
+        delta = int(rng.choice([30, 60, 90, 120, 180, 240, 360, 720, 1440, 2880])) * minute
+        idx = pd.DatetimeIndex(t)
+        labels = pd.Series(np.arange(n), index=idx).resample(pd.Timedelta(delta, "ns")).first().index
+        src = idx.get_indexer(labels, method="nearest")
+        want_labels = labels.values.astype("datetime64[ns]").astype(np.int64)
+        for fn in (oracle_index, product_index):
+            got_labels, got_src = fn(t, delta)
+            assert np.array_equal(got_labels, want_labels), (case, fn.__module__)
+            assert np.array_equal(got_src, src), (case, fn.__module__, t.tolist(), delta)
+
+
 def _svd_on_era5_cases():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "svd_on_era5_reference.npz"), allow_pickle=True)
     return g, [tuple(row) for row in g["meta"]]
