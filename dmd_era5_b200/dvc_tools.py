@@ -133,6 +133,11 @@ _NO_RETRIEVE = ("\n            Found a matching version of the data in the log f
                 "            but could not retrieve it from DVC.\n            ")
 
 
+# the same sentence one block deeper in the reference's source (dvc_tools.py:243-247): its text carries that indentation
+_NO_RETRIEVE_AFTER_FETCH = ("\n                    Found a matching version of the data in the log file,\n"
+                            "                    but could not retrieve it from DVC.\n                    ")
+
+
 def retrieve_data_from_dvc(parsed_config: dict, data_type: str = "era5_slice") -> None:
     """dvc_tools.py:119-253: check out the most recent logged version of the data that matches the configuration.
     FileNotFoundError when the .dvc or log file is missing, ValueError when nothing matches or the matching version
@@ -162,4 +167,4 @@ def retrieve_data_from_dvc(parsed_config: dict, data_type: str = "era5_slice") -
             print("Checked out files:", repo.checkout(targets=[dvc_file_path]))
         if not remote_exists or not data_fetched:
             print("Could not fetch data from default remote DVC repository.")
-            raise ValueError(_NO_RETRIEVE)
+            raise ValueError(_NO_RETRIEVE_AFTER_FETCH)

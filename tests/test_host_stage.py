@@ -936,3 +936,62 @@ def test_setup_logger_writes_the_references_log_file(tmp_path, monkeypatch):
         for h in lg.handlers[:]:
             h.close()
             lg.removeHandler(h)
+
+
+def _golden_dvc_calls():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "dvc_calls.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", list(_golden_dvc_calls()["scenarios"]))
+def test_dvc_live_calls_follow_the_references_own_sequence(name, tmp_path, monkeypatch, capsys):
+    """The calls INTO dvc / git - what a live repository would see - of add_data_to_dvc and retrieve_data_from_dvc against
+    the sequence the reference's OWN dvc_tools.py makes under the same recording stand-ins for ``dvc.repo.Repo`` /
+    ``git.Repo`` (tests/golden/make_golden_dvc_calls.py): constructor roots, ``dvc add``, ``git add`` of the side-log,
+    ``git checkout <commit> <file>.dvc``, cache look-up, ``config["remote"]`` / ``fetch`` / ``checkout``, what is printed,
+    and the exception of each of the three failing retrievals."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    try:
+        from make_golden_dvc_calls import ATTRS, MD5, REQUEST, make_standins
+    finally:
+        sys.path.pop(0)
+    import types
+
+    from dmd_era5_b200 import dvc_tools
+
+    g = _golden_dvc_calls()["scenarios"][name]
+    scenario, root = g["scenario"], str(tmp_path)
+    calls = []
+    DvcRepo, GitRepo = make_standins(calls, root, scenario)
+    for modname, attrs in (("dvc", {}), ("dvc.repo", {"Repo": DvcRepo}), ("git", {"Repo": GitRepo})):
+        m = types.ModuleType(modname)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        monkeypatch.setitem(sys.modules, modname, m)
+    monkeypatch.setenv("DMD_ERA5_ROOT", root)
+    os.makedirs(os.path.join(root, "data/era5_svd"))
+    data_path = os.path.join(root, "data/era5_svd/result.nc")
+    open(data_path, "w").write("x")
+    raised = None
+    try:
+        if scenario["op"] == "add":
+            dvc_tools.add_data_to_dvc(data_path, dict(ATTRS))
+            assert open(data_path + ".yaml").read() == g["log_file"]
+        else:
+            open(data_path + ".dvc", "w").write(f"outs:\n- md5: {MD5}\n")
+            open(data_path + ".yaml", "w").write(f"{MD5}:\n" + "".join(f"  {k}: {v}\n" for k, v in ATTRS.items()))
+            if scenario.get("cached"):
+                os.makedirs(os.path.join(root, ".dvc/cache/files/md5", MD5[:2]))
+                open(os.path.join(root, ".dvc/cache/files/md5", MD5[:2], MD5[2:]), "w").write("x")
+            monkeypatch.setattr(dvc_tools, "find_first_commit_with_md5_hash",
+                                lambda md5, path: (calls.append(["git log -S", md5, os.path.relpath(path, root)]), scenario["commit"])[1])
+            dvc_tools.retrieve_data_from_dvc(dict(REQUEST, era5_svd_path=data_path), "era5_svd")
+    except Exception as e:  # noqa: BLE001
+        raised = {"type": type(e).__name__, "message": str(e)}
+    assert calls == g["calls"]
+    assert raised == g.get("raised")
+    assert capsys.readouterr().out.replace(root, "<ROOT>") == g["printed"]
