@@ -995,3 +995,36 @@ def test_dvc_live_calls_follow_the_references_own_sequence(name, tmp_path, monke
     assert calls == g["calls"]
     assert raised == g.get("raised")
     assert capsys.readouterr().out.replace(root, "<ROOT>") == g["printed"]
+
+
+def test_find_first_commit_with_md5_hash_on_a_real_git_repository(tmp_path, monkeypatch):
+    """dvc_tools.py:66-92 runs ``git log -S <md5> --reverse --oneline -- <file>.dvc`` in the working directory and takes the
+    FIRST line: the OLDEST commit whose change of the .dvc file adds or removes the md5.  Checked on a real repository (git
+    is part of the image): three versions of a .dvc file, the commit that introduced each md5, an unknown md5."""
+    import shutil
+    import subprocess
+
+    from dmd_era5_b200.dvc_tools import find_first_commit_with_md5_hash
+
+    if shutil.which("git") is None:
+        pytest.skip("git is not installed")
+    env = dict(os.environ, GIT_AUTHOR_NAME="t", GIT_AUTHOR_EMAIL="t@t", GIT_COMMITTER_NAME="t", GIT_COMMITTER_EMAIL="t@t",
+               GIT_CONFIG_GLOBAL=os.devnull, GIT_CONFIG_SYSTEM=os.devnull)
+    git = lambda *a: subprocess.run(["git", *a], cwd=tmp_path, env=env, check=True, capture_output=True, text=True).stdout.strip()  # noqa: E731
+    git("init", "-q")
+    md5s = ["a" * 32, "b" * 32, "c" * 32]
+    commits = []
+    for i, md5 in enumerate(md5s):
+        (tmp_path / "result.nc.dvc").write_text(f"outs:\n- md5: {md5}\n  path: result.nc\n")
+        (tmp_path / "other.txt").write_text(f"unrelated change {i}\n")
+        git("add", "-A")
+        git("commit", "-q", "-m", f"version {i}")
+        commits.append(git("rev-parse", "--short", "HEAD"))
+    monkeypatch.chdir(tmp_path)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for md5, commit in zip(md5s, commits):
+        got = find_first_commit_with_md5_hash(md5, "result.nc.dvc")
+        assert got is not None and (commit.startswith(got) or got.startswith(commit)), (md5, got, commit)
+    assert find_first_commit_with_md5_hash("d" * 32, "result.nc.dvc") is None
+    assert find_first_commit_with_md5_hash(md5s[0], "missing.dvc") is None
