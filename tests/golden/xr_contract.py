@@ -335,3 +335,47 @@ def concat(objs, dim):
 
 
 Coordinates = Coords        # only named in the reference's type annotations (era5_svd.py:270)
+
+
+# -- file round trip of the stand-in (tests of the product's xarray BRANCHES only: dataset.write_netcdf / read_netcdf take
+#    them when xarray + netCDF4 are importable; the container format here is a pickle, the call signatures are xarray's) --
+def _to_netcdf(self, path, format=None, **kw):
+    import pickle
+
+    assert format in (None, "NETCDF4", "NETCDF4_CLASSIC", "NETCDF3_64BIT", "NETCDF3_CLASSIC"), format
+    with open(path, "wb") as f:
+        pickle.dump({"format": format,
+                     "data_vars": {k: (v.dims, v.values, v.attrs) for k, v in self.data_vars.items()},
+                     "coords": {k: (c.dims, c.values) for k, c in self.coords.items()}, "attrs": self.attrs}, f)
+
+
+Dataset.to_netcdf = _to_netcdf
+
+
+def _as_netcdf4_returns(v):
+    """How an attribute comes back through netCDF4 / xarray: a one-element sequence as a SCALAR (str or NumPy scalar), a
+    longer list of strings as a list, a longer numeric sequence as an ndarray, Python numbers as NumPy scalars - what the
+    reference's readers cope with (``str_to_list`` / ``int_to_list`` / ``.tolist()``, era5_svd.py:86-99, :175-183)."""
+    if isinstance(v, (list, tuple)):
+        if len(v) == 1:
+            return _as_netcdf4_returns(v[0])
+        return list(v) if all(isinstance(x, str) for x in v) else np.asarray(v)
+    if isinstance(v, bool):
+        return np.int64(int(v))
+    if isinstance(v, int):
+        return np.int64(v)
+    if isinstance(v, float):
+        return np.float64(v)
+    return v
+
+
+def open_dataset(path, **kw):
+    import pickle
+
+    with open(path, "rb") as f:
+        d = pickle.load(f)
+    dec = lambda a: {k: _as_netcdf4_returns(v) for k, v in a.items()}      # noqa: E731
+    ds = Dataset({k: DataArray(v, dims, None, dec(attrs)) for k, (dims, v, attrs) in d["data_vars"].items()},
+                 {k: (dims, v) for k, (dims, v) in d["coords"].items()}, dec(d["attrs"]))
+    ds.file_format = d["format"]
+    return ds
