@@ -107,9 +107,14 @@ def _omega_on_device(ops: CudaOps, n: int, k: int, seed: int | None, dtype: torc
 def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_components: int, delay: int = 1,
                seed: int | None = None, precision: str = "auto", comm=None, row_offset: int = 0,
                m0_global: int | None = None, n_iter: int | None = None, stats: dict | None = None,
-               split: tuple[torch.Tensor, torch.Tensor] | None = None, full_iters: int | None = None):
+               split: tuple[torch.Tensor, torch.Tensor] | None = None, full_iters: int | None = None,
+               centred: bool = True):
     """SVD of the (virtual) delay-embedded matrix whose base rows are X (device, tall dtype).
     ``split`` = (Xhi, Xlo) passes pre-split tf32 images (precision "tf32x3"); X may then be None.
+    ``centred`` = False (the stage passes ``mean_center``): precision "auto" then keeps 3xTF32 in EVERY power iteration -
+    the single-product iterations truncate X to tf32 relative to its VALUES, and a field that still carries its time mean
+    (temperature: 250 K with anomalies of a few K) loses 2^-11 * 250 K = 0.12 K there (sigma error 7e-5 emulated against
+    5e-6 for centred data).
     Dispatch and error text follow svd_on_era5 (era5_svd.py:247-262)."""
     if X is not None and X.dim() == 2 and (X.stride(1) != 1 or X.stride(0) % (4 if X.dtype == torch.float32 else 2) != 0
                                           or X.data_ptr() % 16 != 0):
@@ -128,7 +133,7 @@ def svd_device(ops: CudaOps, X: torch.Tensor | None, *, svd_type: str, n_compone
         # float32 data: tensor-core 3xTF32 passes whenever the sketch / component count fits one MMA tile (<= 128);
         # float64 data (and anything wider): the native path (FP64 DMMA / FP32 FMA)
         width = min(int(n_components) + 10, n) if svd_type == "randomized" else min(int(n_components), n)
-        precision = "tf32mix" if (ref.dtype == torch.float32 and width <= 128) else "native"
+        precision = ("tf32mix" if centred else "tf32x3") if (ref.dtype == torch.float32 and width <= 128) else "native"
     if svd_type == "standard":
         if X is None:
             X = split[0] + split[1]

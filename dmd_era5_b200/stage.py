@@ -409,7 +409,7 @@ def _device_arrays(ds: Dataset, parsed_config: dict, ops, comm=None, rank: int =
             log_and_print(logger, f"Performing {label} SVD...")
         U, s, V = svd_device(ops, built.X, svd_type=parsed_config["svd_type"], n_components=parsed_config["n_components"],
                              delay=d, seed=parsed_config.get("random_seed"), precision=precision, comm=comm,
-                             row_offset=r0, m0_global=m0)
+                             row_offset=r0, m0_global=m0, centred=mean_center)
         if rank == 0:
             log_and_print(logger, f"{label.capitalize()} SVD complete.")
         bad = built.nonfinite.to(torch.float64)

@@ -325,3 +325,30 @@ def test_shard_rows_weighted_partitions_all_rows():
     eq = [shard_rows_weighted(m0, [1.0] * 8, r) for r in range(8)]
     ref = [shard_rows(m0, 8, r) for r in range(8)]
     assert all(abs((b - a) - (d - c)) <= 1024 for (a, b), (c, d) in zip(eq, ref))
+
+
+def test_auto_precision_keeps_three_products_for_uncentred_data():
+    """pipeline.svd_device, precision "auto" on float32 data: the mixed schedule (single-product early power iterations)
+    for centred data, 3xTF32 in every iteration when the stage says the time mean was NOT removed; float64 data stays on
+    the native path either way.  The emulation shows why: with a 250 K mean the truncation of X in the single-product
+    passes costs a factor ~10 in sigma."""
+    from dmd_era5_b200.pipeline import svd_device
+
+    rng = np.random.RandomState(3)
+    X = (5.0 * rng.standard_normal((4000, 120)) + 250.0).astype(np.float32)
+    k = 12
+    U0, s0, V0 = randomized_svd_ref(X.astype(np.float64), k, 1)
+    err = {}
+    for centred in (True, False):
+        stats = {}
+        U, s, Vt = svd_device(FakeOps(), torch.from_numpy(X), svd_type="randomized", n_components=k, seed=1, stats=stats,
+                              centred=centred)
+        q = n_iter_auto(X.shape[0], X.shape[1], k)
+        assert stats["low_precision_iters"] == (q - 1 if centred else 0)
+        err[centred] = sigma_rel_err(s.numpy(), s0)
+    print(err)
+    assert err[False] < 3e-5 and err[False] < 0.5 * err[True]      # a flat (noise) spectrum amplifies every rounding difference
+    stats = {}
+    svd_device(FakeOps(), torch.from_numpy(X.astype(np.float64)), svd_type="randomized", n_components=k, seed=1, stats=stats,
+               centred=False)
+    assert stats["low_precision_iters"] == 0 and "sketch_tc" not in stats
