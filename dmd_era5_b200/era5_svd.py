@@ -90,6 +90,23 @@ def host_to_device_matrix(ops: CudaOps, X: np.ndarray) -> torch.Tensor:
     return view
 
 
+def looks_centred(X: np.ndarray, rows: int = 1024, ratio: float = 8.0) -> bool:
+    """Does the matrix look time-mean-centred?  Median over a sample of rows of |row mean| / row std (a centred or
+    anomaly field: << 1; temperature with its 250 K mean left in: 30 - 50).  svd_on_era5 receives a bare array, so this is
+    how precision "auto" decides between the mixed schedule and 3xTF32 in every pass (pipeline.svd_device, ``centred``):
+    the single-product passes truncate X relative to its VALUES."""
+    m, n = X.shape
+    if n < 2 or m == 0:
+        return True
+    idx = np.unique(np.linspace(0, m - 1, min(m, rows)).astype(np.int64))
+    S = np.asarray(X[idx], dtype=np.float64)
+    mu, sd = S.mean(axis=1), S.std(axis=1)
+    ok = np.isfinite(mu) & np.isfinite(sd) & (sd > 0)
+    if not ok.any():
+        return True
+    return float(np.median(np.abs(mu[ok]) / sd[ok])) <= ratio
+
+
 def svd_on_era5(da, parsed_config: dict) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Perform SVD on the pre-processed ERA5 slice (era5_svd.py:230-263).
 
@@ -109,7 +126,8 @@ def svd_on_era5(da, parsed_config: dict) -> tuple[np.ndarray, np.ndarray, np.nda
         nonfinite = ops.check_finite(Xd)        # asynchronous; read after the SVD has been queued
         U, s, V = svd_device(ops, Xd, svd_type=svd_type, n_components=n_components,
                              seed=parsed_config.get("random_seed"),
-                             precision=parsed_config.get("precision", "auto"))
+                             precision=parsed_config.get("precision", "auto"),
+                             centred=X.dtype != np.float32 or looks_centred(X))
         if int(nonfinite.item()):
             # sklearn check_array (extmath.py:546) / LAPACK on the reference side; main() wraps it as
             # "Error in the SVD on ERA5 process: ..." (era5_svd.py:426-429)

@@ -352,3 +352,18 @@ def test_auto_precision_keeps_three_products_for_uncentred_data():
     svd_device(FakeOps(), torch.from_numpy(X.astype(np.float64)), svd_type="randomized", n_components=k, seed=1, stats=stats,
                centred=False)
     assert stats["low_precision_iters"] == 0 and "sketch_tc" not in stats
+
+
+def test_looks_centred_separates_anomaly_fields_from_fields_with_their_mean():
+    from dmd_era5_b200.era5_svd import looks_centred
+
+    rng = np.random.RandomState(1)
+    assert looks_centred(lowrank_field_np(5000, 200, r=40, rho=0.9, seed=2).astype(np.float32))
+    assert looks_centred(rng.standard_normal((3000, 50)).astype(np.float32))
+    assert not looks_centred((5.0 * rng.standard_normal((3000, 50)) + 250.0).astype(np.float32))
+    raw = (30.0 * rng.rand(25, 2000) + 250.0).astype(np.float32).T                  # the reference's mock temperature
+    assert not looks_centred(raw) and looks_centred(raw - raw.mean(axis=1, keepdims=True))
+    assert looks_centred(np.ones((10, 1), np.float32)) and looks_centred(np.full((10, 5), 3.0, np.float32))   # degenerate
+    bad = rng.standard_normal((100, 8)).astype(np.float32)
+    bad[3, 2] = np.nan
+    assert looks_centred(bad)                                                        # NaN rows are skipped, not decisive
