@@ -53,7 +53,7 @@ class SvdStageStream:
         built = build_matrix_device(self.ops, [src], mean_center=self.mean_center, scale=self.scale)
         return svd_device(self.ops, built.X, svd_type=self.svd_type, n_components=self.k, delay=self.delay,
                           seed=self.seed, precision=self.precision, comm=self.comm, row_offset=self.row_offset,
-                          m0_global=self.m0_global)
+                          m0_global=self.m0_global, centred=self.mean_center)
 
     def run(self, host_slices: Iterable[torch.Tensor],
             consume: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None] | None = None) -> int:
